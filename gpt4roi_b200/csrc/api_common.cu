@@ -1,0 +1,36 @@
+// api_common.cu -- error reporting and device queries shared by every C-ABI entry point.
+#include "common.cuh"
+
+namespace g4r {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? G4R_ENODEVICE : G4R_ECUDA;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace g4r
+
+extern "C" const char* g4r_last_error(void) { return g4r::g_err; }
+extern "C" int g4r_version(void) { return 1000; }
+extern "C" int g4r_built_arch(void) { return 100; }

@@ -1,0 +1,83 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libgpt4roi_b200.so
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gpt4roi_b200.h"
+
+namespace g4r {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);  // defined in api_common.cu
+int cuda_fail(cudaError_t e, const char* what);
+
+#define G4R_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      g4r::set_error(__VA_ARGS__);    \
+      return G4R_EINVAL;              \
+    }                                 \
+  } while (0)
+
+#define G4R_CUDA(call)                                        \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return g4r::cuda_fail(e__, #call); \
+  } while (0)
+
+#define G4R_LAUNCH_CHECK(name)                                   \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return g4r::cuda_fail(e__, name);    \
+  } while (0)
+
+inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case G4R_F32: return 4;
+    case G4R_F16: return 2;
+    case G4R_BF16: return 2;
+    case G4R_F64: return 8;
+  }
+  return 0;
+}
+
+int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// ---- element conversion -----------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vector of N = 16/sizeof(T) elements, widened to fp32 on load.
+template <typename T> struct Vec16 {
+  static constexpr int N = 16 / sizeof(T);
+};
+
+template <typename T>
+__device__ __forceinline__ void load16(const T* p, float (&out)[16 / sizeof(T)]) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 16 / (int)sizeof(T); i++) out[i] = to_f32<T>(e[i]);
+}
+
+template <typename T>
+__device__ __forceinline__ void store16(T* p, const float (&v)[16 / sizeof(T)]) {
+  uint4 raw;
+  T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 16 / (int)sizeof(T); i++) e[i] = from_f32<T>(v[i]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
+}  // namespace g4r

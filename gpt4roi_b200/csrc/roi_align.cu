@@ -1,0 +1,666 @@
+// roi_align.cu -- RoIAlign forward/backward for sm_100a (HBM-bound gather / scatter-add).
+//
+// THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false: the bin / sample / weight
+// arithmetic below is written with the reference's association and must not be
+// contracted into FMAs, so that indices, weights and fp32 outputs are bit-identical
+// to the reference CPU kernel (mmcv-1.4.7/mmcv/ops/csrc/pytorch/cpu/roi_align.cpp)
+// -- checked by tests/test_roi_align_gpu.py against the CPU checker.
+//
+// Replaces (reference, relative to /root/reference/mmcv-1.4.7/mmcv/ops/csrc):
+//   common/cuda/roi_align_cuda_kernel.cuh:17-108   roi_align_forward_cuda_kernel
+//   common/cuda/roi_align_cuda_kernel.cuh:111-210  roi_align_backward_cuda_kernel
+//   common/cuda/common_cuda_helper.hpp:28-119      bilinear_interpolate(_gradient)
+//   pytorch/cuda/roi_align_cuda.cu:5-57            launchers
+//
+// Design (B200): the reference runs one thread per output scalar and recomputes the
+// RoI geometry in every thread.  Here the geometry is separable: a sample's y depends
+// on (ph,iy) only and its x on (pw,ix) only, so a CTA computes PH*gh + PW*gw axis
+// entries {lo,hi,frac,1-frac,valid} once into shared memory and every thread reuses
+// them.  Two data paths:
+//   * NHWC, multi-level (the hot path): one launch covers all pyramid levels and all
+//     RoIs; a thread owns 16 bytes of channels, issues the 4*g*g tap loads of a bin
+//     as independent 128-bit loads (fully coalesced across the warp: consecutive lanes
+//     read consecutive 16 B of the same pixel), accumulates in fp32 in the reference's
+//     order and writes one 128-bit (or 64-bit, bf16 out) store per bin.
+//   * NCHW (the mmcv._ext drop-in layout): CTA = (RoI, channel chunk); output writes
+//     are contiguous; taps are plane gathers like the reference's but without the
+//     per-thread geometry.
+#include "common.cuh"
+
+namespace g4r {
+
+constexpr int kTab = 256;      // axis-table capacity per axis (entries); else on-the-fly
+constexpr int kThreads = 256;
+
+template <typename A>
+struct AxisEntry {
+  A coord;  // raw sample coordinate (max-mode argmax)
+  A l, h;   // frac, 1-frac
+  int lo, hi;
+  int valid;
+};
+
+// One axis of bilinear_interpolate: common_cuda_helper.hpp:33-55 == cpu/roi_align.cpp:44-86.
+template <typename A>
+__device__ __forceinline__ AxisEntry<A> axis_from_coord(A v, int size) {
+  AxisEntry<A> e;
+  e.coord = v;
+  if (v < -1.0 || v > size) {
+    e.valid = 0;
+    e.lo = e.hi = 0;
+    e.l = e.h = 0;
+    return e;
+  }
+  e.valid = 1;
+  if (v <= 0) v = 0;
+  int lo = (int)v;
+  int hi;
+  if (lo >= size - 1) {
+    hi = lo = size - 1;
+    v = (A)lo;
+  } else {
+    hi = lo + 1;
+  }
+  e.lo = lo;
+  e.hi = hi;
+  e.l = v - lo;
+  e.h = (A)1 - e.l;
+  return e;
+}
+
+// y = roi_start_h + ph * bin_size_h + static_cast<T>(iy + .5f) * bin_size_h / static_cast<T>(grid)
+// (roi_align_cuda_kernel.cuh:89-91; same expression in cpu/roi_align.cpp:33-35).
+template <typename A>
+__device__ __forceinline__ AxisEntry<A> axis_entry(A start, A bin, int p, int i, int grid, int size) {
+  const A v = start + p * bin + static_cast<A>(i + .5f) * bin / static_cast<A>(grid);
+  return axis_from_coord<A>(v, size);
+}
+
+template <typename A>
+struct RoiGeom {
+  int batch;
+  A start_w, start_h, bin_w, bin_h;
+  int gh, gw;
+  A count;
+};
+
+// roi_align_cuda_kernel.cuh:31-60 (== cpu/roi_align.cpp:126-159).
+template <typename A>
+__device__ __forceinline__ RoiGeom<A> roi_geom(A r0, A r1, A r2, A r3, A r4, A scale, int PH, int PW,
+                                               int sampling_ratio, bool aligned, bool clamp_count) {
+  RoiGeom<A> g;
+  g.batch = (int)r0;
+  A offset = aligned ? (A)0.5 : (A)0.0;
+  g.start_w = r1 * scale - offset;
+  g.start_h = r2 * scale - offset;
+  A end_w = r3 * scale - offset;
+  A end_h = r4 * scale - offset;
+  A roi_w = end_w - g.start_w;
+  A roi_h = end_h - g.start_h;
+  if (!aligned) {
+    roi_w = roi_w > (A)1. ? roi_w : (A)1.;
+    roi_h = roi_h > (A)1. ? roi_h : (A)1.;
+  }
+  g.bin_h = roi_h / static_cast<A>(PH);
+  g.bin_w = roi_w / static_cast<A>(PW);
+  g.gh = (sampling_ratio > 0) ? sampling_ratio : static_cast<int>(ceilf((float)(roi_h / PH)));
+  g.gw = (sampling_ratio > 0) ? sampling_ratio : static_cast<int>(ceilf((float)(roi_w / PW)));
+  if (g.gh < 0) g.gh = 0;
+  if (g.gw < 0) g.gw = 0;
+  int cnt = g.gh * g.gw;
+  if (clamp_count && cnt < 1) cnt = 1;  // forward: max(gh*gw,1); backward divides by gh*gw
+  g.count = (A)cnt;
+  return g;
+}
+
+template <typename T> struct AccOf { using type = float; };
+template <> struct AccOf<double> { using type = double; };
+
+template <typename T, typename A> __device__ __forceinline__ A ld_as(const T* p) { return (A)to_f32<T>(*p); }
+template <> __device__ __forceinline__ double ld_as<double, double>(const double* p) { return *p; }
+template <typename T, typename A> __device__ __forceinline__ T st_as(A v) { return from_f32<T>((float)v); }
+template <> __device__ __forceinline__ double st_as<double, double>(double v) { return v; }
+
+// ------------------------------------------------------------------------------------
+// NCHW forward (drop-in layout).  grid = (K, ceil(C/c_chunk)); block = kThreads.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+roi_align_fwd_nchw(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
+                   T* __restrict__ argmax_y, T* __restrict__ argmax_x, int C, int H, int W, int PH,
+                   int PW, float spatial_scale, int sampling_ratio, int pool_mode, int aligned,
+                   int c_chunk) {
+  using A = typename AccOf<T>::type;
+  __shared__ AxisEntry<A> ytab[kTab];
+  __shared__ AxisEntry<A> xtab[kTab];
+
+  const int k = blockIdx.x;
+  const int c0 = blockIdx.y * c_chunk;
+  const int c1 = min(C, c0 + c_chunk);
+  const T* r = rois + (size_t)k * 5;
+  const RoiGeom<A> g = roi_geom<A>(ld_as<T, A>(r), ld_as<T, A>(r + 1), ld_as<T, A>(r + 2),
+                                   ld_as<T, A>(r + 3), ld_as<T, A>(r + 4), (A)spatial_scale, PH, PW,
+                                   sampling_ratio, aligned != 0, true);
+  const bool use_tab = (PH * g.gh <= kTab) && (PW * g.gw <= kTab);
+  if (use_tab) {
+    for (int i = threadIdx.x; i < PH * g.gh; i += blockDim.x)
+      ytab[i] = axis_entry<A>(g.start_h, g.bin_h, i / g.gh, i % g.gh, g.gh, H);
+    for (int i = threadIdx.x; i < PW * g.gw; i += blockDim.x)
+      xtab[i] = axis_entry<A>(g.start_w, g.bin_w, i / g.gw, i % g.gw, g.gw, W);
+    __syncthreads();
+  }
+  const int bins = PH * PW;
+  const int items = (c1 - c0) * bins;
+  const size_t hw = (size_t)H * W;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int c = c0 + it / bins;
+    const int b = it % bins;
+    const int ph = b / PW, pw = b % PW;
+    const T* plane = input + ((size_t)g.batch * C + c) * hw;
+    A out_val = 0;
+    A maxval = -10000;  // cpu/roi_align.cpp:177 (the oracle); the CUDA reference uses -FLT_MAX
+    A maxidx_y = -1.f, maxidx_x = -1.f;
+    for (int iy = 0; iy < g.gh; iy++) {
+      const AxisEntry<A> ey = use_tab ? ytab[ph * g.gh + iy]
+                                      : axis_entry<A>(g.start_h, g.bin_h, ph, iy, g.gh, H);
+      for (int ix = 0; ix < g.gw; ix++) {
+        const AxisEntry<A> ex = use_tab ? xtab[pw * g.gw + ix]
+                                        : axis_entry<A>(g.start_w, g.bin_w, pw, ix, g.gw, W);
+        A val = 0;
+        if (ey.valid && ex.valid) {
+          const A w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
+          const A v1 = ld_as<T, A>(plane + (size_t)ey.lo * W + ex.lo);
+          const A v2 = ld_as<T, A>(plane + (size_t)ey.lo * W + ex.hi);
+          const A v3 = ld_as<T, A>(plane + (size_t)ey.hi * W + ex.lo);
+          const A v4 = ld_as<T, A>(plane + (size_t)ey.hi * W + ex.hi);
+          val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+        }
+        if (val > maxval) {
+          maxval = val;
+          maxidx_y = ey.coord;
+          maxidx_x = ex.coord;
+        }
+        out_val += val;
+      }
+    }
+    const size_t o = ((size_t)k * C + c) * bins + b;
+    if (pool_mode == G4R_POOL_MAX) {
+      output[o] = st_as<T, A>(maxval);
+      argmax_y[o] = st_as<T, A>(maxidx_y);
+      argmax_x[o] = st_as<T, A>(maxidx_x);
+    } else {
+      output[o] = st_as<T, A>(out_val / g.count);
+    }
+  }
+}
+
+// ---- atomics for every grad dtype -----------------------------------------------------
+__device__ __forceinline__ void atomic_add_t(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add_t(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add_t(__half* p, float v) { atomicAdd(p, __float2half_rn(v)); }
+__device__ __forceinline__ void atomic_add_t(__nv_bfloat16* p, float v) { atomicAdd(p, __float2bfloat16_rn(v)); }
+
+// ------------------------------------------------------------------------------------
+// NCHW backward.  Same decomposition as forward; 4 atomics per sample like
+// roi_align_cuda_kernel.cuh:191-205 (avg) / :141-150 (max).
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+roi_align_bwd_nchw(const T* __restrict__ grad_output, const T* __restrict__ rois,
+                   const T* __restrict__ argmax_y, const T* __restrict__ argmax_x,
+                   T* __restrict__ grad_input, int C, int H, int W, int PH, int PW,
+                   float spatial_scale, int sampling_ratio, int pool_mode, int aligned, int c_chunk) {
+  using A = typename AccOf<T>::type;
+  __shared__ AxisEntry<A> ytab[kTab];
+  __shared__ AxisEntry<A> xtab[kTab];
+  const int k = blockIdx.x;
+  const int c0 = blockIdx.y * c_chunk;
+  const int c1 = min(C, c0 + c_chunk);
+  const T* r = rois + (size_t)k * 5;
+  const RoiGeom<A> g = roi_geom<A>(ld_as<T, A>(r), ld_as<T, A>(r + 1), ld_as<T, A>(r + 2),
+                                   ld_as<T, A>(r + 3), ld_as<T, A>(r + 4), (A)spatial_scale, PH, PW,
+                                   sampling_ratio, aligned != 0, false);
+  const bool use_tab = (pool_mode == G4R_POOL_AVG) && (PH * g.gh <= kTab) && (PW * g.gw <= kTab);
+  if (use_tab) {
+    for (int i = threadIdx.x; i < PH * g.gh; i += blockDim.x)
+      ytab[i] = axis_entry<A>(g.start_h, g.bin_h, i / g.gh, i % g.gh, g.gh, H);
+    for (int i = threadIdx.x; i < PW * g.gw; i += blockDim.x)
+      xtab[i] = axis_entry<A>(g.start_w, g.bin_w, i / g.gw, i % g.gw, g.gw, W);
+    __syncthreads();
+  }
+  const int bins = PH * PW;
+  const int items = (c1 - c0) * bins;
+  const size_t hw = (size_t)H * W;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int c = c0 + it / bins;
+    const int b = it % bins;
+    const int ph = b / PW, pw = b % PW;
+    const size_t o = ((size_t)k * C + c) * bins + b;
+    const A go = ld_as<T, A>(grad_output + o);
+    T* plane = grad_input + ((size_t)g.batch * C + c) * hw;
+    if (pool_mode == G4R_POOL_MAX) {
+      const A y = ld_as<T, A>(argmax_y + o), x = ld_as<T, A>(argmax_x + o);
+      if (y != -1.f) {
+        const AxisEntry<A> ey = axis_from_coord<A>(y, H), ex = axis_from_coord<A>(x, W);
+        if (ey.valid && ex.valid) {
+          atomic_add_t(plane + (size_t)ey.lo * W + ex.lo, go * (ey.h * ex.h));
+          atomic_add_t(plane + (size_t)ey.lo * W + ex.hi, go * (ey.h * ex.l));
+          atomic_add_t(plane + (size_t)ey.hi * W + ex.lo, go * (ey.l * ex.h));
+          atomic_add_t(plane + (size_t)ey.hi * W + ex.hi, go * (ey.l * ex.l));
+        }
+      }
+    } else {
+      for (int iy = 0; iy < g.gh; iy++) {
+        const AxisEntry<A> ey = use_tab ? ytab[ph * g.gh + iy]
+                                        : axis_entry<A>(g.start_h, g.bin_h, ph, iy, g.gh, H);
+        for (int ix = 0; ix < g.gw; ix++) {
+          const AxisEntry<A> ex = use_tab ? xtab[pw * g.gw + ix]
+                                          : axis_entry<A>(g.start_w, g.bin_w, pw, ix, g.gw, W);
+          if (ey.valid && ex.valid) {
+            atomic_add_t(plane + (size_t)ey.lo * W + ex.lo, go * (ey.h * ex.h) / g.count);
+            atomic_add_t(plane + (size_t)ey.lo * W + ex.hi, go * (ey.h * ex.l) / g.count);
+            atomic_add_t(plane + (size_t)ey.hi * W + ex.lo, go * (ey.l * ex.h) / g.count);
+            atomic_add_t(plane + (size_t)ey.hi * W + ex.hi, go * (ey.l * ex.l) / g.count);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// NHWC multi-level forward (hot path).
+// grid = (K * ceil(PH/rows_per_cta), n_levels); block = kThreads.
+// ------------------------------------------------------------------------------------
+struct MlvlParams {
+  const void* maps[G4R_MAX_LEVELS];
+  const float* gn_scale[G4R_MAX_LEVELS];
+  const float* gn_shift[G4R_MAX_LEVELS];
+  float* grad_maps[G4R_MAX_LEVELS];
+  int H[G4R_MAX_LEVELS], W[G4R_MAX_LEVELS];
+  float scale[G4R_MAX_LEVELS];
+  const float* rois;
+  void* out;  // forward: output; backward: grad_output (const)
+  int N, C, K, PH, PW, sampling_ratio, aligned, rows_per_cta, n_levels;
+};
+
+template <typename Tout, int N>
+__device__ __forceinline__ void store_vec(Tout* p, const float (&v)[N]) {
+  constexpr int kBytes = N * (int)sizeof(Tout);
+  if constexpr (kBytes == 32) {
+    uint4 a, b;
+    Tout* ea = reinterpret_cast<Tout*>(&a);
+    Tout* eb = reinterpret_cast<Tout*>(&b);
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) { ea[i] = from_f32<Tout>(v[i]); eb[i] = from_f32<Tout>(v[N / 2 + i]); }
+    reinterpret_cast<uint4*>(p)[0] = a;
+    reinterpret_cast<uint4*>(p)[1] = b;
+  } else if constexpr (kBytes == 16) {
+    uint4 a;
+    Tout* ea = reinterpret_cast<Tout*>(&a);
+#pragma unroll
+    for (int i = 0; i < N; i++) ea[i] = from_f32<Tout>(v[i]);
+    *reinterpret_cast<uint4*>(p) = a;
+  } else {
+    static_assert(kBytes == 8, "unsupported vector store width");
+    uint2 a;
+    Tout* ea = reinterpret_cast<Tout*>(&a);
+#pragma unroll
+    for (int i = 0; i < N; i++) ea[i] = from_f32<Tout>(v[i]);
+    *reinterpret_cast<uint2*>(p) = a;
+  }
+}
+
+template <typename Tin, typename Tout, int G, bool AFFINE>
+__global__ void __launch_bounds__(kThreads)
+roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
+  constexpr int VEC = 16 / (int)sizeof(Tin);
+  __shared__ AxisEntry<float> ytab[kTab];
+  __shared__ AxisEntry<float> xtab[kTab];
+
+  const int lvl = blockIdx.y;
+  const int row_groups = (p.PH + p.rows_per_cta - 1) / p.rows_per_cta;
+  const int k = blockIdx.x / row_groups;
+  const int ph0 = (blockIdx.x % row_groups) * p.rows_per_cta;
+  const int nrows = min(p.rows_per_cta, p.PH - ph0);
+  const int H = p.H[lvl], W = p.W[lvl], C = p.C, PW = p.PW;
+  const float* r = p.rois + (size_t)k * 5;
+  const RoiGeom<float> g = roi_geom<float>(r[0], r[1], r[2], r[3], r[4], p.scale[lvl], p.PH, PW,
+                                           G > 0 ? G : p.sampling_ratio, p.aligned != 0, true);
+  const int gh = G > 0 ? G : g.gh, gw = G > 0 ? G : g.gw;
+  const bool use_tab = (nrows * gh <= kTab) && (PW * gw <= kTab);
+  if (use_tab) {
+    for (int i = threadIdx.x; i < nrows * gh; i += blockDim.x)
+      ytab[i] = axis_entry<float>(g.start_h, g.bin_h, ph0 + i / gh, i % gh, gh, H);
+    for (int i = threadIdx.x; i < PW * gw; i += blockDim.x)
+      xtab[i] = axis_entry<float>(g.start_w, g.bin_w, i / gw, i % gw, gw, W);
+    __syncthreads();
+  }
+  const int lanes = C / VEC;
+  const int items = nrows * PW * lanes;
+  const Tin* map = reinterpret_cast<const Tin*>(p.maps[lvl]) + (size_t)g.batch * H * W * C;
+  Tout* out = reinterpret_cast<Tout*>(p.out) +
+              (((size_t)lvl * p.K + k) * p.PH + ph0) * (size_t)PW * C;
+
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int lane = it % lanes;
+    const int b = it / lanes;  // bin within this CTA's rows
+    const int prow = b / PW, pw = b % PW;
+    const int coff = lane * VEC;
+    float ga[VEC], gb[VEC];
+    if constexpr (AFFINE) {
+      const float* sa = p.gn_scale[lvl] + (size_t)g.batch * C + coff;
+      const float* sb = p.gn_shift[lvl] + (size_t)g.batch * C + coff;
+#pragma unroll
+      for (int i = 0; i < VEC; i++) { ga[i] = sa[i]; gb[i] = sb[i]; }
+    }
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; i++) acc[i] = 0.f;
+#pragma unroll
+    for (int iy = 0; iy < (G > 0 ? G : gh); iy++) {
+      const AxisEntry<float> ey = use_tab ? ytab[prow * gh + iy]
+                                          : axis_entry<float>(g.start_h, g.bin_h, ph0 + prow, iy, gh, H);
+#pragma unroll
+      for (int ix = 0; ix < (G > 0 ? G : gw); ix++) {
+        const AxisEntry<float> ex = use_tab ? xtab[pw * gw + ix]
+                                            : axis_entry<float>(g.start_w, g.bin_w, pw, ix, gw, W);
+        // invalid samples contribute val = 0 (common_cuda_helper.hpp:33); acc + 0 == acc.
+        if (ey.valid && ex.valid) {
+          const float w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
+          float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+          load16<Tin>(map + ((size_t)ey.lo * W + ex.lo) * C + coff, v1);
+          load16<Tin>(map + ((size_t)ey.lo * W + ex.hi) * C + coff, v2);
+          load16<Tin>(map + ((size_t)ey.hi * W + ex.lo) * C + coff, v3);
+          load16<Tin>(map + ((size_t)ey.hi * W + ex.hi) * C + coff, v4);
+#pragma unroll
+          for (int i = 0; i < VEC; i++) {
+            if constexpr (AFFINE) {
+              v1[i] = fmaxf(v1[i] * ga[i] + gb[i], 0.f);
+              v2[i] = fmaxf(v2[i] * ga[i] + gb[i], 0.f);
+              v3[i] = fmaxf(v3[i] * ga[i] + gb[i], 0.f);
+              v4[i] = fmaxf(v4[i] * ga[i] + gb[i], 0.f);
+            }
+            const float val = w1 * v1[i] + w2 * v2[i] + w3 * v3[i] + w4 * v4[i];
+            acc[i] += val;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; i++) acc[i] = acc[i] / g.count;
+    store_vec<Tout, VEC>(out + ((size_t)prow * PW + pw) * C + coff, acc);
+  }
+}
+
+// NHWC multi-level backward: grad_output [Lv,K,PH,PW,C] (Tg) -> fp32 NHWC grad maps (atomics).
+template <typename Tg>
+__global__ void __launch_bounds__(kThreads)
+roi_align_bwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
+  constexpr int VEC = 4;  // float4 vector atomics (red.global.add.v4.f32, sm_90+)
+  __shared__ AxisEntry<float> ytab[kTab];
+  __shared__ AxisEntry<float> xtab[kTab];
+  const int lvl = blockIdx.y;
+  const int row_groups = (p.PH + p.rows_per_cta - 1) / p.rows_per_cta;
+  const int k = blockIdx.x / row_groups;
+  const int ph0 = (blockIdx.x % row_groups) * p.rows_per_cta;
+  const int nrows = min(p.rows_per_cta, p.PH - ph0);
+  const int H = p.H[lvl], W = p.W[lvl], C = p.C, PW = p.PW;
+  const float* r = p.rois + (size_t)k * 5;
+  const RoiGeom<float> g = roi_geom<float>(r[0], r[1], r[2], r[3], r[4], p.scale[lvl], p.PH, PW,
+                                           p.sampling_ratio, p.aligned != 0, false);
+  const int gh = g.gh, gw = g.gw;
+  const bool use_tab = (nrows * gh <= kTab) && (PW * gw <= kTab);
+  if (use_tab) {
+    for (int i = threadIdx.x; i < nrows * gh; i += blockDim.x)
+      ytab[i] = axis_entry<float>(g.start_h, g.bin_h, ph0 + i / gh, i % gh, gh, H);
+    for (int i = threadIdx.x; i < PW * gw; i += blockDim.x)
+      xtab[i] = axis_entry<float>(g.start_w, g.bin_w, i / gw, i % gw, gw, W);
+    __syncthreads();
+  }
+  const int lanes = C / VEC;
+  const int items = nrows * PW * lanes;
+  float* gmap = p.grad_maps[lvl] + (size_t)g.batch * H * W * C;
+  const Tg* go = reinterpret_cast<const Tg*>(p.out) +
+                 (((size_t)lvl * p.K + k) * p.PH + ph0) * (size_t)PW * C;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int lane = it % lanes;
+    const int b = it / lanes;
+    const int prow = b / PW, pw = b % PW;
+    const int coff = lane * VEC;
+    float gv[VEC];
+    const Tg* gp = go + ((size_t)prow * PW + pw) * C + coff;
+#pragma unroll
+    for (int i = 0; i < VEC; i++) gv[i] = to_f32<Tg>(gp[i]);
+    for (int iy = 0; iy < gh; iy++) {
+      const AxisEntry<float> ey = use_tab ? ytab[prow * gh + iy]
+                                          : axis_entry<float>(g.start_h, g.bin_h, ph0 + prow, iy, gh, H);
+      for (int ix = 0; ix < gw; ix++) {
+        const AxisEntry<float> ex = use_tab ? xtab[pw * gw + ix]
+                                            : axis_entry<float>(g.start_w, g.bin_w, pw, ix, gw, W);
+        if (!(ey.valid && ex.valid)) continue;
+        const float w[4] = {ey.h * ex.h, ey.h * ex.l, ey.l * ex.h, ey.l * ex.l};
+        const size_t off[4] = {((size_t)ey.lo * W + ex.lo) * C, ((size_t)ey.lo * W + ex.hi) * C,
+                               ((size_t)ey.hi * W + ex.lo) * C, ((size_t)ey.hi * W + ex.hi) * C};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          float4 a;
+          a.x = gv[0] * w[t] / g.count;
+          a.y = gv[1] * w[t] / g.count;
+          a.z = gv[2] * w[t] / g.count;
+          a.w = gv[3] * w[t] / g.count;
+          atomicAdd(reinterpret_cast<float4*>(gmap + off[t] + coff), a);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------
+static int pick_c_chunk(int C, int bins) {
+  int c = 4096 / (bins > 0 ? bins : 1);
+  if (c < 1) c = 1;
+  if (c > C) c = C;
+  return c;
+}
+
+template <typename T>
+static int launch_fwd_nchw(const void* input, const void* rois, void* output, void* ay, void* ax,
+                           int C, int H, int W, int K, int PH, int PW, float scale, int sr,
+                           int pool_mode, int aligned, cudaStream_t st) {
+  const int c_chunk = pick_c_chunk(C, PH * PW);
+  dim3 grid(K, (C + c_chunk - 1) / c_chunk);
+  roi_align_fwd_nchw<T><<<grid, kThreads, 0, st>>>((const T*)input, (const T*)rois, (T*)output, (T*)ay,
+                                                   (T*)ax, C, H, W, PH, PW, scale, sr, pool_mode,
+                                                   aligned, c_chunk);
+  G4R_LAUNCH_CHECK("roi_align_fwd_nchw");
+  return G4R_OK;
+}
+
+template <typename T>
+static int launch_bwd_nchw(const void* go, const void* rois, const void* ay, const void* ax, void* gi,
+                           int C, int H, int W, int K, int PH, int PW, float scale, int sr,
+                           int pool_mode, int aligned, cudaStream_t st) {
+  const int c_chunk = pick_c_chunk(C, PH * PW);
+  dim3 grid(K, (C + c_chunk - 1) / c_chunk);
+  roi_align_bwd_nchw<T><<<grid, kThreads, 0, st>>>((const T*)go, (const T*)rois, (const T*)ay,
+                                                   (const T*)ax, (T*)gi, C, H, W, PH, PW, scale, sr,
+                                                   pool_mode, aligned, c_chunk);
+  G4R_LAUNCH_CHECK("roi_align_bwd_nchw");
+  return G4R_OK;
+}
+
+static int pick_rows_per_cta(int K, int n_levels, int PH) {
+  // Whole-RoI CTAs maximise L1 reuse between neighbouring bin rows; split rows only when
+  // there are too few (RoI, level) pairs to give every SM a few CTAs.
+  const long want = 4L * num_sms();
+  int rows = PH;
+  while (rows > 1 && (long)K * n_levels * ((PH + rows - 1) / rows) < want) rows = (rows + 1) / 2;
+  return rows;
+}
+
+template <typename Tin, typename Tout>
+static int launch_fwd_mlvl(const MlvlParams& p, bool affine, cudaStream_t st) {
+  const int row_groups = (p.PH + p.rows_per_cta - 1) / p.rows_per_cta;
+  dim3 grid((unsigned)(p.K * row_groups), p.n_levels);
+  if (p.sampling_ratio == 2) {
+    if (affine) roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, true><<<grid, kThreads, 0, st>>>(p);
+    else roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, false><<<grid, kThreads, 0, st>>>(p);
+  } else {
+    if (affine) roi_align_fwd_nhwc_mlvl<Tin, Tout, 0, true><<<grid, kThreads, 0, st>>>(p);
+    else roi_align_fwd_nhwc_mlvl<Tin, Tout, 0, false><<<grid, kThreads, 0, st>>>(p);
+  }
+  G4R_LAUNCH_CHECK("roi_align_fwd_nhwc_mlvl");
+  return G4R_OK;
+}
+
+}  // namespace g4r
+
+using namespace g4r;
+
+extern "C" int g4r_roi_align_mlvl_forward(const void* const* maps, const int* H, const int* W,
+                                          const float* scales, int n_levels, const float* rois,
+                                          void* output, int N, int C, int K, int PH, int PW,
+                                          int sampling_ratio, int aligned, int in_dtype, int out_dtype,
+                                          const float* const* gn_scale, const float* const* gn_shift,
+                                          void* stream) {
+  G4R_REQUIRE(n_levels >= 1 && n_levels <= G4R_MAX_LEVELS, "n_levels=%d out of range", n_levels);
+  G4R_REQUIRE(maps && H && W && scales && output, "null argument");
+  G4R_REQUIRE(N > 0 && C > 0 && PH > 0 && PW > 0 && K >= 0, "bad sizes N=%d C=%d K=%d PH=%d PW=%d", N, C, K, PH, PW);
+  G4R_REQUIRE(in_dtype == G4R_F32 || in_dtype == G4R_F16 || in_dtype == G4R_BF16, "in_dtype %d unsupported", in_dtype);
+  G4R_REQUIRE(out_dtype == G4R_F32 || out_dtype == G4R_F16 || out_dtype == G4R_BF16, "out_dtype %d unsupported", out_dtype);
+  const int vec = 16 / (int)dtype_size(in_dtype);
+  G4R_REQUIRE(C % vec == 0, "C=%d must be a multiple of %d for 128-bit channel vectors", C, vec);
+  G4R_REQUIRE((gn_scale == nullptr) == (gn_shift == nullptr), "gn_scale/gn_shift must both be given or both NULL");
+  if (K == 0) return G4R_OK;
+  G4R_REQUIRE(rois, "rois is NULL with K=%d", K);
+  MlvlParams p{};
+  for (int l = 0; l < n_levels; l++) {
+    G4R_REQUIRE(maps[l] && H[l] > 0 && W[l] > 0, "level %d: bad map", l);
+    G4R_REQUIRE(((uintptr_t)maps[l] & 15) == 0, "level %d: map not 16-byte aligned", l);
+    p.maps[l] = maps[l];
+    p.H[l] = H[l];
+    p.W[l] = W[l];
+    p.scale[l] = scales[l];
+    p.gn_scale[l] = gn_scale ? gn_scale[l] : nullptr;
+    p.gn_shift[l] = gn_shift ? gn_shift[l] : nullptr;
+    if (gn_scale) G4R_REQUIRE(gn_scale[l] && gn_shift[l], "level %d: null gn_scale/shift", l);
+  }
+  G4R_REQUIRE(((uintptr_t)output & 15) == 0, "output not 16-byte aligned");
+  p.rois = rois;
+  p.out = output;
+  p.N = N; p.C = C; p.K = K; p.PH = PH; p.PW = PW;
+  p.sampling_ratio = sampling_ratio; p.aligned = aligned; p.n_levels = n_levels;
+  p.rows_per_cta = pick_rows_per_cta(K, n_levels, PH);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool aff = gn_scale != nullptr;
+#define G4R_DISPATCH_OUT(TIN)                                                              \
+  switch (out_dtype) {                                                                     \
+    case G4R_F32: return launch_fwd_mlvl<TIN, float>(p, aff, st);                          \
+    case G4R_F16: return launch_fwd_mlvl<TIN, __half>(p, aff, st);                         \
+    default: return launch_fwd_mlvl<TIN, __nv_bfloat16>(p, aff, st);                       \
+  }
+  switch (in_dtype) {
+    case G4R_F32: G4R_DISPATCH_OUT(float)
+    case G4R_F16: G4R_DISPATCH_OUT(__half)
+    default: G4R_DISPATCH_OUT(__nv_bfloat16)
+  }
+#undef G4R_DISPATCH_OUT
+}
+
+extern "C" int g4r_roi_align_mlvl_backward(const void* grad_output, const int* H, const int* W,
+                                           const float* scales, int n_levels, const float* rois,
+                                           float* const* grad_maps, int N, int C, int K, int PH,
+                                           int PW, int sampling_ratio, int aligned, int grad_dtype,
+                                           void* stream) {
+  G4R_REQUIRE(n_levels >= 1 && n_levels <= G4R_MAX_LEVELS, "n_levels=%d out of range", n_levels);
+  G4R_REQUIRE(grad_output && H && W && scales && grad_maps, "null argument");
+  G4R_REQUIRE(N > 0 && C > 0 && PH > 0 && PW > 0 && K >= 0, "bad sizes");
+  G4R_REQUIRE(C % 4 == 0, "C=%d must be a multiple of 4", C);
+  G4R_REQUIRE(grad_dtype == G4R_F32 || grad_dtype == G4R_F16 || grad_dtype == G4R_BF16, "grad_dtype %d unsupported", grad_dtype);
+  if (K == 0) return G4R_OK;
+  G4R_REQUIRE(rois, "rois is NULL");
+  MlvlParams p{};
+  for (int l = 0; l < n_levels; l++) {
+    G4R_REQUIRE(grad_maps[l] && ((uintptr_t)grad_maps[l] & 15) == 0, "level %d: bad grad map", l);
+    p.grad_maps[l] = grad_maps[l];
+    p.H[l] = H[l]; p.W[l] = W[l]; p.scale[l] = scales[l];
+  }
+  p.rois = rois;
+  p.out = const_cast<void*>(grad_output);
+  p.N = N; p.C = C; p.K = K; p.PH = PH; p.PW = PW;
+  p.sampling_ratio = sampling_ratio; p.aligned = aligned; p.n_levels = n_levels;
+  p.rows_per_cta = pick_rows_per_cta(K, n_levels, PH);
+  const int row_groups = (PH + p.rows_per_cta - 1) / p.rows_per_cta;
+  dim3 grid((unsigned)(K * row_groups), n_levels);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (grad_dtype) {
+    case G4R_F32: roi_align_bwd_nhwc_mlvl<float><<<grid, kThreads, 0, st>>>(p); break;
+    case G4R_F16: roi_align_bwd_nhwc_mlvl<__half><<<grid, kThreads, 0, st>>>(p); break;
+    default: roi_align_bwd_nhwc_mlvl<__nv_bfloat16><<<grid, kThreads, 0, st>>>(p); break;
+  }
+  G4R_LAUNCH_CHECK("roi_align_bwd_nhwc_mlvl");
+  return G4R_OK;
+}
+
+static int check_common(const void* a, const void* rois, const void* b, int N, int C, int H, int W,
+                        int K, int PH, int PW, int pool_mode, int dtype, int layout) {
+  G4R_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && K >= 0 && PH > 0 && PW > 0,
+              "bad sizes N=%d C=%d H=%d W=%d K=%d PH=%d PW=%d", N, C, H, W, K, PH, PW);
+  G4R_REQUIRE(pool_mode == G4R_POOL_MAX || pool_mode == G4R_POOL_AVG, "pool_mode=%d", pool_mode);
+  G4R_REQUIRE(dtype >= G4R_F32 && dtype <= G4R_F64, "dtype=%d", dtype);
+  G4R_REQUIRE(layout == G4R_NCHW || layout == G4R_NHWC, "layout=%d", layout);
+  if (K > 0) G4R_REQUIRE(a && rois && b, "null tensor pointer");
+  return G4R_OK;
+}
+
+extern "C" int g4r_roi_align_forward(const void* input, const void* rois, void* output, void* argmax_y,
+                                     void* argmax_x, int N, int C, int H, int W, int K, int PH, int PW,
+                                     float spatial_scale, int sampling_ratio, int pool_mode,
+                                     int aligned, int dtype, int layout, void* stream) {
+  int rc = check_common(input, rois, output, N, C, H, W, K, PH, PW, pool_mode, dtype, layout);
+  if (rc) return rc;
+  if (K == 0) return G4R_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pool_mode == G4R_POOL_MAX) G4R_REQUIRE(argmax_y && argmax_x, "max pooling needs argmax_y/argmax_x");
+  if (layout == G4R_NHWC) {
+    G4R_REQUIRE(pool_mode == G4R_POOL_AVG, "NHWC path implements avg pooling only");
+    G4R_REQUIRE(dtype == G4R_F32, "NHWC single-level entry takes fp32 maps+rois; use g4r_roi_align_mlvl_forward for 16-bit maps");
+    const void* maps[1] = {input};
+    return g4r_roi_align_mlvl_forward(maps, &H, &W, &spatial_scale, 1, (const float*)rois, output, N, C,
+                                      K, PH, PW, sampling_ratio, aligned, dtype, dtype, nullptr, nullptr,
+                                      stream);
+  }
+  switch (dtype) {
+    case G4R_F32: return launch_fwd_nchw<float>(input, rois, output, argmax_y, argmax_x, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+    case G4R_F64: return launch_fwd_nchw<double>(input, rois, output, argmax_y, argmax_x, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+    case G4R_F16: return launch_fwd_nchw<__half>(input, rois, output, argmax_y, argmax_x, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+    default: return launch_fwd_nchw<__nv_bfloat16>(input, rois, output, argmax_y, argmax_x, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+  }
+}
+
+extern "C" int g4r_roi_align_backward(const void* grad_output, const void* rois, const void* argmax_y,
+                                      const void* argmax_x, void* grad_input, int N, int C, int H,
+                                      int W, int K, int PH, int PW, float spatial_scale,
+                                      int sampling_ratio, int pool_mode, int aligned, int dtype,
+                                      int layout, void* stream) {
+  int rc = check_common(grad_output, rois, grad_input, N, C, H, W, K, PH, PW, pool_mode, dtype, layout);
+  if (rc) return rc;
+  if (K == 0) return G4R_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pool_mode == G4R_POOL_MAX) G4R_REQUIRE(argmax_y && argmax_x, "max pooling needs argmax_y/argmax_x");
+  if (layout == G4R_NHWC) {
+    G4R_REQUIRE(pool_mode == G4R_POOL_AVG && dtype == G4R_F32, "NHWC backward: fp32 avg only");
+    float* gm[1] = {(float*)grad_input};
+    return g4r_roi_align_mlvl_backward(grad_output, &H, &W, &spatial_scale, 1, (const float*)rois, gm, N,
+                                       C, K, PH, PW, sampling_ratio, aligned, G4R_F32, stream);
+  }
+  switch (dtype) {
+    case G4R_F32: return launch_bwd_nchw<float>(grad_output, rois, argmax_y, argmax_x, grad_input, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+    case G4R_F64: return launch_bwd_nchw<double>(grad_output, rois, argmax_y, argmax_x, grad_input, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+    case G4R_F16: return launch_bwd_nchw<__half>(grad_output, rois, argmax_y, argmax_x, grad_input, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+    default: return launch_bwd_nchw<__nv_bfloat16>(grad_output, rois, argmax_y, argmax_x, grad_input, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+  }
+}

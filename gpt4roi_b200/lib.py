@@ -1,0 +1,124 @@
+"""ctypes binding of libgpt4roi_b200.so (the C ABI declared in include/gpt4roi_b200.h).
+
+PyTorch is used here only for device memory and streams: every wrapper takes torch
+tensors, checks device/dtype/contiguity the way the reference's dispatch does
+(mmcv-1.4.7/mmcv/ops/csrc/common/pytorch_device_registry.hpp:109-139), and hands raw
+pointers + the current CUDA stream to the C entry point.  There is NO fallback: if the
+shared library is missing, or a tensor is not on a CUDA device, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libgpt4roi_b200.so')
+
+F32, F16, BF16, F64 = 0, 1, 2, 3
+NCHW, NHWC = 0, 1
+POOL_MAX, POOL_AVG = 0, 1
+MAX_LEVELS = 4
+
+_DTYPE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.float64: F64}
+
+_c = ctypes
+_vp, _i, _f, _i64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_int64
+
+# name -> (restype, argtypes); must list EVERY symbol include/gpt4roi_b200.h declares
+# (tests/test_abi_cpu.py parses the header and checks both directions).
+SIGNATURES = {
+    'g4r_last_error': (_c.c_char_p, []),
+    'g4r_version': (_i, []),
+    'g4r_built_arch': (_i, []),
+    'g4r_roi_align_forward': (_i, [_vp] * 5 + [_i] * 7 + [_f] + [_i] * 5 + [_vp]),
+    'g4r_roi_align_backward': (_i, [_vp] * 5 + [_i] * 7 + [_f] + [_i] * 5 + [_vp]),
+    'g4r_roi_align_mlvl_forward': (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 9 + [_vp] * 3),
+    'g4r_roi_align_mlvl_backward': (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 8 + [_vp]),
+    'g4r_splice_region_tokens': (_i, [_vp] * 8 + [_i] * 5 + [_i64] * 4 + [_vp]),
+}
+
+_lib = None
+
+
+class G4RError(RuntimeError):
+    """Non-zero return of a C-ABI entry point (maps the reference's RuntimeError)."""
+
+
+def load():
+    """Load the shared library (once).  Raises ImportError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            'gpt4roi_b200: %s is missing. Build it with `python -m gpt4roi_b200.build` '
+            '(needs nvcc; cross-compiles for sm_100a without a GPU). There is no CPU or '
+            'PyTorch fallback for this path.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().g4r_last_error()
+        raise G4RError('gpt4roi_b200 C-ABI error %d: %s' % (rc, (msg or b'').decode()))
+
+
+def dtype_code(t):
+    try:
+        return _DTYPE[t.dtype]
+    except KeyError:
+        raise TypeError('gpt4roi_b200: unsupported dtype %s' % t.dtype)
+
+
+def require_cuda_same_device(named):
+    """pytorch_device_registry.hpp:111-124: every tensor on the device of the first one."""
+    first = None
+    for idx, (name, t) in enumerate(named):
+        if t is None:
+            continue
+        if first is None:
+            first = t
+            if not t.is_cuda:
+                raise RuntimeError(
+                    'gpt4roi_b200: %s is on %s -- implementation for device %s not found '
+                    '(this library is CUDA sm_100a only; no CPU fallback)' % (name, t.device, t.device.type))
+        elif t.device != first.device:
+            raise RuntimeError('gpt4roi_b200: arg %d (%s) is on %s but arg 0 is on %s'
+                               % (idx, name, t.device, first.device))
+    return first.device
+
+
+def require_contiguous(named):
+    for name, t in named:
+        if t is not None and not t.is_contiguous():
+            raise RuntimeError('gpt4roi_b200: %s must be contiguous (the reference indexes raw '
+                               'data_ptr memory, roi_align_cuda.cu:21-23)' % name)
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def float_array(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])

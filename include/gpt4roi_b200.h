@@ -1,0 +1,149 @@
+/*
+ * gpt4roi_b200.h -- C ABI of libgpt4roi_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the GPT4RoI region-token forward path.  Every entry
+ * point takes raw DEVICE pointers, plain sizes and a cudaStream_t (as void*),
+ * returns 0 on success or a negative G4R_E* code (message via
+ * g4r_last_error()), allocates nothing that outlives the call, and never
+ * synchronises the stream unless stated.  No torch types cross this boundary.
+ *
+ * Each declaration cites the reference interface it replaces; paths are
+ * relative to /root/reference.
+ */
+#ifndef GPT4ROI_B200_H_
+#define GPT4ROI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums (ints on the wire) ------------------------------------------- */
+enum { G4R_F32 = 0, G4R_F16 = 1, G4R_BF16 = 2, G4R_F64 = 3 };       /* dtype   */
+enum { G4R_NCHW = 0, G4R_NHWC = 1 };                                /* layout  */
+enum { G4R_POOL_MAX = 0, G4R_POOL_AVG = 1 };  /* mmcv/ops/roi_align.py:77 */
+
+enum {
+  G4R_OK = 0,
+  G4R_EINVAL = -1,   /* bad argument (message says which)                  */
+  G4R_ECUDA = -2,    /* CUDA runtime / launch error                        */
+  G4R_EUNSUPPORTED = -3,
+  G4R_ENODEVICE = -4
+};
+
+#define G4R_MAX_LEVELS 4
+
+/* Thread-local message for the last non-zero return on this thread. */
+const char* g4r_last_error(void);
+/* Library/ABI version (major*1000+minor) and the SM arch it was built for. */
+int g4r_version(void);
+int g4r_built_arch(void); /* 100 for sm_100a */
+
+/* ---- RoIAlign: operator seam -------------------------------------------- */
+/*
+ * Replaces mmcv._ext.roi_align_forward
+ *   mmcv-1.4.7/mmcv/ops/csrc/pytorch/pybind.cpp:611-615  (python binding)
+ *   mmcv-1.4.7/mmcv/ops/csrc/pytorch/roi_align.cpp:25-32 (dispatch)
+ *   mmcv-1.4.7/mmcv/ops/csrc/pytorch/cuda/roi_align_cuda.cu:5-30 (launcher)
+ *   mmcv-1.4.7/mmcv/ops/csrc/common/cuda/roi_align_cuda_kernel.cuh:17-108
+ * input  [N,C,H,W] (G4R_NCHW) or [N,H,W,C] (G4R_NHWC), contiguous, `dtype`
+ * rois   [K,5] = (batch_idx, x1, y1, x2, y2), SAME dtype as input (reference
+ *        contract, roi_align_cuda.cu:22)
+ * output [K,C,PH,PW] (NCHW) or [K,PH,PW,C] (NHWC), `dtype`; fully overwritten
+ * argmax_y/argmax_x: same shape as output for G4R_POOL_MAX, ignored for AVG.
+ * Arithmetic: index/bin/weight math in fp32 (fp64 for G4R_F64) with the
+ * reference's association and no FMA contraction; fp16/bf16 taps are widened
+ * to fp32, accumulated in fp32 and rounded once on store.
+ */
+int g4r_roi_align_forward(const void* input, const void* rois, void* output,
+                          void* argmax_y, void* argmax_x,
+                          int N, int C, int H, int W, int K,
+                          int pooled_height, int pooled_width,
+                          float spatial_scale, int sampling_ratio,
+                          int pool_mode, int aligned,
+                          int dtype, int layout, void* stream);
+
+/*
+ * Replaces mmcv._ext.roi_align_backward
+ *   pybind.cpp:616-620; roi_align.cpp:34-41; roi_align_cuda.cu:32-57;
+ *   roi_align_cuda_kernel.cuh:111-210.
+ * grad_output contiguous in `layout`; grad_input must be ZEROED by the caller
+ * (mmcv/ops/roi_align.py:113) and is accumulated with atomics.
+ */
+int g4r_roi_align_backward(const void* grad_output, const void* rois,
+                           const void* argmax_y, const void* argmax_x,
+                           void* grad_input,
+                           int N, int C, int H, int W, int K,
+                           int pooled_height, int pooled_width,
+                           float spatial_scale, int sampling_ratio,
+                           int pool_mode, int aligned,
+                           int dtype, int layout, void* stream);
+
+/*
+ * Fused multi-level RoIAlign (one launch for all levels and all RoIs).
+ * Replaces the per-level loop of gpt4roi/models/layers.py:307-313, i.e.
+ * 4x { feats[i].to(float32) -> mmcv RoIAlign -> .to(ori_dtype) }.
+ * maps[l]   : NHWC [N,H[l],W[l],C], dtype in_dtype (F32, F16 or BF16)
+ * scales[l] : spatial_scale of level l as a C float (1/stride)
+ * rois      : fp32 [K,5] in input-pixel units (layers.py:294-302)
+ * output    : [n_levels,K,PH,PW,C] NHWC, dtype out_dtype; avg pooling only
+ * Optional per-(image,channel) affine+ReLU applied to every tap BEFORE the
+ * bilinear weights (fuses the last GroupNorm+ReLU of the fuse stack,
+ * layers.py:178 / mmcv cnn/bricks/conv_module.py:196-208): for level l, tap
+ * value v -> max(v*gn_scale[l][n*C+c] + gn_shift[l][n*C+c], 0); pass NULL
+ * arrays to disable.  fp32 [N,C] each.
+ */
+int g4r_roi_align_mlvl_forward(const void* const* maps, const int* H, const int* W,
+                               const float* scales, int n_levels,
+                               const float* rois, void* output,
+                               int N, int C, int K,
+                               int pooled_height, int pooled_width,
+                               int sampling_ratio, int aligned,
+                               int in_dtype, int out_dtype,
+                               const float* const* gn_scale,
+                               const float* const* gn_shift,
+                               void* stream);
+
+/* Gradient of the above w.r.t. the maps (fp32 NHWC grad maps, pre-zeroed). */
+int g4r_roi_align_mlvl_backward(const void* grad_output, const int* H, const int* W,
+                                const float* scales, int n_levels,
+                                const float* rois, float* const* grad_maps,
+                                int N, int C, int K,
+                                int pooled_height, int pooled_width,
+                                int sampling_ratio, int aligned,
+                                int grad_dtype, void* stream);
+
+/* ---- region-token splice: model seam ------------------------------------- */
+/*
+ * Replaces the per-sample python loop of gpt4roi/models/spi_llava.py:99-196
+ * (use_im_start_end branch) including `embed_tokens(input_ids)` (:44-45):
+ *   row t of sample b <- embed_table[ids[b,t]]             (default)
+ *                     <- image_rows[b, t-(s+1)]            (s = <im_start> pos, s<t<=s+P)
+ *                     <- region_rows[region_offsets[b]+j]  (t is the j-th <bbox> of sample b)
+ * All rows are `D` elements of a 16-bit type (bf16/fp16); data is moved, never
+ * re-rounded.  status[b] (int32, device) receives 0 or the reference's error:
+ *   1 = #<im_start> != #<im_end>            (spi_llava.py:114-118)
+ *   2 = <im_end> not at s+P+1               (spi_llava.py:124-128)
+ *   3 = #<bbox> != K_b                      (shape error at spi_llava.py:154)
+ *   4 = more than one <im_start> (unsupported)
+ *   5 = <im_patch> present but no <im_start> (reference: unbound variable)
+ *   6 = token id outside [0,V) (reference: embedding index error)
+ * region_rows/region_offsets may be NULL (bboxes=None, spi_llava.py:83-87): then
+ * a <bbox> token present in a multimodal sample is error 3 (assert :158-161).
+ * plan: int32 scratch [B,L] (device).
+ */
+int g4r_splice_region_tokens(const int64_t* input_ids, const void* embed_table,
+                             const void* image_rows, const void* region_rows,
+                             const int32_t* region_offsets, void* out,
+                             int32_t* plan, int32_t* status,
+                             int B, int L, int P, int D, int V,
+                             int64_t im_patch_token, int64_t im_start_token,
+                             int64_t im_end_token, int64_t bbox_token,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPT4ROI_B200_H_ */

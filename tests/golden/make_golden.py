@@ -1,0 +1,129 @@
+"""Generate the committed golden fixtures under tests/golden/ FROM THE REFERENCE ITSELF.
+
+Run in the build container (needs /root/reference; the GPU box never runs this):
+    python tests/golden/make_golden.py
+
+Fixtures:
+  mmcv_roi_align_kat.json   the reference's own known-answer vectors, read from
+                            mmcv-1.4.7/tests/test_ops/test_roi_align.py:14-32
+                            (3 cases: input, rois -> forward output and input-gradient;
+                            pool 2x2, scale 1.0, sampling 2, avg, aligned)
+  roi_align_ref_cases.npz   seeded random + adversarial cases run through the reference's
+                            CPU kernel compiled unmodified (oracle/_ref, see oracle/build_ref.py):
+                            forward (avg/max, argmax) and backward, fp32, NCHW.
+"""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import build_ref  # noqa: E402
+
+REF = os.environ.get('GPT4ROI_REFERENCE', '/root/reference')
+
+
+def kat():
+    path = os.path.join(REF, 'mmcv-1.4.7', 'tests', 'test_ops', 'test_roi_align.py')
+    spec = importlib.util.spec_from_file_location('ref_test_roi_align', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = []
+    for (inp, rois), (out, grad) in zip(mod.inputs, mod.outputs):
+        cases.append(dict(input=inp, rois=rois, output=out, grad_input=grad))
+    doc = dict(source='mmcv-1.4.7/tests/test_ops/test_roi_align.py:14-32',
+               pool_h=mod.pool_h, pool_w=mod.pool_w, spatial_scale=mod.spatial_scale,
+               sampling_ratio=mod.sampling_ratio, pool_mode='avg', aligned=True, atol=1e-3,
+               cases=cases)
+    with open(os.path.join(HERE, 'mmcv_roi_align_kat.json'), 'w') as f:
+        json.dump(doc, f, indent=1)
+    print('wrote mmcv_roi_align_kat.json (%d cases)' % len(cases))
+
+
+def adversarial_boxes(S):
+    """xyxy boxes in input-pixel units for an SxS image: degenerate, full-image, border cases."""
+    e = 1.0
+    return np.array([
+        [0, 0, S, S],                    # full image
+        [10.5, 20.25, 10.5, 20.25],      # zero area
+        [5, 5, 5, 60],                   # zero width
+        [-e, -e, S + e, S + e],          # exceeds every border by 1px
+        [S - 0.4, S - 0.4, S, S],        # sub-pixel at the far corner
+        [0, 0, 0.3, 0.3],                # sub-pixel at the origin
+        [S * 0.5, -e, S + e, S * 0.5],   # top-right overhang
+        [3.999, 7.001, 100.5, 50.499],   # generic non-aligned
+        [S, S, S, S],                    # point on the far border
+        [0, 0, 2, 2],                    # minimum 2px training box
+    ], dtype=np.float32)
+
+
+def ref_cases():
+    ext = build_ref.load()
+    assert ext is not None, 'reference tree not available'
+    rng = np.random.default_rng(20260923)
+    out = {}
+    meta = []
+    S = 224
+    #            name         N  C   H    W   PH sr mode   stride
+    configs = [('l0_224',     2, 8, 128, 128, 14, 2, 'avg', 1.75),
+               ('l1_224',     2, 8, 64, 64, 14, 2, 'avg', 3.5),
+               ('l2_224',     2, 8, 32, 32, 14, 2, 'avg', 7.0),
+               ('l3_224',     2, 8, 16, 16, 14, 2, 'avg', 14.0),
+               ('l3_336',     2, 8, 24, 24, 14, 2, 'avg', 14.0),
+               ('mb7',        3, 8, 32, 32, 7, 2, 'avg', 7.0),
+               ('adaptive',   2, 4, 20, 28, 3, 0, 'avg', 4.0),
+               ('max2',       2, 4, 16, 16, 5, 2, 'max', 14.0),
+               ('max_adapt',  2, 4, 12, 9, 4, 0, 'max', 8.0),
+               ('rect',       1, 4, 10, 17, (3, 5), 3, 'avg', 2.0),
+               ('unaligned',  2, 4, 16, 16, 7, 2, 'avg_unaligned', 14.0)]
+    for name, N, C, H, W, PH, sr, mode, stride in configs:
+        x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+        Sx, Sy = W * stride, H * stride
+        K = 12
+        p = np.sort(rng.uniform(0, 1, (K, 2, 2)), axis=1)
+        boxes = np.concatenate([p[:, 0, :], p[:, 1, :]], 1) * np.array([Sx, Sy, Sx, Sy])
+        boxes = boxes.astype(np.float32)
+        if H == W:
+            boxes = np.concatenate([boxes, adversarial_boxes(Sx)], 0)
+        K = len(boxes)
+        bidx = rng.integers(0, N, (K, 1)).astype(np.float32)
+        rois = np.concatenate([bidx, boxes], 1).astype(np.float32)
+        scale = float(np.float32(1.0 / stride))
+        ph, pw = (PH, PH) if isinstance(PH, int) else PH
+        aligned = mode != 'avg_unaligned'
+        pm = 0 if mode == 'max' else 1
+        xt, rt = torch.from_numpy(x), torch.from_numpy(rois)
+        o = xt.new_zeros(K, C, ph, pw)
+        ay = xt.new_zeros(K, C, ph, pw) if pm == 0 else xt.new_zeros(0)
+        ax = xt.new_zeros(K, C, ph, pw) if pm == 0 else xt.new_zeros(0)
+        ext.roi_align_forward(xt, rt, o, ay, ax, aligned_height=ph, aligned_width=pw,
+                              spatial_scale=scale, sampling_ratio=sr, pool_mode=pm, aligned=aligned)
+        g = rng.standard_normal((K, C, ph, pw)).astype(np.float32)
+        gi = xt.new_zeros(N, C, H, W)
+        ext.roi_align_backward(torch.from_numpy(g), rt, ay, ax, gi, aligned_height=ph,
+                               aligned_width=pw, spatial_scale=scale, sampling_ratio=sr,
+                               pool_mode=pm, aligned=aligned)
+        out[name + '.input'] = x
+        out[name + '.rois'] = rois
+        out[name + '.output'] = o.numpy()
+        out[name + '.grad_output'] = g
+        out[name + '.grad_input'] = gi.numpy()
+        if pm == 0:
+            out[name + '.argmax_y'] = ay.numpy()
+            out[name + '.argmax_x'] = ax.numpy()
+        meta.append(dict(name=name, N=N, C=C, H=H, W=W, PH=ph, PW=pw, sampling_ratio=sr,
+                         pool_mode='max' if pm == 0 else 'avg', aligned=aligned,
+                         spatial_scale=scale, K=K))
+    out['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, 'roi_align_ref_cases.npz'), **out)
+    print('wrote roi_align_ref_cases.npz (%d cases)' % len(meta))
+
+
+if __name__ == '__main__':
+    kat()
+    ref_cases()

@@ -1,0 +1,104 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what
+include/gpt4roi_b200.h declares, the Python mirror refuses to run without a GPU (no
+fallback), and the product never touches oracle/."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'gpt4roi_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(g4r_[a-z0-9_]+)\s*\(', src)))
+
+
+@pytest.fixture(scope='module')
+def built_lib():
+    from gpt4roi_b200 import build, lib
+    build.build()
+    return lib
+
+
+def test_header_symbols_are_exported(built_lib):
+    decl = _declared_symbols()
+    assert len(decl) >= 8
+    so = ctypes.CDLL(built_lib.LIB_PATH)
+    for name in decl:
+        assert hasattr(so, name), '%s declared in include/gpt4roi_b200.h but not exported' % name
+
+
+def test_python_signature_table_matches_header(built_lib):
+    assert sorted(built_lib.SIGNATURES) == _declared_symbols()
+    lib = built_lib.load()
+    assert lib.g4r_version() >= 1000
+    assert lib.g4r_built_arch() == 100
+
+
+def test_library_is_sm100a_only(built_lib):
+    out = subprocess.run(['cuobjdump', '--list-elf', built_lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip('cuobjdump unavailable')
+    archs = set(re.findall(r'sm_(\d+a?)', out.stdout))
+    assert archs == {'100a'}, archs
+
+
+def test_no_cpu_fallback():
+    import gpt4roi_b200 as g
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        g.roi_align(torch.zeros(1, 1, 4, 4), torch.zeros(1, 5), 2, 1.0, 2, 'avg', True)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        g.roi_align_mlvl([torch.zeros(1, 4, 4, 8)], torch.zeros(1, 5), 2, [1.0])
+
+
+def test_operator_api_mirrors_reference_signatures():
+    import inspect
+    import gpt4roi_b200 as g
+    m = g.RoIAlign(7, 0.25, 2)
+    assert m.output_size == (7, 7) and m.spatial_scale == 0.25 and m.sampling_ratio == 2
+    assert repr(m) == ('RoIAlign(output_size=(7, 7), spatial_scale=0.25, sampling_ratio=2, '
+                       'pool_mode=avg, aligned=True, use_torchvision=False)')
+    m = g.RoIAlign(out_size=3, sample_num=4)  # deprecated aliases, mmcv/ops/roi_align.py:171-177
+    assert m.output_size == (3, 3) and m.sampling_ratio == 4
+    names = ['input', 'rois', 'output', 'argmax_y', 'argmax_x', 'aligned_height', 'aligned_width',
+             'spatial_scale', 'sampling_ratio', 'pool_mode', 'aligned']
+    assert list(inspect.signature(g.roi_align_forward).parameters) == names
+    names[0], names[2], names[4] = 'grad_output', 'argmax_y', 'grad_input'
+    names[3] = 'argmax_x'
+    assert list(inspect.signature(g.roi_align_backward).parameters) == names
+    with pytest.raises(AssertionError):
+        g.RoIAlignFunction.apply(torch.zeros(1, 1, 2, 2), torch.zeros(1, 4), 2)  # rois.size(1) != 5
+
+
+def test_mmcv_ext_dropin_module():
+    from gpt4roi_b200 import mmcv_ext
+    m = mmcv_ext.make_module()
+    assert hasattr(m, 'roi_align_forward') and hasattr(m, 'roi_align_backward')
+    assert hasattr(m, 'nms') and hasattr(m, 'deform_conv_forward')  # ext_loader only asserts hasattr
+    with pytest.raises(NotImplementedError):
+        m.nms()
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dp, _, fns in os.walk(os.path.join(ROOT, 'gpt4roi_b200')):
+        for fn in fns:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
+                txt = open(os.path.join(dp, fn)).read()
+                if re.search(r'^\s*(from|import)\s+oracle\b|oracle/|liboracle', txt, re.M):
+                    bad.append(os.path.join(dp, fn))
+    assert not bad, 'product code references oracle/: %s' % bad
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from gpt4roi_b200 import lib
+    monkeypatch.setattr(lib, '_lib', None)
+    monkeypatch.setattr(lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(ImportError, match='no CPU'):
+        lib.load()
