@@ -1,0 +1,517 @@
+// gemm_tcgen05.cu -- bf16 x bf16 -> fp32 dense contraction on the 5th-gen tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense op of the region-token path:
+//   D[M,N] = epilogue( A[M,K] . B[N,K]^T )           (GEMM: nn.Linear weights are [N,K] K-major)
+//   D[n,y,x,:] = epilogue( conv3x3(A[n,:,:,:]) )      (implicit GEMM, NHWC, K = 9*Cin, pad 1)
+// replacing the library calls the reference makes through ATen (cuBLAS / cuDNN):
+//   nn.Linear            : gpt4roi/models/layers.py:260-270 (pos_embedd, updims, flatten_linear),
+//                          llava/model/llava.py:52 (mm_projector), :195 (lm_head), HF CLIP / LLaMA linears
+//   nn.Conv2d 1x1 / 3x3  : gpt4roi/models/layers.py:129-144 (input_conv, fuse_convs), :257-259 (pconvs)
+//
+// Structure (per CTA, 1 CTA / SM, persistent over output tiles):
+//   warp 0     : TMA producer  -- cp.async.bulk.tensor loads of the A tile [128 x 64] and the
+//                B tile [BLOCK_N x 64] (128-byte swizzle) into a kStages-deep smem ring,
+//                completion signalled on `full` mbarriers (expect_tx).
+//                In conv mode the A tile is a 4-D box (64 ch, BW, BH, 1) of the NHWC map shifted by
+//                the filter tap; out-of-bounds coordinates are zero-filled by TMA = the padding.
+//   warp 1     : MMA issuer    -- one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage,
+//                accumulating in TMEM; tcgen05.commit releases the smem slot (`empty`) and, after the
+//                last k-block, publishes the accumulator (`tmem_full`).
+//   warp 2     : TMEM allocator (2 accumulator stages x BLOCK_N fp32 columns).
+//   warps 4..7 : epilogue      -- tcgen05.ld 32 columns at a time (thread = accumulator row), fused
+//                bias / activation / residual / SwiGLU / GroupNorm statistics, bf16 or fp32 store;
+//                the second accumulator stage lets tile i+1's MMAs overlap tile i's epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace g4r {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int kSmemBudget = 200 * 1024;  // operand ring budget (bytes)
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_QUICK_GELU = 2, ACT_SWIGLU = 3 };
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_k_blocks;  // num_k_blocks: per split
+  int k_splits;
+  // epilogue
+  void* D;
+  long long ldd;
+  const void* bias;      // [N] bf16 or fp32 (bias_f32), or null
+  int bias_f32;
+  const __nv_bfloat16* residual;  // same row mapping as D, or null
+  long long ldr;
+  int act;
+  int out_f32;   // 1: fp32 output
+  int atomic;    // 1: fp32 atomicAdd (split-K); D must be pre-zeroed
+  // conv mode
+  int conv;
+  int cH, cW, cBH, cBW, tiles_x, tiles_y, cin_blocks, taps;  // taps = 9 (3x3) or 1
+  int a_rows;            // rows delivered by the A box (<= 128)
+  float* gn_stats;       // optional [n_img, groups, 2] (sum, sumsq) of the bf16-rounded output
+  int gn_group_ch;       // channels per group (16)
+  int gn_groups;         // groups per image (64)
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 256 or 512 (power of two)
+  static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+};
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == ACT_RELU) return fmaxf(x, 0.f);
+  if (act == ACT_QUICK_GELU) return x / (1.f + __expf(-1.702f * x));
+  return x;
+}
+
+template <int BLOCK_N, bool CONV>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + Cfg::kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; i++) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < Cfg::kAccStages; i++) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  ptx::tcgen05_before_thread_sync();
+  __syncthreads();
+  ptx::tcgen05_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int total_tiles = tiles_mn * p.k_splits;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int mn = t % tiles_mn;
+        const int n_blk = mn / p.num_m_tiles, m_blk = mn % p.num_m_tiles;  // m fastest: weights stay in L2
+        const int kb0 = split * p.num_k_blocks;
+        int img = 0, y0 = 0, x0 = 0;
+        if (CONV) {
+          const int tx = m_blk % p.tiles_x;
+          const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+          img = m_blk / (p.tiles_x * p.tiles_y);
+          y0 = ty * p.cBH;
+          x0 = tx * p.cBW;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; kb++) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_rows * kBlockK * 2 + Cfg::kBBytes));
+          const int kg = kb0 + kb;
+          if (CONV) {
+            const int tap = kg / p.cin_blocks, cc = kg % p.cin_blocks;
+            const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+            ptx::tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], cc * kBlockK, x0 + dx,
+                             y0 + dy, img);
+          } else {
+            ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], kg * kBlockK,
+                             m_blk * kBlockM);
+          }
+          ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full[stage], kg * kBlockK, n_blk * BLOCK_N);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tcgen05_after_thread_sync();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < p.num_k_blocks; kb++) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tcgen05_after_thread_sync();
+        if (lane == 0) {
+          const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; k++) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (>>4) address field
+            ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty[stage]);
+          if (kb == p.num_k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ============================ epilogue ============================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // accumulator row owned by this thread
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int split = t / tiles_mn;
+      const int mn = t % tiles_mn;
+      const int n_blk = mn / p.num_m_tiles, m_blk = mn % p.num_m_tiles;
+      // row -> output row offset
+      bool row_ok;
+      long long out_row;
+      int img = 0;
+      if (CONV) {
+        const int tx = m_blk % p.tiles_x;
+        const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+        img = m_blk / (p.tiles_x * p.tiles_y);
+        const int y = ty * p.cBH + row / p.cBW, x = tx * p.cBW + row % p.cBW;
+        row_ok = row < p.a_rows && y < p.cH && x < p.cW;
+        out_row = ((long long)img * p.cH + y) * p.cW + x;
+      } else {
+        out_row = (long long)m_blk * kBlockM + row;
+        row_ok = out_row < p.M;
+      }
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tcgen05_after_thread_sync();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= BLOCK_N) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          ptx::tcgen05_before_thread_sync();
+          ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        const int col0 = n_blk * BLOCK_N + c0;
+        if (col0 >= p.N) continue;  // (warp-uniform)
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        const bool full_chunk = col0 + 32 <= p.N;
+        if (p.bias != nullptr && split == 0) {
+          if (p.bias_f32) {
+            const float* b = reinterpret_cast<const float*>(p.bias) + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (full_chunk || col0 + j < p.N) f[j] += b[j];
+          } else {
+            const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (full_chunk || col0 + j < p.N) f[j] += __bfloat162float(b[j]);
+          }
+        }
+        if (p.act == ACT_RELU || p.act == ACT_QUICK_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = act_apply(f[j], p.act);
+        }
+        if (p.act == ACT_SWIGLU) {
+          // interleaved weights: column 2j = gate_j, 2j+1 = up_j -> out[:, j] = silu(gate) * up
+          if (row_ok) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.D) + out_row * p.ldd + col0 / 2;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float g0 = f[4 * j], u0 = f[4 * j + 1], g1 = f[4 * j + 2], u1 = f[4 * j + 3];
+              const float s0 = g0 / (1.f + __expf(-g0)) * u0, s1 = g1 / (1.f + __expf(-g1)) * u1;
+              __nv_bfloat162 h = __floats2bfloat162_rn(s0, s1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            if (full_chunk && (p.ldd % 8 == 0)) {
+              reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
+              for (int j = 0; j < 16; j++) if (col0 + 2 * j + 1 < p.N) o[j] = e[j];
+            }
+          }
+          continue;
+        }
+        if (p.residual != nullptr && row_ok) {
+          const __nv_bfloat16* rr = p.residual + out_row * p.ldr + col0;
+          if (full_chunk && (p.ldr % 8 == 0)) {
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+              const uint4 raw = reinterpret_cast<const uint4*>(rr)[h];
+              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+              for (int j = 0; j < 8; j++) f[h * 8 + j] += __bfloat162float(e[j]);
+            }
+          } else {
+            for (int j = 0; j < 32; j++) if (col0 + j < p.N) f[j] += __bfloat162float(rr[j]);
+          }
+        }
+        if (p.atomic) {
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.D) + out_row * p.ldd + col0;
+            for (int j = 0; j < 32; j++) if (col0 + j < p.N) atomicAdd(o + j, f[j]);
+          }
+        } else if (p.out_f32) {
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.D) + out_row * p.ldd + col0;
+            if (full_chunk && (p.ldd % 4 == 0)) {
+#pragma unroll
+              for (int h = 0; h < 8; h++)
+                reinterpret_cast<float4*>(o)[h] = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
+            } else {
+              for (int j = 0; j < 32; j++) if (col0 + j < p.N) o[j] = f[j];
+            }
+          }
+        } else {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (row_ok) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.D) + out_row * p.ldd + col0;
+            if (full_chunk && (p.ldd % 8 == 0)) {
+#pragma unroll
+              for (int h = 0; h < 4; h++)
+                reinterpret_cast<uint4*>(o)[h] = make_uint4(pk[4 * h], pk[4 * h + 1], pk[4 * h + 2], pk[4 * h + 3]);
+            } else {
+              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
+              for (int j = 0; j < 32; j++) if (col0 + j < p.N) o[j] = e[j];
+            }
+          }
+          if (CONV && p.gn_stats != nullptr) {
+            // GroupNorm statistics of the bf16-rounded conv output (what the reference's GN sees:
+            // mmcv cnn/bricks/conv_module.py:196-208 runs GN on the conv's bf16 result).
+            // 32 columns = 2 groups of 16 channels; reduce over the 32 rows of this warp, then atomics.
+            const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
+            float s[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f};
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const float x = __bfloat162float(e[j]);
+                s[j >> 4] += x;
+                ss[j >> 4] += x * x;
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+              s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+              ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o);
+              ss[1] += __shfl_xor_sync(0xffffffffu, ss[1], o);
+            }
+            if (lane < 2 && full_chunk) {
+              float* st = p.gn_stats + ((long long)img * p.gn_groups + (col0 / p.gn_group_ch + lane)) * 2;
+              atomicAdd(st, lane == 0 ? s[0] : s[1]);
+              atomicAdd(st + 1, lane == 0 ? ss[0] : ss[1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tcgen05_before_thread_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tcgen05_after_thread_sync();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 tensor map, rank 2..4; dims/box innermost first; strides (bytes) for dims 1..rank-1.
+static int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable (driver entry point lookup failed)");
+    return G4R_ECUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu,%llu box %u,%u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return G4R_ECUDA;
+  }
+  return G4R_OK;
+}
+
+template <int BLOCK_N, bool CONV>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tcgen05<BLOCK_N, CONV>;
+  if (!attr_set) {
+    G4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int total = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  G4R_LAUNCH_CHECK("gemm_bf16_tcgen05");
+  return G4R_OK;
+}
+
+static int pick_block_n(int N, int m_tiles, int k_splits) {
+  // 256-wide tiles feed the tensor core best; fall back to 128 when that leaves SMs idle.
+  if (N <= 128) return 128;
+  const long t256 = (long)m_tiles * ((N + 255) / 256) * k_splits;
+  if (t256 >= num_sms()) return 256;
+  return 128;
+}
+
+}  // namespace g4r
+
+using namespace g4r;
+
+extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* D,
+                             long long ldd, int M, int N, int K, const void* bias, int bias_f32,
+                             const void* residual, long long ldr, int act, int out_f32, int k_splits,
+                             void* stream) {
+  G4R_REQUIRE(A && B && D, "null operand");
+  G4R_REQUIRE(M > 0 && N > 0 && K > 0, "bad sizes M=%d N=%d K=%d", M, N, K);
+  G4R_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "lda/ldb must be >= K and multiples of 8 (16-byte TMA strides)");
+  G4R_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "A/B must be 16-byte aligned");
+  G4R_REQUIRE(act >= ACT_NONE && act <= ACT_SWIGLU, "act=%d", act);
+  G4R_REQUIRE(k_splits >= 1, "k_splits=%d", k_splits);
+  if (act == ACT_SWIGLU) G4R_REQUIRE(N % 2 == 0 && !out_f32 && k_splits == 1 && !residual, "SwiGLU epilogue: even N, bf16 out, no split-K/residual");
+  if (k_splits > 1) G4R_REQUIRE(out_f32 && act == ACT_NONE && !residual, "split-K accumulates fp32 atomically: out_f32, no act/residual");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int kb_total = (K + kBlockK - 1) / kBlockK;
+  G4R_REQUIRE(kb_total % k_splits == 0, "K blocks (%d) not divisible by k_splits (%d)", kb_total, k_splits);
+  p.k_splits = k_splits;
+  p.num_k_blocks = kb_total / k_splits;
+  p.D = D; p.ldd = ldd; p.bias = bias; p.bias_f32 = bias_f32;
+  p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr;
+  p.act = act; p.out_f32 = out_f32; p.atomic = k_splits > 1;
+  p.conv = 0; p.a_rows = kBlockM;
+  const int bn = pick_block_n(N, p.num_m_tiles, k_splits);
+  p.num_n_tiles = (N + bn - 1) / bn;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint64_t str[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t box[2] = {kBlockK, kBlockM};
+    int rc = make_tmap(&ta, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t str[1] = {(cuuint64_t)ldb * 2};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)bn};
+    int rc = make_tmap(&tb, B, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return bn == 256 ? launch_gemm<256, false>(ta, tb, p, st) : launch_gemm<128, false>(ta, tb, p, st);
+}
+
+extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_img, int H, int W, int Cin,
+                                  int Cout, int ksize, const void* bias, int bias_f32, int act,
+                                  float* gn_stats, int gn_groups, void* stream) {
+  G4R_REQUIRE(X && Wt && Y, "null operand");
+  G4R_REQUIRE(ksize == 3 || ksize == 1, "ksize=%d (1 or 3)", ksize);
+  G4R_REQUIRE(Cin % kBlockK == 0, "Cin=%d must be a multiple of 64", Cin);
+  G4R_REQUIRE(Cout % 8 == 0, "Cout=%d must be a multiple of 8", Cout);
+  G4R_REQUIRE(n_img > 0 && H > 0 && W > 0, "bad sizes");
+  G4R_REQUIRE(act == ACT_NONE || act == ACT_RELU, "conv epilogue: none or relu");
+  if (gn_stats) G4R_REQUIRE(gn_groups > 0 && Cout % gn_groups == 0 && Cout / gn_groups == 16, "GN stats need 16-channel groups");
+  GemmParams p{};
+  // spatial tile: BW x BH = 128 output pixels (or fewer for small maps)
+  int bw = W >= 16 && W % 16 == 0 ? 16 : (W >= 8 ? 8 : W);
+  if (W == 14) bw = 14;
+  int bh = kBlockM / bw;
+  if (bh > H) bh = H;
+  p.cBW = bw; p.cBH = bh; p.cH = H; p.cW = W;
+  p.tiles_x = (W + bw - 1) / bw;
+  p.tiles_y = (H + bh - 1) / bh;
+  p.a_rows = bw * bh;
+  p.M = n_img * H * W; p.N = Cout; p.K = ksize * ksize * Cin;
+  p.num_m_tiles = n_img * p.tiles_x * p.tiles_y;
+  p.cin_blocks = Cin / kBlockK;
+  p.taps = ksize * ksize;
+  p.num_k_blocks = p.taps * p.cin_blocks;
+  p.k_splits = 1;
+  p.D = Y; p.ldd = Cout; p.bias = bias; p.bias_f32 = bias_f32; p.act = act;
+  p.conv = 1;
+  p.gn_stats = gn_stats; p.gn_groups = gn_groups; p.gn_group_ch = gn_groups ? Cout / gn_groups : 0;
+  const int bn = pick_block_n(Cout, p.num_m_tiles, 1);
+  p.num_n_tiles = (Cout + bn - 1) / bn;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+    cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {kBlockK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    int rc = make_tmap(&ta, X, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)Cout};
+    cuuint64_t str[1] = {(cuuint64_t)p.K * 2};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)bn};
+    int rc = make_tmap(&tb, Wt, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return bn == 256 ? launch_gemm<256, true>(ta, tb, p, st) : launch_gemm<128, true>(ta, tb, p, st);
+}

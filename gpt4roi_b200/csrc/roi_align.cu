@@ -25,6 +25,8 @@
 //   * NCHW (the mmcv._ext drop-in layout): CTA = (RoI, channel chunk); output writes
 //     are contiguous; taps are plane gathers like the reference's but without the
 //     per-thread geometry.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace g4r {
@@ -282,6 +284,7 @@ struct MlvlParams {
   const float* rois;
   void* out;  // forward: output; backward: grad_output (const)
   int N, C, K, PH, PW, sampling_ratio, aligned, rows_per_cta, n_levels;
+  int rows_per_cta_lvl[G4R_MAX_LEVELS];  // forward: bin rows handled by one CTA, per level
 };
 
 template <typename Tout, int N>
@@ -311,79 +314,139 @@ __device__ __forceinline__ void store_vec(Tout* p, const float (&v)[N]) {
   }
 }
 
+// Packed axis entry for the hot path: element offsets pre-multiplied (y: lo*W*C, x: lo*C),
+// off_lo < 0 marks an out-of-range sample (contributes exactly 0, common_cuda_helper.hpp:33).
+struct PackedAxis {
+  int off_lo, off_hi;
+  float l, h;
+};
+
+__device__ __forceinline__ PackedAxis pack_axis(const AxisEntry<float>& e, int mul) {
+  PackedAxis a;
+  a.off_lo = e.valid ? e.lo * mul : -1;
+  a.off_hi = e.hi * mul;
+  a.l = e.l;
+  a.h = e.h;
+  return a;
+}
+
 template <typename Tin, typename Tout, int G, bool AFFINE>
 __global__ void __launch_bounds__(kThreads)
 roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
   constexpr int VEC = 16 / (int)sizeof(Tin);
-  __shared__ AxisEntry<float> ytab[kTab];
-  __shared__ AxisEntry<float> xtab[kTab];
+  __shared__ PackedAxis ytab[kTab];
+  __shared__ PackedAxis xtab[kTab];
 
   const int lvl = blockIdx.y;
-  const int row_groups = (p.PH + p.rows_per_cta - 1) / p.rows_per_cta;
+  const int rpc = p.rows_per_cta_lvl[lvl];
+  const int row_groups = (p.PH + rpc - 1) / rpc;
   const int k = blockIdx.x / row_groups;
-  const int ph0 = (blockIdx.x % row_groups) * p.rows_per_cta;
-  const int nrows = min(p.rows_per_cta, p.PH - ph0);
+  if (k >= p.K) return;  // grid.x is sized for the level with the most row groups
+  const int ph0 = (blockIdx.x % row_groups) * rpc;
+  const int nrows = min(rpc, p.PH - ph0);
   const int H = p.H[lvl], W = p.W[lvl], C = p.C, PW = p.PW;
   const float* r = p.rois + (size_t)k * 5;
   const RoiGeom<float> g = roi_geom<float>(r[0], r[1], r[2], r[3], r[4], p.scale[lvl], p.PH, PW,
                                            G > 0 ? G : p.sampling_ratio, p.aligned != 0, true);
   const int gh = G > 0 ? G : g.gh, gw = G > 0 ? G : g.gw;
-  const bool use_tab = (nrows * gh <= kTab) && (PW * gw <= kTab);
-  if (use_tab) {
-    for (int i = threadIdx.x; i < nrows * gh; i += blockDim.x)
-      ytab[i] = axis_entry<float>(g.start_h, g.bin_h, ph0 + i / gh, i % gh, gh, H);
-    for (int i = threadIdx.x; i < PW * gw; i += blockDim.x)
-      xtab[i] = axis_entry<float>(g.start_w, g.bin_w, i / gw, i % gw, gw, W);
-    __syncthreads();
-  }
+  // tables always fit for G > 0 (launcher guarantees PH*G, PW*G <= kTab); adaptive grids that do
+  // not fit are processed in chunks of kTab samples per axis.
   const int lanes = C / VEC;
-  const int items = nrows * PW * lanes;
   const Tin* map = reinterpret_cast<const Tin*>(p.maps[lvl]) + (size_t)g.batch * H * W * C;
   Tout* out = reinterpret_cast<Tout*>(p.out) +
               (((size_t)lvl * p.K + k) * p.PH + ph0) * (size_t)PW * C;
+  const bool quarter = (gh * gw == 4);  // x/4 == x*0.25f exactly: avoids an IEEE division per value
 
+  if (nrows * gh <= kTab && PW * gw <= kTab) {
+    for (int i = threadIdx.x; i < nrows * gh; i += blockDim.x)
+      ytab[i] = pack_axis(axis_entry<float>(g.start_h, g.bin_h, ph0 + i / gh, i % gh, gh, H), W * C);
+    for (int i = threadIdx.x; i < PW * gw; i += blockDim.x)
+      xtab[i] = pack_axis(axis_entry<float>(g.start_w, g.bin_w, i / gw, i % gw, gw, W), C);
+    __syncthreads();
+    const int items = nrows * PW * lanes;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int lane = it % lanes;
+      const int b = it / lanes;  // bin within this CTA's rows
+      const int prow = b / PW, pw = b % PW;
+      const int coff = lane * VEC;
+      const Tin* mp = map + coff;
+      float ga[VEC], gb[VEC];
+      if constexpr (AFFINE) {
+        const float* sa = p.gn_scale[lvl] + (size_t)g.batch * C + coff;
+        const float* sb = p.gn_shift[lvl] + (size_t)g.batch * C + coff;
+#pragma unroll
+        for (int i = 0; i < VEC; i++) { ga[i] = sa[i]; gb[i] = sb[i]; }
+      }
+      float acc[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; i++) acc[i] = 0.f;
+#pragma unroll
+      for (int iy = 0; iy < (G > 0 ? G : gh); iy++) {
+        const PackedAxis ey = ytab[prow * gh + iy];
+#pragma unroll
+        for (int ix = 0; ix < (G > 0 ? G : gw); ix++) {
+          const PackedAxis ex = xtab[pw * gw + ix];
+          if (ey.off_lo >= 0 && ex.off_lo >= 0) {
+            const float w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
+            float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+            load16<Tin>(mp + (ey.off_lo + ex.off_lo), v1);
+            load16<Tin>(mp + (ey.off_lo + ex.off_hi), v2);
+            load16<Tin>(mp + (ey.off_hi + ex.off_lo), v3);
+            load16<Tin>(mp + (ey.off_hi + ex.off_hi), v4);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+              if constexpr (AFFINE) {
+                v1[i] = fmaxf(v1[i] * ga[i] + gb[i], 0.f);
+                v2[i] = fmaxf(v2[i] * ga[i] + gb[i], 0.f);
+                v3[i] = fmaxf(v3[i] * ga[i] + gb[i], 0.f);
+                v4[i] = fmaxf(v4[i] * ga[i] + gb[i], 0.f);
+              }
+              const float val = w1 * v1[i] + w2 * v2[i] + w3 * v3[i] + w4 * v4[i];
+              acc[i] += val;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; i++) acc[i] = quarter ? acc[i] * 0.25f : acc[i] / g.count;
+      store_vec<Tout, VEC>(out + ((size_t)prow * PW + pw) * C + coff, acc);
+    }
+    return;
+  }
+
+  // generic path (adaptive sampling grids too large for the tables): geometry on the fly
+  const int items = nrows * PW * lanes;
   for (int it = threadIdx.x; it < items; it += blockDim.x) {
     const int lane = it % lanes;
-    const int b = it / lanes;  // bin within this CTA's rows
+    const int b = it / lanes;
     const int prow = b / PW, pw = b % PW;
     const int coff = lane * VEC;
-    float ga[VEC], gb[VEC];
-    if constexpr (AFFINE) {
-      const float* sa = p.gn_scale[lvl] + (size_t)g.batch * C + coff;
-      const float* sb = p.gn_shift[lvl] + (size_t)g.batch * C + coff;
-#pragma unroll
-      for (int i = 0; i < VEC; i++) { ga[i] = sa[i]; gb[i] = sb[i]; }
-    }
     float acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; i++) acc[i] = 0.f;
+    for (int iy = 0; iy < gh; iy++) {
+      const AxisEntry<float> ey = axis_entry<float>(g.start_h, g.bin_h, ph0 + prow, iy, gh, H);
+      for (int ix = 0; ix < gw; ix++) {
+        const AxisEntry<float> ex = axis_entry<float>(g.start_w, g.bin_w, pw, ix, gw, W);
+        if (!(ey.valid && ex.valid)) continue;
+        const float w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
+        float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+        load16<Tin>(map + ((size_t)ey.lo * W + ex.lo) * C + coff, v1);
+        load16<Tin>(map + ((size_t)ey.lo * W + ex.hi) * C + coff, v2);
+        load16<Tin>(map + ((size_t)ey.hi * W + ex.lo) * C + coff, v3);
+        load16<Tin>(map + ((size_t)ey.hi * W + ex.hi) * C + coff, v4);
 #pragma unroll
-    for (int iy = 0; iy < (G > 0 ? G : gh); iy++) {
-      const AxisEntry<float> ey = use_tab ? ytab[prow * gh + iy]
-                                          : axis_entry<float>(g.start_h, g.bin_h, ph0 + prow, iy, gh, H);
-#pragma unroll
-      for (int ix = 0; ix < (G > 0 ? G : gw); ix++) {
-        const AxisEntry<float> ex = use_tab ? xtab[pw * gw + ix]
-                                            : axis_entry<float>(g.start_w, g.bin_w, pw, ix, gw, W);
-        // invalid samples contribute val = 0 (common_cuda_helper.hpp:33); acc + 0 == acc.
-        if (ey.valid && ex.valid) {
-          const float w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
-          float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-          load16<Tin>(map + ((size_t)ey.lo * W + ex.lo) * C + coff, v1);
-          load16<Tin>(map + ((size_t)ey.lo * W + ex.hi) * C + coff, v2);
-          load16<Tin>(map + ((size_t)ey.hi * W + ex.lo) * C + coff, v3);
-          load16<Tin>(map + ((size_t)ey.hi * W + ex.hi) * C + coff, v4);
-#pragma unroll
-          for (int i = 0; i < VEC; i++) {
-            if constexpr (AFFINE) {
-              v1[i] = fmaxf(v1[i] * ga[i] + gb[i], 0.f);
-              v2[i] = fmaxf(v2[i] * ga[i] + gb[i], 0.f);
-              v3[i] = fmaxf(v3[i] * ga[i] + gb[i], 0.f);
-              v4[i] = fmaxf(v4[i] * ga[i] + gb[i], 0.f);
-            }
-            const float val = w1 * v1[i] + w2 * v2[i] + w3 * v3[i] + w4 * v4[i];
-            acc[i] += val;
+        for (int i = 0; i < VEC; i++) {
+          if constexpr (AFFINE) {
+            const float a = p.gn_scale[lvl][(size_t)g.batch * C + coff + i];
+            const float bb = p.gn_shift[lvl][(size_t)g.batch * C + coff + i];
+            v1[i] = fmaxf(v1[i] * a + bb, 0.f);
+            v2[i] = fmaxf(v2[i] * a + bb, 0.f);
+            v3[i] = fmaxf(v3[i] * a + bb, 0.f);
+            v4[i] = fmaxf(v4[i] * a + bb, 0.f);
           }
+          const float val = w1 * v1[i] + w2 * v2[i] + w3 * v3[i] + w4 * v4[i];
+          acc[i] += val;
         }
       }
     }
@@ -502,10 +565,24 @@ static int pick_rows_per_cta(int K, int n_levels, int PH) {
 }
 
 template <typename Tin, typename Tout>
-static int launch_fwd_mlvl(const MlvlParams& p, bool affine, cudaStream_t st) {
-  const int row_groups = (p.PH + p.rows_per_cta - 1) / p.rows_per_cta;
-  dim3 grid((unsigned)(p.K * row_groups), p.n_levels);
-  if (p.sampling_ratio == 2) {
+static int launch_fwd_mlvl(MlvlParams& p, bool affine, cudaStream_t st) {
+  // Rows per CTA, per level.  Whole-RoI CTAs amortise the table build; but on the big (fine)
+  // levels a whole image-level does not fit L2 with many RoIs in flight, so those levels use one
+  // bin row per CTA: ~PH x more CTAs per image => fewer images in flight => taps hit L2.
+  int max_groups = 1;
+  const char* env = getenv("G4R_ROI_ROWS");
+  for (int l = 0; l < p.n_levels; l++) {
+    const double map_mb = (double)p.H[l] * p.W[l] * p.C * sizeof(Tin) / 1e6;
+    int rows = map_mb > 8.0 ? 1 : pick_rows_per_cta(p.K, p.n_levels, p.PH);
+    if (env && atoi(env) > 0) rows = atoi(env);
+    if (rows > p.PH) rows = p.PH;
+    p.rows_per_cta_lvl[l] = rows;
+    const int groups = (p.PH + rows - 1) / rows;
+    if (groups > max_groups) max_groups = groups;
+  }
+  dim3 grid((unsigned)(p.K * max_groups), p.n_levels);
+  const bool g2 = p.sampling_ratio == 2 && p.PH * 2 <= kTab && p.PW * 2 <= kTab;
+  if (g2) {
     if (affine) roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, true><<<grid, kThreads, 0, st>>>(p);
     else roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, false><<<grid, kThreads, 0, st>>>(p);
   } else {
@@ -549,6 +626,8 @@ extern "C" int g4r_roi_align_mlvl_forward(const void* const* maps, const int* H,
     if (gn_scale) G4R_REQUIRE(gn_scale[l] && gn_shift[l], "level %d: null gn_scale/shift", l);
   }
   G4R_REQUIRE(((uintptr_t)output & 15) == 0, "output not 16-byte aligned");
+  for (int l = 0; l < n_levels; l++)
+    G4R_REQUIRE((double)H[l] * W[l] * C < 2147483647.0, "level %d: H*W*C must fit int32 element offsets", l);
   p.rois = rois;
   p.out = output;
   p.N = N; p.C = C; p.K = K; p.PH = PH; p.PW = PW;

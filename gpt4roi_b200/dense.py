@@ -1,0 +1,89 @@
+"""Dense contractions (nn.Linear / nn.Conv2d replacements) on the tcgen05 kernels.
+
+Thin torch-tensor front-ends of `g4r_gemm_bf16` / `g4r_conv_nhwc_bf16`
+(csrc/gemm_tcgen05.cu).  bf16 operands, fp32 accumulation; no library GEMM is called.
+"""
+import torch
+
+from . import lib as _L
+
+ACT = {None: 0, 'none': 0, 'relu': 1, 'quick_gelu': 2, 'swiglu': 3}
+
+
+def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16,
+           k_splits=1):
+    """y = act(x @ weight.T + bias) (+ residual).  x [..., K] bf16, weight [N, K] bf16.
+
+    act='swiglu': weight rows interleaved (gate_j, up_j); returns [..., N/2].
+    k_splits>1: fp32 atomic split-K (out_dtype must be float32; `out` is zeroed here).
+    """
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    M, N = x2.shape[0], weight.shape[0]
+    named = [('x', x2), ('weight', weight), ('bias', bias), ('residual', residual)]
+    dev = _L.require_cuda_same_device(named)
+    if x2.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError('linear: bf16 operands required, got %s / %s' % (x2.dtype, weight.dtype))
+    if x2.stride(-1) != 1 or weight.stride(-1) != 1:
+        raise RuntimeError('linear: operands must be K-major (unit stride on the last dim)')
+    if weight.shape[1] != K:
+        raise RuntimeError('linear: weight is %s but x has K=%d' % (tuple(weight.shape), K))
+    n_out = N // 2 if act == 'swiglu' else N
+    out_f32 = out_dtype == torch.float32
+    if out is None:
+        if k_splits > 1:
+            out = torch.zeros((M, n_out), dtype=out_dtype, device=dev)
+        else:
+            out = torch.empty((M, n_out), dtype=out_dtype, device=dev)
+    else:
+        if out.dtype != out_dtype or out.shape[-1] != n_out or out.stride(-1) != 1:
+            raise RuntimeError('linear: bad `out`')
+        if k_splits > 1:
+            out.zero_()
+    out2 = out.reshape(-1, n_out) if out.is_contiguous() else out
+    res2 = None
+    if residual is not None:
+        if residual.dtype != torch.bfloat16:
+            raise TypeError('linear: residual must be bf16')
+        res2 = residual.reshape(-1, n_out) if residual.is_contiguous() else residual
+    bias_f32 = 0
+    if bias is not None:
+        if bias.dtype == torch.float32:
+            bias_f32 = 1
+        elif bias.dtype != torch.bfloat16:
+            raise TypeError('linear: bias must be bf16 or fp32')
+    with torch.cuda.device(dev):
+        _L.check(_L.load().g4r_gemm_bf16(
+            _L.ptr(x2), x2.stride(0), _L.ptr(weight), weight.stride(0), _L.ptr(out2), out2.stride(0),
+            M, N, K, _L.ptr(bias), bias_f32, _L.ptr(res2), res2.stride(0) if res2 is not None else 0,
+            ACT[act], int(out_f32), int(k_splits), _L.stream_ptr(dev)))
+    return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out
+
+
+def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None):
+    """NHWC conv, stride 1, 'same' padding.  x [N,H,W,Cin] bf16; weight_khwc [Cout,kh,kw,Cin] bf16.
+
+    gn_stats: optional fp32 [N, groups, 2] (zeroed by the caller) accumulating sum / sumsq of the
+    bf16 output per (image, 16-channel group).
+    """
+    dev = _L.require_cuda_same_device([('x', x), ('weight', weight_khwc), ('bias', bias), ('gn_stats', gn_stats)])
+    _L.require_contiguous([('x', x), ('weight', weight_khwc)])
+    n, h, w, cin = x.shape
+    cout, kh, kw, cin2 = weight_khwc.shape
+    if kh != kw or kh not in (1, 3) or cin2 != cin:
+        raise RuntimeError('conv_nhwc: weight must be [Cout,k,k,Cin] with k in (1,3)')
+    if x.dtype != torch.bfloat16 or weight_khwc.dtype != torch.bfloat16:
+        raise TypeError('conv_nhwc: bf16 operands required')
+    if out is None:
+        out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
+    bias_f32 = int(bias is not None and bias.dtype == torch.float32)
+    groups = 0
+    if gn_stats is not None:
+        if gn_stats.dtype != torch.float32 or gn_stats.dim() != 3 or gn_stats.shape[0] != n or gn_stats.shape[2] != 2:
+            raise RuntimeError('gn_stats must be fp32 [N,groups,2]')
+        groups = gn_stats.shape[1]
+    with torch.cuda.device(dev):
+        _L.check(_L.load().g4r_conv_nhwc_bf16(
+            _L.ptr(x), _L.ptr(weight_khwc), _L.ptr(out), n, h, w, cin, cout, kh, _L.ptr(bias), bias_f32,
+            ACT[act], _L.ptr(gn_stats), groups, _L.stream_ptr(dev)))
+    return out

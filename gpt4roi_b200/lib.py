@@ -23,6 +23,7 @@ _DTYPE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.fl
 
 _c = ctypes
 _vp, _i, _f, _i64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_int64
+_ll = _c.c_longlong
 
 # name -> (restype, argtypes); must list EVERY symbol include/gpt4roi_b200.h declares
 # (tests/test_abi_cpu.py parses the header and checks both directions).
@@ -35,6 +36,8 @@ SIGNATURES = {
     'g4r_roi_align_mlvl_forward': (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 9 + [_vp] * 3),
     'g4r_roi_align_mlvl_backward': (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 8 + [_vp]),
     'g4r_splice_region_tokens': (_i, [_vp] * 8 + [_i] * 5 + [_i64] * 4 + [_vp]),
+    'g4r_gemm_bf16': (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _vp]),
+    'g4r_conv_nhwc_bf16': (_i, [_vp] * 3 + [_i] * 6 + [_vp, _i, _i, _vp, _i, _vp]),
 }
 
 _lib = None

@@ -143,6 +143,45 @@ int g4r_splice_region_tokens(const int64_t* input_ids, const void* embed_table,
                              int64_t im_end_token, int64_t bbox_token,
                              void* stream);
 
+/* ---- dense contractions on tcgen05 tensor cores ---------------------------- */
+enum { G4R_ACT_NONE = 0, G4R_ACT_RELU = 1, G4R_ACT_QUICK_GELU = 2, G4R_ACT_SWIGLU = 3 };
+
+/*
+ * D[M,N] = epilogue(A[M,K] . B[N,K]^T): bf16 operands (both K-major, i.e. B is an
+ * nn.Linear weight [out,in]), fp32 accumulation in TMEM, TMA-fed, persistent.
+ * Replaces the cuBLAS calls behind torch.nn.Linear at
+ *   gpt4roi/models/layers.py:260-270,326-329  (pos_embedd, flatten_linear, updims)
+ *   llava/model/llava.py:52,76 / gpt4roi/models/spi_llava.py:89-97 (mm_projector)
+ *   llava/model/llava.py:195,235-236 (lm_head)
+ *   transformers CLIP / LLaMA q,k,v,o,fc1,fc2,gate,up,down projections (third party)
+ * epilogue: (+bias[N]) -> act -> (+residual[M,N] bf16) -> store bf16 (or fp32 if out_f32).
+ *   G4R_ACT_SWIGLU: B rows interleaved (2j = gate_j, 2j+1 = up_j); D is [M,N/2] = silu(g)*u.
+ *   k_splits > 1: fp32 atomic accumulation into a pre-zeroed D (out_f32 required).
+ * lda/ldb/ldd/ldr are row strides in elements; lda, ldb multiples of 8.
+ */
+int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb,
+                  void* D, long long ldd, int M, int N, int K,
+                  const void* bias, int bias_f32,
+                  const void* residual, long long ldr,
+                  int act, int out_f32, int k_splits, void* stream);
+
+/*
+ * NHWC convolution as an implicit GEMM (stride 1, pad (ksize-1)/2, ksize 1 or 3):
+ *   Y[n,y,x,co] = act( sum_{ky,kx,ci} X[n,y+ky-1,x+kx-1,ci] * Wt[co,(ky*ks+kx)*Cin+ci] + bias[co] )
+ * X bf16 [n_img,H,W,Cin]; Wt bf16 [Cout, ks*ks*Cin] (torch [Cout,Cin,kh,kw] permuted to
+ * [Cout,kh,kw,Cin] once at load time); Y bf16 [n_img,H,W,Cout].  The A operand is fetched
+ * with 4-D TMA boxes shifted by the filter tap; TMA's out-of-bounds zero fill is the padding.
+ * Replaces cuDNN behind nn.Conv2d at gpt4roi/models/layers.py:129-144,191,178 (input_conv,
+ * fuse_convs[i].conv) and :257-259,320-325 (pconvs).
+ * gn_stats (optional, fp32 [n_img,gn_groups,2], pre-zeroed): accumulates per-(image,group)
+ * sum and sum of squares of the bf16-rounded output -- the statistics GroupNorm(64) needs
+ * (mmcv cnn/bricks/conv_module.py:196-208), so no extra pass over Y is required.
+ */
+int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y,
+                       int n_img, int H, int W, int Cin, int Cout, int ksize,
+                       const void* bias, int bias_f32, int act,
+                       float* gn_stats, int gn_groups, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,85 @@
+"""GPU numerics tests for the tcgen05 GEMM / implicit-GEMM conv (floating point: tolerance
+tests against a plain PyTorch fp32 reference of the same op on the same bf16 inputs)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpt4roi_b200 import dense
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _close(got, want, rtol=1.6e-2, atol=None):
+    want = want.float()
+    got = got.float()
+    atol = atol if atol is not None else 1e-2 * want.abs().max().item()
+    torch.testing.assert_close(got, want, rtol=rtol, atol=atol)
+    # bf16 output of an fp32 accumulation: mean error must be far below one bf16 ulp
+    rel = (got - want).abs().mean() / want.abs().mean().clamp_min(1e-6)
+    assert rel < 4e-3, rel
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (128, 256, 128), (256, 512, 4096), (200, 384, 320),
+                                   (64, 1024, 1024), (5648, 4096, 4096), (706, 32006, 4096), (577, 3072, 1024),
+                                   (100, 72, 136)])
+def test_gemm_plain(M, N, K):
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.5).bfloat16()
+    got = dense.linear(a, b)
+    want = a.float() @ b.float().t()
+    _close(got, want)
+
+
+def test_gemm_epilogues():
+    torch.manual_seed(0)
+    M, N, K = 300, 640, 512
+    a = (torch.randn(M, K, device=DEV) * 0.3).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.3).bfloat16()
+    bias = torch.randn(N, device=DEV).bfloat16()
+    res = torch.randn(M, N, device=DEV).bfloat16()
+    base = a.float() @ b.float().t()
+    _close(dense.linear(a, b, bias), base + bias.float())
+    _close(dense.linear(a, b, bias.float()), base + bias.float())
+    _close(dense.linear(a, b, bias, act='relu'), torch.relu(base + bias.float()))
+    z = base + bias.float()
+    _close(dense.linear(a, b, bias, act='quick_gelu'), z * torch.sigmoid(1.702 * z))
+    _close(dense.linear(a, b, bias, residual=res), base + bias.float() + res.float())
+    _close(dense.linear(a, b, out_dtype=torch.float32), base, rtol=1e-4, atol=1e-3)
+    # SwiGLU with interleaved gate/up rows
+    g, u = base[:, 0::2], base[:, 1::2]
+    _close(dense.linear(a, b, act='swiglu'), F.silu(g) * u)
+    # split-K (fp32 atomics)
+    _close(dense.linear(a, b, out_dtype=torch.float32, k_splits=4), base, rtol=1e-4, atol=1e-3)
+
+
+def test_gemm_strided_rows_and_3d_input():
+    torch.manual_seed(1)
+    x = (torch.randn(2, 50, 256, device=DEV)).bfloat16()
+    w = (torch.randn(384, 256, device=DEV) * 0.1).bfloat16()
+    got = dense.linear(x, w)
+    assert got.shape == (2, 50, 384)
+    _close(got, x.float() @ w.float().t())
+    big = torch.zeros(100, 512, device=DEV, dtype=torch.bfloat16)
+    dense.linear(x.reshape(100, 256), w, out=big[:, :384])  # padded row stride (lm_head style)
+    _close(big[:, :384], (x.float() @ w.float().t()).reshape(100, 384))
+
+
+@pytest.mark.parametrize('H,W,Cin,Cout,k', [(16, 16, 64, 128, 3), (24, 24, 128, 256, 3), (48, 48, 64, 64, 3),
+                                            (14, 14, 128, 128, 3), (32, 32, 1088, 1024, 1), (96, 96, 1024, 1024, 3)])
+def test_conv_nhwc(H, W, Cin, Cout, k):
+    torch.manual_seed(H + Cin)
+    n = 2
+    x = (torch.randn(n, H, W, Cin, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, device=DEV) * (1.0 / (Cin * k * k) ** 0.5)).bfloat16()
+    bias = torch.randn(Cout, device=DEV).bfloat16()
+    stats = torch.zeros(n, Cout // 16, 2, device=DEV)
+    got = dense.conv_nhwc(x, w.permute(0, 2, 3, 1).contiguous(), bias, act='relu', gn_stats=stats)
+    want = torch.relu(F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias.float(), padding=k // 2))
+    want = want.permute(0, 2, 3, 1)
+    _close(got, want)
+    # fused GroupNorm statistics of the bf16 output
+    g = got.float().reshape(n, H * W, Cout // 16, 16)
+    torch.testing.assert_close(stats[..., 0], g.sum((1, 3)), rtol=1e-3, atol=1e-1)
+    torch.testing.assert_close(stats[..., 1], (g * g).sum((1, 3)), rtol=1e-3, atol=1e-1)
