@@ -1,0 +1,532 @@
+// elementwise.cu -- the HBM-bound glue of the region-token path (sm_100a): normalisations,
+// rotary embedding, patchify, bilinear resampling / channel shuffle, GroupNorm finalisation and
+// the small box-position MLP.  bf16 in / bf16 out, fp32 math, 128-bit accesses.
+//
+// Each kernel cites the reference op sequence it replaces; rounding points follow what the
+// reference produces under bf16 autocast (the only mode in which the SPI module runs, see
+// DESIGN.md "numerics").
+#include "common.cuh"
+
+namespace g4r {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return raw;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------------------------------
+// Row-wise LayerNorm / RMSNorm: one warp per row, the row lives in registers (D <= 8192).
+//   LayerNorm: CLIP pre_layrnorm / layer_norm1 / layer_norm2 (transformers modeling_clip.py) and
+//              nn.LayerNorm in pos_embedd (gpt4roi/models/layers.py:263,266)
+//   RMSNorm  : LlamaRMSNorm (transformers modeling_llama.py:53-67):
+//              w * (x * rsqrt(mean(x^2) + eps)).to(bf16)
+// ------------------------------------------------------------------------------------------
+// PER_LANE = ceil(D/8/32) vectors per lane, compile-time so the row stays in registers.
+template <bool RMS, int PER_LANE>
+__global__ void __launch_bounds__(256)
+norm_rows_bf16(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+               const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, long long ldo, int M,
+               int D, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  float v[PER_LANE][8];
+  float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i++) {
+    const int vi = lane + (i << 5);
+    if (vi < nvec) {
+      unpack8(xr[vi], v[i]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sum += v[i][j]; sumsq += v[i][j] * v[i][j]; }
+  }
+  sum = warp_sum(sum);
+  sumsq = warp_sum(sumsq);
+  float mean = 0.f, rstd;
+  if (RMS) {
+    rstd = rsqrtf(sumsq / D + eps);
+  } else {
+    mean = sum / D;
+    float var = 0.f;  // second pass over registers (two-pass variance, like torch)
+#pragma unroll
+    for (int i = 0; i < PER_LANE; i++) {
+      if (lane + (i << 5) < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const float d = v[i][j] - mean; var += d * d; }
+      }
+    }
+    var = warp_sum(var);
+    rstd = rsqrtf(var / D + eps);
+  }
+  uint4* orow = reinterpret_cast<uint4*>(out + (long long)row * ldo);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  const uint4* bv = reinterpret_cast<const uint4*>(b);
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i++) {
+    const int vi = lane + (i << 5);
+    if (vi >= nvec) continue;
+    float wf[8], o[8];
+    unpack8(wv[vi], wf);
+    if (RMS) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = wf[j] * bf16_round(v[i][j] * rstd);
+    } else {
+      float bf[8];
+      unpack8(bv[vi], bf);
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = (v[i][j] - mean) * rstd * wf[j] + bf[j];
+    }
+    orow[vi] = pack8(o);
+  }
+}
+
+template <bool RMS>
+static int launch_norm(const void* x, long long ldx, const void* w, const void* b, void* out, long long ldo,
+                       int M, int D, float eps, cudaStream_t st) {
+  const int per_lane = (D / 8 + 31) / 32;
+  const dim3 grid((M + 7) / 8);
+#define G4R_NORM_CASE(PL)                                                                              \
+  norm_rows_bf16<RMS, PL><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,   \
+                                                 (const __nv_bfloat16*)b, (__nv_bfloat16*)out, ldo, M, D, eps)
+  if (per_lane <= 1) G4R_NORM_CASE(1);
+  else if (per_lane <= 2) G4R_NORM_CASE(2);
+  else if (per_lane <= 4) G4R_NORM_CASE(4);
+  else if (per_lane <= 8) G4R_NORM_CASE(8);
+  else if (per_lane <= 16) G4R_NORM_CASE(16);
+  else G4R_NORM_CASE(32);
+#undef G4R_NORM_CASE
+  G4R_LAUNCH_CHECK(RMS ? "rmsnorm" : "layernorm");
+  return G4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Rotary embedding, in place on the q and k parts of a packed [rows, (q|k|v)] buffer.
+// transformers modeling_llama.py:138-168: q*cos + rotate_half(q)*sin with cos/sin already cast
+// to bf16; each bf16 tensor op rounds, so: out = bf16( bf16(q*cos) + bf16(rot*sin) ).
+// cos/sin: bf16 tables [L, head_dim] (computed on the host exactly as LlamaRotaryEmbedding does).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rope_inplace_bf16(__nv_bfloat16* __restrict__ qkv, long long ld, const __nv_bfloat16* __restrict__ cos_t,
+                  const __nv_bfloat16* __restrict__ sin_t, int rows, int L, int n_heads_qk, int head_dim) {
+  const int half = head_dim >> 1;
+  const long long total = (long long)rows * n_heads_qk * half;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % half);
+    const int h = (int)((i / half) % n_heads_qk);
+    const long long r = i / ((long long)half * n_heads_qk);
+    const int pos = (int)(r % L);
+    __nv_bfloat16* p = qkv + r * ld + (long long)h * head_dim;
+    const float x1 = __bfloat162float(p[d]), x2 = __bfloat162float(p[d + half]);
+    const float c1 = __bfloat162float(cos_t[(long long)pos * head_dim + d]);
+    const float s1 = __bfloat162float(sin_t[(long long)pos * head_dim + d]);
+    const float c2 = __bfloat162float(cos_t[(long long)pos * head_dim + d + half]);
+    const float s2 = __bfloat162float(sin_t[(long long)pos * head_dim + d + half]);
+    // rotate_half(x) = cat(-x2, x1)
+    const float o1 = bf16_round(x1 * c1) + bf16_round(-x2 * s1);
+    const float o2 = bf16_round(x2 * c2) + bf16_round(x1 * s2);
+    p[d] = __float2bfloat16_rn(o1);
+    p[d + half] = __float2bfloat16_rn(o2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CLIP patchify: images [B,3,S,S] (bf16, NCHW) -> rows [B*P, Kpad], column (c*ps+ky)*ps+kx
+// (the flatten order of the patch_embedding conv weight [hidden,3,ps,ps]); columns >= 3*ps*ps
+// are zero.  transformers modeling_clip.py:148-154,209-216 (Conv2d stride=patch, no bias).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patchify_bf16(const __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int ps,
+              int Kpad) {
+  const int G = S / ps;
+  const long long total = (long long)B * G * G * Kpad;
+  const int kreal = 3 * ps * ps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % Kpad);
+    const long long prow = i / Kpad;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (col < kreal) {
+      const int kx = col % ps, ky = (col / ps) % ps, c = col / (ps * ps);
+      const int px = (int)(prow % G), py = (int)((prow / G) % G);
+      const int b = (int)(prow / ((long long)G * G));
+      v = img[(((long long)b * 3 + c) * S + (py * ps + ky)) * S + px * ps + kx];
+    }
+    out[i] = v;
+  }
+}
+
+// x[b,0,:] = cls + pos[0]; x[b,1+p,:] = patch[b,p,:] + pos[1+p]  (modeling_clip.py:209-216)
+__global__ void __launch_bounds__(256)
+vit_embed_bf16(const __nv_bfloat16* __restrict__ patch, const __nv_bfloat16* __restrict__ cls,
+               const __nv_bfloat16* __restrict__ pos, __nv_bfloat16* __restrict__ out, int B, int P, int D) {
+  const int nvec = D >> 3;
+  const long long total = (long long)B * (P + 1) * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int t = (int)((i / nvec) % (P + 1));
+    const int b = (int)(i / ((long long)nvec * (P + 1)));
+    float a[8], pz[8], o[8];
+    if (t == 0) unpack8(reinterpret_cast<const uint4*>(cls)[v], a);
+    else unpack8(reinterpret_cast<const uint4*>(patch + ((long long)b * P + t - 1) * D)[v], a);
+    unpack8(reinterpret_cast<const uint4*>(pos + (long long)t * D)[v], pz);
+#pragma unroll
+    for (int j = 0; j < 8; j++) o[j] = a[j] + pz[j];
+    reinterpret_cast<uint4*>(out + ((long long)b * (P + 1) + t) * D)[v] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bilinear resampling helpers, align_corners=True (ATen upsample_bilinear2d):
+//   scale = (in-1)/(out-1) (0 if out==1); src = scale*dst; i0=(int)src; i1=i0+(i0<in-1); l1=src-i0
+// ------------------------------------------------------------------------------------------
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_ac(int dst, int in, int out) {
+  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  const float src = scale * dst;
+  Lerp r;
+  r.i0 = (int)src;
+  if (r.i0 > in - 1) r.i0 = in - 1;
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l1 = src - r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+// ViT tokens -> pyramid level input (gpt4roi/models/layers.py:219-232 + :117-126,185-188):
+//   tokens [B, G*G, C] (row stride ldt, batch stride bst; CLS already skipped by the caller) are the
+//   NHWC map [B,G,G,C]; resize to [B,Ho,Ho,C] (bf16 out, fp32 math), append x = linspace(-1,1,Wo)[xo],
+//   y = linspace(-1,1,Ho)[yo] as channels C, C+1 (bf16-rounded, as autocast does at the conv input)
+//   and zero-pad to Cpad channels (K of the following 1x1-conv GEMM must be a multiple of 8).
+__global__ void __launch_bounds__(256)
+upsample_tokens_coords_bf16(const __nv_bfloat16* __restrict__ tok, long long ldt, long long bst,
+                            __nv_bfloat16* __restrict__ out, int B, int G, int Ho, int C, int Cpad) {
+  const int nvec = Cpad >> 3;
+  const long long total = (long long)B * Ho * Ho * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int xo = (int)((i / nvec) % Ho);
+    const int yo = (int)((i / ((long long)nvec * Ho)) % Ho);
+    const int b = (int)(i / ((long long)nvec * Ho * Ho));
+    float o[8];
+    if (v * 8 < C) {
+      const Lerp ly = lerp_ac(yo, G, Ho), lx = lerp_ac(xo, G, Ho);
+      const __nv_bfloat16* base = tok + (long long)b * bst + v * 8;
+      float a[8], bb[8], c[8], d[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ly.i0 * G + lx.i0) * ldt), a);
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ly.i0 * G + lx.i1) * ldt), bb);
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ly.i1 * G + lx.i0) * ldt), c);
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ly.i1 * G + lx.i1) * ldt), d);
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * bb[j]) + ly.l1 * (lx.l0 * c[j] + lx.l1 * d[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = 0.f;
+      if (v * 8 == C) {
+        // torch.linspace(-1, 1, n): start + i*step for i < n/2, end - (n-1-i)*step otherwise
+        const float step = Ho > 1 ? 2.f / (float)(Ho - 1) : 0.f;
+        o[0] = xo < Ho / 2 ? -1.f + step * xo : 1.f - step * (Ho - 1 - xo);
+        o[1] = yo < Ho / 2 ? -1.f + step * yo : 1.f - step * (Ho - 1 - yo);
+      }
+    }
+    reinterpret_cast<uint4*>(out + (((long long)b * Ho + yo) * Ho + xo) * Cpad)[v] = pack8(o);
+  }
+}
+
+// One level of MLVLFuseModule._single_shuffle (gpt4roi/models/layers.py:152-180): builds the conv
+// input [own[:, :C/2] | resize(top[:, 3C/4:]) | resize(down[:, C/2:3C/4])], NHWC bf16.
+// Sources are the PREVIOUS round's raw conv outputs (bf16); when sc/sh (fp32 [B,C]) are given the
+// previous round's GroupNorm+ReLU is applied to every tap first: relu(v*sc + sh) in fp32 -- i.e.
+// ConvModule's GN->ReLU (mmcv cnn/bricks/conv_module.py:196-208) is fused into this gather and the
+// resampling runs on fp32 values exactly like F.interpolate(x.to(float32), ...) at :166-175.
+struct FuseSrc {
+  const __nv_bfloat16* p;
+  const float* sc;
+  const float* sh;
+  int H;
+};
+__device__ __forceinline__ void load_act8(const FuseSrc& s, int b, int y, int x, int c0, int C, float (&f)[8]) {
+  unpack8(*reinterpret_cast<const uint4*>(s.p + (((long long)b * s.H + y) * s.H + x) * C + c0), f);
+  if (s.sc != nullptr) {
+    const float4* a = reinterpret_cast<const float4*>(s.sc + (long long)b * C + c0);
+    const float4* d = reinterpret_cast<const float4*>(s.sh + (long long)b * C + c0);
+    const float4 a0 = a[0], a1 = a[1], d0 = d[0], d1 = d[1];
+    const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = fmaxf(f[j] * aa[j] + dd[j], 0.f);
+  }
+}
+__global__ void __launch_bounds__(256)
+fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restrict__ out, int B, int C) {
+  const int H = own.H;
+  const int nvec = C >> 3;
+  const int q = C >> 2;  // shuffle_channels = C/4; remain = C/2
+  const long long total = (long long)B * H * H * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int x = (int)((i / nvec) % H);
+    const int y = (int)((i / ((long long)nvec * H)) % H);
+    const int b = (int)(i / ((long long)nvec * H * H));
+    const int c = v * 8;
+    float o[8];
+    if (c < 2 * q) {
+      load_act8(own, b, y, x, c, C, o);
+    } else {
+      // out channels [C/2, 3C/4) <- top[:, 3C/4 + j]; [3C/4, C) <- down[:, C/2 + j]
+      const bool from_top = c < 3 * q;
+      const FuseSrc& s = from_top ? top : down;
+      const int sc0 = from_top ? c + q : c - q;
+      if (s.H == H) {
+        load_act8(s, b, y, x, sc0, C, o);  // same-size resize is the identity
+      } else {
+        const Lerp ly = lerp_ac(y, s.H, H), lx = lerp_ac(x, s.H, H);
+        float a[8], bb[8], cc[8], d[8];
+        load_act8(s, b, ly.i0, lx.i0, sc0, C, a);
+        load_act8(s, b, ly.i0, lx.i1, sc0, C, bb);
+        load_act8(s, b, ly.i1, lx.i0, sc0, C, cc);
+        load_act8(s, b, ly.i1, lx.i1, sc0, C, d);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * bb[j]) + ly.l1 * (lx.l0 * cc[j] + lx.l1 * d[j]);
+      }
+    }
+    reinterpret_cast<uint4*>(out + (((long long)b * H + y) * H + x) * C)[v] = pack8(o);
+  }
+}
+
+// GroupNorm finalisation: stats [B,groups,2] (sum, sumsq over H*W*cpg elements) + gamma/beta ->
+// per-(image,channel) scale/shift so that GN(x) = x*scale + shift (eps inside the rsqrt, biased
+// variance, like torch.nn.GroupNorm).
+__global__ void gn_finalize(const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+                            const __nv_bfloat16* __restrict__ beta, float* __restrict__ scale,
+                            float* __restrict__ shift, int B, int C, int groups, float count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  const int g = c / (C / groups);
+  const float s = stats[((long long)b * groups + g) * 2], ss = stats[((long long)b * groups + g) * 2 + 1];
+  const float mean = s / count;
+  float var = ss / count - mean * mean;
+  var = var < 0.f ? 0.f : var;
+  const float rstd = rsqrtf(var + eps);
+  const float a = __bfloat162float(gamma[c]) * rstd;
+  scale[i] = a;
+  shift[i] = __bfloat162float(beta[c]) - mean * a;
+}
+
+// ------------------------------------------------------------------------------------------
+// pos_embedd (gpt4roi/models/layers.py:260-267,285): Linear(4,256) ReLU LN(256) Linear(256,1024)
+// ReLU LN(1024) on the normalised xyxy boxes.  One CTA (256 threads) per box.  Under autocast the
+// Linears run in bf16 (inputs/weights bf16, fp32 accumulate, bf16 output) and LayerNorm in fp32;
+// the output stays fp32 (it is added to flatten_linear's result in fp32, :328).
+// ------------------------------------------------------------------------------------------
+__device__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t += red[i];
+  __syncthreads();
+  return t;
+}
+__global__ void __launch_bounds__(256)
+pos_embed_mlp(const float* __restrict__ boxes, const __nv_bfloat16* __restrict__ w0,
+              const __nv_bfloat16* __restrict__ b0, const __nv_bfloat16* __restrict__ g2,
+              const __nv_bfloat16* __restrict__ be2, const __nv_bfloat16* __restrict__ w3,
+              const __nv_bfloat16* __restrict__ b3, const __nv_bfloat16* __restrict__ g5,
+              const __nv_bfloat16* __restrict__ be5, float* __restrict__ out, float eps) {
+  __shared__ float h1[256];
+  __shared__ float red[8];
+  const int k = blockIdx.x, t = threadIdx.x;
+  float bx[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) bx[j] = bf16_round(boxes[k * 4 + j]);  // autocast: input -> bf16
+  float a = __bfloat162float(b0[t]);
+#pragma unroll
+  for (int j = 0; j < 4; j++) a += bx[j] * __bfloat162float(w0[t * 4 + j]);
+  a = fmaxf(bf16_round(a), 0.f);
+  // LayerNorm(256) in fp32
+  float mean = block_sum_256(a, red) / 256.f;
+  float d = a - mean;
+  float var = block_sum_256(d * d, red) / 256.f;
+  float y = d * rsqrtf(var + eps) * __bfloat162float(g2[t]) + __bfloat162float(be2[t]);
+  h1[t] = bf16_round(y);  // next Linear's input is cast to bf16
+  __syncthreads();
+  float o[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int n = t + r * 256;
+    float acc = 0.f;
+    const uint4* wr = reinterpret_cast<const uint4*>(w3 + (long long)n * 256);
+    for (int v = 0; v < 32; v++) {
+      float wf[8];
+      unpack8(wr[v], wf);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc += wf[j] * h1[v * 8 + j];
+    }
+    acc += __bfloat162float(b3[n]);
+    o[r] = fmaxf(bf16_round(acc), 0.f);
+  }
+  float s = o[0] + o[1] + o[2] + o[3];
+  mean = block_sum_256(s, red) / 1024.f;
+  float vs = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; r++) { const float dd = o[r] - mean; vs += dd * dd; }
+  var = block_sum_256(vs, red) / 1024.f;
+  const float rstd = rsqrtf(var + eps);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int n = t + r * 256;
+    out[(long long)k * 1024 + n] = (o[r] - mean) * rstd * __bfloat162float(g5[n]) + __bfloat162float(be5[n]);
+  }
+}
+
+// t[k,:] = bf16( bf16(acc[k,:] + bias) + pos[k,:] )   (gpt4roi/models/layers.py:327-328: flatten_linear
+// output is bf16 under autocast, `+ pos_embedd` promotes to fp32, updims casts its input to bf16)
+__global__ void add_bias_pos_cast(const float* __restrict__ acc, const __nv_bfloat16* __restrict__ bias,
+                                  const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, int K, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * D) return;
+  const int c = i % D;
+  const float f = bf16_round(acc[i] + __bfloat162float(bias[c]));
+  out[i] = __float2bfloat16_rn(f + pos[i]);
+}
+
+static inline int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace g4r
+
+using namespace g4r;
+
+extern "C" int g4r_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* out,
+                                  long long ldo, int M, int D, float eps, void* stream) {
+  G4R_REQUIRE(x && w && b && out && M > 0 && D > 0 && D % 8 == 0 && D <= 8192 && ldx % 8 == 0 && ldo % 8 == 0,
+              "layernorm: bad arguments (D=%d must be a multiple of 8, <= 8192)", D);
+  return launch_norm<false>(x, ldx, w, b, out, ldo, M, D, eps, (cudaStream_t)stream);
+}
+
+extern "C" int g4r_rmsnorm_bf16(const void* x, long long ldx, const void* w, void* out, long long ldo, int M,
+                                int D, float eps, void* stream) {
+  G4R_REQUIRE(x && w && out && M > 0 && D > 0 && D % 8 == 0 && D <= 8192 && ldx % 8 == 0 && ldo % 8 == 0,
+              "rmsnorm: bad arguments (D=%d)", D);
+  return launch_norm<true>(x, ldx, w, nullptr, out, ldo, M, D, eps, (cudaStream_t)stream);
+}
+
+extern "C" int g4r_rope_inplace_bf16(void* qkv, long long ld, const void* cos_t, const void* sin_t, int rows,
+                                     int L, int n_heads_qk, int head_dim, void* stream) {
+  G4R_REQUIRE(qkv && cos_t && sin_t && rows > 0 && L > 0 && n_heads_qk > 0 && head_dim % 2 == 0, "rope: bad arguments");
+  const long long total = (long long)rows * n_heads_qk * (head_dim / 2);
+  rope_inplace_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)qkv, ld, (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, rows, L, n_heads_qk, head_dim);
+  G4R_LAUNCH_CHECK("rope");
+  return G4R_OK;
+}
+
+extern "C" int g4r_patchify_bf16(const void* img, void* out, int B, int S, int ps, int Kpad, void* stream) {
+  G4R_REQUIRE(img && out && B > 0 && S > 0 && ps > 0 && S % ps == 0 && Kpad >= 3 * ps * ps, "patchify: bad arguments");
+  const long long total = (long long)B * (S / ps) * (S / ps) * Kpad;
+  patchify_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)img, (__nv_bfloat16*)out, B, S, ps, Kpad);
+  G4R_LAUNCH_CHECK("patchify");
+  return G4R_OK;
+}
+
+extern "C" int g4r_vit_embed_bf16(const void* patch, const void* cls, const void* pos, void* out, int B, int P,
+                                  int D, void* stream) {
+  G4R_REQUIRE(patch && cls && pos && out && B > 0 && P > 0 && D % 8 == 0, "vit_embed: bad arguments");
+  const long long total = (long long)B * (P + 1) * (D / 8);
+  vit_embed_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)patch, (const __nv_bfloat16*)cls, (const __nv_bfloat16*)pos, (__nv_bfloat16*)out, B, P, D);
+  G4R_LAUNCH_CHECK("vit_embed");
+  return G4R_OK;
+}
+
+extern "C" int g4r_upsample_tokens_coords_bf16(const void* tok, long long ldt, long long bst, void* out, int B,
+                                               int G, int Ho, int C, int Cpad, void* stream) {
+  G4R_REQUIRE(tok && out && B > 0 && G > 0 && Ho > 0 && C % 8 == 0 && Cpad % 8 == 0 && Cpad >= C + 8 && ldt % 8 == 0 && bst % 8 == 0,
+              "upsample_tokens_coords: bad arguments");
+  const long long total = (long long)B * Ho * Ho * (Cpad / 8);
+  upsample_tokens_coords_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)tok, ldt, bst, (__nv_bfloat16*)out, B, G, Ho, C, Cpad);
+  G4R_LAUNCH_CHECK("upsample_tokens_coords");
+  return G4R_OK;
+}
+
+extern "C" int g4r_fuse_gather_bf16(const void* own, const float* own_sc, const float* own_sh, int H,
+                                    const void* top, const float* top_sc, const float* top_sh, int Ht,
+                                    const void* down, const float* down_sc, const float* down_sh, int Hd,
+                                    void* out, int B, int C, void* stream) {
+  G4R_REQUIRE(own && top && down && out && B > 0 && C % 32 == 0 && H > 0 && Ht > 0 && Hd > 0, "fuse_gather: bad arguments");
+  FuseSrc a{(const __nv_bfloat16*)own, own_sc, own_sh, H};
+  FuseSrc t{(const __nv_bfloat16*)top, top_sc, top_sh, Ht};
+  FuseSrc d{(const __nv_bfloat16*)down, down_sc, down_sh, Hd};
+  const long long total = (long long)B * H * H * (C / 8);
+  fuse_gather_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, t, d, (__nv_bfloat16*)out, B, C);
+  G4R_LAUNCH_CHECK("fuse_gather");
+  return G4R_OK;
+}
+
+extern "C" int g4r_gn_finalize(const float* stats, const void* gamma, const void* beta, float* scale,
+                               float* shift, int B, int C, int groups, float count, float eps, void* stream) {
+  G4R_REQUIRE(stats && gamma && beta && scale && shift && B > 0 && C > 0 && groups > 0 && C % groups == 0, "gn_finalize: bad arguments");
+  gn_finalize<<<(B * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+                                                                   scale, shift, B, C, groups, count, eps);
+  G4R_LAUNCH_CHECK("gn_finalize");
+  return G4R_OK;
+}
+
+extern "C" int g4r_pos_embed_mlp(const float* boxes, const void* w0, const void* b0, const void* g2,
+                                 const void* be2, const void* w3, const void* b3, const void* g5,
+                                 const void* be5, float* out, int K, float eps, void* stream) {
+  G4R_REQUIRE(boxes && w0 && b0 && g2 && be2 && w3 && b3 && g5 && be5 && out && K > 0, "pos_embed_mlp: bad arguments");
+  pos_embed_mlp<<<K, 256, 0, (cudaStream_t)stream>>>(boxes, (const __nv_bfloat16*)w0, (const __nv_bfloat16*)b0,
+      (const __nv_bfloat16*)g2, (const __nv_bfloat16*)be2, (const __nv_bfloat16*)w3, (const __nv_bfloat16*)b3,
+      (const __nv_bfloat16*)g5, (const __nv_bfloat16*)be5, out, eps);
+  G4R_LAUNCH_CHECK("pos_embed_mlp");
+  return G4R_OK;
+}
+
+extern "C" int g4r_add_bias_pos_cast(const float* acc, const void* bias, const float* pos, void* out, int K, int D,
+                                     void* stream) {
+  G4R_REQUIRE(acc && bias && pos && out && K > 0 && D > 0, "add_bias_pos_cast: bad arguments");
+  add_bias_pos_cast<<<(K * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(acc, (const __nv_bfloat16*)bias, pos, (__nv_bfloat16*)out, K, D);
+  G4R_LAUNCH_CHECK("add_bias_pos_cast");
+  return G4R_OK;
+}

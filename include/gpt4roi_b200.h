@@ -182,6 +182,61 @@ int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y,
                        const void* bias, int bias_f32, int act,
                        float* gn_stats, int gn_groups, void* stream);
 
+/* ---- fused attention ------------------------------------------------------- */
+/*
+ * out[b,i,h,:] = softmax_j( bf16(bf16(q_i.k_j) * scale) [+ causal mask] ) . v_j
+ * q/k/v: bf16, element (b, token, head h, d) at  base + b*bs + token*ld + h*head_dim + d
+ * (so the packed [B,L,(q|k|v)] output of the QKV GEMM is read in place); out likewise with
+ * ldo/bso.  head_dim 64 (CLIP-ViT-L/14) or 128 (LLaMA-7B).  Replaces transformers'
+ * eager_attention_forward (modeling_clip.py / modeling_llama.py:199-222), third party to the
+ * reference (pyproject.toml:19).
+ */
+int g4r_attention_bf16(const void* q, const void* k, const void* v, void* out,
+                       long long ld, long long bs, long long ldo, long long bso,
+                       int B, int H, int L, int head_dim, int causal, float scale,
+                       void* stream);
+
+/* ---- HBM-bound glue (csrc/elementwise.cu); bf16 rows, fp32 math ------------- */
+/* nn.LayerNorm over the last dim (CLIP layer norms; gpt4roi/models/layers.py:263,266). */
+int g4r_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b,
+                       void* out, long long ldo, int M, int D, float eps, void* stream);
+/* LlamaRMSNorm: w * bf16(x * rsqrt(mean(x^2)+eps))  (transformers modeling_llama.py:53-67). */
+int g4r_rmsnorm_bf16(const void* x, long long ldx, const void* w,
+                     void* out, long long ldo, int M, int D, float eps, void* stream);
+/* apply_rotary_pos_emb in place on the first n_heads_qk heads of each packed row
+ * (modeling_llama.py:138-168); cos/sin bf16 [L, head_dim]; position = row % L. */
+int g4r_rope_inplace_bf16(void* qkv, long long ld, const void* cos_t, const void* sin_t,
+                          int rows, int L, int n_heads_qk, int head_dim, void* stream);
+/* CLIP patchify (im2col of the stride-14 patch_embedding conv, modeling_clip.py:148-154):
+ * img bf16 [B,3,S,S] -> out bf16 [B*(S/ps)^2, Kpad], column (c*ps+ky)*ps+kx, zero padded. */
+int g4r_patchify_bf16(const void* img, void* out, int B, int S, int ps, int Kpad, void* stream);
+/* [CLS | patches] + position_embedding  (modeling_clip.py:209-216). */
+int g4r_vit_embed_bf16(const void* patch, const void* cls, const void* pos, void* out,
+                       int B, int P, int D, void* stream);
+/* ViT tokens [B,G*G,C] (row stride ldt, batch stride bst) -> bilinear align_corners resize to
+ * [B,Ho,Ho,Cpad] NHWC with the two coordinate channels appended and zero padding
+ * (gpt4roi/models/layers.py:219-232 + :117-126,185-188). */
+int g4r_upsample_tokens_coords_bf16(const void* tok, long long ldt, long long bst, void* out,
+                                    int B, int G, int Ho, int C, int Cpad, void* stream);
+/* One level of MLVLFuseModule._single_shuffle (layers.py:152-180): out = [own[:, :C/2] |
+ * resize(top[:, 3C/4:]) | resize(down[:, C/2:3C/4])]; optional per-(image,channel) scale/shift
+ * (fp32 [B,C]) apply the previous round's GroupNorm+ReLU to every tap first. */
+int g4r_fuse_gather_bf16(const void* own, const float* own_sc, const float* own_sh, int H,
+                         const void* top, const float* top_sc, const float* top_sh, int Ht,
+                         const void* down, const float* down_sc, const float* down_sh, int Hd,
+                         void* out, int B, int C, void* stream);
+/* GroupNorm statistics -> per-(image,channel) scale/shift (torch.nn.GroupNorm semantics). */
+int g4r_gn_finalize(const float* stats, const void* gamma, const void* beta,
+                    float* scale, float* shift, int B, int C, int groups,
+                    float count, float eps, void* stream);
+/* pos_embedd MLP of MlvlRoIExtractor (layers.py:260-267,285): boxes fp32 [K,4] -> fp32 [K,1024]. */
+int g4r_pos_embed_mlp(const float* boxes, const void* w0, const void* b0, const void* g2,
+                      const void* be2, const void* w3, const void* b3, const void* g5,
+                      const void* be5, float* out, int K, float eps, void* stream);
+/* out = bf16( bf16(acc + bias) + pos )  (layers.py:327-328). acc fp32 [K,D], pos fp32 [K,D]. */
+int g4r_add_bias_pos_cast(const float* acc, const void* bias, const float* pos, void* out,
+                          int K, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
