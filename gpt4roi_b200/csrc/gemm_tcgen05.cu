@@ -53,6 +53,7 @@ struct GemmParams {
   int conv;
   int cH, cW, cBH, cBW, tiles_x, tiles_y, cin_blocks, taps;  // taps = 9 (3x3) or 1
   int a_rows;            // rows delivered by the A box (<= 128)
+  int levels, lvl_img_stride;  // conv: sum over `levels` inputs (image index + lvl*stride), K concatenated
   float* gn_stats;       // optional [n_img, groups, 2] (sum, sumsq) of the bf16-rounded output
   int gn_group_ch;       // channels per group (16)
   int gn_groups;         // groups per image (64)
@@ -142,10 +143,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           ptx::mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_rows * kBlockK * 2 + Cfg::kBBytes));
           const int kg = kb0 + kb;
           if (CONV) {
-            const int tap = kg / p.cin_blocks, cc = kg % p.cin_blocks;
+            const int tap_all = kg / p.cin_blocks, cc = kg % p.cin_blocks;
+            const int lvl = tap_all / p.taps, tap = tap_all % p.taps;
             const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
             ptx::tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], cc * kBlockK, x0 + dx,
-                             y0 + dy, img);
+                             y0 + dy, img + lvl * p.lvl_img_stride);
           } else {
             ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], kg * kBlockK,
                              m_blk * kBlockM);
@@ -467,13 +469,14 @@ extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long l
 }
 
 extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_img, int H, int W, int Cin,
-                                  int Cout, int ksize, const void* bias, int bias_f32, int act,
+                                  int Cout, int ksize, int levels, const void* bias, int bias_f32, int act,
                                   float* gn_stats, int gn_groups, void* stream) {
   G4R_REQUIRE(X && Wt && Y, "null operand");
   G4R_REQUIRE(ksize == 3 || ksize == 1, "ksize=%d (1 or 3)", ksize);
   G4R_REQUIRE(Cin % kBlockK == 0, "Cin=%d must be a multiple of 64", Cin);
   G4R_REQUIRE(Cout % 8 == 0, "Cout=%d must be a multiple of 8", Cout);
   G4R_REQUIRE(n_img > 0 && H > 0 && W > 0, "bad sizes");
+  G4R_REQUIRE(levels >= 1 && levels <= 8, "levels=%d", levels);
   G4R_REQUIRE(act == ACT_NONE || act == ACT_RELU, "conv epilogue: none or relu");
   if (gn_stats) G4R_REQUIRE(gn_groups > 0 && Cout % gn_groups == 0 && Cout / gn_groups == 16, "GN stats need 16-channel groups");
   GemmParams p{};
@@ -486,11 +489,12 @@ extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_
   p.tiles_x = (W + bw - 1) / bw;
   p.tiles_y = (H + bh - 1) / bh;
   p.a_rows = bw * bh;
-  p.M = n_img * H * W; p.N = Cout; p.K = ksize * ksize * Cin;
+  p.M = n_img * H * W; p.N = Cout; p.K = levels * ksize * ksize * Cin;
+  p.levels = levels; p.lvl_img_stride = n_img;
   p.num_m_tiles = n_img * p.tiles_x * p.tiles_y;
   p.cin_blocks = Cin / kBlockK;
   p.taps = ksize * ksize;
-  p.num_k_blocks = p.taps * p.cin_blocks;
+  p.num_k_blocks = levels * p.taps * p.cin_blocks;
   p.k_splits = 1;
   p.D = Y; p.ldd = Cout; p.bias = bias; p.bias_f32 = bias_f32; p.act = act;
   p.conv = 1;
@@ -499,7 +503,7 @@ extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_
   p.num_n_tiles = (Cout + bn - 1) / bn;
   CUtensorMap ta, tb;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img * levels};
     cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
     cuuint32_t box[4] = {kBlockK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     int rc = make_tmap(&ta, X, 4, dims, str, box);

@@ -60,7 +60,7 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out
 
 
-def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None):
+def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None, levels=1):
     """NHWC conv, stride 1, 'same' padding.  x [N,H,W,Cin] bf16; weight_khwc [Cout,kh,kw,Cin] bf16.
 
     gn_stats: optional fp32 [N, groups, 2] (zeroed by the caller) accumulating sum / sumsq of the
@@ -69,7 +69,14 @@ def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None):
     dev = _L.require_cuda_same_device([('x', x), ('weight', weight_khwc), ('bias', bias), ('gn_stats', gn_stats)])
     _L.require_contiguous([('x', x), ('weight', weight_khwc)])
     n, h, w, cin = x.shape
-    cout, kh, kw, cin2 = weight_khwc.shape
+    if levels > 1:
+        # x [levels*n,H,W,Cin] level-major; weight [Cout, levels, k, k, Cin]: sum of `levels` convs
+        cout, lv, kh, kw, cin2 = weight_khwc.shape
+        if lv != levels or n % levels:
+            raise RuntimeError('conv_nhwc: levels mismatch')
+        n //= levels
+    else:
+        cout, kh, kw, cin2 = weight_khwc.shape
     if kh != kw or kh not in (1, 3) or cin2 != cin:
         raise RuntimeError('conv_nhwc: weight must be [Cout,k,k,Cin] with k in (1,3)')
     if x.dtype != torch.bfloat16 or weight_khwc.dtype != torch.bfloat16:
@@ -84,6 +91,6 @@ def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None):
         groups = gn_stats.shape[1]
     with torch.cuda.device(dev):
         _L.check(_L.load().g4r_conv_nhwc_bf16(
-            _L.ptr(x), _L.ptr(weight_khwc), _L.ptr(out), n, h, w, cin, cout, kh, _L.ptr(bias), bias_f32,
+            _L.ptr(x), _L.ptr(weight_khwc), _L.ptr(out), n, h, w, cin, cout, kh, int(levels), _L.ptr(bias), bias_f32,
             ACT[act], _L.ptr(gn_stats), groups, _L.stream_ptr(dev)))
     return out

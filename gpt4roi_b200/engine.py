@@ -1,0 +1,331 @@
+"""Region-token prefill engine: CLIP-ViT-L/14 -> MLVL fuse -> multi-level RoIAlign -> region
+projector -> splice -> LLaMA prefill -> lm_head, every op a hand-written sm_100a kernel behind
+the C ABI.  PyTorch supplies device memory, streams and CUDA-graph capture only.
+
+Reference call stack reproduced:
+  gpt4roi/models/spi_llava.py:23-205   SPILlavaLlamaModel.forward
+  gpt4roi/models/layers.py:182-195     MLVLFuseModule.forward
+  gpt4roi/models/layers.py:218-236     MLVLROIQueryModule.forward
+  gpt4roi/models/layers.py:280-335     MlvlRoIExtractor.forward
+  llava/model/llava.py:203-261         LlavaLlamaForCausalLM.forward (lm_head)
+  transformers CLIPVisionModel / LlamaModel (third party, pyproject.toml:19)
+
+Weights come in with the reference's parameter names and are re-laid-out
+ONCE at load time (fused QKV, interleaved gate/up, NHWC conv filters, flatten_linear permuted
+from (c,ph,pw) to (ph,pw,c)).  Numerics: bf16 storage, fp32 accumulation, rounding points of the
+reference under bf16 autocast.
+"""
+import math
+
+import torch
+
+from . import dense, kernels
+from .roi_align import roi_align_mlvl
+from .splice import splice_region_tokens
+
+BF16 = torch.bfloat16
+
+
+class EngineConfig:
+    def __init__(self, image_size=336, patch_size=14, vit_hidden=1024, vit_heads=16, vit_layers=24,
+                 vit_mlp=4096, vit_eps=1e-5, select_layer=-2, num_levels=4,
+                 hidden=4096, n_heads=32, n_layers=32, mlp=11008, vocab=32006, rms_eps=1e-6,
+                 rope_theta=10000.0, roi_out=14, roi_sampling=2, spi_dim=1024, gn_groups=64,
+                 im_patch_token=32001, bbox_token=32002, im_start_token=32004, im_end_token=32005):
+        self.__dict__.update(locals())
+        del self.__dict__['self']
+        self.grid = image_size // patch_size
+        self.num_patches = self.grid ** 2
+        self.head_dim = hidden // n_heads
+        self.vit_head_dim = vit_hidden // vit_heads
+        self.strides = [patch_size / 8, patch_size / 4, patch_size / 2, patch_size][-num_levels:] \
+            if num_levels <= 4 else None
+        self.level_sizes = [self.grid * 2 ** (num_levels - 1 - l) for l in range(num_levels)]
+        # spi_llava.py:68-82: hidden_states[select::-3][::-1][-num_levels:]
+        sel = select_layer if select_layer >= 0 else vit_layers + 1 + select_layer
+        lv = list(range(sel, -1, -3))[::-1][-num_levels:]
+        self.select_index = sel
+        self.level_layers = lv
+
+
+def _b(t, dev):
+    return t.detach().to(device=dev, dtype=BF16).contiguous()
+
+
+class PrefillEngine:
+    """Holds re-laid-out weights on one GPU and runs the fused forward."""
+
+    def __init__(self, cfg, llm_sd, vit_sd, device):
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self._prepare_vit(vit_sd)
+        self._prepare_spi(llm_sd)
+        self._prepare_llm(llm_sd)
+        self._rope_cache = {}
+
+    # ------------------------------------------------------------------ weight preparation
+    def _prepare_vit(self, sd):
+        c, dev = self.cfg, self.dev
+        p = 'vision_model.'
+        kreal = 3 * c.patch_size ** 2
+        self.vit_kpad = (kreal + 7) // 8 * 8
+        w = sd[p + 'embeddings.patch_embedding.weight'].reshape(c.vit_hidden, kreal)
+        wp = torch.zeros(c.vit_hidden, self.vit_kpad, dtype=BF16, device=dev)
+        wp[:, :kreal] = w.to(dev, BF16)
+        self.vit_patch_w = wp
+        self.vit_cls = _b(sd[p + 'embeddings.class_embedding'], dev)
+        self.vit_pos = _b(sd[p + 'embeddings.position_embedding.weight'], dev)
+        self.vit_pre_ln = (_b(sd[p + 'pre_layrnorm.weight'], dev), _b(sd[p + 'pre_layrnorm.bias'], dev))
+        self.vit_layers = []
+        for i in range(c.select_index):  # layers beyond the selected hidden state are dead work
+            q = p + 'encoder.layers.%d.' % i
+            wqkv = torch.cat([sd[q + 'self_attn.%s_proj.weight' % n] for n in 'qkv'], 0)
+            bqkv = torch.cat([sd[q + 'self_attn.%s_proj.bias' % n] for n in 'qkv'], 0)
+            self.vit_layers.append(dict(
+                ln1=(_b(sd[q + 'layer_norm1.weight'], dev), _b(sd[q + 'layer_norm1.bias'], dev)),
+                wqkv=_b(wqkv, dev), bqkv=_b(bqkv, dev),
+                wo=_b(sd[q + 'self_attn.out_proj.weight'], dev), bo=_b(sd[q + 'self_attn.out_proj.bias'], dev),
+                ln2=(_b(sd[q + 'layer_norm2.weight'], dev), _b(sd[q + 'layer_norm2.bias'], dev)),
+                w1=_b(sd[q + 'mlp.fc1.weight'], dev), b1=_b(sd[q + 'mlp.fc1.bias'], dev),
+                w2=_b(sd[q + 'mlp.fc2.weight'], dev), b2=_b(sd[q + 'mlp.fc2.bias'], dev)))
+
+    def _prepare_spi(self, sd):
+        c, dev = self.cfg, self.dev
+        p = 'model.spi_module.'
+        C = c.spi_dim
+        self.spi_cpad = (C + 2 + 63) // 64 * 64  # 1026 -> 1088
+        self.in_w, self.in_b = [], []
+        for l in range(c.num_levels):
+            w = sd[p + 'mlvl_fuse.input_conv.%d.weight' % l].reshape(C, C + 2)
+            wp = torch.zeros(C, self.spi_cpad, dtype=BF16, device=dev)
+            wp[:, :C + 2] = w.to(dev, BF16)
+            self.in_w.append(wp)
+            self.in_b.append(_b(sd[p + 'mlvl_fuse.input_conv.%d.bias' % l], dev))
+        self.fuse = []
+        for r in range(5):
+            q = p + 'mlvl_fuse.fuse_convs.%d.' % r
+            w = sd[q + 'conv.weight'].to(dev, BF16).permute(0, 2, 3, 1).contiguous()  # [Cout,kh,kw,Cin]
+            self.fuse.append(dict(w=w, gamma=_b(sd[q + 'gn.weight'], dev), beta=_b(sd[q + 'gn.bias'], dev)))
+        q = p + 'roi_align.'
+        pw = torch.stack([sd[q + 'pconvs.%d.weight' % l].to(dev, BF16).permute(0, 2, 3, 1)
+                          for l in range(c.num_levels)], 1).contiguous()  # [Cout, L, kh, kw, Cin]
+        self.pconv_w = pw
+        self.pconv_b = sum(sd[q + 'pconvs.%d.bias' % l].to(dev, torch.float32) for l in range(c.num_levels)).contiguous()
+        R = c.roi_out
+        fw = sd[q + 'flatten_linear.weight']  # [1024, C*R*R] in (c, ph, pw) order (layers.py:326)
+        self.flat_w = fw.to(dev, BF16).reshape(-1, C, R, R).permute(0, 2, 3, 1).reshape(fw.shape[0], -1).contiguous()
+        self.flat_b = _b(sd[q + 'flatten_linear.bias'], dev)
+        self.pos = [_b(sd[q + 'pos_embedd.%s' % n], dev) for n in
+                    ('0.weight', '0.bias', '2.weight', '2.bias', '3.weight', '3.bias', '5.weight', '5.bias')]
+        self.up_w, self.up_b = _b(sd[q + 'updims.weight'], dev), _b(sd[q + 'updims.bias'], dev)
+        self.proj_w, self.proj_b = _b(sd['model.mm_projector.weight'], dev), _b(sd['model.mm_projector.bias'], dev)
+        kb = self.flat_w.shape[1] // 64
+        self.flat_splits = next(s for s in (16, 14, 8, 7, 4, 2, 1) if kb % s == 0)
+
+    def _prepare_llm(self, sd):
+        c, dev = self.cfg, self.dev
+        self.embed = _b(sd['model.embed_tokens.weight'], dev)
+        self.layers = []
+        for i in range(c.n_layers):
+            q = 'model.layers.%d.' % i
+            wqkv = torch.cat([sd[q + 'self_attn.%s_proj.weight' % n].to(dev, BF16) for n in 'qkv'], 0).contiguous()
+            g, u = sd[q + 'mlp.gate_proj.weight'].to(dev, BF16), sd[q + 'mlp.up_proj.weight'].to(dev, BF16)
+            wgu = torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]).contiguous()  # rows: g0,u0,g1,u1,...
+            self.layers.append(dict(
+                ln_in=_b(sd[q + 'input_layernorm.weight'], dev), wqkv=wqkv,
+                wo=_b(sd[q + 'self_attn.o_proj.weight'], dev),
+                ln_post=_b(sd[q + 'post_attention_layernorm.weight'], dev), wgu=wgu,
+                wdown=_b(sd[q + 'mlp.down_proj.weight'], dev)))
+            del g, u
+        self.norm_w = _b(sd['model.norm.weight'], dev)
+        self.lm_head = _b(sd['lm_head.weight'], dev)
+        self.vocab_pad = (c.vocab + 63) // 64 * 64
+
+    def _rope(self, L):
+        """cos/sin tables exactly as LlamaRotaryEmbedding (modeling_llama.py:118-135): fp32 then bf16."""
+        if L not in self._rope_cache:
+            c = self.cfg
+            inv = 1.0 / (c.rope_theta ** (torch.arange(0, c.head_dim, 2, dtype=torch.int64).float() / c.head_dim))
+            freqs = torch.arange(L, dtype=torch.float32)[:, None] * inv[None, :]
+            emb = torch.cat((freqs, freqs), -1)
+            self._rope_cache[L] = (emb.cos().to(self.dev, BF16).contiguous(), emb.sin().to(self.dev, BF16).contiguous())
+        return self._rope_cache[L]
+
+    # ------------------------------------------------------------------ stages
+    def vit(self, images):
+        """images bf16 [B,3,S,S] -> dict{layer index: hidden state [B,P+1,C]} for the consumed layers."""
+        c = self.cfg
+        B = images.shape[0]
+        P, T = c.num_patches, c.num_patches + 1
+        patches = kernels.patchify(images, c.patch_size, self.vit_kpad)
+        pe = dense.linear(patches, self.vit_patch_w)
+        x = kernels.vit_embed(pe, self.vit_cls, self.vit_pos, B, P)
+        x = kernels.layernorm(x, *self.vit_pre_ln, eps=c.vit_eps).view(B * T, c.vit_hidden)
+        taps = {}
+        scale = c.vit_head_dim ** -0.5
+        for i, w in enumerate(self.vit_layers):
+            h = kernels.layernorm(x, *w['ln1'], eps=c.vit_eps)
+            qkv = dense.linear(h, w['wqkv'], w['bqkv'])
+            a = kernels.attention(qkv, B, T, c.vit_heads, c.vit_head_dim, False, scale)
+            x = dense.linear(a, w['wo'], w['bo'], residual=x)
+            h = kernels.layernorm(x, *w['ln2'], eps=c.vit_eps)
+            f = dense.linear(h, w['w1'], w['b1'], act='quick_gelu')
+            x = dense.linear(f, w['w2'], w['b2'], residual=x)
+            if (i + 1) in c.level_layers:
+                taps[i + 1] = x.view(B, T, c.vit_hidden)
+        return taps
+
+    def fuse_maps(self, taps):
+        """MLVLROIQueryModule upsampling + MLVLFuseModule: returns the last round's raw conv outputs
+        (bf16 NHWC) and the per-(image,channel) GroupNorm scale/shift still to be applied."""
+        c = self.cfg
+        C = c.spi_dim
+        B = next(iter(taps.values())).shape[0]
+        maps = []
+        for l, layer in enumerate(c.level_layers):
+            H = c.level_sizes[l]
+            up = kernels.upsample_tokens_coords(taps[layer], c.grid, H, self.spi_cpad)
+            m = dense.linear(up.view(-1, self.spi_cpad), self.in_w[l], self.in_b[l]).view(B, H, H, C)
+            maps.append(m)
+        ss = [None] * c.num_levels
+        n = c.num_levels
+        for r in range(5):
+            new, stats = [], []
+            for l in range(n):
+                top, down = min(l + 1, n - 1), max(l - 1, 0)
+                x_in = kernels.fuse_gather(maps[l], maps[top], maps[down], ss[l], ss[top], ss[down])
+                st = torch.zeros((B, c.gn_groups, 2), dtype=torch.float32, device=self.dev)
+                new.append(dense.conv_nhwc(x_in, self.fuse[r]['w'], gn_stats=st))
+                stats.append(st)
+            maps = new
+            ss = [kernels.gn_finalize(stats[l], self.fuse[r]['gamma'], self.fuse[r]['beta'],
+                                      count=c.level_sizes[l] ** 2 * (C // c.gn_groups)) for l in range(n)]
+        return maps, ss
+
+    def region_tokens(self, maps, ss, boxes, batch_idx):
+        """MlvlRoIExtractor.forward: boxes fp32 [K,4] normalised xyxy, batch_idx fp32 [K] -> [K,hidden]."""
+        c = self.cfg
+        K = boxes.shape[0]
+        rois = torch.cat([batch_idx[:, None], boxes * float(c.image_size)], 1).contiguous()  # layers.py:294-302
+        scales = [float(torch.tensor(1.0 / s, dtype=torch.float32)) for s in c.strides]
+        feats = roi_align_mlvl(maps, rois, c.roi_out, scales, c.roi_sampling, True, out_dtype=BF16,
+                               gn_scale=[s for s, _ in ss], gn_shift=[b for _, b in ss])
+        R = c.roi_out
+        pc = dense.conv_nhwc(feats.view(c.num_levels * K, R, R, c.spi_dim), self.pconv_w, self.pconv_b,
+                             act='relu', levels=c.num_levels)
+        acc = dense.linear(pc.view(K, -1), self.flat_w, out_dtype=torch.float32, k_splits=self.flat_splits)
+        pos = kernels.pos_embed_mlp(boxes.contiguous(), *self.pos)
+        t = kernels.add_bias_pos_cast(acc, self.flat_b, pos)
+        return dense.linear(t, self.up_w, self.up_b)
+
+    def llama(self, embeds, B, L, last_only=False):
+        c = self.cfg
+        x = embeds.view(B * L, c.hidden)
+        cos, sin = self._rope(L)
+        scale = c.head_dim ** -0.5
+        for w in self.layers:
+            h = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
+            qkv = dense.linear(h, w['wqkv'])
+            kernels.rope_inplace(qkv, cos, sin, L, 2 * c.n_heads, c.head_dim)
+            a = kernels.attention(qkv, B, L, c.n_heads, c.head_dim, True, scale)
+            x = dense.linear(a, w['wo'], residual=x)
+            h = kernels.rmsnorm(x, w['ln_post'], c.rms_eps)
+            f = dense.linear(h, w['wgu'], act='swiglu')
+            x = dense.linear(f, w['wdown'], residual=x)
+        if last_only:
+            x = x.view(B, L, c.hidden)[:, -1].contiguous()
+        x = kernels.rmsnorm(x, self.norm_w, c.rms_eps)
+        rows = x.shape[0]
+        # padded row stride keeps the epilogue's 128-bit stores aligned (vocab 32006 is not a multiple of 8)
+        buf = torch.empty((rows, self.vocab_pad), dtype=BF16, device=self.dev)
+        dense.linear(x, self.lm_head, out=buf[:, :c.vocab])
+        return buf.view(B, rows // B, self.vocab_pad)[:, :, :c.vocab]
+
+    # ------------------------------------------------------------------ whole path
+    def forward(self, input_ids, images, bboxes, validate=True, last_only=False):
+        """input_ids int64 [B,L]; images [B,3,S,S]; bboxes list (len B) of [K_i,4] normalised xyxy or
+        None.  Returns logits [B,L,V] (bf16) -- or [B,1,V] with last_only.  attention_mask is all-ones
+        (no padding) in this round."""
+        c = self.cfg
+        B, L = input_ids.shape
+        taps = self.vit(images.to(self.dev, BF16))
+        feat = taps[c.select_index][:, 1:].contiguous()  # spi_llava.py:68-73
+        img_rows = dense.linear(feat.view(-1, c.vit_hidden), self.proj_w, self.proj_b).view(B, c.num_patches, c.hidden)
+        region = None
+        if bboxes is not None and len(bboxes) > 0:
+            counts = [0 if b is None else int(b.shape[0]) for b in bboxes]
+            K = sum(counts)
+            offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()), dtype=torch.int32).to(self.dev)
+            if K > 0:
+                boxes = torch.cat([b.to(self.dev, torch.float32) for b in bboxes if b is not None and b.shape[0]], 0)
+                bidx = torch.cat([torch.full((n,), float(i)) for i, n in enumerate(counts)]).to(self.dev)
+                maps, ss = self.fuse_maps(taps)
+                rows = self.region_tokens(maps, ss, boxes, bidx)
+            else:
+                rows = torch.zeros((1, c.hidden), dtype=BF16, device=self.dev)
+            region = (rows, offs)
+        embeds = splice_region_tokens(input_ids, self.embed, img_rows, region, c.num_patches, c.im_patch_token,
+                                      c.im_start_token, c.im_end_token, c.bbox_token, validate=validate)
+        return self.llama(embeds, B, L, last_only=last_only)
+
+
+def random_state_dicts(cfg, device, seed=0, dtype=BF16):
+    """Seeded random-init weights with the reference's parameter names and init scales
+    (conv normal(0,0.01): layers.py:146-150,275-278; GN (1,0); HF defaults elsewhere).
+    Used by bench.py / tests: no checkpoints are available offline."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+
+    def rn(*shape, std=0.02):
+        return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * std).to(dtype)
+
+    C, D = cfg.vit_hidden, cfg.hidden
+    vit = {'vision_model.embeddings.class_embedding': rn(C),
+           'vision_model.embeddings.patch_embedding.weight': rn(C, 3, cfg.patch_size, cfg.patch_size),
+           'vision_model.embeddings.position_embedding.weight': rn(cfg.num_patches + 1, C),
+           'vision_model.pre_layrnorm.weight': torch.ones(C, device=device, dtype=dtype),
+           'vision_model.pre_layrnorm.bias': torch.zeros(C, device=device, dtype=dtype)}
+    for i in range(cfg.vit_layers):
+        q = 'vision_model.encoder.layers.%d.' % i
+        for n in ('q', 'k', 'v', 'out'):
+            vit[q + 'self_attn.%s_proj.weight' % n] = rn(C, C)
+            vit[q + 'self_attn.%s_proj.bias' % n] = rn(C)
+        for n in ('layer_norm1', 'layer_norm2'):
+            vit[q + n + '.weight'] = torch.ones(C, device=device, dtype=dtype)
+            vit[q + n + '.bias'] = torch.zeros(C, device=device, dtype=dtype)
+        vit[q + 'mlp.fc1.weight'], vit[q + 'mlp.fc1.bias'] = rn(cfg.vit_mlp, C), rn(cfg.vit_mlp)
+        vit[q + 'mlp.fc2.weight'], vit[q + 'mlp.fc2.bias'] = rn(C, cfg.vit_mlp), rn(C)
+    sd = {'model.embed_tokens.weight': rn(cfg.vocab, D), 'lm_head.weight': rn(cfg.vocab, D),
+          'model.norm.weight': torch.ones(D, device=device, dtype=dtype),
+          'model.mm_projector.weight': rn(D, C), 'model.mm_projector.bias': rn(D)}
+    for i in range(cfg.n_layers):
+        q = 'model.layers.%d.' % i
+        for n in ('q', 'k', 'v', 'o'):
+            sd[q + 'self_attn.%s_proj.weight' % n] = rn(D, D)
+        sd[q + 'mlp.gate_proj.weight'], sd[q + 'mlp.up_proj.weight'] = rn(cfg.mlp, D), rn(cfg.mlp, D)
+        sd[q + 'mlp.down_proj.weight'] = rn(D, cfg.mlp)
+        sd[q + 'input_layernorm.weight'] = torch.ones(D, device=device, dtype=dtype)
+        sd[q + 'post_attention_layernorm.weight'] = torch.ones(D, device=device, dtype=dtype)
+    S = cfg.spi_dim
+    p = 'model.spi_module.'
+    for l in range(cfg.num_levels):
+        sd[p + 'mlvl_fuse.input_conv.%d.weight' % l] = rn(S, S + 2, 1, 1, std=0.01)
+        sd[p + 'mlvl_fuse.input_conv.%d.bias' % l] = torch.zeros(S, device=device, dtype=dtype)
+        sd[p + 'roi_align.pconvs.%d.weight' % l] = rn(S, S, 3, 3, std=0.01)
+        sd[p + 'roi_align.pconvs.%d.bias' % l] = torch.zeros(S, device=device, dtype=dtype)
+    for r in range(5):
+        sd[p + 'mlvl_fuse.fuse_convs.%d.conv.weight' % r] = rn(S, S, 3, 3, std=0.01)
+        sd[p + 'mlvl_fuse.fuse_convs.%d.gn.weight' % r] = torch.ones(S, device=device, dtype=dtype)
+        sd[p + 'mlvl_fuse.fuse_convs.%d.gn.bias' % r] = torch.zeros(S, device=device, dtype=dtype)
+    q = p + 'roi_align.'
+    sd[q + 'pos_embedd.0.weight'], sd[q + 'pos_embedd.0.bias'] = rn(256, 4, std=0.5), rn(256, std=0.1)
+    sd[q + 'pos_embedd.2.weight'] = torch.ones(256, device=device, dtype=dtype)
+    sd[q + 'pos_embedd.2.bias'] = torch.zeros(256, device=device, dtype=dtype)
+    sd[q + 'pos_embedd.3.weight'], sd[q + 'pos_embedd.3.bias'] = rn(1024, 256, std=0.06), rn(1024, std=0.06)
+    sd[q + 'pos_embedd.5.weight'] = torch.ones(1024, device=device, dtype=dtype)
+    sd[q + 'pos_embedd.5.bias'] = torch.zeros(1024, device=device, dtype=dtype)
+    sd[q + 'updims.weight'], sd[q + 'updims.bias'] = rn(D, 1024, std=0.03), rn(D, std=0.03)
+    R = cfg.roi_out
+    sd[q + 'flatten_linear.weight'] = rn(1024, S * R * R, std=0.002)
+    sd[q + 'flatten_linear.bias'] = rn(1024, std=0.002)
+    return sd, vit

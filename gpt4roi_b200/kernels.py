@@ -1,0 +1,130 @@
+"""Torch-tensor front-ends of the elementwise / attention entry points of the C ABI
+(csrc/elementwise.cu, csrc/attention.cu).  No computation happens in Python."""
+import torch
+
+from . import lib as _L
+
+
+def _call(fn_name, dev, *args):
+    with torch.cuda.device(dev):
+        _L.check(getattr(_L.load(), fn_name)(*args, _L.stream_ptr(dev)))
+
+
+def _bf16(*ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.bfloat16:
+            raise TypeError('bf16 tensor required, got %s' % t.dtype)
+
+
+def layernorm(x, weight, bias, eps=1e-5, out=None):
+    _bf16(x, weight, bias)
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    out = torch.empty_like(x2) if out is None else out
+    _call('g4r_layernorm_bf16', x.device, _L.ptr(x2), x2.stride(0), _L.ptr(weight), _L.ptr(bias), _L.ptr(out),
+          out.stride(0), x2.shape[0], D, float(eps))
+    return out.view(x.shape) if out.is_contiguous() and out.numel() == x.numel() else out
+
+
+def rmsnorm(x, weight, eps=1e-6, out=None):
+    _bf16(x, weight)
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    out = torch.empty_like(x2) if out is None else out
+    _call('g4r_rmsnorm_bf16', x.device, _L.ptr(x2), x2.stride(0), _L.ptr(weight), _L.ptr(out), out.stride(0),
+          x2.shape[0], D, float(eps))
+    return out.view(x.shape) if out.is_contiguous() and out.numel() == x.numel() else out
+
+
+def rope_inplace(qkv, cos, sin, L, n_heads_qk, head_dim):
+    """qkv [rows, width] packed; rotates the first n_heads_qk heads of every row in place."""
+    _bf16(qkv, cos, sin)
+    _call('g4r_rope_inplace_bf16', qkv.device, _L.ptr(qkv), qkv.stride(0), _L.ptr(cos), _L.ptr(sin),
+          qkv.shape[0], int(L), int(n_heads_qk), int(head_dim))
+    return qkv
+
+
+def attention(qkv, B, L, n_heads, head_dim, causal, scale, out=None):
+    """qkv: packed bf16 [B*L, 3*n_heads*head_dim] = (q | k | v); returns [B*L, n_heads*head_dim]."""
+    _bf16(qkv)
+    hd = n_heads * head_dim
+    if out is None:
+        out = torch.empty((B * L, hd), dtype=torch.bfloat16, device=qkv.device)
+    ld = qkv.stride(0)
+    esz = 2
+    base = qkv.data_ptr()
+    import ctypes
+    q, k, v = (ctypes.c_void_p(base + i * hd * esz) for i in range(3))
+    _call('g4r_attention_bf16', qkv.device, q, k, v, _L.ptr(out), ld, L * ld, out.stride(0), L * out.stride(0),
+          B, n_heads, L, head_dim, int(bool(causal)), float(scale))
+    return out
+
+
+def patchify(images, ps, kpad):
+    _bf16(images)
+    B, _, S, _ = images.shape
+    G = S // ps
+    out = torch.empty((B * G * G, kpad), dtype=torch.bfloat16, device=images.device)
+    _call('g4r_patchify_bf16', images.device, _L.ptr(images.contiguous()), _L.ptr(out), B, S, ps, kpad)
+    return out
+
+
+def vit_embed(patch, cls, pos, B, P):
+    _bf16(patch, cls, pos)
+    D = patch.shape[-1]
+    out = torch.empty((B, P + 1, D), dtype=torch.bfloat16, device=patch.device)
+    _call('g4r_vit_embed_bf16', patch.device, _L.ptr(patch), _L.ptr(cls), _L.ptr(pos), _L.ptr(out), B, P, D)
+    return out
+
+
+def upsample_tokens_coords(hidden, G, Ho, cpad):
+    """hidden: [B, 1+G*G, C] ViT hidden state (CLS first); returns NHWC [B,Ho,Ho,cpad]."""
+    _bf16(hidden)
+    B, T, C = hidden.shape
+    assert T == G * G + 1 and hidden.is_contiguous()
+    out = torch.empty((B, Ho, Ho, cpad), dtype=torch.bfloat16, device=hidden.device)
+    import ctypes
+    tok = ctypes.c_void_p(hidden.data_ptr() + C * 2)  # skip CLS
+    _call('g4r_upsample_tokens_coords_bf16', hidden.device, tok, C, T * C, _L.ptr(out), B, G, Ho, C, cpad)
+    return out
+
+
+def fuse_gather(own, top, down, own_ss=None, top_ss=None, down_ss=None, out=None):
+    """own/top/down: NHWC bf16 [B,H,H,C]; *_ss: optional (scale, shift) fp32 [B,C] pairs."""
+    _bf16(own, top, down)
+    B, H, _, C = own.shape
+    out = torch.empty_like(own) if out is None else out
+
+    def ss(p):
+        return (None, None) if p is None else (_L.ptr(p[0]), _L.ptr(p[1]))
+    a, b, c = ss(own_ss), ss(top_ss), ss(down_ss)
+    _call('g4r_fuse_gather_bf16', own.device, _L.ptr(own), a[0], a[1], H, _L.ptr(top), b[0], b[1], top.shape[1],
+          _L.ptr(down), c[0], c[1], down.shape[1], _L.ptr(out), B, C)
+    return out
+
+
+def gn_finalize(stats, gamma, beta, count, eps=1e-5):
+    B, groups, _ = stats.shape
+    C = gamma.shape[0]
+    scale = torch.empty((B, C), dtype=torch.float32, device=stats.device)
+    shift = torch.empty_like(scale)
+    _call('g4r_gn_finalize', stats.device, _L.ptr(stats), _L.ptr(gamma), _L.ptr(beta), _L.ptr(scale),
+          _L.ptr(shift), B, C, groups, float(count), float(eps))
+    return scale, shift
+
+
+def pos_embed_mlp(boxes, w0, b0, g2, be2, w3, b3, g5, be5, eps=1e-5):
+    K = boxes.shape[0]
+    out = torch.empty((K, 1024), dtype=torch.float32, device=boxes.device)
+    if K:
+        _call('g4r_pos_embed_mlp', boxes.device, _L.ptr(boxes), _L.ptr(w0), _L.ptr(b0), _L.ptr(g2), _L.ptr(be2),
+              _L.ptr(w3), _L.ptr(b3), _L.ptr(g5), _L.ptr(be5), _L.ptr(out), K, float(eps))
+    return out
+
+
+def add_bias_pos_cast(acc, bias, pos):
+    K, D = acc.shape
+    out = torch.empty((K, D), dtype=torch.bfloat16, device=acc.device)
+    if K:
+        _call('g4r_add_bias_pos_cast', acc.device, _L.ptr(acc), _L.ptr(bias), _L.ptr(pos), _L.ptr(out), K, D)
+    return out

@@ -173,12 +173,15 @@ int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb,
  * with 4-D TMA boxes shifted by the filter tap; TMA's out-of-bounds zero fill is the padding.
  * Replaces cuDNN behind nn.Conv2d at gpt4roi/models/layers.py:129-144,191,178 (input_conv,
  * fuse_convs[i].conv) and :257-259,320-325 (pconvs).
+ * levels > 1 sums `levels` convolutions in one contraction (K concatenated): X is
+ * [levels*n_img,H,W,Cin] (level-major), Wt [Cout, levels*ks*ks*Cin]; this is
+ * sum_l pconvs[l](roi_feats[l]) of layers.py:320-325 as ONE GEMM.
  * gn_stats (optional, fp32 [n_img,gn_groups,2], pre-zeroed): accumulates per-(image,group)
  * sum and sum of squares of the bf16-rounded output -- the statistics GroupNorm(64) needs
  * (mmcv cnn/bricks/conv_module.py:196-208), so no extra pass over Y is required.
  */
 int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y,
-                       int n_img, int H, int W, int Cin, int Cout, int ksize,
+                       int n_img, int H, int W, int Cin, int Cout, int ksize, int levels,
                        const void* bias, int bias_f32, int act,
                        float* gn_stats, int gn_groups, void* stream);
 

@@ -127,3 +127,51 @@ def ref_cases():
 if __name__ == '__main__':
     kat()
     ref_cases()
+
+
+# ---------------------------------------------------------------------------------------
+# SPI module golden: the reference's MLVLROIQueryModule run UNMODIFIED (224 px) and with the three
+# literals lifted (336 px), fp32 on CPU, with seeded weights that the tests can
+# regenerate (gpt4roi_b200.engine.random_state_dicts on CPU) and seeded inputs.
+# ---------------------------------------------------------------------------------------
+def spi_inputs(image_size, B, ks, seed):
+    g = torch.Generator().manual_seed(seed)
+    G = image_size // 14
+    toks = [torch.randn(B, G * G, 1024, generator=g) for _ in range(4)]
+    boxes = []
+    for k in ks:
+        p = torch.rand(k, 2, 2, generator=g).sort(dim=1).values
+        b = torch.cat([p[:, 0, :], p[:, 1, :]], 1)
+        b[:, 2:] = torch.maximum(b[:, 2:], b[:, :2] + 2.0 / image_size).clamp(max=1.0)
+        boxes.append(b)
+    return toks, boxes
+
+
+def spi_module_golden():
+    sys.path.insert(0, HERE)
+    import ref_shims
+    from gpt4roi_b200.engine import EngineConfig, random_state_dicts
+    out = {}
+    for size, B, ks in ((224, 1, [3]), (336, 2, [2, 1])):
+        layers = ref_shims.load_layers(size)
+        cfg = EngineConfig(image_size=size, n_layers=0, vit_layers=0)
+        sd, _ = random_state_dicts(cfg, 'cpu', seed=1234, dtype=torch.float32)
+        mod = layers.MLVLROIQueryModule(embed_dims=1024, out_dims=4096, num_levels=4)
+        spi = {k[len('model.spi_module.'):]: v for k, v in sd.items() if k.startswith('model.spi_module.')}
+        missing = mod.load_state_dict(spi, strict=True)
+        mod.eval()
+        toks, boxes = spi_inputs(size, B, ks, seed=size)
+        with torch.no_grad():
+            res = mod([t.clone() for t in toks], boxes)
+        out['spi%d.out' % size] = torch.cat(res, 0).numpy()
+        out['spi%d.in_checksum' % size] = np.array([float(t.double().sum()) for t in toks] +
+                                                   [float(torch.cat(boxes).double().sum())])
+        out['spi%d.w_checksum' % size] = np.array([float(sd['model.spi_module.roi_align.flatten_linear.weight'].double().sum()),
+                                                   float(sd['model.spi_module.mlvl_fuse.fuse_convs.4.conv.weight'].double().abs().sum())])
+        print('spi golden %d: out %s' % (size, out['spi%d.out' % size].shape))
+    np.savez_compressed(os.path.join(HERE, 'spi_module_ref.npz'), **out)
+    print('wrote spi_module_ref.npz')
+
+
+if __name__ == '__main__' and '--spi' in sys.argv:
+    spi_module_golden()
