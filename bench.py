@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- GPT4RoI region-token prefill throughput on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank/GPU)
+  python bench.py --impl reference ...                     (the reference's CPU path, bounded sample)
+
+A step = one prefill of the headline workload (configs[1]): batch 8, 336 px image, 8 RoIs per
+image, 128 text tokens -> L = 706, CLIP-ViT-L/14 + SPI module + LLaMA-7B + lm_head, bf16, random-init
+weights of the real architecture, synthetic inputs.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(batch_per_gpu=8, image_size=336, rois_per_image=8, text_tokens=128)
+# algorithmic FLOPs per sample of the headline workload (SURVEY.md App. B, 2*MAC)
+FLOPS_PER_SAMPLE = 14.69e12
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return p, 'measured'
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), 'fallback'
+
+
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def synthetic_inputs(cfg, B, k_per_img, T, seed=0):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    P = cfg.num_patches
+    L = T + P + 2
+    ids = torch.randint(3, 32000, (B, L), generator=g)
+    boxes = []
+    for b in range(B):
+        ids[b, 0] = 1
+        ids[b, 1] = cfg.im_start_token
+        ids[b, 2:2 + P] = cfg.im_patch_token
+        ids[b, 2 + P] = cfg.im_end_token
+        pos = torch.randperm(L - (3 + P), generator=g)[:k_per_img] + 3 + P
+        ids[b, pos] = cfg.bbox_token
+        p = torch.rand(k_per_img, 2, 2, generator=g).sort(dim=1).values
+        bx = torch.cat([p[:, 0, :], p[:, 1, :]], 1)
+        bx[:, 2:] = torch.maximum(bx[:, 2:], bx[:, :2] + 2.0 / cfg.image_size).clamp(max=1.0)
+        boxes.append(bx)
+    images = torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=g).to(torch.bfloat16)
+    return ids, images, boxes
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the reference's path (PyTorch-CPU + transformers + mmcv-CPU RoIAlign) on a BOUNDED
+# sample of ONE headline sample; per-stage times are scaled by the stage repeat count.
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(budget_note=True):
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from gpt4roi_b200.engine import EngineConfig
+    torch.set_grad_enabled(False)
+    cores = torch.get_num_threads()
+    cfg = EngineConfig(image_size=WORKLOAD['image_size'])
+    S, K, T = cfg.image_size, WORKLOAD['rois_per_image'], WORKLOAD['text_tokens']
+    L = T + cfg.num_patches + 2
+    parts = {}
+
+    def timeit(fn, reps=1):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    # ViT: 1 encoder layer of 24 (reference runs all 24, llava.py:126)
+    from transformers import CLIPVisionConfig
+    from transformers.models.clip.modeling_clip import CLIPEncoderLayer
+    vc = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24,
+                          num_attention_heads=16, image_size=S, patch_size=14)
+    vc._attn_implementation = 'eager'
+    vl = CLIPEncoderLayer(vc).eval()
+    xv = torch.randn(1, cfg.num_patches + 1, 1024)
+    try:
+        parts['vit'] = 24 * timeit(lambda: vl(xv, None, None))
+    except TypeError:
+        parts['vit'] = 24 * timeit(lambda: vl(xv, attention_mask=None))
+    # fuse stack: 1 round (4 levels) of 5 + the input stage (layers.py:182-195)
+    maps = [torch.randn(1, 1024, h, h) for h in cfg.level_sizes]
+    w3 = torch.randn(1024, 1024, 3, 3) * 0.01
+    gam, bet = torch.ones(1024), torch.zeros(1024)
+
+    def fuse_round():
+        for l, m in enumerate(maps):
+            top, down = maps[min(l + 1, 3)], maps[max(l - 1, 0)]
+            z = torch.cat([m[:, :512], F.interpolate(top[:, 768:], size=m.shape[-2:], mode='bilinear', align_corners=True),
+                           F.interpolate(down[:, 512:768], size=m.shape[-2:], mode='bilinear', align_corners=True)], 1)
+            F.relu(F.group_norm(F.conv2d(z, w3, padding=1), 64, gam, bet))
+    parts['fuse'] = 5 * timeit(fuse_round)
+    w1 = torch.randn(1024, 1026, 1, 1) * 0.01
+    parts['input_conv'] = timeit(lambda: [F.conv2d(torch.cat([m, m[:, :2]], 1), w1) for m in maps])
+    # RoIAlign: the reference's own CPU kernel (oracle/_ref) when present, else the C port
+    rois = torch.cat([torch.zeros(K, 1), torch.rand(K, 2) * S * 0.5, torch.rand(K, 2) * S * 0.5 + S * 0.5], 1)
+    kind = 'port'
+    try:
+        from oracle import build_ref
+        ext = build_ref.load()
+    except Exception:
+        ext = None
+    if ext is not None:
+        kind = 'reference'
+        e0 = torch.zeros(0)
+
+        def ra():
+            for l, m in enumerate(maps):
+                o = m.new_zeros(K, 1024, 14, 14)
+                ext.roi_align_forward(m, rois, o, e0, e0, aligned_height=14, aligned_width=14,
+                                      spatial_scale=float(np.float32(1 / cfg.strides[l])), sampling_ratio=2,
+                                      pool_mode=1, aligned=True)
+    else:
+        from oracle import roi_align_oracle as O
+
+        def ra():
+            for l, m in enumerate(maps):
+                O.roi_align_forward(m.numpy(), rois.numpy(), 14, 1 / cfg.strides[l], 2, 'avg', True)
+    parts['roi_align'] = timeit(ra)
+    rf = torch.randn(K, 1024, 14, 14)
+    wf = torch.randn(1024, 200704) * 0.002
+    parts['pconv_flatten'] = timeit(lambda: (sum(F.conv2d(rf, w3, padding=1) for _ in range(4)),
+                                             F.linear(rf.flatten(1), wf)))
+    # LLaMA: 1 decoder layer of 32 at L tokens + lm_head
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaDecoderLayer, LlamaRotaryEmbedding
+    lc = LlamaConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
+                     num_key_value_heads=32, vocab_size=32006)
+    lc._attn_implementation = 'eager'
+    dl = LlamaDecoderLayer(lc, 0).eval()
+    xl = torch.randn(1, L, 4096)
+    pos_ids = torch.arange(L)[None]
+    pe = LlamaRotaryEmbedding(lc)(xl, pos_ids)
+    mask = torch.full((L, L), float('-inf')).triu(1)[None, None]
+    parts['llama'] = 32 * timeit(lambda: dl(xl, attention_mask=mask, position_ids=pos_ids, position_embeddings=pe))
+    wl = torch.randn(32006, 4096) * 0.02
+    parts['lm_head'] = timeit(lambda: F.linear(xl[0], wl))
+    sec = sum(parts.values())
+    sample = ('1 sample (336px, 8 RoIs, L=%d), fp32 on host cores: 1 of 24 CLIP layers x24, 1 of 5 fuse rounds x5, '
+              '1 of 32 LLaMA layers x32, RoIAlign/pconv/flatten_linear/lm_head in full; RoIAlign = %s' %
+              (L, 'reference cpu/roi_align.cpp (oracle/_ref)' if kind == 'reference' else 'C port'))
+    return dict(value=1.0 / sec, unit='samples/s', cores=cores, kind=kind, sample=sample,
+                stage_seconds={k: round(v, 3) for k, v in parts.items()})
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):  # each step = one bounded sample (~20-60 s of CPU work)
+        vals.append(cpu_reference_sample())
+    best = max(vals, key=lambda d: d['value'])
+    L = WORKLOAD['text_tokens'] + (WORKLOAD['image_size'] // 14) ** 2 + 2
+    line = dict(impl='reference', metric='samples_per_sec_prefill_336px_8roi_128tok_7b', value=best['value'],
+                unit='samples/s', n_gpus=args.gpus, steps=len(vals), warmup=1,
+                ms_per_step=1e3 / best['value'], higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic',
+                config=dict(workload='configs[1] per-sample: 336px, 8 RoIs, 128-tok prompt (L=%d), 7B prefill; '
+                                     'reference CPU path (PyTorch-CPU + transformers + mmcv-CPU RoIAlign)' % L,
+                            note='bounded sample, stage times scaled by repeat count'),
+                cpu_baseline=dict(value=best['value'], unit='samples/s', cores=best['cores'], kind=best['kind'],
+                                  sample=best['sample']),
+                e2e=dict(value=best['value'], unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                stage_seconds=best['stage_seconds'])
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gpt4roi_b200 import dense, lib
+    from gpt4roi_b200.engine import EngineConfig, GraphedPrefill, PrefillEngine, random_state_dicts
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg = EngineConfig(image_size=WORKLOAD['image_size'], n_layers=args.layers, vit_layers=24)
+    B, K, T = WORKLOAD['batch_per_gpu'], WORKLOAD['rois_per_image'], WORKLOAD['text_tokens']
+    sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
+    eng = PrefillEngine(cfg, sd, vit_sd, dev)
+    del sd, vit_sd
+    torch.cuda.empty_cache()
+    ids, images, boxes = synthetic_inputs(cfg, B, K, T, seed=rank)
+    L = ids.shape[1]
+    h_ids, h_img = ids.pin_memory(), images.pin_memory()
+    h_boxes = [b.pin_memory() for b in boxes]
+    lib.LAUNCHES = 0
+    graph = GraphedPrefill(eng, ids, images, boxes, last_only=False)
+    launches_per_step = lib.LAUNCHES // 3  # 2 eager warm-ups + 1 capture
+    h_out = torch.empty((B, cfg.vocab), dtype=torch.bfloat16).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: inputs resident in HBM, graph replays only --------------------------------
+    for _ in range(max(args.warmup, 3)):
+        graph.graph.replay()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        graph.graph.replay()
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+
+    # ---- e2e: public API with pinned HOST buffers, H2D + replay + D2H of the step result ---
+    def e2e_step():
+        out = graph.run(h_ids, h_img, h_boxes)
+        h_out.copy_(out[:, -1, :], non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    h2d = h_ids.numel() * 8 + h_img.numel() * 2 + sum(b.numel() * 4 for b in h_boxes)
+    d2h = h_out.numel() * 2
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): one instrumented
+    #      eager step with CUDA events around every launch on the launching stream ------------
+    dense.PROFILE = []
+    plan = eng.plan_boxes(boxes)
+    eng.forward_device(graph.ids, graph.images, plan, validate=False, last_only=False)
+    torch.cuda.synchronize(dev)
+    prof, dense.PROFILE = dense.PROFILE, None
+    gemm_ms = sum(s.elapsed_time(e) for _, _, s, e in prof)
+    gemm_flops = sum(f for _, f, _, _ in prof)
+    pk, how = peaks()
+    achieved = gemm_flops / 1e12 / (gemm_ms / 1e3)
+    roof = dict(bound='tensor', kernel='gemm_bf16_tcgen05', achieved=achieved, peak=pk['bf16_tflops_sustained'],
+                unit='TFLOP/s', frac=achieved / pk['bf16_tflops_sustained'], traffic=None,
+                peak_kind=how + ' (sustained cuBLAS bf16; kernel timed inside a long step)',
+                launches=len(prof), flops_per_launch_avg=gemm_flops / max(len(prof), 1),
+                avg_launch_ms=gemm_ms / max(len(prof), 1), share_of_step=gemm_ms / ms_step / (1.0 if True else 1),
+                note='events around each launch in one eager instrumented step after the timed region')
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_reference_sample() if (world == 1 and not args.no_cpu_baseline) else None
+    line = dict(metric='samples_per_sec_prefill_336px_8roi_128tok_7b', value=value, unit='samples/s',
+                n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
+                config=dict(workload='configs[1]: batch %d/GPU, 336px, %d RoIs/img, %d-tok prompt (L=%d), '
+                                     'CLIP-ViT-L/14 + SPI + LLaMA-7B (%d layers) + lm_head, full logits' %
+                                     (B, K, T, L, cfg.n_layers),
+                            global_batch=world * B, seq_len=L, parallelism='replicas x%d (batch split, no collective)' % world,
+                            l2='weights (14.6 GB) >> 126 MB L2: inputs larger than L2, no explicit flush',
+                            cuda_graph=True, flops_per_sample=FLOPS_PER_SAMPLE),
+                clocks=clocks, gpu_launches=launches_per_step * args.steps,
+                e2e=dict(value=world * B / (e2e_ms / 1e3), unit='samples/s', h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
+                roofline=roof,
+                model_tflops=value * FLOPS_PER_SAMPLE / 1e12 / world,
+                cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--layers', type=int, default=32, help=argparse.SUPPRESS)  # debugging only; 32 = LLaMA-7B
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -9,6 +9,26 @@ from . import lib as _L
 
 ACT = {None: 0, 'none': 0, 'relu': 1, 'quick_gelu': 2, 'swiglu': 3}
 
+# bench.py instrumentation: when PROFILE is a list, every tensor-core launch appends
+# (kind, flops, start_event, end_event) -- used for the roofline of the dominant kernel.
+PROFILE = None
+
+
+def _prof_begin(dev):
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record(torch.cuda.current_stream(dev))
+    return e
+
+
+def _prof_end(dev, start, kind, flops):
+    if start is None:
+        return
+    e = torch.cuda.Event(enable_timing=True)
+    e.record(torch.cuda.current_stream(dev))
+    PROFILE.append((kind, flops, start, e))
+
 
 def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16,
            k_splits=1):
@@ -53,10 +73,12 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
         elif bias.dtype != torch.bfloat16:
             raise TypeError('linear: bias must be bf16 or fp32')
     with torch.cuda.device(dev):
+        _ps = _prof_begin(dev)
         _L.check(_L.load().g4r_gemm_bf16(
             _L.ptr(x2), x2.stride(0), _L.ptr(weight), weight.stride(0), _L.ptr(out2), out2.stride(0),
             M, N, K, _L.ptr(bias), bias_f32, _L.ptr(res2), res2.stride(0) if res2 is not None else 0,
             ACT[act], int(out_f32), int(k_splits), _L.stream_ptr(dev)))
+        _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
     return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out
 
 
@@ -90,7 +112,9 @@ def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None, leve
             raise RuntimeError('gn_stats must be fp32 [N,groups,2]')
         groups = gn_stats.shape[1]
     with torch.cuda.device(dev):
+        _ps = _prof_begin(dev)
         _L.check(_L.load().g4r_conv_nhwc_bf16(
             _L.ptr(x), _L.ptr(weight_khwc), _L.ptr(out), n, h, w, cin, cout, kh, int(levels), _L.ptr(bias), bias_f32,
             ACT[act], _L.ptr(gn_stats), groups, _L.stream_ptr(dev)))
+        _prof_end(dev, _ps, 'conv', 2.0 * n * h * w * cout * kh * kw * cin * levels)
     return out

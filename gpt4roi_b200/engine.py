@@ -242,31 +242,88 @@ class PrefillEngine:
         return buf.view(B, rows // B, self.vocab_pad)[:, :, :c.vocab]
 
     # ------------------------------------------------------------------ whole path
-    def forward(self, input_ids, images, bboxes, validate=True, last_only=False):
-        """input_ids int64 [B,L]; images [B,3,S,S]; bboxes list (len B) of [K_i,4] normalised xyxy or
-        None.  Returns logits [B,L,V] (bf16) -- or [B,1,V] with last_only.  attention_mask is all-ones
-        (no padding) in this round."""
+    def plan_boxes(self, bboxes):
+        """Host-side packing of the per-sample box lists (the reference does this with torch.cat and
+        python loops at layers.py:283-302): returns device tensors so that `forward_device` contains no
+        host->device traffic and can be captured in a CUDA graph."""
+        if bboxes is None or len(bboxes) == 0:
+            return None
+        counts = [0 if b is None else int(b.shape[0]) for b in bboxes]
+        K = sum(counts)
+        offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()), dtype=torch.int32).to(self.dev)
+        if K > 0:
+            boxes = torch.cat([b.to(self.dev, torch.float32) for b in bboxes if b is not None and b.shape[0]], 0).contiguous()
+            bidx = torch.cat([torch.full((n,), float(i)) for i, n in enumerate(counts)]).to(self.dev)
+        else:
+            boxes = torch.zeros((0, 4), dtype=torch.float32, device=self.dev)
+            bidx = torch.zeros((0,), dtype=torch.float32, device=self.dev)
+        return dict(K=K, boxes=boxes, bidx=bidx, offs=offs)
+
+    def forward_device(self, input_ids, images, plan, validate=True, last_only=False):
+        """Device-only forward (capturable): input_ids int64 [B,L], images bf16 [B,3,S,S] on the GPU."""
         c = self.cfg
         B, L = input_ids.shape
-        taps = self.vit(images.to(self.dev, BF16))
+        taps = self.vit(images)
         feat = taps[c.select_index][:, 1:].contiguous()  # spi_llava.py:68-73
         img_rows = dense.linear(feat.view(-1, c.vit_hidden), self.proj_w, self.proj_b).view(B, c.num_patches, c.hidden)
         region = None
-        if bboxes is not None and len(bboxes) > 0:
-            counts = [0 if b is None else int(b.shape[0]) for b in bboxes]
-            K = sum(counts)
-            offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()), dtype=torch.int32).to(self.dev)
-            if K > 0:
-                boxes = torch.cat([b.to(self.dev, torch.float32) for b in bboxes if b is not None and b.shape[0]], 0)
-                bidx = torch.cat([torch.full((n,), float(i)) for i, n in enumerate(counts)]).to(self.dev)
+        if plan is not None:
+            if plan['K'] > 0:
                 maps, ss = self.fuse_maps(taps)
-                rows = self.region_tokens(maps, ss, boxes, bidx)
+                rows = self.region_tokens(maps, ss, plan['boxes'], plan['bidx'])
             else:
                 rows = torch.zeros((1, c.hidden), dtype=BF16, device=self.dev)
-            region = (rows, offs)
+            region = (rows, plan['offs'])
         embeds = splice_region_tokens(input_ids, self.embed, img_rows, region, c.num_patches, c.im_patch_token,
                                       c.im_start_token, c.im_end_token, c.bbox_token, validate=validate)
         return self.llama(embeds, B, L, last_only=last_only)
+
+    def forward(self, input_ids, images, bboxes, validate=True, last_only=False):
+        """Public entry: input_ids int64 [B,L]; images [B,3,S,S]; bboxes list (len B) of [K_i,4]
+        normalised xyxy or None (host or device tensors).  Returns logits [B,L,V] (bf16) -- [B,1,V]
+        with last_only.  attention_mask is all-ones (no padding) in this round."""
+        plan = self.plan_boxes(bboxes)
+        return self.forward_device(input_ids.to(self.dev, non_blocking=True),
+                                   images.to(self.dev, BF16, non_blocking=True), plan, validate, last_only)
+
+
+class GraphedPrefill:
+    """CUDA-graph replay of PrefillEngine.forward_device for a fixed (B, L, box counts) shape:
+    the ~1500 kernel launches of one prefill become one graph launch.  Inputs are staged through
+    static device buffers; `run` accepts (pinned) host tensors."""
+
+    def __init__(self, engine, input_ids, images, bboxes, last_only=True):
+        self.eng = engine
+        dev = engine.dev
+        self.ids = input_ids.to(dev).clone()
+        self.images = images.to(dev, BF16).clone()
+        self.plan = engine.plan_boxes(bboxes)
+        self.counts = None if bboxes is None else [0 if b is None else int(b.shape[0]) for b in bboxes]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            engine.forward_device(self.ids, self.images, self.plan, validate=True, last_only=last_only)  # warm-up + validation
+            engine.forward_device(self.ids, self.images, self.plan, validate=False, last_only=last_only)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = engine.forward_device(self.ids, self.images, self.plan, validate=False, last_only=last_only)
+
+    def run(self, input_ids, images, bboxes):
+        self.ids.copy_(input_ids, non_blocking=True)
+        self.images.copy_(images, non_blocking=True)
+        if self.plan is not None and self.plan['K'] > 0:
+            counts = [0 if b is None else int(b.shape[0]) for b in bboxes]
+            if counts != self.counts:
+                raise ValueError('box counts differ from the captured shape')
+            off = 0
+            for b in bboxes:
+                if b is not None and b.shape[0]:
+                    self.plan['boxes'][off:off + b.shape[0]].copy_(b, non_blocking=True)
+                    off += b.shape[0]
+        self.graph.replay()
+        return self.out
 
 
 def random_state_dicts(cfg, device, seed=0, dtype=BF16):

@@ -52,6 +52,12 @@ SIGNATURES = {
 }
 
 _lib = None
+LAUNCHES = 0  # kernels launched through the C ABI (bench.py reports it as gpu_launches)
+
+
+def count_launches(n=1):
+    global LAUNCHES
+    LAUNCHES += n
 
 
 class G4RError(RuntimeError):
@@ -77,7 +83,9 @@ def load():
     return lib
 
 
-def check(rc):
+def check(rc, launches=1):
+    global LAUNCHES
+    LAUNCHES += launches
     if rc != 0:
         msg = load().g4r_last_error()
         raise G4RError('gpt4roi_b200 C-ABI error %d: %s' % (rc, (msg or b'').decode()))

@@ -70,7 +70,7 @@ def splice_region_tokens(input_ids, embed_weight, image_features, region_feature
         _L.check(_L.load().g4r_splice_region_tokens(
             _L.ptr(input_ids), _L.ptr(embed_weight), _L.ptr(image_features), _L.ptr(rows), _L.ptr(offs),
             _L.ptr(out), _L.ptr(plan), _L.ptr(status), B, L, P, D, V, int(im_patch_token),
-            int(im_start_token), int(im_end_token), int(bbox_token), _L.stream_ptr(dev)))
+            int(im_start_token), int(im_end_token), int(bbox_token), _L.stream_ptr(dev)), launches=2)
     if validate:
         st = status.cpu()
         bad = torch.nonzero(st)
