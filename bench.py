@@ -240,6 +240,18 @@ def run_ours(args):
     L = ids.shape[1]
     h_ids, h_img = ids.pin_memory(), images.pin_memory()
     h_boxes = [b.pin_memory() for b in boxes]
+    if args.ncu:
+        # profiling mode (run under `ncu --profile-from-start off`): one eager forward inside the
+        # cudaProfilerStart/Stop window, nothing else.
+        plan = eng.plan_boxes(boxes)
+        d_ids, d_img = ids.to(dev), images.to(dev)
+        eng.forward_device(d_ids, d_img, plan, validate=True, last_only=False)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        eng.forward_device(d_ids, d_img, plan, validate=False, last_only=False)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
     lib.LAUNCHES = 0
     graph = GraphedPrefill(eng, ids, images, boxes, last_only=False)
     launches_per_step = lib.LAUNCHES // 3  # 2 eager warm-ups + 1 capture
@@ -343,6 +355,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--layers', type=int, default=32, help=argparse.SUPPRESS)  # debugging only; 32 = LLaMA-7B
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu', action='store_true', help='one eager forward inside a cudaProfiler window')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

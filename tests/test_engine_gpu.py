@@ -46,8 +46,10 @@ def make_inputs(cfg, B, ks, T, seed=0):
 def test_spi_path_matches_reference_golden_336():
     """fuse stack + fused GN/RoIAlign + pconv + flatten_linear + pos + updims vs the reference module's
     own fp32 output (golden).  bf16 tensor-core path vs fp32: rel-L2 <= 3e-2."""
-    cfg, sd, toks, boxes, want = golden_case(336)
+    _, sd, toks, boxes, want = golden_case(336)
+    cfg = EngineConfig(image_size=336, vit_layers=24, n_layers=0)
     vit_dummy = {k: v for k, v in random_state_dicts(EngineConfig(image_size=336, vit_layers=0, n_layers=0), 'cpu')[1].items()}
+    cfg.select_index = 0  # no ViT layers are run in this test; taps are supplied directly
     eng = PrefillEngine(cfg, sd, vit_dummy, DEV)
     B = toks[0].shape[0]
     taps = {}
