@@ -103,8 +103,9 @@ def cpu_reference_sample(budget_note=True):
     from gpt4roi_b200.engine import EngineConfig
     torch.set_grad_enabled(False)
     cores = torch.get_num_threads()
-    cfg = EngineConfig(image_size=WORKLOAD['image_size'])
-    S, K, T = cfg.image_size, WORKLOAD['rois_per_image'], WORKLOAD['text_tokens']
+    tiny = os.environ.get('G4R_BENCH_TINY') == '1'   # CPU unit test only: same code path, toy sizes
+    cfg = EngineConfig(image_size=56 if tiny else WORKLOAD['image_size'])
+    S, K, T = cfg.image_size, (1 if tiny else WORKLOAD['rois_per_image']), (4 if tiny else WORKLOAD['text_tokens'])
     L = T + cfg.num_patches + 2
     parts = {}
 
@@ -218,18 +219,15 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from gpt4roi_b200 import dense, lib
+    from gpt4roi_b200 import dense, dist_utils, lib
     from gpt4roi_b200.engine import EngineConfig, GraphedPrefill, PrefillEngine, random_state_dicts
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world, rank, local = dist_utils.env_world()
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    dist_utils.init('nccl', dev)   # NCCL only for the barrier + max-over-ranks time (no data-path collective)
     cfg = EngineConfig(image_size=WORKLOAD['image_size'], n_layers=args.layers, vit_layers=24)
     B, K, T = WORKLOAD['batch_per_gpu'], WORKLOAD['rois_per_image'], WORKLOAD['text_tokens']
     sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
@@ -259,16 +257,10 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        dist_utils.barrier(dev)
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return dist_utils.max_over_ranks(ms, dev)
 
     # ---- value: inputs resident in HBM, graph replays only --------------------------------
     for _ in range(max(args.warmup, 3)):

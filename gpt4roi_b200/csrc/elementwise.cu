@@ -133,25 +133,34 @@ static int launch_norm(const void* x, long long ldx, const void* w, const void* 
 __global__ void __launch_bounds__(256)
 rope_inplace_bf16(__nv_bfloat16* __restrict__ qkv, long long ld, const __nv_bfloat16* __restrict__ cos_t,
                   const __nv_bfloat16* __restrict__ sin_t, int rows, int L, int n_heads_qk, int head_dim) {
+  // one thread = 8 consecutive dims of the first half of a head and their partners in the second half
   const int half = head_dim >> 1;
-  const long long total = (long long)rows * n_heads_qk * half;
+  const int vph = half >> 3;  // 16-byte vectors per half head
+  const long long total = (long long)rows * n_heads_qk * vph;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int d = (int)(i % half);
-    const int h = (int)((i / half) % n_heads_qk);
-    const long long r = i / ((long long)half * n_heads_qk);
+    const int v = (int)(i % vph);
+    const int h = (int)((i / vph) % n_heads_qk);
+    const long long r = i / ((long long)vph * n_heads_qk);
     const int pos = (int)(r % L);
-    __nv_bfloat16* p = qkv + r * ld + (long long)h * head_dim;
-    const float x1 = __bfloat162float(p[d]), x2 = __bfloat162float(p[d + half]);
-    const float c1 = __bfloat162float(cos_t[(long long)pos * head_dim + d]);
-    const float s1 = __bfloat162float(sin_t[(long long)pos * head_dim + d]);
-    const float c2 = __bfloat162float(cos_t[(long long)pos * head_dim + d + half]);
-    const float s2 = __bfloat162float(sin_t[(long long)pos * head_dim + d + half]);
-    // rotate_half(x) = cat(-x2, x1)
-    const float o1 = bf16_round(x1 * c1) + bf16_round(-x2 * s1);
-    const float o2 = bf16_round(x2 * c2) + bf16_round(x1 * s2);
-    p[d] = __float2bfloat16_rn(o1);
-    p[d + half] = __float2bfloat16_rn(o2);
+    __nv_bfloat16* p = qkv + r * ld + (long long)h * head_dim + v * 8;
+    float x1[8], x2[8], c1[8], s1[8], c2[8], s2[8], o1[8], o2[8];
+    unpack8(*reinterpret_cast<const uint4*>(p), x1);
+    unpack8(*reinterpret_cast<const uint4*>(p + half), x2);
+    const __nv_bfloat16* ct = cos_t + (long long)pos * head_dim + v * 8;
+    const __nv_bfloat16* st = sin_t + (long long)pos * head_dim + v * 8;
+    unpack8(*reinterpret_cast<const uint4*>(ct), c1);
+    unpack8(*reinterpret_cast<const uint4*>(st), s1);
+    unpack8(*reinterpret_cast<const uint4*>(ct + half), c2);
+    unpack8(*reinterpret_cast<const uint4*>(st + half), s2);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      // rotate_half(x) = cat(-x2, x1)
+      o1[j] = bf16_round(x1[j] * c1[j]) + bf16_round(-x2[j] * s1[j]);
+      o2[j] = bf16_round(x2[j] * c2[j]) + bf16_round(x1[j] * s2[j]);
+    }
+    *reinterpret_cast<uint4*>(p) = pack8(o1);
+    *reinterpret_cast<uint4*>(p + half) = pack8(o2);
   }
 }
 
@@ -271,19 +280,15 @@ upsample_tokens_coords_bf16(const __nv_bfloat16* __restrict__ tok, long long ldt
 // ConvModule's GN->ReLU (mmcv cnn/bricks/conv_module.py:196-208) is fused into this gather and the
 // resampling runs on fp32 values exactly like F.interpolate(x.to(float32), ...) at :166-175.
 struct FuseSrc {
-  const __nv_bfloat16* p;
-  const float* sc;
-  const float* sh;
+  const __nv_bfloat16* __restrict__ p;
+  const float* __restrict__ sc;
+  const float* __restrict__ sh;
   int H;
 };
-__device__ __forceinline__ void load_act8(const FuseSrc& s, int b, int y, int x, int c0, int C, float (&f)[8]) {
-  unpack8(*reinterpret_cast<const uint4*>(s.p + (((long long)b * s.H + y) * s.H + x) * C + c0), f);
-  if (s.sc != nullptr) {
-    const float4* a = reinterpret_cast<const float4*>(s.sc + (long long)b * C + c0);
-    const float4* d = reinterpret_cast<const float4*>(s.sh + (long long)b * C + c0);
-    const float4 a0 = a[0], a1 = a[1], d0 = d[0], d1 = d[1];
-    const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+__device__ __forceinline__ void act8(const uint4& raw, bool affine, const float (&aa)[8], const float (&dd)[8],
+                                     float (&f)[8]) {
+  unpack8(raw, f);
+  if (affine) {
 #pragma unroll
     for (int j = 0; j < 8; j++) f[j] = fmaxf(f[j] * aa[j] + dd[j], 0.f);
   }
@@ -301,27 +306,37 @@ fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restri
     const int y = (int)((i / ((long long)nvec * H)) % H);
     const int b = (int)(i / ((long long)nvec * H * H));
     const int c = v * 8;
+    // out channels [0,C/2) <- own; [C/2,3C/4) <- top[:, 3C/4 + j]; [3C/4,C) <- down[:, C/2 + j]
+    const bool is_own = c < 2 * q, from_top = c < 3 * q;
+    const FuseSrc& s = is_own ? own : (from_top ? top : down);
+    const int sc0 = is_own ? c : (from_top ? c + q : c - q);
+    const bool affine = s.sc != nullptr;
+    float aa[8], dd[8];
+    if (affine) {
+      const float4* a = reinterpret_cast<const float4*>(s.sc + (long long)b * C + sc0);
+      const float4* d = reinterpret_cast<const float4*>(s.sh + (long long)b * C + sc0);
+      const float4 a0 = a[0], a1 = a[1], d0 = d[0], d1 = d[1];
+      aa[0] = a0.x; aa[1] = a0.y; aa[2] = a0.z; aa[3] = a0.w; aa[4] = a1.x; aa[5] = a1.y; aa[6] = a1.z; aa[7] = a1.w;
+      dd[0] = d0.x; dd[1] = d0.y; dd[2] = d0.z; dd[3] = d0.w; dd[4] = d1.x; dd[5] = d1.y; dd[6] = d1.z; dd[7] = d1.w;
+    }
+    const __nv_bfloat16* base = s.p + (long long)b * s.H * s.H * C + sc0;
     float o[8];
-    if (c < 2 * q) {
-      load_act8(own, b, y, x, c, C, o);
+    if (s.H == H) {  // own channels, or a same-size "resize" (identity)
+      act8(*reinterpret_cast<const uint4*>(base + ((long long)y * H + x) * C), affine, aa, dd, o);
     } else {
-      // out channels [C/2, 3C/4) <- top[:, 3C/4 + j]; [3C/4, C) <- down[:, C/2 + j]
-      const bool from_top = c < 3 * q;
-      const FuseSrc& s = from_top ? top : down;
-      const int sc0 = from_top ? c + q : c - q;
-      if (s.H == H) {
-        load_act8(s, b, y, x, sc0, C, o);  // same-size resize is the identity
-      } else {
-        const Lerp ly = lerp_ac(y, s.H, H), lx = lerp_ac(x, s.H, H);
-        float a[8], bb[8], cc[8], d[8];
-        load_act8(s, b, ly.i0, lx.i0, sc0, C, a);
-        load_act8(s, b, ly.i0, lx.i1, sc0, C, bb);
-        load_act8(s, b, ly.i1, lx.i0, sc0, C, cc);
-        load_act8(s, b, ly.i1, lx.i1, sc0, C, d);
+      const Lerp ly = lerp_ac(y, s.H, H), lx = lerp_ac(x, s.H, H);
+      const uint4 r00 = *reinterpret_cast<const uint4*>(base + ((long long)ly.i0 * s.H + lx.i0) * C);
+      const uint4 r01 = *reinterpret_cast<const uint4*>(base + ((long long)ly.i0 * s.H + lx.i1) * C);
+      const uint4 r10 = *reinterpret_cast<const uint4*>(base + ((long long)ly.i1 * s.H + lx.i0) * C);
+      const uint4 r11 = *reinterpret_cast<const uint4*>(base + ((long long)ly.i1 * s.H + lx.i1) * C);
+      float a[8], bb[8], cc[8], d[8];
+      act8(r00, affine, aa, dd, a);
+      act8(r01, affine, aa, dd, bb);
+      act8(r10, affine, aa, dd, cc);
+      act8(r11, affine, aa, dd, d);
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-          o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * bb[j]) + ly.l1 * (lx.l0 * cc[j] + lx.l1 * d[j]);
-      }
+      for (int j = 0; j < 8; j++)
+        o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * bb[j]) + ly.l1 * (lx.l0 * cc[j] + lx.l1 * d[j]);
     }
     reinterpret_cast<uint4*>(out + (((long long)b * H + y) * H + x) * C)[v] = pack8(o);
   }
@@ -452,8 +467,8 @@ extern "C" int g4r_rmsnorm_bf16(const void* x, long long ldx, const void* w, voi
 
 extern "C" int g4r_rope_inplace_bf16(void* qkv, long long ld, const void* cos_t, const void* sin_t, int rows,
                                      int L, int n_heads_qk, int head_dim, void* stream) {
-  G4R_REQUIRE(qkv && cos_t && sin_t && rows > 0 && L > 0 && n_heads_qk > 0 && head_dim % 2 == 0, "rope: bad arguments");
-  const long long total = (long long)rows * n_heads_qk * (head_dim / 2);
+  G4R_REQUIRE(qkv && cos_t && sin_t && rows > 0 && L > 0 && n_heads_qk > 0 && head_dim % 16 == 0 && ld % 8 == 0, "rope: bad arguments");
+  const long long total = (long long)rows * n_heads_qk * (head_dim / 16);
   rope_inplace_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (__nv_bfloat16*)qkv, ld, (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t, rows, L, n_heads_qk, head_dim);
   G4R_LAUNCH_CHECK("rope");

@@ -331,7 +331,7 @@ __device__ __forceinline__ PackedAxis pack_axis(const AxisEntry<float>& e, int m
 }
 
 template <typename Tin, typename Tout, int G, bool AFFINE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 5)
 roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
   constexpr int VEC = 16 / (int)sizeof(Tin);
   __shared__ PackedAxis ytab[kTab];

@@ -124,7 +124,7 @@ def ref_cases():
     print('wrote roi_align_ref_cases.npz (%d cases)' % len(meta))
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     kat()
     ref_cases()
 
@@ -175,3 +175,89 @@ def spi_module_golden():
 
 if __name__ == '__main__' and '--spi' in sys.argv:
     spi_module_golden()
+
+
+# ---------------------------------------------------------------------------------------
+# Full-model golden: the reference's OWN SPILlavaMPTForCausalLM.forward (gpt4roi/models/spi_llava.py +
+# llava/model/llava.py, unmodified, 224 px, fp32, CPU) with a full-width CLIP-L/14 (24 layers) and a
+# 2-layer LLaMA of hidden 4096.  Pins oracle/model_oracle.py (composition: level pick, projector,
+# splice, region scatter, lm_head) to the real code path.  Stored: logits at 24 probe positions.
+# ---------------------------------------------------------------------------------------
+def model_inputs(cfg, ks, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, P = len(ks), cfg.num_patches
+    L = T + P + 2
+    ids = torch.randint(3, 32000, (B, L), generator=g)
+    boxes = []
+    for b in range(B):
+        ids[b, 0] = 1
+        ids[b, 1] = cfg.im_start_token
+        ids[b, 2:2 + P] = cfg.im_patch_token
+        ids[b, 2 + P] = cfg.im_end_token
+        pos = torch.randperm(L - (3 + P), generator=g)[:ks[b]] + 3 + P
+        ids[b, pos] = cfg.bbox_token
+        p = torch.rand(ks[b], 2, 2, generator=g).sort(dim=1).values
+        bx = torch.cat([p[:, 0, :], p[:, 1, :]], 1)
+        bx[:, 2:] = torch.maximum(bx[:, 2:], bx[:, :2] + 2.0 / cfg.image_size).clamp(max=1.0)
+        boxes.append(bx)
+    images = torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=g)
+    return ids, images, boxes
+
+
+def full_model_golden():
+    sys.path.insert(0, HERE)
+    import importlib
+    import ref_shims
+    from gpt4roi_b200.engine import EngineConfig, random_state_dicts
+    ref_shims.install()
+    spi_llava = importlib.import_module('gpt4roi.models.spi_llava')
+    llava = importlib.import_module('llava.model.llava')
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    cfg = EngineConfig(image_size=224, vit_layers=24, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, 'cpu', seed=4321, dtype=torch.float32)
+    lc = llava.LlavaConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=2, num_attention_heads=32,
+                           num_key_value_heads=32, vocab_size=32006, rms_norm_eps=1e-6, max_position_embeddings=2048)
+    lc._attn_implementation = 'eager'
+    lc.mm_vision_select_layer = -2
+    lc.use_mm_proj = True
+    lc.mm_hidden_size = 1024
+    model = spi_llava.SPILlavaMPTForCausalLM(lc)
+    vc = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                          image_size=224, patch_size=14)
+    vc._attn_implementation = 'eager'
+    vt = CLIPVisionModel(vc)
+    missing, unexpected = vt.load_state_dict(vit_sd, strict=False)
+    assert not unexpected
+    model.model.vision_tower = [vt.eval()]
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all('rotary' in k or 'inv_freq' in k for k in missing), missing
+    model.eval()
+    vconf = vt.config
+    vconf.im_patch_token, vconf.bbox_token = cfg.im_patch_token, cfg.bbox_token
+    vconf.im_start_token, vconf.im_end_token = cfg.im_start_token, cfg.im_end_token
+    vconf.use_im_start_end = True
+
+    class Tok:
+        def convert_tokens_to_ids(self, toks):
+            return [cfg.bbox_token for _ in toks]
+    for m in model.modules():
+        m.tokenizer = Tok()
+    ids, images, boxes = model_inputs(cfg, [2, 1], 20, seed=99)
+    with torch.no_grad():
+        out = model(input_ids=ids, images=images, img_metas=[None] * len(boxes), bboxes=boxes,
+                    attention_mask=torch.ones_like(ids))
+    logits = out.logits.float()
+    L = ids.shape[1]
+    probe = torch.unique(torch.cat([torch.arange(0, L, L // 12), torch.tensor([1, 2, cfg.num_patches + 2, L - 1]),
+                                    torch.where(ids[0] == cfg.bbox_token)[0]]))
+    np.savez_compressed(os.path.join(HERE, 'full_model_ref_224.npz'),
+                        probe=probe.numpy(), logits=logits[:, probe].numpy(),
+                        argmax=logits.argmax(-1).numpy(), lmean=np.array([float(logits.double().mean()), float(logits.double().std())]),
+                        ids_checksum=np.array([int(ids.sum())]),
+                        w_checksum=np.array([float(sd['lm_head.weight'].double().sum())]))
+    print('wrote full_model_ref_224.npz', logits.shape, probe.tolist())
+
+
+if __name__ == '__main__' and '--model' in sys.argv:
+    full_model_golden()

@@ -106,3 +106,50 @@ def test_no_boxes_and_text_only_paths():
     bad[0, 2 + cfg.num_patches] = 5                                             # break the <im_end> position
     with pytest.raises(ValueError):
         eng.forward(bad.to(DEV), images.to(DEV, torch.bfloat16), None)
+
+
+def test_full_size_properties_7b():
+    """BASELINE configs[1] at full size (B=8, 336 px, 8 RoIs, L=706, 32 layers): properties that do
+    not need an oracle run -- causality, sample independence / permutation equivariance, box locality."""
+    cfg = EngineConfig(image_size=336, vit_layers=24, n_layers=32)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=11)
+    eng = PrefillEngine(cfg, sd, vit_sd, DEV)
+    del sd, vit_sd
+    torch.cuda.empty_cache()
+    ids, images, boxes = make_inputs(cfg, 8, [8] * 8, 128, seed=5)
+    ids, images = ids.to(DEV), images.to(DEV, torch.bfloat16)
+    base = eng.forward(ids, images, boxes).float()
+    assert base.shape == (8, 706, 32006) and torch.isfinite(base).all()
+    tol = 2e-2 * base.abs().max().item()   # GN statistics use fp32 atomics: not bit-reproducible
+    # (1) causality: editing the last text token leaves all earlier positions unchanged
+    ids2 = ids.clone()
+    ids2[:, -1] = (ids2[:, -1] + 7) % 31000 + 3
+    out2 = eng.forward(ids2, images, boxes).float()
+    assert (out2[:, :-1] - base[:, :-1]).abs().max().item() < tol
+    assert (out2[:, -1] - base[:, -1]).abs().max().item() > tol
+    # (2) samples are independent: permuting the batch permutes the logits
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4])
+    out3 = eng.forward(ids[perm], images[perm], [boxes[i] for i in perm.tolist()]).float()
+    assert (out3 - base[perm]).abs().max().item() < tol
+    # (3) box locality: moving sample 0's last box changes nothing before its <bbox> token and nothing in other samples
+    boxes4 = [b.clone() for b in boxes]
+    boxes4[0][-1] = torch.tensor([0.05, 0.05, 0.95, 0.95])
+    out4 = eng.forward(ids, images, boxes4).float()
+    assert (out4[1:] - base[1:]).abs().max().item() < tol
+    pos = torch.where(ids[0] == cfg.bbox_token)[0]
+    assert (out4[0, :pos[-1]] - base[0, :pos[-1]]).abs().max().item() < tol
+    assert (out4[0, pos[-1]:] - base[0, pos[-1]:]).abs().max().item() > tol
+
+
+def test_engine_vs_reference_forward_golden_224():
+    """Engine (bf16) vs logits of the reference's own SPILlavaMPTForCausalLM.forward (fp32 golden,
+    224 px reference-exact mode, CLIP-L/14 x24 + 2-layer LLaMA-4096).  rel-L2 <= 2.5e-2."""
+    from tests.test_model_oracle_cpu import full_model_case
+    cfg, sd, vit_sd, ids, images, boxes, z = full_model_case()
+    eng = PrefillEngine(cfg, sd, vit_sd, DEV)
+    got = eng.forward(ids.to(DEV), images.to(DEV, torch.bfloat16), boxes).float().cpu()
+    probe = torch.from_numpy(z['probe'])
+    e = rel(got[:, probe], torch.from_numpy(z['logits']))
+    print('engine vs reference-forward golden (224): rel-L2 %.3e' % e)
+    assert e < 2.5e-2
+    assert (got.argmax(-1).numpy() == z['argmax']).mean() > 0.9
