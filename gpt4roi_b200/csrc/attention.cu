@@ -7,9 +7,9 @@
 // Round-1 implementation note (DESIGN.md "attention"): attention is ~1.5 % of the path's FLOPs
 // (SURVEY.md App. B), so this first version uses warp-level mma.sync.m16n8k16 tiles (legacy tensor
 // path, HMMA) with cp.async double buffering; the tcgen05/TMEM version is scheduled after the GEMMs.
-// Rounding points follow the reference in bf16: scores are rounded to bf16 after QK^T and again
-// after *scale (two bf16 tensor ops in the reference), softmax runs in fp32, P is cast to bf16
-// before the PV product, the output is rounded once.
+// Numerics: QK^T accumulates in fp32 and the scaled scores stay fp32 through the softmax (the
+// reference rounds them to bf16 twice -- after the matmul and after *scale -- which only adds
+// noise); P is cast to bf16 before the PV product like the reference, the output is rounded once.
 #include "common.cuh"
 
 namespace g4r {
@@ -132,29 +132,37 @@ flash_attn_fwd(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restr
         mma_bf16(s[2 * n2 + 1], qf[kk], b2, b3);
       }
     }
-    // scores -> bf16 (QK^T output) -> *scale -> bf16, mask, online softmax
+    // online softmax in fp32 on the raw fp32 scores (scale folded into the exp2 argument).
+    // Only the diagonal block (causal) and the tail block (keys >= L) need masking.
     const int key0 = kb * kBN;
+    const int qrow0 = q0 + warp * 16;
+    if (key0 + kBN > L || (CAUSAL && key0 + kBN - 1 > qrow0)) {
+#pragma unroll
+      for (int nt = 0; nt < kBN / 8; nt++) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int key = key0 + nt * 8 + 2 * t + (e & 1);
+          const int qrow = qrow0 + g + ((e >> 1) << 3);
+          if (key >= L || (CAUSAL && key > qrow)) s[nt][e] = -INFINITY;
+        }
+      }
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < kBN / 8; nt++) {
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int key = key0 + nt * 8 + 2 * t + (e & 1);
-        const int qrow = q0 + warp * 16 + g + ((e >> 1) << 3);
-        float v = bf16r(bf16r(s[nt][e]) * scale);
-        if (key >= L || (CAUSAL && key > qrow)) v = -INFINITY;
-        s[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
-    float alpha[2], msub[2];
+    const float c = scale * kLog2e;
+    float alpha[2], mc[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
-      msub[r] = m_new == -INFINITY ? 0.f : m_new;
-      alpha[r] = exp2f((m_run[r] - msub[r]) * kLog2e);  // m_run = -inf -> 0
+      const float msub = m_new == -INFINITY ? 0.f : m_new;
+      alpha[r] = exp2f((m_run[r] - msub) * c);  // m_run = -inf -> 0
+      mc[r] = msub * c;
       m_run[r] = m_new;
       l_run[r] *= alpha[r];
     }
@@ -164,7 +172,7 @@ flash_attn_fwd(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restr
       float p[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        p[e] = exp2f((s[nt][e] - msub[e >> 1]) * kLog2e);
+        p[e] = exp2f(fmaf(s[nt][e], c, -mc[e >> 1]));
         l_run[e >> 1] += p[e];
       }
       pf[nt >> 1][(nt & 1) * 2] = pack_bf16(p[0], p[1]);

@@ -347,12 +347,19 @@ fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restri
 // variance, like torch.nn.GroupNorm).
 __global__ void gn_finalize(const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
                             const __nv_bfloat16* __restrict__ beta, float* __restrict__ scale,
-                            float* __restrict__ shift, int B, int C, int groups, float count, float eps) {
+                            float* __restrict__ shift, int B, int C, int groups, int slots, float count,
+                            float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
   const int g = c / (C / groups);
-  const float s = stats[((long long)b * groups + g) * 2], ss = stats[((long long)b * groups + g) * 2 + 1];
+  // stats: [B][slots][groups][2] per-(tile,warp) partial sums written by the conv epilogue; fixed-order sum
+  float s = 0.f, ss = 0.f;
+  for (int t = 0; t < slots; t++) {
+    const float* st = stats + (((long long)b * slots + t) * groups + g) * 2;
+    s += st[0];
+    ss += st[1];
+  }
   const float mean = s / count;
   float var = ss / count - mean * mean;
   var = var < 0.f ? 0.f : var;
@@ -432,12 +439,14 @@ pos_embed_mlp(const float* __restrict__ boxes, const __nv_bfloat16* __restrict__
 
 // t[k,:] = bf16( bf16(acc[k,:] + bias) + pos[k,:] )   (gpt4roi/models/layers.py:327-328: flatten_linear
 // output is bf16 under autocast, `+ pos_embedd` promotes to fp32, updims casts its input to bf16)
-__global__ void add_bias_pos_cast(const float* __restrict__ acc, const __nv_bfloat16* __restrict__ bias,
+__global__ void add_bias_pos_cast(const float* __restrict__ acc, int splits, const __nv_bfloat16* __restrict__ bias,
                                   const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, int K, int D) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * D) return;
   const int c = i % D;
-  const float f = bf16_round(acc[i] + __bfloat162float(bias[c]));
+  float a = 0.f;
+  for (int s = 0; s < splits; s++) a += acc[(long long)s * K * D + i];  // split-K slabs, fixed order
+  const float f = bf16_round(a + __bfloat162float(bias[c]));
   out[i] = __float2bfloat16_rn(f + pos[i]);
 }
 
@@ -519,10 +528,11 @@ extern "C" int g4r_fuse_gather_bf16(const void* own, const float* own_sc, const 
 }
 
 extern "C" int g4r_gn_finalize(const float* stats, const void* gamma, const void* beta, float* scale,
-                               float* shift, int B, int C, int groups, float count, float eps, void* stream) {
-  G4R_REQUIRE(stats && gamma && beta && scale && shift && B > 0 && C > 0 && groups > 0 && C % groups == 0, "gn_finalize: bad arguments");
+                               float* shift, int B, int C, int groups, int slots, float count, float eps,
+                               void* stream) {
+  G4R_REQUIRE(stats && gamma && beta && scale && shift && B > 0 && C > 0 && groups > 0 && C % groups == 0 && slots > 0, "gn_finalize: bad arguments");
   gn_finalize<<<(B * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-                                                                   scale, shift, B, C, groups, count, eps);
+                                                                   scale, shift, B, C, groups, slots, count, eps);
   G4R_LAUNCH_CHECK("gn_finalize");
   return G4R_OK;
 }
@@ -538,10 +548,10 @@ extern "C" int g4r_pos_embed_mlp(const float* boxes, const void* w0, const void*
   return G4R_OK;
 }
 
-extern "C" int g4r_add_bias_pos_cast(const float* acc, const void* bias, const float* pos, void* out, int K, int D,
-                                     void* stream) {
-  G4R_REQUIRE(acc && bias && pos && out && K > 0 && D > 0, "add_bias_pos_cast: bad arguments");
-  add_bias_pos_cast<<<(K * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(acc, (const __nv_bfloat16*)bias, pos, (__nv_bfloat16*)out, K, D);
+extern "C" int g4r_add_bias_pos_cast(const float* acc, int splits, const void* bias, const float* pos, void* out,
+                                     int K, int D, void* stream) {
+  G4R_REQUIRE(acc && bias && pos && out && K > 0 && D > 0 && splits >= 1, "add_bias_pos_cast: bad arguments");
+  add_bias_pos_cast<<<(K * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(acc, splits, (const __nv_bfloat16*)bias, pos, (__nv_bfloat16*)out, K, D);
   G4R_LAUNCH_CHECK("add_bias_pos_cast");
   return G4R_OK;
 }

@@ -21,6 +21,8 @@
 //   warps 4..7 : epilogue      -- tcgen05.ld 32 columns at a time (thread = accumulator row), fused
 //                bias / activation / residual / SwiGLU / GroupNorm statistics, bf16 or fp32 store;
 //                the second accumulator stage lets tile i+1's MMAs overlap tile i's epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -48,7 +50,7 @@ struct GemmParams {
   long long ldr;
   int act;
   int out_f32;   // 1: fp32 output
-  int atomic;    // 1: fp32 atomicAdd (split-K); D must be pre-zeroed
+  int atomic;    // unused (split-K writes per-split slabs)
   // conv mode
   int conv;
   int cH, cW, cBH, cBW, tiles_x, tiles_y, cin_blocks, taps;  // taps = 9 (3x3) or 1
@@ -75,6 +77,160 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == ACT_RELU) return fmaxf(x, 0.f);
   if (act == ACT_QUICK_GELU) return x / (1.f + __expf(-1.702f * x));
   return x;
+}
+
+// Epilogue of one 128-row accumulator tile owned by this CTA: thread `row` (= TMEM lane) walks the
+// BLOCK_N columns 32 at a time.  `arrive()` is called once all TMEM reads of the stage are done.
+template <int BLOCK_N, bool CONV, typename Arrive>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int m_blk, int n_blk, int split,
+                                              int row, int lane, Arrive arrive) {
+  // row -> output row offset
+  bool row_ok;
+  long long out_row;
+  int img = 0;
+  if (CONV) {
+    const int tx = m_blk % p.tiles_x;
+    const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+    img = m_blk / (p.tiles_x * p.tiles_y);
+    const int y = ty * p.cBH + row / p.cBW, x = tx * p.cBW + row % p.cBW;
+    row_ok = m_blk < p.num_m_tiles && row < p.a_rows && y < p.cH && x < p.cW;
+    out_row = ((long long)img * p.cH + y) * p.cW + x;
+  } else {
+    out_row = (long long)m_blk * kBlockM + row;
+    row_ok = m_blk < p.num_m_tiles && out_row < p.M;
+  }
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(taddr + c0, v);
+    ptx::tmem_ld_wait();
+    if (c0 + 32 >= BLOCK_N) {
+      // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+      ptx::tcgen05_before_thread_sync();
+      arrive();
+    }
+    const int col0 = n_blk * BLOCK_N + c0;
+    if (col0 >= p.N) continue;  // (warp-uniform)
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+    const bool full_chunk = col0 + 32 <= p.N;
+    if (p.bias != nullptr && split == 0) {
+      if (p.bias_f32) {
+        const float* b = reinterpret_cast<const float*>(p.bias) + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (full_chunk || col0 + j < p.N) f[j] += b[j];
+      } else {
+        const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (full_chunk || col0 + j < p.N) f[j] += __bfloat162float(b[j]);
+      }
+    }
+    if (p.act == ACT_RELU || p.act == ACT_QUICK_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) f[j] = act_apply(f[j], p.act);
+    }
+    if (p.act == ACT_SWIGLU) {
+      // interleaved weights: column 2j = gate_j, 2j+1 = up_j -> out[:, j] = silu(gate) * up
+      if (row_ok) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.D) + out_row * p.ldd + col0 / 2;
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float g0 = f[4 * j], u0 = f[4 * j + 1], g1 = f[4 * j + 2], u1 = f[4 * j + 3];
+          const float s0 = g0 / (1.f + __expf(-g0)) * u0, s1 = g1 / (1.f + __expf(-g1)) * u1;
+          __nv_bfloat162 h = __floats2bfloat162_rn(s0, s1);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (full_chunk && (p.ldd % 8 == 0)) {
+          reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+          const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
+          for (int j = 0; j < 16; j++) if (col0 + 2 * j + 1 < p.N) o[j] = e[j];
+        }
+      }
+      continue;
+    }
+    if (p.residual != nullptr && row_ok) {
+      const __nv_bfloat16* rr = p.residual + out_row * p.ldr + col0;
+      if (full_chunk && (p.ldr % 8 == 0)) {
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+          const uint4 raw = reinterpret_cast<const uint4*>(rr)[h];
+          const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[h * 8 + j] += __bfloat162float(e[j]);
+        }
+      } else {
+        for (int j = 0; j < 32; j++) if (col0 + j < p.N) f[j] += __bfloat162float(rr[j]);
+      }
+    }
+    if (p.out_f32) {
+      if (row_ok) {
+        // split-K: split s writes slab s of a [k_splits][M][ldd] fp32 buffer (no atomics; the consumer
+        // sums the slabs in a fixed order, so the result is bitwise reproducible)
+        float* o = reinterpret_cast<float*>(p.D) + ((long long)split * p.M + out_row) * p.ldd + col0;
+        if (full_chunk && (p.ldd % 4 == 0)) {
+#pragma unroll
+          for (int h = 0; h < 8; h++)
+            reinterpret_cast<float4*>(o)[h] = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
+        } else {
+          for (int j = 0; j < 32; j++) if (col0 + j < p.N) o[j] = f[j];
+        }
+      }
+    } else {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      if (row_ok) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.D) + out_row * p.ldd + col0;
+        if (full_chunk && (p.ldd % 8 == 0)) {
+#pragma unroll
+          for (int h = 0; h < 4; h++)
+            reinterpret_cast<uint4*>(o)[h] = make_uint4(pk[4 * h], pk[4 * h + 1], pk[4 * h + 2], pk[4 * h + 3]);
+        } else {
+          const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
+          for (int j = 0; j < 32; j++) if (col0 + j < p.N) o[j] = e[j];
+        }
+      }
+      if (CONV && p.gn_stats != nullptr) {
+        // GroupNorm statistics of the bf16-rounded conv output (what the reference's GN sees:
+        // mmcv cnn/bricks/conv_module.py:196-208 runs GN on the conv's bf16 result).
+        // 32 columns = 2 groups of 16 channels; reduce over the 32 rows of this warp, then ONE plain
+        // store per (tile, warp) slot -- no atomics, so the statistics are bitwise reproducible;
+        // gn_finalize sums the slots in a fixed order.
+        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
+        float s[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f};
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float x = __bfloat162float(e[j]);
+            s[j >> 4] += x;
+            ss[j >> 4] += x * x;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+          s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+          ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o);
+          ss[1] += __shfl_xor_sync(0xffffffffu, ss[1], o);
+        }
+        if (lane < 2 && full_chunk && m_blk < p.num_m_tiles) {
+          const int tiles_per_img = p.tiles_x * p.tiles_y;
+          const int slot = (m_blk % tiles_per_img) * 4 + (row >> 5);
+          float* st = p.gn_stats + (((long long)img * (tiles_per_img * 4) + slot) * p.gn_groups +
+                                    (col0 / p.gn_group_ch + lane)) * 2;
+          st[0] = lane == 0 ? s[0] : s[1];
+          st[1] = lane == 0 ? ss[0] : ss[1];
+        }
+      }
+    }
+  }
 }
 
 template <int BLOCK_N, bool CONV>
@@ -198,154 +354,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int split = t / tiles_mn;
       const int mn = t % tiles_mn;
       const int n_blk = mn / p.num_m_tiles, m_blk = mn % p.num_m_tiles;
-      // row -> output row offset
-      bool row_ok;
-      long long out_row;
-      int img = 0;
-      if (CONV) {
-        const int tx = m_blk % p.tiles_x;
-        const int ty = (m_blk / p.tiles_x) % p.tiles_y;
-        img = m_blk / (p.tiles_x * p.tiles_y);
-        const int y = ty * p.cBH + row / p.cBW, x = tx * p.cBW + row % p.cBW;
-        row_ok = row < p.a_rows && y < p.cH && x < p.cW;
-        out_row = ((long long)img * p.cH + y) * p.cW + x;
-      } else {
-        out_row = (long long)m_blk * kBlockM + row;
-        row_ok = out_row < p.M;
-      }
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tcgen05_after_thread_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(taddr + c0, v);
-        ptx::tmem_ld_wait();
-        if (c0 + 32 >= BLOCK_N) {
-          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-          ptx::tcgen05_before_thread_sync();
-          ptx::mbar_arrive(&tmem_empty[acc]);
-        }
-        const int col0 = n_blk * BLOCK_N + c0;
-        if (col0 >= p.N) continue;  // (warp-uniform)
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-        const bool full_chunk = col0 + 32 <= p.N;
-        if (p.bias != nullptr && split == 0) {
-          if (p.bias_f32) {
-            const float* b = reinterpret_cast<const float*>(p.bias) + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j++) if (full_chunk || col0 + j < p.N) f[j] += b[j];
-          } else {
-            const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j++) if (full_chunk || col0 + j < p.N) f[j] += __bfloat162float(b[j]);
-          }
-        }
-        if (p.act == ACT_RELU || p.act == ACT_QUICK_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = act_apply(f[j], p.act);
-        }
-        if (p.act == ACT_SWIGLU) {
-          // interleaved weights: column 2j = gate_j, 2j+1 = up_j -> out[:, j] = silu(gate) * up
-          if (row_ok) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.D) + out_row * p.ldd + col0 / 2;
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const float g0 = f[4 * j], u0 = f[4 * j + 1], g1 = f[4 * j + 2], u1 = f[4 * j + 3];
-              const float s0 = g0 / (1.f + __expf(-g0)) * u0, s1 = g1 / (1.f + __expf(-g1)) * u1;
-              __nv_bfloat162 h = __floats2bfloat162_rn(s0, s1);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            if (full_chunk && (p.ldd % 8 == 0)) {
-              reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            } else {
-              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
-              for (int j = 0; j < 16; j++) if (col0 + 2 * j + 1 < p.N) o[j] = e[j];
-            }
-          }
-          continue;
-        }
-        if (p.residual != nullptr && row_ok) {
-          const __nv_bfloat16* rr = p.residual + out_row * p.ldr + col0;
-          if (full_chunk && (p.ldr % 8 == 0)) {
-#pragma unroll
-            for (int h = 0; h < 4; h++) {
-              const uint4 raw = reinterpret_cast<const uint4*>(rr)[h];
-              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
-#pragma unroll
-              for (int j = 0; j < 8; j++) f[h * 8 + j] += __bfloat162float(e[j]);
-            }
-          } else {
-            for (int j = 0; j < 32; j++) if (col0 + j < p.N) f[j] += __bfloat162float(rr[j]);
-          }
-        }
-        if (p.atomic) {
-          if (row_ok) {
-            float* o = reinterpret_cast<float*>(p.D) + out_row * p.ldd + col0;
-            for (int j = 0; j < 32; j++) if (col0 + j < p.N) atomicAdd(o + j, f[j]);
-          }
-        } else if (p.out_f32) {
-          if (row_ok) {
-            float* o = reinterpret_cast<float*>(p.D) + out_row * p.ldd + col0;
-            if (full_chunk && (p.ldd % 4 == 0)) {
-#pragma unroll
-              for (int h = 0; h < 8; h++)
-                reinterpret_cast<float4*>(o)[h] = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
-            } else {
-              for (int j = 0; j < 32; j++) if (col0 + j < p.N) o[j] = f[j];
-            }
-          }
-        } else {
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          if (row_ok) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.D) + out_row * p.ldd + col0;
-            if (full_chunk && (p.ldd % 8 == 0)) {
-#pragma unroll
-              for (int h = 0; h < 4; h++)
-                reinterpret_cast<uint4*>(o)[h] = make_uint4(pk[4 * h], pk[4 * h + 1], pk[4 * h + 2], pk[4 * h + 3]);
-            } else {
-              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
-              for (int j = 0; j < 32; j++) if (col0 + j < p.N) o[j] = e[j];
-            }
-          }
-          if (CONV && p.gn_stats != nullptr) {
-            // GroupNorm statistics of the bf16-rounded conv output (what the reference's GN sees:
-            // mmcv cnn/bricks/conv_module.py:196-208 runs GN on the conv's bf16 result).
-            // 32 columns = 2 groups of 16 channels; reduce over the 32 rows of this warp, then atomics.
-            const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(pk);
-            float s[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f};
-            if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) {
-                const float x = __bfloat162float(e[j]);
-                s[j >> 4] += x;
-                ss[j >> 4] += x * x;
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
-              s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
-              ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o);
-              ss[1] += __shfl_xor_sync(0xffffffffu, ss[1], o);
-            }
-            if (lane < 2 && full_chunk) {
-              float* st = p.gn_stats + ((long long)img * p.gn_groups + (col0 / p.gn_group_ch + lane)) * 2;
-              atomicAdd(st, lane == 0 ? s[0] : s[1]);
-              atomicAdd(st + 1, lane == 0 ? ss[0] : ss[1]);
-            }
-          }
-        }
-      }
+      epilogue_tile<BLOCK_N, CONV>(p, taddr, m_blk, n_blk, split, row, lane,
+                                   [&]() { ptx::mbar_arrive(&tmem_empty[acc]); });
     }
   }
   ptx::tcgen05_before_thread_sync();
@@ -353,6 +366,173 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 2) {
     ptx::tcgen05_after_thread_sync();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-CTA variant: a cluster of two CTAs (one TPC) computes a 256 x 256 output tile with
+// tcgen05.mma.cta_group::2 (UMMA_M = 256).  Each CTA TMA-loads its own 128 A rows and HALF of the
+// B tile (128 of the 256 N rows), so the B operand is fetched from L2 and staged in shared memory
+// once per pair instead of once per CTA; accumulators land in each CTA's own TMEM and the epilogue
+// is unchanged.  Barriers: `full` (leader's, 2 arrivals + both CTAs' TMA bytes), `empty` / `tmem_full`
+// (per CTA, signalled by the leader's multicast tcgen05.commit), `tmem_empty` (leader's, 2x128
+// epilogue arrivals, the peer's via mapa).
+// ------------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int BLOCK_N = 256;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB: this CTA's 128 rows of A
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;    // 16 KB: this CTA's half of B
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;      // 6
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = kAccStages * BLOCK_N;         // 512
+  static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+};
+
+template <bool CONV>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BLOCK_N = Cfg::BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + Cfg::kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; i++) {
+      ptx::mbar_init(&full[i], 2);    // leader's own arrive.expect_tx + the peer's remote arrive
+      ptx::mbar_init(&empty[i], 1);   // multicast commit
+    }
+    for (int i = 0; i < Cfg::kAccStages; i++) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 256);  // epilogue threads of both CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  ptx::cluster_sync();  // barriers of both CTAs initialised before any remote signal; required before 2-CTA TMEM alloc
+  if (warp == 2) ptx::tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+  ptx::tcgen05_before_thread_sync();
+  ptx::cluster_sync();
+  ptx::tcgen05_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m_pairs = (p.num_m_tiles + 1) >> 1;
+  const int tiles_mn = num_m_pairs * p.num_n_tiles;
+  const int total_tiles = tiles_mn * p.k_splits;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        const int split = t / tiles_mn;
+        const int mn = t % tiles_mn;
+        const int n_blk = mn / num_m_pairs, m_blk = (mn % num_m_pairs) * 2 + (int)rank;
+        const int kb0 = split * p.num_k_blocks;
+        int img = 0, y0 = 0, x0 = 0;
+        if (CONV) {
+          const int tx = m_blk % p.tiles_x;
+          const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+          img = m_blk / (p.tiles_x * p.tiles_y);  // >= n_img for the padding tile of an odd count: TMA zero-fills
+          y0 = ty * p.cBH;
+          x0 = tx * p.cBW;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; kb++) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          const int kg = kb0 + kb;
+          if (CONV) {
+            const int tap_all = kg / p.cin_blocks, cc = kg % p.cin_blocks;
+            const int lvl = tap_all / p.taps, tap = tap_all % p.taps;
+            const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+            const int im = img < p.lvl_img_stride ? img + lvl * p.lvl_img_stride : p.lvl_img_stride * p.levels;
+            ptx::tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], cc * kBlockK, x0 + dx,
+                                 y0 + dy, im);
+          } else {
+            ptx::tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], kg * kBlockK,
+                                 m_blk * kBlockM);
+          }
+          ptx::tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full[stage], kg * kBlockK,
+                               n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2));
+          if (leader) {
+            ptx::mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)(p.a_rows * kBlockK * 2 + Cfg::kBBytes));
+          } else {
+            ptx::mbar_arrive_cluster(&full[stage], 0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ============================ MMA issuer (leader CTA only) ============================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters, it++) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tcgen05_after_thread_sync();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < p.num_k_blocks; kb++) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tcgen05_after_thread_sync();
+        if (lane == 0) {
+          const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; k++)
+            ptx::umma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit_2sm(&empty[stage], 3);
+          if (kb == p.num_k_blocks - 1) ptx::umma_commit_2sm(&tmem_full[acc], 3);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ============================ epilogue (both CTAs) ============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters, it++) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int split = t / tiles_mn;
+      const int mn = t % tiles_mn;
+      const int n_blk = mn / num_m_pairs, m_blk = (mn % num_m_pairs) * 2 + (int)rank;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tcgen05_after_thread_sync();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      epilogue_tile<BLOCK_N, CONV>(p, taddr, m_blk, n_blk, split, row, lane,
+                                   [&]() { ptx::mbar_arrive_cluster(&tmem_empty[acc], 0); });
+    }
+  }
+  ptx::tcgen05_before_thread_sync();
+  ptx::cluster_sync();  // nobody leaves while the peer may still signal its barriers / read its TMEM
+  if (warp == 2) {
+    ptx::tcgen05_after_thread_sync();
+    ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -412,6 +592,35 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return G4R_OK;
 }
 
+template <bool CONV>
+static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using Cfg = Gemm2Cfg;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tcgen05_2sm<CONV>;
+  if (!attr_set) {
+    G4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles * p.k_splits;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = pairs < max_clusters ? pairs : max_clusters;
+  kern<<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);  // __cluster_dims__(2,1,1)
+  G4R_LAUNCH_CHECK("gemm_bf16_tcgen05_2sm");
+  return G4R_OK;
+}
+
+// 2-CTA tiles when there is enough work to keep all SM pairs busy (G4R_GEMM_2SM=0 disables).
+static bool use_2sm(int N, int m_tiles, int k_splits) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("G4R_GEMM_2SM");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!env || N <= 128 || m_tiles < 2) return false;
+  const long pairs = (long)((m_tiles + 1) / 2) * ((N + 255) / 256) * k_splits;
+  return pairs >= num_sms() / 2;
+}
+
 static int pick_block_n(int N, int m_tiles, int k_splits) {
   // 256-wide tiles feed the tensor core best; fall back to 128 when that leaves SMs idle.
   if (N <= 128) return 128;
@@ -435,7 +644,7 @@ extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long l
   G4R_REQUIRE(act >= ACT_NONE && act <= ACT_SWIGLU, "act=%d", act);
   G4R_REQUIRE(k_splits >= 1, "k_splits=%d", k_splits);
   if (act == ACT_SWIGLU) G4R_REQUIRE(N % 2 == 0 && !out_f32 && k_splits == 1 && !residual, "SwiGLU epilogue: even N, bf16 out, no split-K/residual");
-  if (k_splits > 1) G4R_REQUIRE(out_f32 && act == ACT_NONE && !residual, "split-K accumulates fp32 atomically: out_f32, no act/residual");
+  if (k_splits > 1) G4R_REQUIRE(out_f32 && act == ACT_NONE && !residual && !bias, "split-K writes fp32 partial slabs [k_splits][M][ldd]: out_f32, no bias/act/residual");
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
@@ -447,7 +656,8 @@ extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long l
   p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr;
   p.act = act; p.out_f32 = out_f32; p.atomic = k_splits > 1;
   p.conv = 0; p.a_rows = kBlockM;
-  const int bn = pick_block_n(N, p.num_m_tiles, k_splits);
+  const bool two = use_2sm(N, p.num_m_tiles, k_splits);
+  const int bn = two ? 256 : pick_block_n(N, p.num_m_tiles, k_splits);
   p.num_n_tiles = (N + bn - 1) / bn;
   CUtensorMap ta, tb;
   {
@@ -460,12 +670,29 @@ extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long l
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t str[1] = {(cuuint64_t)ldb * 2};
-    cuuint32_t box[2] = {kBlockK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)(two ? bn / 2 : bn)};
     int rc = make_tmap(&tb, B, 2, dims, str, box);
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (two) return launch_gemm_2sm<false>(ta, tb, p, st);
   return bn == 256 ? launch_gemm<256, false>(ta, tb, p, st) : launch_gemm<128, false>(ta, tb, p, st);
+}
+
+// spatial tiling used by the conv kernel for an H x W map (also tells callers how many GN partial slots exist)
+static void conv_tiling(int H, int W, int* bw_out, int* bh_out) {
+  int bw = W >= 16 && W % 16 == 0 ? 16 : (W >= 8 ? 8 : W);
+  if (W == 14) bw = 14;
+  int bh = kBlockM / bw;
+  if (bh > H) bh = H;
+  *bw_out = bw;
+  *bh_out = bh;
+}
+
+extern "C" int g4r_conv_gn_slots(int H, int W) {
+  int bw, bh;
+  conv_tiling(H, W, &bw, &bh);
+  return ((W + bw - 1) / bw) * ((H + bh - 1) / bh) * 4;
 }
 
 extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_img, int H, int W, int Cin,
@@ -481,10 +708,8 @@ extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_
   if (gn_stats) G4R_REQUIRE(gn_groups > 0 && Cout % gn_groups == 0 && Cout / gn_groups == 16, "GN stats need 16-channel groups");
   GemmParams p{};
   // spatial tile: BW x BH = 128 output pixels (or fewer for small maps)
-  int bw = W >= 16 && W % 16 == 0 ? 16 : (W >= 8 ? 8 : W);
-  if (W == 14) bw = 14;
-  int bh = kBlockM / bw;
-  if (bh > H) bh = H;
+  int bw, bh;
+  conv_tiling(H, W, &bw, &bh);
   p.cBW = bw; p.cBH = bh; p.cH = H; p.cW = W;
   p.tiles_x = (W + bw - 1) / bw;
   p.tiles_y = (H + bh - 1) / bh;
@@ -499,7 +724,8 @@ extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_
   p.D = Y; p.ldd = Cout; p.bias = bias; p.bias_f32 = bias_f32; p.act = act;
   p.conv = 1;
   p.gn_stats = gn_stats; p.gn_groups = gn_groups; p.gn_group_ch = gn_groups ? Cout / gn_groups : 0;
-  const int bn = pick_block_n(Cout, p.num_m_tiles, 1);
+  const bool two = use_2sm(Cout, p.num_m_tiles, 1);
+  const int bn = two ? 256 : pick_block_n(Cout, p.num_m_tiles, 1);
   p.num_n_tiles = (Cout + bn - 1) / bn;
   CUtensorMap ta, tb;
   {
@@ -512,10 +738,11 @@ extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_
   {
     cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)Cout};
     cuuint64_t str[1] = {(cuuint64_t)p.K * 2};
-    cuuint32_t box[2] = {kBlockK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)(two ? bn / 2 : bn)};
     int rc = make_tmap(&tb, Wt, 2, dims, str, box);
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (two) return launch_gemm_2sm<true>(ta, tb, p, st);
   return bn == 256 ? launch_gemm<256, true>(ta, tb, p, st) : launch_gemm<128, true>(ta, tb, p, st);
 }

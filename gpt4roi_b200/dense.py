@@ -35,7 +35,8 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     """y = act(x @ weight.T + bias) (+ residual).  x [..., K] bf16, weight [N, K] bf16.
 
     act='swiglu': weight rows interleaved (gate_j, up_j); returns [..., N/2].
-    k_splits>1: fp32 atomic split-K (out_dtype must be float32; `out` is zeroed here).
+    k_splits>1: deterministic split-K -- returns fp32 partial slabs [k_splits, M, N] (no bias);
+    the caller sums them in a fixed order (kernels.add_bias_pos_cast does).
     """
     K = x.shape[-1]
     x2 = x.reshape(-1, K)
@@ -50,16 +51,22 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
         raise RuntimeError('linear: weight is %s but x has K=%d' % (tuple(weight.shape), K))
     n_out = N // 2 if act == 'swiglu' else N
     out_f32 = out_dtype == torch.float32
+    if k_splits > 1:
+        if out is not None or bias is not None:
+            raise RuntimeError('linear: split-K returns its own [k_splits,M,N] slabs and takes no bias')
+        slabs = torch.empty((k_splits, M, n_out), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _ps = _prof_begin(dev)
+            _L.check(_L.load().g4r_gemm_bf16(
+                _L.ptr(x2), x2.stride(0), _L.ptr(weight), weight.stride(0), _L.ptr(slabs), n_out,
+                M, N, K, None, 0, None, 0, 0, 1, int(k_splits), _L.stream_ptr(dev)))
+            _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
+        return slabs
     if out is None:
-        if k_splits > 1:
-            out = torch.zeros((M, n_out), dtype=out_dtype, device=dev)
-        else:
-            out = torch.empty((M, n_out), dtype=out_dtype, device=dev)
+        out = torch.empty((M, n_out), dtype=out_dtype, device=dev)
     else:
         if out.dtype != out_dtype or out.shape[-1] != n_out or out.stride(-1) != 1:
             raise RuntimeError('linear: bad `out`')
-        if k_splits > 1:
-            out.zero_()
     out2 = out.reshape(-1, n_out) if out.is_contiguous() else out
     res2 = None
     if residual is not None:
@@ -82,11 +89,16 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out
 
 
+def gn_slots(h, w):
+    """Number of per-(tile,warp) GroupNorm partial-sum slots the conv kernel writes for an h x w map."""
+    return int(_L.load().g4r_conv_gn_slots(int(h), int(w)))
+
+
 def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None, levels=1):
     """NHWC conv, stride 1, 'same' padding.  x [N,H,W,Cin] bf16; weight_khwc [Cout,kh,kw,Cin] bf16.
 
-    gn_stats: optional fp32 [N, groups, 2] (zeroed by the caller) accumulating sum / sumsq of the
-    bf16 output per (image, 16-channel group).
+    gn_stats: optional fp32 [N, gn_slots(H,W), groups, 2] receiving per-(tile,warp) partial sum / sumsq
+    of the bf16 output per (image, 16-channel group); see kernels.gn_finalize.
     """
     dev = _L.require_cuda_same_device([('x', x), ('weight', weight_khwc), ('bias', bias), ('gn_stats', gn_stats)])
     _L.require_contiguous([('x', x), ('weight', weight_khwc)])
@@ -108,9 +120,11 @@ def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None, leve
     bias_f32 = int(bias is not None and bias.dtype == torch.float32)
     groups = 0
     if gn_stats is not None:
-        if gn_stats.dtype != torch.float32 or gn_stats.dim() != 3 or gn_stats.shape[0] != n or gn_stats.shape[2] != 2:
-            raise RuntimeError('gn_stats must be fp32 [N,groups,2]')
-        groups = gn_stats.shape[1]
+        slots = gn_slots(h, w)
+        if gn_stats.dtype != torch.float32 or gn_stats.dim() != 4 or gn_stats.shape[0] != n or \
+                gn_stats.shape[1] != slots or gn_stats.shape[3] != 2 or not gn_stats.is_contiguous():
+            raise RuntimeError('gn_stats must be contiguous fp32 [N,%d,groups,2]' % slots)
+        groups = gn_stats.shape[2]
     with torch.cuda.device(dev):
         _ps = _prof_begin(dev)
         _L.check(_L.load().g4r_conv_nhwc_bf16(

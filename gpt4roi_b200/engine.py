@@ -194,7 +194,8 @@ class PrefillEngine:
             for l in range(n):
                 top, down = min(l + 1, n - 1), max(l - 1, 0)
                 x_in = kernels.fuse_gather(maps[l], maps[top], maps[down], ss[l], ss[top], ss[down])
-                st = torch.zeros((B, c.gn_groups, 2), dtype=torch.float32, device=self.dev)
+                st = torch.zeros((B, dense.gn_slots(c.level_sizes[l], c.level_sizes[l]), c.gn_groups, 2),
+                                 dtype=torch.float32, device=self.dev)
                 new.append(dense.conv_nhwc(x_in, self.fuse[r]['w'], gn_stats=st))
                 stats.append(st)
             maps = new
@@ -213,7 +214,8 @@ class PrefillEngine:
         R = c.roi_out
         pc = dense.conv_nhwc(feats.view(c.num_levels * K, R, R, c.spi_dim), self.pconv_w, self.pconv_b,
                              act='relu', levels=c.num_levels)
-        acc = dense.linear(pc.view(K, -1), self.flat_w, out_dtype=torch.float32, k_splits=self.flat_splits)
+        acc = dense.linear(pc.view(K, -1), self.flat_w, out_dtype=torch.float32, k_splits=self.flat_splits) \
+            if self.flat_splits > 1 else dense.linear(pc.view(K, -1), self.flat_w, out_dtype=torch.float32)
         pos = kernels.pos_embed_mlp(boxes.contiguous(), *self.pos)
         t = kernels.add_bias_pos_cast(acc, self.flat_b, pos)
         return dense.linear(t, self.up_w, self.up_b)

@@ -104,12 +104,13 @@ def fuse_gather(own, top, down, own_ss=None, top_ss=None, down_ss=None, out=None
 
 
 def gn_finalize(stats, gamma, beta, count, eps=1e-5):
-    B, groups, _ = stats.shape
+    """stats: fp32 [B, slots, groups, 2] partial sums from dense.conv_nhwc(gn_stats=...)."""
+    B, slots, groups, _ = stats.shape
     C = gamma.shape[0]
     scale = torch.empty((B, C), dtype=torch.float32, device=stats.device)
     shift = torch.empty_like(scale)
     _call('g4r_gn_finalize', stats.device, _L.ptr(stats), _L.ptr(gamma), _L.ptr(beta), _L.ptr(scale),
-          _L.ptr(shift), B, C, groups, float(count), float(eps))
+          _L.ptr(shift), B, C, groups, slots, float(count), float(eps))
     return scale, shift
 
 
@@ -123,8 +124,11 @@ def pos_embed_mlp(boxes, w0, b0, g2, be2, w3, b3, g5, be5, eps=1e-5):
 
 
 def add_bias_pos_cast(acc, bias, pos):
-    K, D = acc.shape
+    """acc: fp32 [splits, K, D] (split-K slabs) or [K, D]."""
+    if acc.dim() == 2:
+        acc = acc[None]
+    splits, K, D = acc.shape
     out = torch.empty((K, D), dtype=torch.bfloat16, device=acc.device)
     if K:
-        _call('g4r_add_bias_pos_cast', acc.device, _L.ptr(acc), _L.ptr(bias), _L.ptr(pos), _L.ptr(out), K, D)
+        _call('g4r_add_bias_pos_cast', acc.device, _L.ptr(acc), splits, _L.ptr(bias), _L.ptr(pos), _L.ptr(out), K, D)
     return out

@@ -46,9 +46,10 @@ SIGNATURES = {
     'g4r_vit_embed_bf16': (_i, [_vp] * 4 + [_i] * 3 + [_vp]),
     'g4r_upsample_tokens_coords_bf16': (_i, [_vp, _ll, _ll, _vp, _i, _i, _i, _i, _i, _vp]),
     'g4r_fuse_gather_bf16': (_i, [_vp, _vp, _vp, _i] * 3 + [_vp, _i, _i, _vp]),
-    'g4r_gn_finalize': (_i, [_vp] * 5 + [_i] * 3 + [_f, _f, _vp]),
+    'g4r_gn_finalize': (_i, [_vp] * 5 + [_i] * 4 + [_f, _f, _vp]),
+    'g4r_conv_gn_slots': (_i, [_i, _i]),
     'g4r_pos_embed_mlp': (_i, [_vp] * 10 + [_i, _f, _vp]),
-    'g4r_add_bias_pos_cast': (_i, [_vp] * 4 + [_i, _i, _vp]),
+    'g4r_add_bias_pos_cast': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
 }
 
 _lib = None

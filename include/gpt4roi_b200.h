@@ -156,7 +156,8 @@ enum { G4R_ACT_NONE = 0, G4R_ACT_RELU = 1, G4R_ACT_QUICK_GELU = 2, G4R_ACT_SWIGL
  *   transformers CLIP / LLaMA q,k,v,o,fc1,fc2,gate,up,down projections (third party)
  * epilogue: (+bias[N]) -> act -> (+residual[M,N] bf16) -> store bf16 (or fp32 if out_f32).
  *   G4R_ACT_SWIGLU: B rows interleaved (2j = gate_j, 2j+1 = up_j); D is [M,N/2] = silu(g)*u.
- *   k_splits > 1: fp32 atomic accumulation into a pre-zeroed D (out_f32 required).
+ *   k_splits > 1: D is an fp32 buffer [k_splits][M][ldd]; split s writes slab s (no atomics, no
+ *   bias/act/residual); the consumer sums the slabs in a fixed order (bitwise reproducible).
  * lda/ldb/ldd/ldr are row strides in elements; lda, ldb multiples of 8.
  */
 int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb,
@@ -176,10 +177,12 @@ int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb,
  * levels > 1 sums `levels` convolutions in one contraction (K concatenated): X is
  * [levels*n_img,H,W,Cin] (level-major), Wt [Cout, levels*ks*ks*Cin]; this is
  * sum_l pconvs[l](roi_feats[l]) of layers.py:320-325 as ONE GEMM.
- * gn_stats (optional, fp32 [n_img,gn_groups,2], pre-zeroed): accumulates per-(image,group)
- * sum and sum of squares of the bf16-rounded output -- the statistics GroupNorm(64) needs
- * (mmcv cnn/bricks/conv_module.py:196-208), so no extra pass over Y is required.
+ * gn_stats (optional, fp32 [n_img, g4r_conv_gn_slots(H,W), gn_groups, 2]): per-(tile,warp) partial
+ * sum / sum of squares of the bf16-rounded output per (image, 16-channel group) -- the statistics
+ * GroupNorm(64) needs (mmcv cnn/bricks/conv_module.py:196-208) -- written with plain stores
+ * (reproducible) and summed in a fixed order by g4r_gn_finalize; no extra pass over Y.
  */
+int g4r_conv_gn_slots(int H, int W);
 int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y,
                        int n_img, int H, int W, int Cin, int Cout, int ksize, int levels,
                        const void* bias, int bias_f32, int act,
@@ -187,7 +190,7 @@ int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y,
 
 /* ---- fused attention ------------------------------------------------------- */
 /*
- * out[b,i,h,:] = softmax_j( bf16(bf16(q_i.k_j) * scale) [+ causal mask] ) . v_j
+ * out[b,i,h,:] = softmax_j( (q_i.k_j) * scale [+ causal mask] ) . v_j   (scores kept in fp32)
  * q/k/v: bf16, element (b, token, head h, d) at  base + b*bs + token*ld + h*head_dim + d
  * (so the packed [B,L,(q|k|v)] output of the QKV GEMM is read in place); out likewise with
  * ldo/bso.  head_dim 64 (CLIP-ViT-L/14) or 128 (LLaMA-7B).  Replaces transformers'
@@ -230,14 +233,15 @@ int g4r_fuse_gather_bf16(const void* own, const float* own_sc, const float* own_
                          void* out, int B, int C, void* stream);
 /* GroupNorm statistics -> per-(image,channel) scale/shift (torch.nn.GroupNorm semantics). */
 int g4r_gn_finalize(const float* stats, const void* gamma, const void* beta,
-                    float* scale, float* shift, int B, int C, int groups,
+                    float* scale, float* shift, int B, int C, int groups, int slots,
                     float count, float eps, void* stream);
 /* pos_embedd MLP of MlvlRoIExtractor (layers.py:260-267,285): boxes fp32 [K,4] -> fp32 [K,1024]. */
 int g4r_pos_embed_mlp(const float* boxes, const void* w0, const void* b0, const void* g2,
                       const void* be2, const void* w3, const void* b3, const void* g5,
                       const void* be5, float* out, int K, float eps, void* stream);
-/* out = bf16( bf16(acc + bias) + pos )  (layers.py:327-328). acc fp32 [K,D], pos fp32 [K,D]. */
-int g4r_add_bias_pos_cast(const float* acc, const void* bias, const float* pos, void* out,
+/* out = bf16( bf16(sum_s acc[s] + bias) + pos )  (layers.py:327-328). acc fp32 [splits,K,D]
+ * (split-K slabs of flatten_linear), pos fp32 [K,D]. */
+int g4r_add_bias_pos_cast(const float* acc, int splits, const void* bias, const float* pos, void* out,
                           int K, int D, void* stream);
 
 #ifdef __cplusplus

@@ -125,7 +125,8 @@ def test_gn_finalize_and_pos_mlp():
     B, H, C, G = 2, 12, 1024, 64
     y = (torch.randn(B, H, H, C, device=DEV) * 1.5 + 0.3).to(BF)
     g = y.float().view(B, H * H, G, C // G)
-    stats = torch.stack([g.sum((1, 3)), (g * g).sum((1, 3))], -1).contiguous()
+    full = torch.stack([g.sum((1, 3)), (g * g).sum((1, 3))], -1)
+    stats = torch.stack([full * 0.25, full * 0.5, full * 0.25], 1).contiguous()  # 3 partial slots
     gamma, beta = (torch.rand(C, device=DEV) + 0.5).to(BF), torch.randn(C, device=DEV).to(BF)
     sc, sh = kernels.gn_finalize(stats, gamma, beta, H * H * (C // G))
     want = F.group_norm(y.float().permute(0, 3, 1, 2), G, gamma.float(), beta.float(), 1e-5).permute(0, 2, 3, 1)
