@@ -67,7 +67,7 @@ template <int D, bool CAUSAL>
 __global__ void __launch_bounds__(kAttnThreads)
 flash_attn_fwd(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K,
                const __nv_bfloat16* __restrict__ V, __nv_bfloat16* __restrict__ O, long long ld, long long bs,
-               long long ldo, long long bso, int L, float scale) {
+               long long ldo, long long bso, int L, float scale, const int* __restrict__ seqlens) {
   extern __shared__ __align__(128) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sK = sQ + kBM * D;       // 2 buffers
@@ -81,7 +81,10 @@ flash_attn_fwd(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  const int n_kv = CAUSAL ? min((L + kBN - 1) / kBN, (q0 + kBM + kBN - 1) / kBN) : (L + kBN - 1) / kBN;
+  // right-padded batches: keys >= seqlens[b] are masked (attention_mask of data_modules.py:33-44);
+  // rows >= seqlens[b] produce don't-care values (their labels are -100 in the reference).
+  const int Lk = seqlens ? min(max(seqlens[b], 1), L) : L;
+  const int n_kv = CAUSAL ? min((Lk + kBN - 1) / kBN, (q0 + kBM + kBN - 1) / kBN) : (Lk + kBN - 1) / kBN;
 
   load_tile<D>(sQ, gq, ld, q0, L);
   load_tile<D>(sK, gk, ld, 0, L);
@@ -136,14 +139,14 @@ flash_attn_fwd(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restr
     // Only the diagonal block (causal) and the tail block (keys >= L) need masking.
     const int key0 = kb * kBN;
     const int qrow0 = q0 + warp * 16;
-    if (key0 + kBN > L || (CAUSAL && key0 + kBN - 1 > qrow0)) {
+    if (key0 + kBN > Lk || (CAUSAL && key0 + kBN - 1 > qrow0)) {
 #pragma unroll
       for (int nt = 0; nt < kBN / 8; nt++) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int key = key0 + nt * 8 + 2 * t + (e & 1);
           const int qrow = qrow0 + g + ((e >> 1) << 3);
-          if (key >= L || (CAUSAL && key > qrow)) s[nt][e] = -INFINITY;
+          if (key >= Lk || (CAUSAL && key > qrow)) s[nt][e] = -INFINITY;
         }
       }
     }
@@ -219,7 +222,8 @@ flash_attn_fwd(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restr
 
 template <int D, bool CAUSAL>
 static int launch_attn(const void* q, const void* k, const void* v, void* o, long long ld, long long bs,
-                       long long ldo, long long bso, int B, int H, int L, float scale, cudaStream_t st) {
+                       long long ldo, long long bso, int B, int H, int L, float scale, const int* seqlens,
+                       cudaStream_t st) {
   const int smem = (kBM * D + 4 * kBN * D) * 2;
   static bool set = false;
   auto kern = flash_attn_fwd<D, CAUSAL>;
@@ -229,7 +233,7 @@ static int launch_attn(const void* q, const void* k, const void* v, void* o, lon
   }
   dim3 grid((L + kBM - 1) / kBM, H, B);
   kern<<<grid, kAttnThreads, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
-                                          (const __nv_bfloat16*)v, (__nv_bfloat16*)o, ld, bs, ldo, bso, L, scale);
+                                          (const __nv_bfloat16*)v, (__nv_bfloat16*)o, ld, bs, ldo, bso, L, scale, seqlens);
   G4R_LAUNCH_CHECK("flash_attn_fwd");
   return G4R_OK;
 }
@@ -240,16 +244,16 @@ using namespace g4r;
 
 extern "C" int g4r_attention_bf16(const void* q, const void* k, const void* v, void* out, long long ld,
                                   long long bs, long long ldo, long long bso, int B, int H, int L,
-                                  int head_dim, int causal, float scale, void* stream) {
+                                  int head_dim, int causal, float scale, const int* seqlens, void* stream) {
   G4R_REQUIRE(q && k && v && out && B > 0 && H > 0 && L > 0, "attention: bad arguments");
   G4R_REQUIRE(head_dim == 64 || head_dim == 128, "attention: head_dim %d (64 or 128)", head_dim);
   G4R_REQUIRE(ld % 8 == 0 && bs % 8 == 0 && ldo % 2 == 0 && bso % 2 == 0, "attention: strides must keep 16-byte row alignment");
   G4R_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 && ((uintptr_t)out & 3) == 0, "attention: misaligned pointers");
   cudaStream_t st = (cudaStream_t)stream;
   if (head_dim == 64) {
-    return causal ? launch_attn<64, true>(q, k, v, out, ld, bs, ldo, bso, B, H, L, scale, st)
-                  : launch_attn<64, false>(q, k, v, out, ld, bs, ldo, bso, B, H, L, scale, st);
+    return causal ? launch_attn<64, true>(q, k, v, out, ld, bs, ldo, bso, B, H, L, scale, seqlens, st)
+                  : launch_attn<64, false>(q, k, v, out, ld, bs, ldo, bso, B, H, L, scale, seqlens, st);
   }
-  return causal ? launch_attn<128, true>(q, k, v, out, ld, bs, ldo, bso, B, H, L, scale, st)
-                : launch_attn<128, false>(q, k, v, out, ld, bs, ldo, bso, B, H, L, scale, st);
+  return causal ? launch_attn<128, true>(q, k, v, out, ld, bs, ldo, bso, B, H, L, scale, seqlens, st)
+                : launch_attn<128, false>(q, k, v, out, ld, bs, ldo, bso, B, H, L, scale, seqlens, st);
 }

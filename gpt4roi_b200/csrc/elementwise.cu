@@ -31,6 +31,23 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return raw;
 }
+// 8 consecutive elements of a bf16 or fp32 row
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack8(*reinterpret_cast<const uint4*>(p), f);
+}
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&f)[8]);
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = pack8(f);
+}
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ------------------------------------------------------------------------------------------
@@ -41,23 +58,23 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 //              w * (x * rsqrt(mean(x^2) + eps)).to(bf16)
 // ------------------------------------------------------------------------------------------
 // PER_LANE = ceil(D/8/32) vectors per lane, compile-time so the row stays in registers.
-template <bool RMS, int PER_LANE>
+template <bool RMS, int PER_LANE, typename TI = __nv_bfloat16, typename TO = __nv_bfloat16>
 __global__ void __launch_bounds__(256)
-norm_rows_bf16(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
-               const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, long long ldo, int M,
+norm_rows_bf16(const TI* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+               const __nv_bfloat16* __restrict__ b, TO* __restrict__ out, long long ldo, int M,
                int D, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  const TI* xr = x + (long long)row * ldx;
   float v[PER_LANE][8];
   float sum = 0.f, sumsq = 0.f;
 #pragma unroll
   for (int i = 0; i < PER_LANE; i++) {
     const int vi = lane + (i << 5);
     if (vi < nvec) {
-      unpack8(xr[vi], v[i]);
+      load8<TI>(xr + vi * 8, v[i]);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; j++) v[i][j] = 0.f;
@@ -83,7 +100,7 @@ norm_rows_bf16(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bf
     var = warp_sum(var);
     rstd = rsqrtf(var / D + eps);
   }
-  uint4* orow = reinterpret_cast<uint4*>(out + (long long)row * ldo);
+  TO* orow = out + (long long)row * ldo;
   const uint4* wv = reinterpret_cast<const uint4*>(w);
   const uint4* bv = reinterpret_cast<const uint4*>(b);
 #pragma unroll
@@ -101,7 +118,7 @@ norm_rows_bf16(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bf
 #pragma unroll
       for (int j = 0; j < 8; j++) o[j] = (v[i][j] - mean) * rstd * wf[j] + bf[j];
     }
-    orow[vi] = pack8(o);
+    store8<TO>(orow + vi * 8, o);
   }
 }
 
@@ -122,6 +139,42 @@ static int launch_norm(const void* x, long long ldx, const void* w, const void* 
 #undef G4R_NORM_CASE
   G4R_LAUNCH_CHECK(RMS ? "rmsnorm" : "layernorm");
   return G4R_OK;
+}
+
+template <typename TI, typename TO>
+static int launch_ln_ex(const void* x, long long ldx, const void* w, const void* b, void* out, long long ldo,
+                        int M, int D, float eps, cudaStream_t st) {
+  const int per_lane = (D / 8 + 31) / 32;
+  const dim3 grid((M + 7) / 8);
+#define G4R_LN_CASE(PL)                                                                                   \
+  norm_rows_bf16<false, PL, TI, TO><<<grid, 256, 0, st>>>((const TI*)x, ldx, (const __nv_bfloat16*)w,      \
+                                                          (const __nv_bfloat16*)b, (TO*)out, ldo, M, D, eps)
+  if (per_lane <= 1) G4R_LN_CASE(1);
+  else if (per_lane <= 2) G4R_LN_CASE(2);
+  else if (per_lane <= 4) G4R_LN_CASE(4);
+  else if (per_lane <= 8) G4R_LN_CASE(8);
+  else if (per_lane <= 16) G4R_LN_CASE(16);
+  else G4R_LN_CASE(32);
+#undef G4R_LN_CASE
+  G4R_LAUNCH_CHECK("layernorm_ex");
+  return G4R_OK;
+}
+
+// rows [B][rows_per_batch][D] (row stride ld, batch stride bst) fp32 -> dense bf16 [B*rows_per_batch, D]
+__global__ void __launch_bounds__(256)
+cast_rows_f32_bf16(const float* __restrict__ x, long long ld, long long bst, __nv_bfloat16* __restrict__ out,
+                   int B, int rows_per_batch, int D) {
+  const int nvec = D >> 3;
+  const long long total = (long long)B * rows_per_batch * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int r = (int)((i / nvec) % rows_per_batch);
+    const int b = (int)(i / ((long long)nvec * rows_per_batch));
+    float f[8];
+    load8<float>(x + (long long)b * bst + (long long)r * ld + v * 8, f);
+    store8<__nv_bfloat16>(out + ((long long)b * rows_per_batch + r) * D + v * 8, f);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -236,8 +289,9 @@ __device__ __forceinline__ Lerp lerp_ac(int dst, int in, int out) {
 //   NHWC map [B,G,G,C]; resize to [B,Ho,Ho,C] (bf16 out, fp32 math), append x = linspace(-1,1,Wo)[xo],
 //   y = linspace(-1,1,Ho)[yo] as channels C, C+1 (bf16-rounded, as autocast does at the conv input)
 //   and zero-pad to Cpad channels (K of the following 1x1-conv GEMM must be a multiple of 8).
+template <typename TT>
 __global__ void __launch_bounds__(256)
-upsample_tokens_coords_bf16(const __nv_bfloat16* __restrict__ tok, long long ldt, long long bst,
+upsample_tokens_coords_bf16(const TT* __restrict__ tok, long long ldt, long long bst,
                             __nv_bfloat16* __restrict__ out, int B, int G, int Ho, int C, int Cpad) {
   const int nvec = Cpad >> 3;
   const long long total = (long long)B * Ho * Ho * nvec;
@@ -250,12 +304,12 @@ upsample_tokens_coords_bf16(const __nv_bfloat16* __restrict__ tok, long long ldt
     float o[8];
     if (v * 8 < C) {
       const Lerp ly = lerp_ac(yo, G, Ho), lx = lerp_ac(xo, G, Ho);
-      const __nv_bfloat16* base = tok + (long long)b * bst + v * 8;
+      const TT* base = tok + (long long)b * bst + v * 8;
       float a[8], bb[8], c[8], d[8];
-      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ly.i0 * G + lx.i0) * ldt), a);
-      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ly.i0 * G + lx.i1) * ldt), bb);
-      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ly.i1 * G + lx.i0) * ldt), c);
-      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ly.i1 * G + lx.i1) * ldt), d);
+      load8<TT>(base + ((long long)ly.i0 * G + lx.i0) * ldt, a);
+      load8<TT>(base + ((long long)ly.i0 * G + lx.i1) * ldt, bb);
+      load8<TT>(base + ((long long)ly.i1 * G + lx.i0) * ldt, c);
+      load8<TT>(base + ((long long)ly.i1 * G + lx.i1) * ldt, d);
 #pragma unroll
       for (int j = 0; j < 8; j++)
         o[j] = ly.l0 * (lx.l0 * a[j] + lx.l1 * bb[j]) + ly.l1 * (lx.l0 * c[j] + lx.l1 * d[j]);
@@ -507,9 +561,41 @@ extern "C" int g4r_upsample_tokens_coords_bf16(const void* tok, long long ldt, l
   G4R_REQUIRE(tok && out && B > 0 && G > 0 && Ho > 0 && C % 8 == 0 && Cpad % 8 == 0 && Cpad >= C + 8 && ldt % 8 == 0 && bst % 8 == 0,
               "upsample_tokens_coords: bad arguments");
   const long long total = (long long)B * Ho * Ho * (Cpad / 8);
-  upsample_tokens_coords_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  upsample_tokens_coords_bf16<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)tok, ldt, bst, (__nv_bfloat16*)out, B, G, Ho, C, Cpad);
   G4R_LAUNCH_CHECK("upsample_tokens_coords");
+  return G4R_OK;
+}
+
+extern "C" int g4r_upsample_tokens_coords_f32(const void* tok, long long ldt, long long bst, void* out, int B,
+                                              int G, int Ho, int C, int Cpad, void* stream) {
+  G4R_REQUIRE(tok && out && B > 0 && G > 0 && Ho > 0 && C % 8 == 0 && Cpad % 8 == 0 && Cpad >= C + 8 && ldt % 4 == 0 && bst % 4 == 0,
+              "upsample_tokens_coords_f32: bad arguments");
+  const long long total = (long long)B * Ho * Ho * (Cpad / 8);
+  upsample_tokens_coords_bf16<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)tok, ldt, bst, (__nv_bfloat16*)out, B, G, Ho, C, Cpad);
+  G4R_LAUNCH_CHECK("upsample_tokens_coords_f32");
+  return G4R_OK;
+}
+
+extern "C" int g4r_layernorm_ex(const void* x, long long ldx, int x_f32, const void* w, const void* b, void* out,
+                                long long ldo, int out_f32, int M, int D, float eps, void* stream) {
+  G4R_REQUIRE(x && w && b && out && M > 0 && D > 0 && D % 8 == 0 && D <= 8192 && ldx % 8 == 0 && ldo % 8 == 0,
+              "layernorm_ex: bad arguments (D=%d)", D);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_f32) return out_f32 ? launch_ln_ex<float, float>(x, ldx, w, b, out, ldo, M, D, eps, st)
+                            : launch_ln_ex<float, __nv_bfloat16>(x, ldx, w, b, out, ldo, M, D, eps, st);
+  return out_f32 ? launch_ln_ex<__nv_bfloat16, float>(x, ldx, w, b, out, ldo, M, D, eps, st)
+                 : launch_ln_ex<__nv_bfloat16, __nv_bfloat16>(x, ldx, w, b, out, ldo, M, D, eps, st);
+}
+
+extern "C" int g4r_cast_f32_bf16(const void* x, long long ld, long long bst, void* out, int B, int rows_per_batch,
+                                 int D, void* stream) {
+  G4R_REQUIRE(x && out && B > 0 && rows_per_batch > 0 && D % 8 == 0 && ld % 4 == 0 && bst % 4 == 0, "cast_f32_bf16: bad arguments");
+  const long long total = (long long)B * rows_per_batch * (D / 8);
+  cast_rows_f32_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, ld, bst, (__nv_bfloat16*)out, B,
+                                                                            rows_per_batch, D);
+  G4R_LAUNCH_CHECK("cast_f32_bf16");
   return G4R_OK;
 }
 

@@ -46,7 +46,9 @@ struct GemmParams {
   long long ldd;
   const void* bias;      // [N] bf16 or fp32 (bias_f32), or null
   int bias_f32;
-  const __nv_bfloat16* residual;  // same row mapping as D, or null
+  const __nv_bfloat16* residual;  // same row mapping as D, or null (bf16, or fp32 when residual_f32)
+  int residual_f32;
+  int round_branch;  // round (acc + bias, act) to bf16 before the residual add (bf16 linear output + fp32 stream)
   long long ldr;
   int act;
   int out_f32;   // 1: fp32 output
@@ -152,18 +154,37 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
       }
       continue;
     }
+    if (p.round_branch) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+    }
     if (p.residual != nullptr && row_ok) {
-      const __nv_bfloat16* rr = p.residual + out_row * p.ldr + col0;
-      if (full_chunk && (p.ldr % 8 == 0)) {
+      if (p.residual_f32) {
+        // fp32 residual stream (CLIP under autocast keeps it in fp32: LayerNorm outputs fp32 and
+        // `residual + bf16_branch` promotes)
+        const float* rr = reinterpret_cast<const float*>(p.residual) + out_row * p.ldr + col0;
+        if (full_chunk && (p.ldr % 4 == 0)) {
 #pragma unroll
-        for (int h = 0; h < 4; h++) {
-          const uint4 raw = reinterpret_cast<const uint4*>(rr)[h];
-          const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
-#pragma unroll
-          for (int j = 0; j < 8; j++) f[h * 8 + j] += __bfloat162float(e[j]);
+          for (int h = 0; h < 8; h++) {
+            const float4 r4 = reinterpret_cast<const float4*>(rr)[h];
+            f[4 * h] += r4.x; f[4 * h + 1] += r4.y; f[4 * h + 2] += r4.z; f[4 * h + 3] += r4.w;
+          }
+        } else {
+          for (int j = 0; j < 32; j++) if (col0 + j < p.N) f[j] += rr[j];
         }
       } else {
-        for (int j = 0; j < 32; j++) if (col0 + j < p.N) f[j] += __bfloat162float(rr[j]);
+        const __nv_bfloat16* rr = p.residual + out_row * p.ldr + col0;
+        if (full_chunk && (p.ldr % 8 == 0)) {
+#pragma unroll
+          for (int h = 0; h < 4; h++) {
+            const uint4 raw = reinterpret_cast<const uint4*>(rr)[h];
+            const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[h * 8 + j] += __bfloat162float(e[j]);
+          }
+        } else {
+          for (int j = 0; j < 32; j++) if (col0 + j < p.N) f[j] += __bfloat162float(rr[j]);
+        }
       }
     }
     if (p.out_f32) {
@@ -636,7 +657,23 @@ using namespace g4r;
 extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* D,
                              long long ldd, int M, int N, int K, const void* bias, int bias_f32,
                              const void* residual, long long ldr, int act, int out_f32, int k_splits,
+                             void* stream);
+extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, void* D,
+                                long long ldd, int M, int N, int K, const void* bias, int bias_f32,
+                                const void* residual, long long ldr, int residual_f32, int bias_round_bf16,
+                                int act, int out_f32, int k_splits, void* stream);
+extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* D,
+                             long long ldd, int M, int N, int K, const void* bias, int bias_f32,
+                             const void* residual, long long ldr, int act, int out_f32, int k_splits,
                              void* stream) {
+  return g4r_gemm_bf16_ex(A, lda, B, ldb, D, ldd, M, N, K, bias, bias_f32, residual, ldr, 0, 0, act, out_f32,
+                          k_splits, stream);
+}
+
+extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, void* D,
+                                long long ldd, int M, int N, int K, const void* bias, int bias_f32,
+                                const void* residual, long long ldr, int residual_f32, int bias_round_bf16,
+                                int act, int out_f32, int k_splits, void* stream) {
   G4R_REQUIRE(A && B && D, "null operand");
   G4R_REQUIRE(M > 0 && N > 0 && K > 0, "bad sizes M=%d N=%d K=%d", M, N, K);
   G4R_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "lda/ldb must be >= K and multiples of 8 (16-byte TMA strides)");
@@ -653,7 +690,8 @@ extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long l
   p.k_splits = k_splits;
   p.num_k_blocks = kb_total / k_splits;
   p.D = D; p.ldd = ldd; p.bias = bias; p.bias_f32 = bias_f32;
-  p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr;
+  p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.residual_f32 = residual_f32;
+  p.round_branch = bias_round_bf16;
   p.act = act; p.out_f32 = out_f32; p.atomic = k_splits > 1;
   p.conv = 0; p.a_rows = kBlockM;
   const bool two = use_2sm(N, p.num_m_tiles, k_splits);

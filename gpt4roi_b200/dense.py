@@ -31,10 +31,12 @@ def _prof_end(dev, start, kind, flops):
 
 
 def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16,
-           k_splits=1):
+           k_splits=1, round_branch=False):
     """y = act(x @ weight.T + bias) (+ residual).  x [..., K] bf16, weight [N, K] bf16.
 
     act='swiglu': weight rows interleaved (gate_j, up_j); returns [..., N/2].
+    residual may be bf16 or fp32; round_branch=True rounds act(x@W.T+bias) to bf16 before the residual
+    add (a bf16 Linear output added to an fp32 residual stream, as CLIP does under autocast).
     k_splits>1: deterministic split-K -- returns fp32 partial slabs [k_splits, M, N] (no bias);
     the caller sums them in a fixed order (kernels.add_bias_pos_cast does).
     """
@@ -70,8 +72,8 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     out2 = out.reshape(-1, n_out) if out.is_contiguous() else out
     res2 = None
     if residual is not None:
-        if residual.dtype != torch.bfloat16:
-            raise TypeError('linear: residual must be bf16')
+        if residual.dtype not in (torch.bfloat16, torch.float32):
+            raise TypeError('linear: residual must be bf16 or fp32')
         res2 = residual.reshape(-1, n_out) if residual.is_contiguous() else residual
     bias_f32 = 0
     if bias is not None:
@@ -81,9 +83,10 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
             raise TypeError('linear: bias must be bf16 or fp32')
     with torch.cuda.device(dev):
         _ps = _prof_begin(dev)
-        _L.check(_L.load().g4r_gemm_bf16(
+        _L.check(_L.load().g4r_gemm_bf16_ex(
             _L.ptr(x2), x2.stride(0), _L.ptr(weight), weight.stride(0), _L.ptr(out2), out2.stride(0),
             M, N, K, _L.ptr(bias), bias_f32, _L.ptr(res2), res2.stride(0) if res2 is not None else 0,
+            int(res2 is not None and res2.dtype == torch.float32), int(bool(round_branch)),
             ACT[act], int(out_f32), int(k_splits), _L.stream_ptr(dev)))
         _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
     return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out

@@ -160,17 +160,21 @@ class PrefillEngine:
         patches = kernels.patchify(images, c.patch_size, self.vit_kpad)
         pe = dense.linear(patches, self.vit_patch_w)
         x = kernels.vit_embed(pe, self.vit_cls, self.vit_pos, B, P)
-        x = kernels.layernorm(x, *self.vit_pre_ln, eps=c.vit_eps).view(B * T, c.vit_hidden)
+        # Residual stream in fp32, as the reference has it under autocast: nn.LayerNorm returns fp32
+        # (pre_layrnorm turns the bf16 embeddings into an fp32 stream) and `residual + bf16_branch`
+        # stays fp32; the Linears see bf16 inputs (autocast cast) and produce bf16 outputs.
+        F32 = torch.float32
+        x = kernels.layernorm_ex(x, *self.vit_pre_ln, eps=c.vit_eps, out_dtype=F32).view(B * T, c.vit_hidden)
         taps = {}
         scale = c.vit_head_dim ** -0.5
         for i, w in enumerate(self.vit_layers):
-            h = kernels.layernorm(x, *w['ln1'], eps=c.vit_eps)
+            h = kernels.layernorm_ex(x, *w['ln1'], eps=c.vit_eps)
             qkv = dense.linear(h, w['wqkv'], w['bqkv'])
             a = kernels.attention(qkv, B, T, c.vit_heads, c.vit_head_dim, False, scale)
-            x = dense.linear(a, w['wo'], w['bo'], residual=x)
-            h = kernels.layernorm(x, *w['ln2'], eps=c.vit_eps)
+            x = dense.linear(a, w['wo'], w['bo'], residual=x, out_dtype=F32, round_branch=True)
+            h = kernels.layernorm_ex(x, *w['ln2'], eps=c.vit_eps)
             f = dense.linear(h, w['w1'], w['b1'], act='quick_gelu')
-            x = dense.linear(f, w['w2'], w['b2'], residual=x)
+            x = dense.linear(f, w['w2'], w['b2'], residual=x, out_dtype=F32, round_branch=True)
             if (i + 1) in c.level_layers:
                 taps[i + 1] = x.view(B, T, c.vit_hidden)
         return taps
@@ -220,7 +224,7 @@ class PrefillEngine:
         t = kernels.add_bias_pos_cast(acc, self.flat_b, pos)
         return dense.linear(t, self.up_w, self.up_b)
 
-    def llama(self, embeds, B, L, last_only=False):
+    def llama(self, embeds, B, L, last_only=False, seqlens=None):
         c = self.cfg
         x = embeds.view(B * L, c.hidden)
         cos, sin = self._rope(L)
@@ -229,7 +233,7 @@ class PrefillEngine:
             h = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
             qkv = dense.linear(h, w['wqkv'])
             kernels.rope_inplace(qkv, cos, sin, L, 2 * c.n_heads, c.head_dim)
-            a = kernels.attention(qkv, B, L, c.n_heads, c.head_dim, True, scale)
+            a = kernels.attention(qkv, B, L, c.n_heads, c.head_dim, True, scale, seqlens=seqlens)
             x = dense.linear(a, w['wo'], residual=x)
             h = kernels.rmsnorm(x, w['ln_post'], c.rms_eps)
             f = dense.linear(h, w['wgu'], act='swiglu')
@@ -261,13 +265,13 @@ class PrefillEngine:
             bidx = torch.zeros((0,), dtype=torch.float32, device=self.dev)
         return dict(K=K, boxes=boxes, bidx=bidx, offs=offs)
 
-    def forward_device(self, input_ids, images, plan, validate=True, last_only=False):
+    def forward_device(self, input_ids, images, plan, validate=True, last_only=False, seqlens=None):
         """Device-only forward (capturable): input_ids int64 [B,L], images bf16 [B,3,S,S] on the GPU."""
         c = self.cfg
         B, L = input_ids.shape
         taps = self.vit(images)
-        feat = taps[c.select_index][:, 1:].contiguous()  # spi_llava.py:68-73
-        img_rows = dense.linear(feat.view(-1, c.vit_hidden), self.proj_w, self.proj_b).view(B, c.num_patches, c.hidden)
+        feat = kernels.cast_tokens_f32_bf16(taps[c.select_index])  # spi_llava.py:68-73 (+ autocast cast, CLS dropped)
+        img_rows = dense.linear(feat, self.proj_w, self.proj_b).view(B, c.num_patches, c.hidden)
         region = None
         if plan is not None:
             if plan['K'] > 0:
@@ -278,15 +282,23 @@ class PrefillEngine:
             region = (rows, plan['offs'])
         embeds = splice_region_tokens(input_ids, self.embed, img_rows, region, c.num_patches, c.im_patch_token,
                                       c.im_start_token, c.im_end_token, c.bbox_token, validate=validate)
-        return self.llama(embeds, B, L, last_only=last_only)
+        return self.llama(embeds, B, L, last_only=last_only, seqlens=seqlens)
 
-    def forward(self, input_ids, images, bboxes, validate=True, last_only=False):
+    def forward(self, input_ids, images, bboxes, validate=True, last_only=False, attention_mask=None):
         """Public entry: input_ids int64 [B,L]; images [B,3,S,S]; bboxes list (len B) of [K_i,4]
         normalised xyxy or None (host or device tensors).  Returns logits [B,L,V] (bf16) -- [B,1,V]
-        with last_only.  attention_mask is all-ones (no padding) in this round."""
+        with last_only.  attention_mask: None / all-ones, or a RIGHT-padded 0/1 mask [B,L] (the collator's
+        pad_sequence layout, data_modules.py:33-44); logits at padded positions are don't-care."""
         plan = self.plan_boxes(bboxes)
+        seqlens = None
+        if attention_mask is not None:
+            m = attention_mask.to(self.dev).to(torch.int32)
+            lens = m.sum(1)
+            if not bool((m == (torch.arange(m.shape[1], device=self.dev)[None] < lens[:, None])).all()):
+                raise NotImplementedError('only right-padded attention masks are supported')
+            seqlens = lens.to(torch.int32).contiguous()
         return self.forward_device(input_ids.to(self.dev, non_blocking=True),
-                                   images.to(self.dev, BF16, non_blocking=True), plan, validate, last_only)
+                                   images.to(self.dev, BF16, non_blocking=True), plan, validate, last_only, seqlens)
 
 
 class GraphedPrefill:

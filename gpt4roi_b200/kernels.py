@@ -26,6 +26,26 @@ def layernorm(x, weight, bias, eps=1e-5, out=None):
     return out.view(x.shape) if out.is_contiguous() and out.numel() == x.numel() else out
 
 
+def layernorm_ex(x, weight, bias, eps=1e-5, out_dtype=torch.bfloat16):
+    """LayerNorm with bf16/fp32 input rows and bf16/fp32 output rows (CLIP's fp32 residual stream)."""
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    out = torch.empty(x2.shape, dtype=out_dtype, device=x.device)
+    _call('g4r_layernorm_ex', x.device, _L.ptr(x2), x2.stride(0), int(x.dtype == torch.float32), _L.ptr(weight),
+          _L.ptr(bias), _L.ptr(out), out.stride(0), int(out_dtype == torch.float32), x2.shape[0], D, float(eps))
+    return out.view(x.shape)
+
+
+def cast_tokens_f32_bf16(hidden, skip_first=1):
+    """hidden fp32 [B,T,C] -> dense bf16 [B*(T-skip_first), C] (drops the CLS row)."""
+    B, T, C = hidden.shape
+    out = torch.empty((B * (T - skip_first), C), dtype=torch.bfloat16, device=hidden.device)
+    import ctypes
+    src = ctypes.c_void_p(hidden.data_ptr() + skip_first * C * 4)
+    _call('g4r_cast_f32_bf16', hidden.device, src, C, T * C, _L.ptr(out), B, T - skip_first, C)
+    return out
+
+
 def rmsnorm(x, weight, eps=1e-6, out=None):
     _bf16(x, weight)
     D = x.shape[-1]
@@ -44,7 +64,7 @@ def rope_inplace(qkv, cos, sin, L, n_heads_qk, head_dim):
     return qkv
 
 
-def attention(qkv, B, L, n_heads, head_dim, causal, scale, out=None):
+def attention(qkv, B, L, n_heads, head_dim, causal, scale, out=None, seqlens=None):
     """qkv: packed bf16 [B*L, 3*n_heads*head_dim] = (q | k | v); returns [B*L, n_heads*head_dim]."""
     _bf16(qkv)
     hd = n_heads * head_dim
@@ -56,7 +76,7 @@ def attention(qkv, B, L, n_heads, head_dim, causal, scale, out=None):
     import ctypes
     q, k, v = (ctypes.c_void_p(base + i * hd * esz) for i in range(3))
     _call('g4r_attention_bf16', qkv.device, q, k, v, _L.ptr(out), ld, L * ld, out.stride(0), L * out.stride(0),
-          B, n_heads, L, head_dim, int(bool(causal)), float(scale))
+          B, n_heads, L, head_dim, int(bool(causal)), float(scale), _L.ptr(seqlens))
     return out
 
 
@@ -78,14 +98,15 @@ def vit_embed(patch, cls, pos, B, P):
 
 
 def upsample_tokens_coords(hidden, G, Ho, cpad):
-    """hidden: [B, 1+G*G, C] ViT hidden state (CLS first); returns NHWC [B,Ho,Ho,cpad]."""
-    _bf16(hidden)
+    """hidden: [B, 1+G*G, C] ViT hidden state, bf16 or fp32 (CLS first); returns bf16 NHWC [B,Ho,Ho,cpad]."""
     B, T, C = hidden.shape
     assert T == G * G + 1 and hidden.is_contiguous()
     out = torch.empty((B, Ho, Ho, cpad), dtype=torch.bfloat16, device=hidden.device)
     import ctypes
-    tok = ctypes.c_void_p(hidden.data_ptr() + C * 2)  # skip CLS
-    _call('g4r_upsample_tokens_coords_bf16', hidden.device, tok, C, T * C, _L.ptr(out), B, G, Ho, C, cpad)
+    f32 = hidden.dtype == torch.float32
+    tok = ctypes.c_void_p(hidden.data_ptr() + C * (4 if f32 else 2))  # skip CLS
+    _call('g4r_upsample_tokens_coords_f32' if f32 else 'g4r_upsample_tokens_coords_bf16', hidden.device, tok, C,
+          T * C, _L.ptr(out), B, G, Ho, C, cpad)
     return out
 
 

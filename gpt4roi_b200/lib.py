@@ -37,14 +37,18 @@ SIGNATURES = {
     'g4r_roi_align_mlvl_backward': (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 8 + [_vp]),
     'g4r_splice_region_tokens': (_i, [_vp] * 8 + [_i] * 5 + [_i64] * 4 + [_vp]),
     'g4r_gemm_bf16': (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _vp]),
+    'g4r_gemm_bf16_ex': (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     'g4r_conv_nhwc_bf16': (_i, [_vp] * 3 + [_i] * 7 + [_vp, _i, _i, _vp, _i, _vp]),
-    'g4r_attention_bf16': (_i, [_vp] * 4 + [_ll] * 4 + [_i] * 5 + [_f, _vp]),
+    'g4r_attention_bf16': (_i, [_vp] * 4 + [_ll] * 4 + [_i] * 5 + [_f, _vp, _vp]),
     'g4r_layernorm_bf16': (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _vp]),
+    'g4r_layernorm_ex': (_i, [_vp, _ll, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
+    'g4r_cast_f32_bf16': (_i, [_vp, _ll, _ll, _vp, _i, _i, _i, _vp]),
     'g4r_rmsnorm_bf16': (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _vp]),
     'g4r_rope_inplace_bf16': (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp]),
     'g4r_patchify_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'g4r_vit_embed_bf16': (_i, [_vp] * 4 + [_i] * 3 + [_vp]),
     'g4r_upsample_tokens_coords_bf16': (_i, [_vp, _ll, _ll, _vp, _i, _i, _i, _i, _i, _vp]),
+    'g4r_upsample_tokens_coords_f32': (_i, [_vp, _ll, _ll, _vp, _i, _i, _i, _i, _i, _vp]),
     'g4r_fuse_gather_bf16': (_i, [_vp, _vp, _vp, _i] * 3 + [_vp, _i, _i, _vp]),
     'g4r_gn_finalize': (_i, [_vp] * 5 + [_i] * 4 + [_f, _f, _vp]),
     'g4r_conv_gn_slots': (_i, [_i, _i]),

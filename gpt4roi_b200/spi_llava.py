@@ -15,8 +15,8 @@ The modules below are PARAMETER CONTAINERS with the reference's state-dict layou
 Appendix C; mmcv's ConvModule names `.conv` / `.gn` included).  Their `forward` does not run
 PyTorch ops: it hands the weights to `engine.PrefillEngine` (re-laid-out once, cached until the
 weights change) which launches the hand-written kernels.  Round-1 limits, stated: inference
-prefill only (no KV-cache decode step, no backward through the dense blocks yet), all-ones
-attention_mask; anything else raises NotImplementedError instead of falling back.
+prefill only (no KV-cache decode step, no backward through the dense blocks yet), right-padded
+attention masks only; anything else raises NotImplementedError instead of falling back.
 """
 from typing import List, Optional
 
@@ -179,14 +179,12 @@ class SPILlavaMPTForCausalLM(LlamaForCausalLM):
                                       '(no KV-cache decode step / inputs_embeds / attention maps yet)')
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             raise NotImplementedError('training (backward through the dense blocks) is a next-round item')
-        if attention_mask is not None and not bool(attention_mask.all()):
-            raise NotImplementedError('padded batches (attention_mask with zeros) are a next-round item')
         if images is None:
             raise NotImplementedError('text-only forward: use the stock LlamaForCausalLM path')
         if type(images) is list:
             raise NotImplementedError('list-of-images input is undefined in the reference SPI branch (spi_llava.py:52-64)')
         eng = self._get_engine(input_ids.device)
-        logits = eng.forward(input_ids, images, bboxes)
+        logits = eng.forward(input_ids, images, bboxes, attention_mask=attention_mask)
         loss = None
         if labels is not None:  # llava.py:238-249
             shift_logits = logits[..., :-1, :].float().reshape(-1, self.config.vocab_size)

@@ -166,6 +166,15 @@ int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb,
                   const void* residual, long long ldr,
                   int act, int out_f32, int k_splits, void* stream);
 
+/* Extended form: residual may be fp32 (residual_f32=1; CLIP's residual stream is fp32 under autocast)
+ * and the branch (acc + bias, act) can be rounded to bf16 before the residual add (bias_round_bf16=1),
+ * reproducing "bf16 linear output + fp32 stream". */
+int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb,
+                     void* D, long long ldd, int M, int N, int K,
+                     const void* bias, int bias_f32,
+                     const void* residual, long long ldr, int residual_f32, int bias_round_bf16,
+                     int act, int out_f32, int k_splits, void* stream);
+
 /*
  * NHWC convolution as an implicit GEMM (stride 1, pad (ksize-1)/2, ksize 1 or 3):
  *   Y[n,y,x,co] = act( sum_{ky,kx,ci} X[n,y+ky-1,x+kx-1,ci] * Wt[co,(ky*ks+kx)*Cin+ci] + bias[co] )
@@ -200,12 +209,22 @@ int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y,
 int g4r_attention_bf16(const void* q, const void* k, const void* v, void* out,
                        long long ld, long long bs, long long ldo, long long bso,
                        int B, int H, int L, int head_dim, int causal, float scale,
+                       const int* seqlens /* device int32 [B] or NULL: keys >= seqlens[b] are masked */,
                        void* stream);
 
 /* ---- HBM-bound glue (csrc/elementwise.cu); bf16 rows, fp32 math ------------- */
 /* nn.LayerNorm over the last dim (CLIP layer norms; gpt4roi/models/layers.py:263,266). */
 int g4r_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b,
                        void* out, long long ldo, int M, int D, float eps, void* stream);
+/* LayerNorm with fp32 or bf16 input/output rows (x_f32 / out_f32).  Under autocast the reference's
+ * nn.LayerNorm returns fp32, so CLIP's residual stream is fp32: pre_layrnorm is bf16->fp32, layer_norm1/2
+ * are fp32->bf16 (their output is cast to bf16 by the following autocast Linear). */
+int g4r_layernorm_ex(const void* x, long long ldx, int x_f32, const void* w, const void* b,
+                     void* out, long long ldo, int out_f32, int M, int D, float eps, void* stream);
+/* fp32 rows [B][rows_per_batch][D] (row stride ld, batch stride bst) -> dense bf16 [B*rows_per_batch, D]
+ * (the autocast cast at mm_projector's input, spi_llava.py:89-93, skipping the CLS row). */
+int g4r_cast_f32_bf16(const void* x, long long ld, long long bst, void* out,
+                      int B, int rows_per_batch, int D, void* stream);
 /* LlamaRMSNorm: w * bf16(x * rsqrt(mean(x^2)+eps))  (transformers modeling_llama.py:53-67). */
 int g4r_rmsnorm_bf16(const void* x, long long ldx, const void* w,
                      void* out, long long ldo, int M, int D, float eps, void* stream);
@@ -224,6 +243,9 @@ int g4r_vit_embed_bf16(const void* patch, const void* cls, const void* pos, void
  * (gpt4roi/models/layers.py:219-232 + :117-126,185-188). */
 int g4r_upsample_tokens_coords_bf16(const void* tok, long long ldt, long long bst, void* out,
                                     int B, int G, int Ho, int C, int Cpad, void* stream);
+/* same with fp32 tokens (CLIP hidden states are fp32 under autocast) */
+int g4r_upsample_tokens_coords_f32(const void* tok, long long ldt, long long bst, void* out,
+                                   int B, int G, int Ho, int C, int Cpad, void* stream);
 /* One level of MLVLFuseModule._single_shuffle (layers.py:152-180): out = [own[:, :C/2] |
  * resize(top[:, 3C/4:]) | resize(down[:, C/2:3C/4])]; optional per-(image,channel) scale/shift
  * (fp32 [B,C]) apply the previous round's GroupNorm+ReLU to every tap first. */
