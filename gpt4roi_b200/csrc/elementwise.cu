@@ -399,28 +399,35 @@ fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restri
 // GroupNorm finalisation: stats [B,groups,2] (sum, sumsq over H*W*cpg elements) + gamma/beta ->
 // per-(image,channel) scale/shift so that GN(x) = x*scale + shift (eps inside the rsqrt, biased
 // variance, like torch.nn.GroupNorm).
-__global__ void gn_finalize(const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
-                            const __nv_bfloat16* __restrict__ beta, float* __restrict__ scale,
-                            float* __restrict__ shift, int B, int C, int groups, int slots, float count,
-                            float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * C) return;
-  const int b = i / C, c = i % C;
-  const int g = c / (C / groups);
-  // stats: [B][slots][groups][2] per-(tile,warp) partial sums written by the conv epilogue; fixed-order sum
+// One warp per (image, group): lanes stride over the per-(tile,warp) partial slots (fixed order per
+// lane + fixed shuffle tree => bitwise reproducible), then the first cpg lanes write scale/shift.
+__global__ void __launch_bounds__(256)
+gn_finalize(const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+            const __nv_bfloat16* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int B,
+            int C, int groups, int slots, float count, float eps) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= B * groups) return;
+  const int lane = threadIdx.x & 31;
+  const int b = w / groups, g = w % groups;
   float s = 0.f, ss = 0.f;
-  for (int t = 0; t < slots; t++) {
-    const float* st = stats + (((long long)b * slots + t) * groups + g) * 2;
-    s += st[0];
-    ss += st[1];
+  for (int t = lane; t < slots; t += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(stats + (((long long)b * slots + t) * groups + g) * 2);
+    s += v.x;
+    ss += v.y;
   }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
   const float mean = s / count;
   float var = ss / count - mean * mean;
   var = var < 0.f ? 0.f : var;
   const float rstd = rsqrtf(var + eps);
-  const float a = __bfloat162float(gamma[c]) * rstd;
-  scale[i] = a;
-  shift[i] = __bfloat162float(beta[c]) - mean * a;
+  const int cpg = C / groups;
+  for (int j = lane; j < cpg; j += 32) {
+    const int c = g * cpg + j;
+    const float a = __bfloat162float(gamma[c]) * rstd;
+    scale[(long long)b * C + c] = a;
+    shift[(long long)b * C + c] = __bfloat162float(beta[c]) - mean * a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -617,7 +624,7 @@ extern "C" int g4r_gn_finalize(const float* stats, const void* gamma, const void
                                float* shift, int B, int C, int groups, int slots, float count, float eps,
                                void* stream) {
   G4R_REQUIRE(stats && gamma && beta && scale && shift && B > 0 && C > 0 && groups > 0 && C % groups == 0 && slots > 0, "gn_finalize: bad arguments");
-  gn_finalize<<<(B * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+  gn_finalize<<<(B * groups + 7) / 8, 256, 0, (cudaStream_t)stream>>>(stats, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
                                                                    scale, shift, B, C, groups, slots, count, eps);
   G4R_LAUNCH_CHECK("gn_finalize");
   return G4R_OK;

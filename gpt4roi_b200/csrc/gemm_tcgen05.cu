@@ -630,14 +630,17 @@ static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const G
   return G4R_OK;
 }
 
-// 2-CTA tiles when there is enough work to keep all SM pairs busy (G4R_GEMM_2SM=0 disables).
-static bool use_2sm(int N, int m_tiles, int k_splits) {
+// 2-CTA tiles when there is enough work to keep all SM pairs busy.  Measured on B200 (profiles/):
+// equal to the 1-CTA kernel for the convs (tile counts are exact multiples) and ~3 % slower for the
+// LLaMA GEMMs, whose M = B*L = 5648 rows leave a 94 %-empty last 256-row pair.  Default: conv only;
+// G4R_GEMM_2SM=1 forces it for plain GEMMs too, =0 disables it everywhere.
+static bool use_2sm(int N, int m_tiles, int k_splits, bool conv) {
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("G4R_GEMM_2SM");
-    env = (e && e[0] == '0') ? 0 : 1;
+    env = !e ? 2 : (e[0] == '0' ? 0 : 1);
   }
-  if (!env || N <= 128 || m_tiles < 2) return false;
+  if (env == 0 || (env == 2 && !conv) || N <= 128 || m_tiles < 2) return false;
   const long pairs = (long)((m_tiles + 1) / 2) * ((N + 255) / 256) * k_splits;
   return pairs >= num_sms() / 2;
 }
@@ -694,7 +697,7 @@ extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, lon
   p.round_branch = bias_round_bf16;
   p.act = act; p.out_f32 = out_f32; p.atomic = k_splits > 1;
   p.conv = 0; p.a_rows = kBlockM;
-  const bool two = use_2sm(N, p.num_m_tiles, k_splits);
+  const bool two = use_2sm(N, p.num_m_tiles, k_splits, false);
   const int bn = two ? 256 : pick_block_n(N, p.num_m_tiles, k_splits);
   p.num_n_tiles = (N + bn - 1) / bn;
   CUtensorMap ta, tb;
@@ -762,7 +765,7 @@ extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_
   p.D = Y; p.ldd = Cout; p.bias = bias; p.bias_f32 = bias_f32; p.act = act;
   p.conv = 1;
   p.gn_stats = gn_stats; p.gn_groups = gn_groups; p.gn_group_ch = gn_groups ? Cout / gn_groups : 0;
-  const bool two = use_2sm(Cout, p.num_m_tiles, 1);
+  const bool two = use_2sm(Cout, p.num_m_tiles, 1, true);
   const int bn = two ? 256 : pick_block_n(Cout, p.num_m_tiles, 1);
   p.num_n_tiles = (Cout + bn - 1) / bn;
   CUtensorMap ta, tb;

@@ -212,6 +212,15 @@ int g4r_attention_bf16(const void* q, const void* k, const void* v, void* out,
                        const int* seqlens /* device int32 [B] or NULL: keys >= seqlens[b] are masked */,
                        void* stream);
 
+/*
+ * Same contract on the tcgen05 tensor cores (TMA-fed, S and O accumulators in TMEM, V consumed as an
+ * MN-major operand); requires the packed layout bs == L*ld.  csrc/attention_tcgen05.cu.
+ */
+int g4r_attention_tc_bf16(const void* q, const void* k, const void* v, void* out,
+                          long long ld, long long bs, long long ldo, long long bso,
+                          int B, int H, int L, int head_dim, int causal, float scale,
+                          const int* seqlens, void* stream);
+
 /* ---- HBM-bound glue (csrc/elementwise.cu); bf16 rows, fp32 math ------------- */
 /* nn.LayerNorm over the last dim (CLIP layer norms; gpt4roi/models/layers.py:263,266). */
 int g4r_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b,

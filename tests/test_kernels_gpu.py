@@ -48,13 +48,14 @@ def test_rope_matches_hf_formula():
     assert (got[:, :, :2 * H].float() - want.float()).abs().mean() < 1e-3
 
 
+@pytest.mark.parametrize('impl', ['tc', 'mma'])
 @pytest.mark.parametrize('L,H,D,causal', [(577, 16, 64, False), (706, 32, 128, True), (64, 2, 128, True),
-                                          (130, 3, 64, True), (50, 2, 128, False)])
-def test_attention(L, H, D, causal):
+                                          (130, 3, 64, True), (50, 2, 128, False), (300, 2, 128, True)])
+def test_attention(L, H, D, causal, impl):
     torch.manual_seed(L)
     B = 2
     qkv = (torch.randn(B * L, 3 * H * D, device=DEV) * 0.7).to(BF)
-    out = kernels.attention(qkv, B, L, H, D, causal, D ** -0.5).view(B, L, H, D)
+    out = kernels.attention(qkv, B, L, H, D, causal, D ** -0.5, impl=impl).view(B, L, H, D)
     q, k, v = (t.permute(0, 2, 1, 3).float() for t in qkv.view(B, L, 3, H, D).unbind(2))
     s = (q @ k.transpose(-1, -2)) * D ** -0.5
     if causal:
@@ -149,3 +150,18 @@ def test_gn_finalize_and_pos_mlp():
     bias = torch.randn(1024, device=DEV).to(BF)
     got = kernels.add_bias_pos_cast(acc, bias, pos)
     close(got, (acc + bias.float()).to(BF).float() + pos, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('impl', ['tc', 'mma'])
+def test_attention_seqlens(impl):
+    """Right-padded batch: keys >= seqlens[b] are masked; valid rows equal the unpadded computation."""
+    torch.manual_seed(5)
+    B, L, H, D = 3, 200, 2, 128
+    lens = torch.tensor([200, 137, 64], dtype=torch.int32, device=DEV)
+    qkv = (torch.randn(B * L, 3 * H * D, device=DEV) * 0.7).to(BF)
+    out = kernels.attention(qkv, B, L, H, D, True, D ** -0.5, seqlens=lens, impl=impl).view(B, L, H, D)
+    for b in range(B):
+        n = int(lens[b])
+        solo = qkv.view(B, L, -1)[b, :n].contiguous()
+        ref = kernels.attention(solo, 1, n, H, D, True, D ** -0.5, impl=impl).view(n, H, D)
+        torch.testing.assert_close(out[b, :n].float(), ref.float(), rtol=1e-2, atol=1e-2)
