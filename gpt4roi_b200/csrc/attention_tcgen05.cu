@@ -15,14 +15,16 @@
 //               pass 2 tcgen05.ld S -> p = exp2(s*c - m*c) -> bf16 -> swizzled smem tile P (A operand of PV)
 // QK_{j+1} is issued before PV_j so the tensor core works on the next scores while the softmax
 // warps process block j.  Scores stay fp32 through the softmax (see attention.cu header).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace g4r {
 
-constexpr int kFaBM = 128, kFaBN = 128;
+constexpr int kFaBM = 128;
 constexpr int kFaThreads = 256;
-constexpr int kAtomBytes = 128 * 128;  // [128 rows][64 bf16] swizzle-128B atom
+constexpr int kAtomBytes = 128 * 128;  // [128 rows][64 bf16] swizzle-128B atom (Q, P)
 
 struct FaParams {
   __nv_bfloat16* out;
@@ -57,17 +59,23 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, 
   return d;
 }
 
-template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(kFaThreads, 1)
+// BN = keys per block.  BN=64 keeps a CTA at 112 KB of shared memory and 256 TMEM columns (D=128), so
+// TWO CTAs share an SM: one CTA's prologue / epilogue overlaps the other's MMAs and 8 softmax warps
+// instead of 4 hide the tcgen05.ld / MUFU latencies.
+template <int D, int BN, bool CAUSAL>
+__global__ void __launch_bounds__(kFaThreads, (BN == 64 ? 2 : 1))
 fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ FaParams p) {
+  constexpr int kFaBN = BN;
   constexpr int ATOMS = D / 64;
-  constexpr int TILE_BYTES = ATOMS * kAtomBytes;  // Q / K / V tile: 128 rows x D
-  constexpr int P_BYTES = 2 * kAtomBytes;         // P: 128 x 128 keys
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int Q_BYTES = ATOMS * kAtomBytes;     // Q tile: 128 rows x D
+  constexpr int KV_ATOM = BN * 128;               // [BN keys][64 bf16]
+  constexpr int TILE_BYTES = ATOMS * KV_ATOM;     // K / V tile: BN rows x D
+  constexpr int P_BYTES = (BN / 64) * kAtomBytes; // P: 128 x BN keys
+  constexpr int TMEM_COLS = (2 * BN + D) <= 256 ? 256 : 512;
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;       // 2 stages
+  uint8_t* sK = sQ + Q_BYTES;          // 2 stages
   uint8_t* sV = sK + 2 * TILE_BYTES;   // 2 stages
   uint8_t* sP = sV + 2 * TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
@@ -87,7 +95,7 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   const int q0 = qb * kFaBM;
   const int row_base = b * p.L;
   const int Lk = p.seqlens ? min(max(p.seqlens[b], 1), p.L) : p.L;
-  const int nblk = CAUSAL ? min((Lk + kFaBN - 1) / kFaBN, qb + 1) : (Lk + kFaBN - 1) / kFaBN;
+  const int nblk = CAUSAL ? min((Lk + kFaBN - 1) / kFaBN, (q0 + kFaBM + kFaBN - 1) / kFaBN) : (Lk + kFaBN - 1) / kFaBN;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_q);
@@ -108,17 +116,17 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     ptx::mbar_init(pv_done, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   ptx::tcgen05_before_thread_sync();
   __syncthreads();
   ptx::tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_o = tmem_base + 2 * kFaBN;
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      ptx::mbar_arrive_expect_tx(q_full, Q_BYTES);
       for (int a = 0; a < ATOMS; a++)
         ptx::tma_load_2d(sQ + a * kAtomBytes, &tm_q, q_full, h * D + a * 64, row_base + q0);
       for (int j = 0; j < nblk; j++) {
@@ -127,12 +135,12 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         ptx::mbar_wait(&k_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
         for (int a = 0; a < ATOMS; a++)
-          ptx::tma_load_2d(sK + st * TILE_BYTES + a * kAtomBytes, &tm_k, &k_full[st], h * D + a * 64,
+          ptx::tma_load_2d(sK + st * TILE_BYTES + a * KV_ATOM, &tm_k, &k_full[st], h * D + a * 64,
                            row_base + j * kFaBN);
         ptx::mbar_wait(&v_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
         for (int a = 0; a < ATOMS; a++)
-          ptx::tma_load_2d(sV + st * TILE_BYTES + a * kAtomBytes, &tm_v, &v_full[st], h * D + a * 64,
+          ptx::tma_load_2d(sV + st * TILE_BYTES + a * KV_ATOM, &tm_v, &v_full[st], h * D + a * 64,
                            row_base + j * kFaBN);
       }
     }
@@ -152,7 +160,7 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         for (int kk = 0; kk < D / 16; kk++) {
           const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ + (kk >> 2) * kAtomBytes)) + 2 * (kk & 3);
           const uint64_t db =
-              ptx::make_smem_desc_sw128(ptx::smem_u32(sK + st * TILE_BYTES + (kk >> 2) * kAtomBytes)) + 2 * (kk & 3);
+              ptx::make_smem_desc_sw128(ptx::smem_u32(sK + st * TILE_BYTES + (kk >> 2) * KV_ATOM)) + 2 * (kk & 3);
           ptx::umma_f16_ss(tmem_base + sb * kFaBN, da, db, idesc_qk, kk != 0);
         }
         ptx::umma_commit(&s_full[sb]);
@@ -171,7 +179,7 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
         for (int ks = 0; ks < kFaBN / 16; ks++) {
           const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(sP + (ks >> 2) * kAtomBytes)) + 2 * (ks & 3);
-          const uint64_t db = make_smem_desc_mn_sw128(ptx::smem_u32(sV + st * TILE_BYTES + ks * 2048), kAtomBytes);
+          const uint64_t db = make_smem_desc_mn_sw128(ptx::smem_u32(sV + st * TILE_BYTES + ks * 2048), KV_ATOM);
           ptx::umma_f16_ss(tmem_o, da, db, idesc_pv, (j | ks) != 0);
         }
         ptx::umma_commit(pv_done);
@@ -297,7 +305,7 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   __syncthreads();
   if (warp == 2) {
     ptx::tcgen05_after_thread_sync();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -306,7 +314,8 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                    CUtensorMapFloatOOBfill);
 
-static int make_tmap_rows(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld) {
+static int make_tmap_rows(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld,
+                          int box_rows) {
   static EncodeTiledFn2 enc = nullptr;
   if (!enc) {
     void* fp = nullptr;
@@ -320,7 +329,7 @@ static int make_tmap_rows(CUtensorMap* m, const void* base, long long cols, long
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t str[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, str, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -332,12 +341,12 @@ static int make_tmap_rows(CUtensorMap* m, const void* base, long long cols, long
   return G4R_OK;
 }
 
-template <int D, bool CAUSAL>
+template <int D, int BN, bool CAUSAL>
 static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FaParams& p, int B,
                      cudaStream_t st) {
-  constexpr int smem = (D / 64) * kAtomBytes * 5 + 2 * kAtomBytes + 256 + 1024;
+  constexpr int smem = (D / 64) * kAtomBytes + 4 * (D / 64) * BN * 128 + (BN / 64) * kAtomBytes + 256;
   static bool set = false;
-  auto kern = fa_fwd_tcgen05<D, CAUSAL>;
+  auto kern = fa_fwd_tcgen05<D, BN, CAUSAL>;
   if (!set) {
     G4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     set = true;
@@ -365,11 +374,18 @@ extern "C" int g4r_attention_tc_bf16(const void* q, const void* k, const void* v
   CUtensorMap tq, tk, tv;
   const long long cols = (long long)H * head_dim, rows = (long long)B * L;
   int rc;
-  if ((rc = make_tmap_rows(&tq, q, cols, rows, ld))) return rc;
-  if ((rc = make_tmap_rows(&tk, k, cols, rows, ld))) return rc;
-  if ((rc = make_tmap_rows(&tv, v, cols, rows, ld))) return rc;
+  static int bn = 0;
+  if (!bn) {
+    const char* e = getenv("G4R_ATTN_BN");
+    bn = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  if ((rc = make_tmap_rows(&tq, q, cols, rows, ld, 128))) return rc;
+  if ((rc = make_tmap_rows(&tk, k, cols, rows, ld, bn))) return rc;
+  if ((rc = make_tmap_rows(&tv, v, cols, rows, ld, bn))) return rc;
   FaParams p{(__nv_bfloat16*)out, ldo, bso, L, H, scale, seqlens};
   cudaStream_t st = (cudaStream_t)stream;
-  if (head_dim == 64) return causal ? launch_fa<64, true>(tq, tk, tv, p, B, st) : launch_fa<64, false>(tq, tk, tv, p, B, st);
-  return causal ? launch_fa<128, true>(tq, tk, tv, p, B, st) : launch_fa<128, false>(tq, tk, tv, p, B, st);
+#define G4R_FA(DD, BB) (causal ? launch_fa<DD, BB, true>(tq, tk, tv, p, B, st) : launch_fa<DD, BB, false>(tq, tk, tv, p, B, st))
+  if (head_dim == 64) return bn == 128 ? G4R_FA(64, 128) : G4R_FA(64, 64);
+  return bn == 128 ? G4R_FA(128, 128) : G4R_FA(128, 64);
+#undef G4R_FA
 }
