@@ -307,8 +307,14 @@ def run_ours(args):
     gemm_flops = sum(f for _, f, _, _ in prof)
     pk, how = peaks()
     achieved = gemm_flops / 1e12 / (gemm_ms / 1e3)
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read+write per launch from the committed ncu --set full capture of this kernel
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_gemm_traffic.json')))
+        traffic, traffic_src = tj['traffic_bytes_per_launch_avg'], tj['source']
+    except Exception:
+        pass
     roof = dict(bound='tensor', kernel='gemm_bf16_tcgen05', achieved=achieved, peak=pk['bf16_tflops_sustained'],
-                unit='TFLOP/s', frac=achieved / pk['bf16_tflops_sustained'], traffic=None,
+                unit='TFLOP/s', frac=achieved / pk['bf16_tflops_sustained'], traffic=traffic, traffic_source=traffic_src,
                 peak_kind=how + ' (sustained cuBLAS bf16; kernel timed inside a long step)',
                 launches=len(prof), flops_per_launch_avg=gemm_flops / max(len(prof), 1),
                 avg_launch_ms=gemm_ms / max(len(prof), 1), share_of_step=gemm_ms / ms_step / (1.0 if True else 1),

@@ -58,6 +58,11 @@ struct GemmParams {
   int cH, cW, cBH, cBW, tiles_x, tiles_y, cin_blocks, taps;  // taps = 9 (3x3) or 1
   int a_rows;            // rows delivered by the A box (<= 128)
   int levels, lvl_img_stride;  // conv: sum over `levels` inputs (image index + lvl*stride), K concatenated
+  // fused rotary embedding (LLaMA QKV GEMM): columns [0, rope_cols) are heads of 128 dims rotated with
+  // bf16 cos/sin tables [rope_L][128]; row position = out_row % rope_L
+  const __nv_bfloat16* rope_cos;
+  const __nv_bfloat16* rope_sin;
+  int rope_cols, rope_L;
   float* gn_stats;       // optional [n_img, groups, 2] (sum, sumsq) of the bf16-rounded output
   int gn_group_ch;       // channels per group (16)
   int gn_groups;         // groups per image (64)
@@ -100,6 +105,67 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
   } else {
     out_row = (long long)m_blk * kBlockM + row;
     row_ok = m_blk < p.num_m_tiles && out_row < p.M;
+  }
+  if (!CONV && p.rope_cos != nullptr && n_blk * BLOCK_N < p.rope_cols) {
+    // ---- fused RoPE (transformers modeling_llama.py:138-168): the tile holds BLOCK_N/128 whole heads;
+    // dims (d, d+64) of a head are 64 columns apart -> load both 32-column chunks, rotate, store.
+    // Rounding as in the reference: q/k are bf16 GEMM outputs, each bf16 tensor op rounds:
+    //   out = bf16( bf16(x*cos) + bf16(rot*sin) ),  rotate_half(x) = cat(-x2, x1).
+    const int pos = (int)(out_row % p.rope_L);
+    const __nv_bfloat16* ct = p.rope_cos + (long long)pos * 128;
+    const __nv_bfloat16* st = p.rope_sin + (long long)pos * 128;
+#pragma unroll 1
+    for (int hc = 0; hc < BLOCK_N / 64; hc++) {   // hc = head*2 + half-chunk (0: dims 0-31, 1: dims 32-63)
+      const int cA = (hc >> 1) * 128 + (hc & 1) * 32, cB = cA + 64;
+      uint32_t va[32], vb[32];
+      ptx::tmem_ld_32x32b_x32(taddr + cA, va);
+      ptx::tmem_ld_32x32b_x32(taddr + cB, vb);
+      ptx::tmem_ld_wait();
+      if (hc == BLOCK_N / 64 - 1) {
+        ptx::tcgen05_before_thread_sync();
+        arrive();
+      }
+      if (!row_ok) continue;
+      const int d0 = (hc & 1) * 32;
+      uint32_t oa[16], ob[16];
+#pragma unroll
+      for (int h8 = 0; h8 < 4; h8++) {
+        const uint4 c1r = *reinterpret_cast<const uint4*>(ct + d0 + h8 * 8);
+        const uint4 s1r = *reinterpret_cast<const uint4*>(st + d0 + h8 * 8);
+        const uint4 c2r = *reinterpret_cast<const uint4*>(ct + 64 + d0 + h8 * 8);
+        const uint4 s2r = *reinterpret_cast<const uint4*>(st + 64 + d0 + h8 * 8);
+        const __nv_bfloat16* c1 = reinterpret_cast<const __nv_bfloat16*>(&c1r);
+        const __nv_bfloat16* s1 = reinterpret_cast<const __nv_bfloat16*>(&s1r);
+        const __nv_bfloat16* c2 = reinterpret_cast<const __nv_bfloat16*>(&c2r);
+        const __nv_bfloat16* s2 = reinterpret_cast<const __nv_bfloat16*>(&s2r);
+        float r1[8], r2[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float x1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(va[h8 * 8 + j])));
+          const float x2 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vb[h8 * 8 + j])));
+          const float a1 = __bfloat162float(__float2bfloat16_rn(x1 * __bfloat162float(c1[j])));
+          const float b1 = __bfloat162float(__float2bfloat16_rn(-x2 * __bfloat162float(s1[j])));
+          const float a2 = __bfloat162float(__float2bfloat16_rn(x2 * __bfloat162float(c2[j])));
+          const float b2 = __bfloat162float(__float2bfloat16_rn(x1 * __bfloat162float(s2[j])));
+          r1[j] = a1 + b1;
+          r2[j] = a2 + b2;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(r1[2 * j], r1[2 * j + 1]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(r2[2 * j], r2[2 * j + 1]);
+          oa[h8 * 4 + j] = *reinterpret_cast<uint32_t*>(&h1);
+          ob[h8 * 4 + j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+      }
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.D) + out_row * p.ldd + n_blk * BLOCK_N;
+#pragma unroll
+      for (int h4 = 0; h4 < 4; h4++) {
+        reinterpret_cast<uint4*>(o + cA)[h4] = make_uint4(oa[4 * h4], oa[4 * h4 + 1], oa[4 * h4 + 2], oa[4 * h4 + 3]);
+        reinterpret_cast<uint4*>(o + cB)[h4] = make_uint4(ob[4 * h4], ob[4 * h4 + 1], ob[4 * h4 + 2], ob[4 * h4 + 3]);
+      }
+    }
+    return;
   }
 #pragma unroll 1
   for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -673,10 +739,35 @@ extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long l
                           k_splits, stream);
 }
 
+static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
+                     int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr,
+                     int residual_f32, int bias_round_bf16, int act, int out_f32, int k_splits,
+                     const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream);
+
 extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, void* D,
                                 long long ldd, int M, int N, int K, const void* bias, int bias_f32,
                                 const void* residual, long long ldr, int residual_f32, int bias_round_bf16,
                                 int act, int out_f32, int k_splits, void* stream) {
+  return gemm_impl(A, lda, B, ldb, D, ldd, M, N, K, bias, bias_f32, residual, ldr, residual_f32, bias_round_bf16,
+                   act, out_f32, k_splits, nullptr, nullptr, 0, 0, stream);
+}
+
+// QKV projection with the rotary embedding fused into the epilogue: D[M, N] = A.B^T, columns
+// [0, rope_cols) (the q and k heads, head_dim 128) rotated with cos/sin[row % L].  Replaces
+// q_proj/k_proj/v_proj + apply_rotary_pos_emb (transformers modeling_llama.py:138-168,240-260).
+extern "C" int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* B, long long ldb, void* D,
+                                      long long ldd, int M, int N, int K, const void* rope_cos,
+                                      const void* rope_sin, int rope_cols, int L, void* stream) {
+  G4R_REQUIRE(rope_cos && rope_sin && L > 0, "qkv_rope: null tables");
+  G4R_REQUIRE(rope_cols % 256 == 0 && rope_cols <= N && N % 128 == 0 && ldd % 8 == 0, "qkv_rope: rope_cols must be a multiple of 256 (whole tiles of 128-dim heads)");
+  return gemm_impl(A, lda, B, ldb, D, ldd, M, N, K, nullptr, 0, nullptr, 0, 0, 0, ACT_NONE, 0, 1, rope_cos, rope_sin,
+                   rope_cols, L, stream);
+}
+
+static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
+                     int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr,
+                     int residual_f32, int bias_round_bf16, int act, int out_f32, int k_splits,
+                     const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream) {
   G4R_REQUIRE(A && B && D, "null operand");
   G4R_REQUIRE(M > 0 && N > 0 && K > 0, "bad sizes M=%d N=%d K=%d", M, N, K);
   G4R_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "lda/ldb must be >= K and multiples of 8 (16-byte TMA strides)");
@@ -695,6 +786,8 @@ extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, lon
   p.D = D; p.ldd = ldd; p.bias = bias; p.bias_f32 = bias_f32;
   p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.residual_f32 = residual_f32;
   p.round_branch = bias_round_bf16;
+  p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin;
+  p.rope_cols = rope_cols; p.rope_L = rope_L;
   p.act = act; p.out_f32 = out_f32; p.atomic = k_splits > 1;
   p.conv = 0; p.a_rows = kBlockM;
   const bool two = use_2sm(N, p.num_m_tiles, k_splits, false);

@@ -92,6 +92,22 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out
 
 
+def qkv_rope(x, wqkv, cos, sin, L, rope_cols):
+    """Fused LLaMA q/k/v projection + rotary embedding: x [M,K] bf16, wqkv [N,K] (q|k|v rows), cos/sin
+    bf16 [L,128]; columns [0,rope_cols) (q and k heads, head_dim 128) are rotated at position row % L."""
+    M, K = x.shape
+    N = wqkv.shape[0]
+    dev = _L.require_cuda_same_device([('x', x), ('wqkv', wqkv), ('cos', cos), ('sin', sin)])
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _ps = _prof_begin(dev)
+        _L.check(_L.load().g4r_gemm_qkv_rope_bf16(
+            _L.ptr(x), x.stride(0), _L.ptr(wqkv), wqkv.stride(0), _L.ptr(out), N, M, N, K, _L.ptr(cos), _L.ptr(sin),
+            int(rope_cols), int(L), _L.stream_ptr(dev)))
+        _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
+    return out
+
+
 def gn_slots(h, w):
     """Number of per-(tile,warp) GroupNorm partial-sum slots the conv kernel writes for an h x w map."""
     return int(_L.load().g4r_conv_gn_slots(int(h), int(w)))

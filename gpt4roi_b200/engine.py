@@ -231,8 +231,11 @@ class PrefillEngine:
         scale = c.head_dim ** -0.5
         for w in self.layers:
             h = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
-            qkv = dense.linear(h, w['wqkv'])
-            kernels.rope_inplace(qkv, cos, sin, L, 2 * c.n_heads, c.head_dim)
+            if c.head_dim == 128 and (2 * c.hidden) % 256 == 0:
+                qkv = dense.qkv_rope(h, w['wqkv'], cos, sin, L, 2 * c.hidden)   # RoPE fused into the GEMM epilogue
+            else:
+                qkv = dense.linear(h, w['wqkv'])
+                kernels.rope_inplace(qkv, cos, sin, L, 2 * c.n_heads, c.head_dim)
             a = kernels.attention(qkv, B, L, c.n_heads, c.head_dim, True, scale, seqlens=seqlens)
             x = dense.linear(a, w['wo'], residual=x)
             h = kernels.rmsnorm(x, w['ln_post'], c.rms_eps)

@@ -175,6 +175,14 @@ int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb,
                      const void* residual, long long ldr, int residual_f32, int bias_round_bf16,
                      int act, int out_f32, int k_splits, void* stream);
 
+/* LLaMA QKV projection with apply_rotary_pos_emb fused into the epilogue (transformers
+ * modeling_llama.py:138-168): D[M,N] = A.B^T; columns [0,rope_cols) are 128-dim heads rotated with the
+ * bf16 cos/sin tables [L,128] at position (row % L); rounding points as in the reference's bf16 ops. */
+int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* B, long long ldb,
+                           void* D, long long ldd, int M, int N, int K,
+                           const void* rope_cos, const void* rope_sin, int rope_cols, int L,
+                           void* stream);
+
 /*
  * NHWC convolution as an implicit GEMM (stride 1, pad (ksize-1)/2, ksize 1 or 3):
  *   Y[n,y,x,co] = act( sum_{ky,kx,ci} X[n,y+ky-1,x+kx-1,ci] * Wt[co,(ky*ks+kx)*Cin+ci] + bias[co] )

@@ -89,3 +89,20 @@ def test_conv_nhwc(H, W, Cin, Cout, k):
     stats2 = torch.zeros_like(stats)
     dense.conv_nhwc(x, w.permute(0, 2, 3, 1).contiguous(), bias, act='relu', gn_stats=stats2)
     assert torch.equal(stats, stats2)  # plain stores into fixed slots: bitwise reproducible
+
+
+def test_qkv_rope_fused_equals_unfused():
+    """RoPE fused into the QKV GEMM epilogue == GEMM followed by the stand-alone rope kernel, bitwise."""
+    from gpt4roi_b200 import kernels
+    torch.manual_seed(3)
+    B, L, H, D = 2, 77, 4, 128
+    hid = H * D
+    x = (torch.randn(B * L, hid, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(3 * hid, hid, device=DEV) * 0.05).bfloat16()
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+    emb = torch.cat([torch.arange(L).float()[:, None] * inv[None]] * 2, -1)
+    cos, sin = emb.cos().to(DEV, torch.bfloat16).contiguous(), emb.sin().to(DEV, torch.bfloat16).contiguous()
+    fused = dense.qkv_rope(x, w, cos, sin, L, 2 * hid)
+    ref = dense.linear(x, w)
+    kernels.rope_inplace(ref, cos, sin, L, 2 * H, D)
+    assert torch.equal(fused, ref)
