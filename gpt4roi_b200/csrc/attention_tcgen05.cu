@@ -194,7 +194,11 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const int qrow = q0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float c = p.scale * 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
+    // m_used: the row maximum the running sums are expressed against.  It is only advanced (and O / l
+    // rescaled) when the true maximum grew by more than 2^kTau -- exponentials stay <= 2^kTau, exact in
+    // fp32 and harmless in bf16 -- so the TMEM read-modify-write of O is skipped for almost every block.
+    constexpr float kTau = 8.0f;
+    float m_used = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nblk; j++) {
       const int sb = j & 1;
       ptx::mbar_wait(&s_full[sb], (j >> 1) & 1);
@@ -202,77 +206,80 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       const uint32_t ts = tmem_base + sb * kFaBN + lane_off;
       const int key0 = j * kFaBN;
       const bool need_mask = (key0 + kFaBN > Lk) || (CAUSAL && key0 + kFaBN - 1 > q0);
-      // ---- pass 1: row max
+      // ---- one TMEM read of the score row (kept in registers for both the max and the exponentials)
+      uint32_t sv[kFaBN / 32][32];
+#pragma unroll
+      for (int cc = 0; cc < kFaBN / 32; cc++) ptx::tmem_ld_32x32b_x32(ts + cc * 32, sv[cc]);
+      ptx::tmem_ld_wait();
+      ptx::tcgen05_before_thread_sync();
+      ptx::mbar_arrive(&s_free[sb]);  // S buffer may be overwritten by QK_{j+2}
       float mx = -INFINITY;
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < kFaBN / 32; cc++) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(ts + cc * 32, v);
-        ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-          float s = __uint_as_float(v[i]);
+          float sc = __uint_as_float(sv[cc][i]);
           if (need_mask) {
             const int key = key0 + cc * 32 + i;
-            if (key >= Lk || (CAUSAL && key > qrow)) s = -INFINITY;
+            if (key >= Lk || (CAUSAL && key > qrow)) sc = -INFINITY;
+            sv[cc][i] = __float_as_uint(sc);
           }
-          mx = fmaxf(mx, s);
+          mx = fmaxf(mx, sc);
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float msub = m_new == -INFINITY ? 0.f : m_new;
-      const float alpha = exp2f((m_run - msub) * c);
-      const float mc = msub * c;
-      m_run = m_new;
+      const float m_new = fmaxf(m_used, mx);
+      const bool grow = (m_new - m_used) * c > kTau;  // false when both are -inf (NaN compare)
+      float alpha = 1.f;
+      if (grow) {
+        alpha = exp2f((m_used - m_new) * c);  // m_used = -inf -> 0
+        m_used = m_new;
+      }
+      const float mc = (m_used == -INFINITY ? 0.f : m_used) * c;
+      // ---- exponentials -> bf16 (registers)
+      uint32_t pk[kFaBN / 2];
+      float lsum = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < kFaBN / 32; cc++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const float p0 = exp2f(fmaf(__uint_as_float(sv[cc][2 * i]), c, -mc));
+          const float p1 = exp2f(fmaf(__uint_as_float(sv[cc][2 * i + 1]), c, -mc));
+          lsum += p0 + p1;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          pk[cc * 16 + i] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+      }
+      l_run = l_run * alpha + lsum;
       // ---- P buffer free and O consistent once PV_{j-1} has completed
       if (j > 0) {
         ptx::mbar_wait(pv_done, (j - 1) & 1);
         ptx::tcgen05_after_thread_sync();
-        // rescale the running output by exp2(m_old - m_new)
+        if (__any_sync(0xffffffffu, grow)) {  // warp-uniform: tcgen05.ld/st are warp-collective
 #pragma unroll 1
-        for (int cc = 0; cc < D / 32; cc++) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + cc * 32, v);
-          ptx::tmem_ld_wait();
+          for (int cc = 0; cc < D / 32; cc++) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + cc * 32, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st_32x32b_x32(tmem_o + lane_off + cc * 32, v);
-        }
-        tmem_st_wait();
-      }
-      // ---- pass 2: probabilities -> bf16 -> swizzled smem tile (A operand of the PV product)
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < kFaBN / 32; cc++) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(ts + cc * 32, v);
-        ptx::tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
-          if (need_mask) {
-            const int key = key0 + cc * 32 + 2 * i;
-            if (key >= Lk || (CAUSAL && key > qrow)) s0 = -INFINITY;
-            if (key + 1 >= Lk || (CAUSAL && key + 1 > qrow)) s1 = -INFINITY;
+            for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_o + lane_off + cc * 32, v);
           }
-          const float p0 = exp2f(fmaf(s0, c, -mc)), p1 = exp2f(fmaf(s1, c, -mc));
-          lsum += p0 + p1;
-          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-          pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+          tmem_st_wait();
         }
-        // 32 keys = 4 16-byte chunks of this row inside atom (cc>>1); chunk index (cc&1)*4 + t, XOR-swizzled by row&7
+      }
+      // ---- P -> swizzled smem tile (A operand of the PV product): 32 keys = 4 16-byte chunks of this row
+      // inside atom (cc>>1); chunk index (cc&1)*4 + t, XOR-swizzled by row&7
+#pragma unroll
+      for (int cc = 0; cc < kFaBN / 32; cc++) {
         uint8_t* prow = sP + (cc >> 1) * kAtomBytes + row * 128;
 #pragma unroll
         for (int t = 0; t < 4; t++) {
           const int chunk = ((cc & 1) * 4 + t) ^ (row & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) =
+              make_uint4(pk[cc * 16 + 4 * t], pk[cc * 16 + 4 * t + 1], pk[cc * 16 + 4 * t + 2], pk[cc * 16 + 4 * t + 3]);
         }
       }
-      l_run = l_run * alpha + lsum;
-      // S buffer may be overwritten by QK_{j+2}; P and the rescaled O are ready for PV_j
       ptx::tcgen05_before_thread_sync();
-      ptx::mbar_arrive(&s_free[sb]);
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(p_full);
     }
