@@ -352,13 +352,16 @@ fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restri
   const int H = own.H;
   const int nvec = C >> 3;
   const int q = C >> 2;  // shuffle_channels = C/4; remain = C/2
-  const long long total = (long long)B * H * H * nvec;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nvec);
-    const int x = (int)((i / nvec) % H);
-    const int y = (int)((i / ((long long)nvec * H)) % H);
-    const int b = (int)(i / ((long long)nvec * H * H));
+  // a group of `nvec` consecutive threads owns one output pixel (coalesced 16-byte channel vectors);
+  // the pixel decomposition is done once per thread, not per element
+  const int ppb = blockDim.x / nvec;  // pixels per block (launcher guarantees blockDim % nvec == 0)
+  const long long npix = (long long)B * H * H;
+  const int v = threadIdx.x % nvec;
+  for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / nvec; pix < npix;
+       pix += (long long)gridDim.x * ppb) {
+    const int x = (int)(pix % H);
+    const int y = (int)((pix / H) % H);
+    const int b = (int)(pix / ((long long)H * H));
     const int c = v * 8;
     // out channels [0,C/2) <- own; [C/2,3C/4) <- top[:, 3C/4 + j]; [3C/4,C) <- down[:, C/2 + j]
     const bool is_own = c < 2 * q, from_top = c < 3 * q;
@@ -614,8 +617,15 @@ extern "C" int g4r_fuse_gather_bf16(const void* own, const float* own_sc, const 
   FuseSrc a{(const __nv_bfloat16*)own, own_sc, own_sh, H};
   FuseSrc t{(const __nv_bfloat16*)top, top_sc, top_sh, Ht};
   FuseSrc d{(const __nv_bfloat16*)down, down_sc, down_sh, Hd};
-  const long long total = (long long)B * H * H * (C / 8);
-  fuse_gather_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, t, d, (__nv_bfloat16*)out, B, C);
+  const int nvec = C / 8;
+  G4R_REQUIRE(nvec <= 1024, "fuse_gather: C too large");
+  const int threads = nvec >= 256 ? nvec : (256 / nvec) * nvec;  // whole pixels per block
+  const long long npix = (long long)B * H * H;
+  const int ppb = threads / nvec;
+  long long blocks = (npix + ppb - 1) / ppb;
+  const long long cap = (long long)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  fuse_gather_bf16<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(a, t, d, (__nv_bfloat16*)out, B, C);
   G4R_LAUNCH_CHECK("fuse_gather");
   return G4R_OK;
 }
