@@ -330,10 +330,13 @@ __device__ __forceinline__ PackedAxis pack_axis(const AxisEntry<float>& e, int m
   return a;
 }
 
-template <typename Tin, typename Tout, int G, bool AFFINE>
-__global__ void __launch_bounds__(kThreads, 5)
+// NV = 16-byte channel vectors per thread (1 or 2): with 2, the per-bin table reads, address arithmetic
+// and weight products are amortised over twice the channels (the kernel is issue / L1 bound, not HBM bound).
+template <typename Tin, typename Tout, int G, bool AFFINE, int NV>
+__global__ void __launch_bounds__(kThreads, (NV == 1 ? 5 : 3))
 roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
   constexpr int VEC = 16 / (int)sizeof(Tin);
+  constexpr int CH = VEC * NV;
   __shared__ PackedAxis ytab[kTab];
   __shared__ PackedAxis xtab[kTab];
 
@@ -351,7 +354,7 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
   const int gh = G > 0 ? G : g.gh, gw = G > 0 ? G : g.gw;
   // tables always fit for G > 0 (launcher guarantees PH*G, PW*G <= kTab); adaptive grids that do
   // not fit are processed in chunks of kTab samples per axis.
-  const int lanes = C / VEC;
+  const int lanes = C / CH;
   const Tin* map = reinterpret_cast<const Tin*>(p.maps[lvl]) + (size_t)g.batch * H * W * C;
   Tout* out = reinterpret_cast<Tout*>(p.out) +
               (((size_t)lvl * p.K + k) * p.PH + ph0) * (size_t)PW * C;
@@ -368,18 +371,18 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
       const int lane = it % lanes;
       const int b = it / lanes;  // bin within this CTA's rows
       const int prow = b / PW, pw = b % PW;
-      const int coff = lane * VEC;
+      const int coff = lane * CH;
       const Tin* mp = map + coff;
-      float ga[VEC], gb[VEC];
+      float ga[CH], gb[CH];
       if constexpr (AFFINE) {
         const float* sa = p.gn_scale[lvl] + (size_t)g.batch * C + coff;
         const float* sb = p.gn_shift[lvl] + (size_t)g.batch * C + coff;
 #pragma unroll
-        for (int i = 0; i < VEC; i++) { ga[i] = sa[i]; gb[i] = sb[i]; }
+        for (int i = 0; i < CH; i++) { ga[i] = sa[i]; gb[i] = sb[i]; }
       }
-      float acc[VEC];
+      float acc[CH];
 #pragma unroll
-      for (int i = 0; i < VEC; i++) acc[i] = 0.f;
+      for (int i = 0; i < CH; i++) acc[i] = 0.f;
 #pragma unroll
       for (int iy = 0; iy < (G > 0 ? G : gh); iy++) {
         const PackedAxis ey = ytab[prow * gh + iy];
@@ -388,13 +391,21 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
           const PackedAxis ex = xtab[pw * gw + ix];
           if (ey.off_lo >= 0 && ex.off_lo >= 0) {
             const float w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
-            float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-            load16<Tin>(mp + (ey.off_lo + ex.off_lo), v1);
-            load16<Tin>(mp + (ey.off_lo + ex.off_hi), v2);
-            load16<Tin>(mp + (ey.off_hi + ex.off_lo), v3);
-            load16<Tin>(mp + (ey.off_hi + ex.off_hi), v4);
+            float v1[CH], v2[CH], v3[CH], v4[CH];
 #pragma unroll
-            for (int i = 0; i < VEC; i++) {
+            for (int n = 0; n < NV; n++) {
+              float t1[VEC], t2[VEC], t3[VEC], t4[VEC];
+              load16<Tin>(mp + (ey.off_lo + ex.off_lo) + n * VEC, t1);
+              load16<Tin>(mp + (ey.off_lo + ex.off_hi) + n * VEC, t2);
+              load16<Tin>(mp + (ey.off_hi + ex.off_lo) + n * VEC, t3);
+              load16<Tin>(mp + (ey.off_hi + ex.off_hi) + n * VEC, t4);
+#pragma unroll
+              for (int i = 0; i < VEC; i++) {
+                v1[n * VEC + i] = t1[i]; v2[n * VEC + i] = t2[i]; v3[n * VEC + i] = t3[i]; v4[n * VEC + i] = t4[i];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
               if constexpr (AFFINE) {
                 v1[i] = fmaxf(v1[i] * ga[i] + gb[i], 0.f);
                 v2[i] = fmaxf(v2[i] * ga[i] + gb[i], 0.f);
@@ -408,17 +419,24 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
         }
       }
 #pragma unroll
-      for (int i = 0; i < VEC; i++) acc[i] = quarter ? acc[i] * 0.25f : acc[i] / g.count;
-      store_vec<Tout, VEC>(out + ((size_t)prow * PW + pw) * C + coff, acc);
+      for (int i = 0; i < CH; i++) acc[i] = quarter ? acc[i] * 0.25f : acc[i] / g.count;
+#pragma unroll
+      for (int n = 0; n < NV; n++) {
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; i++) o[i] = acc[n * VEC + i];
+        store_vec<Tout, VEC>(out + ((size_t)prow * PW + pw) * C + coff + n * VEC, o);
+      }
     }
     return;
   }
 
   // generic path (adaptive sampling grids too large for the tables): geometry on the fly
-  const int items = nrows * PW * lanes;
+  const int lanes1 = C / VEC;
+  const int items = nrows * PW * lanes1;
   for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int lane = it % lanes;
-    const int b = it / lanes;
+    const int lane = it % lanes1;
+    const int b = it / lanes1;
     const int prow = b / PW, pw = b % PW;
     const int coff = lane * VEC;
     float acc[VEC];
@@ -582,12 +600,28 @@ static int launch_fwd_mlvl(MlvlParams& p, bool affine, cudaStream_t st) {
   }
   dim3 grid((unsigned)(p.K * max_groups), p.n_levels);
   const bool g2 = p.sampling_ratio == 2 && p.PH * 2 <= kTab && p.PW * 2 <= kTab;
+  constexpr int VEC = 16 / (int)sizeof(Tin);
+  static int nv_env = -1;
+  if (nv_env < 0) {
+    const char* e = getenv("G4R_ROI_NV");
+    nv_env = e ? atoi(e) : 0;
+  }
+  // 2 vectors per thread only for fp32 maps (8 channels/thread); 16-bit maps already carry 8 per vector
+  const bool nv2 = sizeof(Tin) == 4 && p.C % (2 * VEC) == 0 && p.C / (2 * VEC) >= 32 && nv_env != 1;
   if (g2) {
-    if (affine) roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, true><<<grid, kThreads, 0, st>>>(p);
-    else roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, false><<<grid, kThreads, 0, st>>>(p);
+    if constexpr (sizeof(Tin) == 4) {
+      if (nv2) {
+        if (affine) roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, true, 2><<<grid, kThreads, 0, st>>>(p);
+        else roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, false, 2><<<grid, kThreads, 0, st>>>(p);
+      }
+    }
+    if (!nv2) {
+      if (affine) roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, true, 1><<<grid, kThreads, 0, st>>>(p);
+      else roi_align_fwd_nhwc_mlvl<Tin, Tout, 2, false, 1><<<grid, kThreads, 0, st>>>(p);
+    }
   } else {
-    if (affine) roi_align_fwd_nhwc_mlvl<Tin, Tout, 0, true><<<grid, kThreads, 0, st>>>(p);
-    else roi_align_fwd_nhwc_mlvl<Tin, Tout, 0, false><<<grid, kThreads, 0, st>>>(p);
+    if (affine) roi_align_fwd_nhwc_mlvl<Tin, Tout, 0, true, 1><<<grid, kThreads, 0, st>>>(p);
+    else roi_align_fwd_nhwc_mlvl<Tin, Tout, 0, false, 1><<<grid, kThreads, 0, st>>>(p);
   }
   G4R_LAUNCH_CHECK("roi_align_fwd_nhwc_mlvl");
   return G4R_OK;
