@@ -193,6 +193,49 @@ def cpu_reference_sample(budget_note=True):
                 stage_seconds={k: round(v, 3) for k, v in parts.items()})
 
 
+def roialign_microbench(dev, pk, how, n_maps=128, rois_per_map=100):
+    """BASELINE configs[4] (scaled to 128 of 256 maps to sit beside the 7B weights): 224-pyramid
+    (128,64,32,16) x 1024 ch NHWC fp32, 100 RoIs per map, 7x7, sampling 2, one fused launch.
+    achieved = algorithmic bytes (whole maps read once + output written once + rois) / CUDA-event time."""
+    import numpy as np
+    import torch
+    import gpt4roi_b200 as g
+    rng = np.random.default_rng(0)
+    sizes, C = (128, 64, 32, 16), 1024
+    rows = []
+    for i in range(n_maps):
+        p = np.sort(rng.uniform(0, 1, (rois_per_map, 2, 2)), axis=1)
+        b = np.concatenate([p[:, 0, :], p[:, 1, :]], 1) * 224
+        b[:, 2:] = np.minimum(np.maximum(b[:, 2:], b[:, :2] + 2.0), 224)
+        rows.append(np.concatenate([np.full((rois_per_map, 1), i), b], 1))
+    rois = torch.from_numpy(np.concatenate(rows).astype(np.float32)).to(dev)
+    K = rois.shape[0]
+    maps = [torch.randn(n_maps, h, h, C, device=dev) for h in sizes]
+    out = torch.empty((4, K, 7, 7, C), device=dev)
+    scales = [float(np.float32(1.0 / s)) for s in (14 / 8, 14 / 4, 14 / 2, 14)]
+    for _ in range(3):
+        g.roi_align_mlvl(maps, rois, 7, scales, 2, out=out)
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.roi_align_mlvl(maps, rois, 7, scales, 2, out=out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    alg = sum(m.numel() for m in maps) * 4 + out.numel() * 4 + K * 20
+    ach = alg / 1e9 / (ms / 1e3)
+    del maps, out
+    torch.cuda.empty_cache()
+    return dict(bound='hbm', kernel='roi_align_fwd_nhwc_mlvl', achieved=ach, peak=pk['hbm_gbs'], unit='GB/s',
+                frac=ach / pk['hbm_gbs'], peak_kind=how, ms=ms, algorithmic_GB=alg / 1e9,
+                config='%d maps x %d RoIs, 7x7, 4 levels x 1024 ch (128,64,32,16), fp32 NHWC, inputs (%.1f GB) > L2'
+                       % (n_maps, rois_per_map, sum(h * h for h in sizes) * n_maps * C * 4 / 1e9),
+                traffic=None)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -320,6 +363,14 @@ def run_ours(args):
                 avg_launch_ms=gemm_ms / max(len(prof), 1), share_of_step=gemm_ms / ms_step / (1.0 if True else 1),
                 note='events around each launch in one eager instrumented step after the timed region')
 
+    # ---- second half of the BASELINE metric: RoIAlign HBM GB/s (config 5, 224-pyramid, 7x7, fp32) ----
+    roi = None
+    if rank == 0 and not args.no_roialign:
+        try:
+            roi = roialign_microbench(dev, pk, how)
+        except Exception as e:  # e.g. not enough free memory next to the 7B weights
+            roi = dict(skipped=str(e)[:200])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -339,6 +390,7 @@ def run_ours(args):
                          d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
                 roofline=roof,
                 model_tflops=value * FLOPS_PER_SAMPLE / 1e12 / world,
+                roialign_roofline=roi,
                 cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -353,6 +405,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--layers', type=int, default=32, help=argparse.SUPPRESS)  # debugging only; 32 = LLaMA-7B
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-roialign', action='store_true')
     ap.add_argument('--ncu', action='store_true', help='one eager forward inside a cudaProfiler window')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -607,7 +607,9 @@ static int launch_fwd_mlvl(MlvlParams& p, bool affine, cudaStream_t st) {
     nv_env = e ? atoi(e) : 0;
   }
   // 2 vectors per thread only for fp32 maps (8 channels/thread); 16-bit maps already carry 8 per vector
-  const bool nv2 = sizeof(Tin) == 4 && p.C % (2 * VEC) == 0 && p.C / (2 * VEC) >= 32 && nv_env != 1;
+  // measured on B200 (profiles/r1_roialign_microbench_v3.jsonl): 2 vectors/thread is 25 % SLOWER (fewer
+  // threads per bin => less latency hiding), so it stays opt-in (G4R_ROI_NV=2)
+  const bool nv2 = sizeof(Tin) == 4 && p.C % (2 * VEC) == 0 && p.C / (2 * VEC) >= 32 && nv_env == 2;
   if (g2) {
     if constexpr (sizeof(Tin) == 4) {
       if (nv2) {
