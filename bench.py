@@ -102,6 +102,11 @@ def cpu_reference_sample(budget_note=True):
     import torch.nn.functional as F
     from gpt4roi_b200.engine import EngineConfig
     torch.set_grad_enabled(False)
+    # torchrun exports OMP_NUM_THREADS=1 for nproc>1: use all host cores explicitly (rank 0 runs alone)
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     tiny = os.environ.get('G4R_BENCH_TINY') == '1'   # CPU unit test only: same code path, toy sizes
     cfg = EngineConfig(image_size=56 if tiny else WORKLOAD['image_size'])

@@ -183,3 +183,20 @@ def test_right_padded_batch_matches_oracle_on_valid_positions():
     assert rel(got[1, :short], solo[0]) < 1e-6           # padding does not leak into valid positions
     full0 = eng.forward(ids[0:1].to(DEV), images[0:1].to(DEV), [boxes[0]]).float()
     assert rel(got[0], full0[0]) < 1e-6
+
+
+def test_zero_box_samples():
+    """Edge cases of layers.py:315-318 / det_llava.py:463: a sample with K_i = 0 inside a batch that has
+    boxes, and a batch with no boxes at all (empty tensors, not None)."""
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=1)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=13)
+    eng = PrefillEngine(cfg, sd, vit_sd, DEV)
+    ids, images, boxes = make_inputs(cfg, 2, [2, 0], 16, seed=4)
+    images = images.to(torch.bfloat16)
+    got = eng.forward(ids.to(DEV), images.to(DEV), boxes).float()
+    ref = model_oracle.forward(cfg, sd, vit_sd, ids, images.float(), boxes, DEV)
+    assert rel(got, ref) < 2e-2
+    ids0, images0, boxes0 = make_inputs(cfg, 2, [0, 0], 16, seed=6)
+    got0 = eng.forward(ids0.to(DEV), images0.to(DEV, torch.bfloat16), boxes0).float()       # K = 0 overall
+    none0 = eng.forward(ids0.to(DEV), images0.to(DEV, torch.bfloat16), None).float()        # bboxes=None
+    assert torch.equal(got0, none0)
