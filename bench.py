@@ -265,6 +265,9 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # keep stdout to the single JSON line: NCCL prints its version banner there unless told otherwise
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     import torch
     import torch.distributed as dist
     from gpt4roi_b200 import dense, dist_utils, lib
