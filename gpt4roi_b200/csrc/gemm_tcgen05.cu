@@ -62,7 +62,7 @@ struct GemmParams {
   // bf16 cos/sin tables [rope_L][128]; row position = out_row % rope_L
   const __nv_bfloat16* rope_cos;
   const __nv_bfloat16* rope_sin;
-  int rope_cols, rope_L;
+  int rope_cols, rope_L, rope_pos0;
   float* gn_stats;       // optional [n_img, groups, 2] (sum, sumsq) of the bf16-rounded output
   int gn_group_ch;       // channels per group (16)
   int gn_groups;         // groups per image (64)
@@ -111,7 +111,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     // dims (d, d+64) of a head are 64 columns apart -> load both 32-column chunks, rotate, store.
     // Rounding as in the reference: q/k are bf16 GEMM outputs, each bf16 tensor op rounds:
     //   out = bf16( bf16(x*cos) + bf16(rot*sin) ),  rotate_half(x) = cat(-x2, x1).
-    const int pos = (int)(out_row % p.rope_L);
+    const int pos = p.rope_pos0 + (int)(out_row % p.rope_L);
     const __nv_bfloat16* ct = p.rope_cos + (long long)pos * 128;
     const __nv_bfloat16* st = p.rope_sin + (long long)pos * 128;
 #pragma unroll 1
@@ -742,7 +742,8 @@ extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long l
 static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
                      int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr,
                      int residual_f32, int bias_round_bf16, int act, int out_f32, int k_splits,
-                     const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream);
+                     const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream,
+                     int rope_pos0 = 0);
 
 extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, void* D,
                                 long long ldd, int M, int N, int K, const void* bias, int bias_f32,
@@ -757,17 +758,18 @@ extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, lon
 // q_proj/k_proj/v_proj + apply_rotary_pos_emb (transformers modeling_llama.py:138-168,240-260).
 extern "C" int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* B, long long ldb, void* D,
                                       long long ldd, int M, int N, int K, const void* rope_cos,
-                                      const void* rope_sin, int rope_cols, int L, void* stream) {
+                                      const void* rope_sin, int rope_cols, int L, int pos0, void* stream) {
   G4R_REQUIRE(rope_cos && rope_sin && L > 0, "qkv_rope: null tables");
   G4R_REQUIRE(rope_cols % 256 == 0 && rope_cols <= N && N % 128 == 0 && ldd % 8 == 0, "qkv_rope: rope_cols must be a multiple of 256 (whole tiles of 128-dim heads)");
   return gemm_impl(A, lda, B, ldb, D, ldd, M, N, K, nullptr, 0, nullptr, 0, 0, 0, ACT_NONE, 0, 1, rope_cos, rope_sin,
-                   rope_cols, L, stream);
+                   rope_cols, L, stream, pos0);
 }
 
 static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
                      int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr,
                      int residual_f32, int bias_round_bf16, int act, int out_f32, int k_splits,
-                     const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream) {
+                     const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream,
+                     int rope_pos0) {
   G4R_REQUIRE(A && B && D, "null operand");
   G4R_REQUIRE(M > 0 && N > 0 && K > 0, "bad sizes M=%d N=%d K=%d", M, N, K);
   G4R_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "lda/ldb must be >= K and multiples of 8 (16-byte TMA strides)");
@@ -787,7 +789,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.residual_f32 = residual_f32;
   p.round_branch = bias_round_bf16;
   p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin;
-  p.rope_cols = rope_cols; p.rope_L = rope_L;
+  p.rope_cols = rope_cols; p.rope_L = rope_L; p.rope_pos0 = rope_pos0;
   p.act = act; p.out_f32 = out_f32; p.atomic = k_splits > 1;
   p.conv = 0; p.a_rows = kBlockM;
   const bool two = use_2sm(N, p.num_m_tiles, k_splits, false);

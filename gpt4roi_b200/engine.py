@@ -224,18 +224,20 @@ class PrefillEngine:
         t = kernels.add_bias_pos_cast(acc, self.flat_b, pos)
         return dense.linear(t, self.up_w, self.up_b)
 
-    def llama(self, embeds, B, L, last_only=False, seqlens=None):
+    def llama(self, embeds, B, L, last_only=False, seqlens=None, cache=None):
         c = self.cfg
         x = embeds.view(B * L, c.hidden)
         cos, sin = self._rope(L)
         scale = c.head_dim ** -0.5
-        for w in self.layers:
+        for li, w in enumerate(self.layers):
             h = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
             if c.head_dim == 128 and (2 * c.hidden) % 256 == 0:
                 qkv = dense.qkv_rope(h, w['wqkv'], cos, sin, L, 2 * c.hidden)   # RoPE fused into the GEMM epilogue
             else:
                 qkv = dense.linear(h, w['wqkv'])
                 kernels.rope_inplace(qkv, cos, sin, L, 2 * c.n_heads, c.head_dim)
+            if cache is not None:  # keep post-RoPE K and V for the decode loop
+                kernels.kv_append(qkv, cache.k[li], cache.v[li], B, L, 0)
             a = kernels.attention(qkv, B, L, c.n_heads, c.head_dim, True, scale, seqlens=seqlens)
             x = dense.linear(a, w['wo'], residual=x)
             h = kernels.rmsnorm(x, w['ln_post'], c.rms_eps)
@@ -268,7 +270,7 @@ class PrefillEngine:
             bidx = torch.zeros((0,), dtype=torch.float32, device=self.dev)
         return dict(K=K, boxes=boxes, bidx=bidx, offs=offs)
 
-    def forward_device(self, input_ids, images, plan, validate=True, last_only=False, seqlens=None):
+    def forward_device(self, input_ids, images, plan, validate=True, last_only=False, seqlens=None, cache=None):
         """Device-only forward (capturable): input_ids int64 [B,L], images bf16 [B,3,S,S] on the GPU."""
         c = self.cfg
         B, L = input_ids.shape
@@ -285,7 +287,9 @@ class PrefillEngine:
             region = (rows, plan['offs'])
         embeds = splice_region_tokens(input_ids, self.embed, img_rows, region, c.num_patches, c.im_patch_token,
                                       c.im_start_token, c.im_end_token, c.bbox_token, validate=validate)
-        return self.llama(embeds, B, L, last_only=last_only, seqlens=seqlens)
+        if cache is not None:
+            cache.length = L
+        return self.llama(embeds, B, L, last_only=last_only, seqlens=seqlens, cache=cache)
 
     def forward(self, input_ids, images, bboxes, validate=True, last_only=False, attention_mask=None):
         """Public entry: input_ids int64 [B,L]; images [B,3,S,S]; bboxes list (len B) of [K_i,4]
@@ -302,6 +306,81 @@ class PrefillEngine:
             seqlens = lens.to(torch.int32).contiguous()
         return self.forward_device(input_ids.to(self.dev, non_blocking=True),
                                    images.to(self.dev, BF16, non_blocking=True), plan, validate, last_only, seqlens)
+
+
+class KVCache:
+    """Per-layer K/V cache [B, Lmax, n_heads*head_dim] (bf16, post-RoPE keys) for the decode loop."""
+
+    def __init__(self, cfg, B, max_len, device):
+        hd = cfg.n_heads * cfg.head_dim
+        self.k = [torch.empty((B, max_len, hd), dtype=BF16, device=device) for _ in range(cfg.n_layers)]
+        self.v = [torch.empty((B, max_len, hd), dtype=BF16, device=device) for _ in range(cfg.n_layers)]
+        self.B, self.max_len, self.length = B, max_len, 0
+
+
+def _decode_step(self, token_ids, cache):
+    """One decode step: token_ids int64 [B,1] -> logits [B,1,V]; the vision / SPI branch
+    is skipped exactly as the reference does for input_ids.shape[1] == 1 (spi_llava.py:47-48)."""
+    c = self.cfg
+    B = token_ids.shape[0]
+    pos = cache.length
+    if pos + 1 > cache.max_len:
+        raise RuntimeError('KV cache is full (%d)' % cache.max_len)
+    x = splice_region_tokens(token_ids, self.embed, None, None, 0, c.im_patch_token, c.im_start_token,
+                             c.im_end_token, c.bbox_token, validate=False).view(B, c.hidden)
+    cos, sin = self._rope(cache.max_len)
+    scale = c.head_dim ** -0.5
+    fused = c.head_dim == 128 and (2 * c.hidden) % 256 == 0
+    for li, w in enumerate(self.layers):
+        h = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
+        if fused:
+            qkv = dense.qkv_rope(h, w['wqkv'], cos, sin, 1, 2 * c.hidden, pos0=pos)
+        else:
+            qkv = dense.linear(h, w['wqkv'])
+            kernels.rope_inplace(qkv, cos[pos:pos + 1].contiguous(), sin[pos:pos + 1].contiguous(), 1, 2 * c.n_heads, c.head_dim)
+        kernels.kv_append(qkv, cache.k[li], cache.v[li], B, 1, pos)
+        a = kernels.decode_attention(qkv, cache.k[li], cache.v[li], B, c.n_heads, c.head_dim, pos + 1, scale)
+        x = dense.linear(a, w['wo'], residual=x)
+        h = kernels.rmsnorm(x, w['ln_post'], c.rms_eps)
+        f = dense.linear(h, w['wgu'], act='swiglu')
+        x = dense.linear(f, w['wdown'], residual=x)
+    cache.length = pos + 1
+    x = kernels.rmsnorm(x, self.norm_w, c.rms_eps)
+    buf = torch.empty((B, self.vocab_pad), dtype=BF16, device=self.dev)
+    dense.linear(x, self.lm_head, out=buf[:, :c.vocab])
+    return buf[:, None, :c.vocab]
+
+
+@torch.no_grad()
+def _generate(self, input_ids, images, bboxes, max_new_tokens=32, do_sample=False, temperature=1.0,
+              stopping_criteria=None, eos_token_id=None, generator=None):
+    """Prefill + greedy / temperature-sampled decode (gpt4roi/app.py:286-300 calls
+    model.generate(input_ids, images=..., do_sample=True, temperature=0.2, max_new_tokens=1024,
+    stopping_criteria=[...]) with the boxes bound to forward).  Returns ids [B, L + new]."""
+    B, L = input_ids.shape
+    cache = KVCache(self.cfg, B, L + max_new_tokens, self.dev)
+    plan = self.plan_boxes(bboxes)
+    ids = input_ids.to(self.dev)
+    logits = self.forward_device(ids, images.to(self.dev, BF16), plan, validate=True, last_only=True, cache=cache)
+    out = ids
+    for step in range(max_new_tokens):
+        last = logits[:, -1].float()
+        if do_sample and temperature > 0:
+            nxt = torch.multinomial(torch.softmax(last / temperature, -1), 1, generator=generator)
+        else:
+            nxt = last.argmax(-1, keepdim=True)
+        out = torch.cat([out, nxt], 1)
+        if eos_token_id is not None and bool((nxt == eos_token_id).all()):
+            break
+        if stopping_criteria is not None and any(bool(torch.as_tensor(sc(out, last)).all()) for sc in stopping_criteria):
+            break
+        if step + 1 < max_new_tokens:
+            logits = self.decode_step(nxt, cache)
+    return out
+
+
+PrefillEngine.decode_step = _decode_step
+PrefillEngine.generate = _generate
 
 
 class GraphedPrefill:

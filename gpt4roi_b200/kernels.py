@@ -157,3 +157,18 @@ def add_bias_pos_cast(acc, bias, pos):
     if K:
         _call('g4r_add_bias_pos_cast', acc.device, _L.ptr(acc), splits, _L.ptr(bias), _L.ptr(pos), _L.ptr(out), K, D)
     return out
+
+
+def kv_append(qkv, kcache, vcache, B, Ln, pos0):
+    """Copy the k|v parts of packed qkv rows [B*Ln, 3*HD] into caches [B, Lmax, HD] at pos0..pos0+Ln-1."""
+    HD = kcache.shape[-1]
+    _call('g4r_kv_append_bf16', qkv.device, _L.ptr(qkv), qkv.stride(0), _L.ptr(kcache), _L.ptr(vcache), B, Ln,
+          int(pos0), kcache.shape[1], HD)
+
+
+def decode_attention(qkv, kcache, vcache, B, n_heads, head_dim, kv_len, scale):
+    """qkv [B, 3*HD] (one new token per sample); caches [B, Lmax, HD]; returns [B, HD]."""
+    out = torch.empty((B, n_heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    _call('g4r_decode_attention_bf16', qkv.device, _L.ptr(qkv), qkv.stride(0), _L.ptr(kcache), _L.ptr(vcache),
+          _L.ptr(out), out.stride(0), B, n_heads, head_dim, int(kv_len), kcache.shape[1], float(scale))
+    return out

@@ -14,9 +14,10 @@ scripts can import these classes instead:
 The modules below are PARAMETER CONTAINERS with the reference's state-dict layout (SURVEY.md
 Appendix C; mmcv's ConvModule names `.conv` / `.gn` included).  Their `forward` does not run
 PyTorch ops: it hands the weights to `engine.PrefillEngine` (re-laid-out once, cached until the
-weights change) which launches the hand-written kernels.  Round-1 limits, stated: inference
-prefill only (no KV-cache decode step, no backward through the dense blocks yet), right-padded
-attention masks only; anything else raises NotImplementedError instead of falling back.
+weights change) which launches the hand-written kernels.  Round-1 limits, stated: inference only
+(prefill `forward` + `generate()` with its own KV-cache decode loop; HF `past_key_values` plumbing and
+backward through the dense blocks are not provided), right-padded attention masks only; anything else
+raises NotImplementedError instead of falling back.
 """
 from typing import List, Optional
 
@@ -193,6 +194,18 @@ class SPILlavaMPTForCausalLM(LlamaForCausalLM):
         if return_dict is False:
             return (loss, logits) if loss is not None else (logits,)
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=None, attentions=None)
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, images=None, bboxes=None, max_new_tokens=32, do_sample=False,
+                 temperature=1.0, stopping_criteria=None, eos_token_id=None, **kwargs):
+        """Region-token prefill + KV-cache decode on the sm_100a engine.  Accepts the arguments the demo
+        passes (gpt4roi/app.py:293-300); boxes may be given here or bound the way app.py does
+        (`self.forward = partial(self.forward, bboxes=...)`, :286-291).  Returns ids [B, L+new] like HF."""
+        if bboxes is None:
+            bboxes = getattr(getattr(self, 'forward', None), 'keywords', {}).get('bboxes')
+        eng = self._get_engine(input_ids.device)
+        return eng.generate(input_ids, images, bboxes, max_new_tokens=max_new_tokens, do_sample=do_sample,
+                            temperature=temperature, stopping_criteria=stopping_criteria, eos_token_id=eos_token_id)
 
     def initialize_vision_tokenizer(self, mm_use_im_start_end, tokenizer, device, tune_mm_mlp_adapter=False,
                                     pretrain_mm_mlp_adapter=None):

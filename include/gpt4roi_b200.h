@@ -177,11 +177,24 @@ int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb,
 
 /* LLaMA QKV projection with apply_rotary_pos_emb fused into the epilogue (transformers
  * modeling_llama.py:138-168): D[M,N] = A.B^T; columns [0,rope_cols) are 128-dim heads rotated with the
- * bf16 cos/sin tables [L,128] at position (row % L); rounding points as in the reference's bf16 ops. */
+ * bf16 cos/sin tables [>= pos0+L, 128] at position pos0 + (row % L) (pos0 > 0: decode steps);
+ * rounding points as in the reference's bf16 ops. */
 int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* B, long long ldb,
                            void* D, long long ldd, int M, int N, int K,
-                           const void* rope_cos, const void* rope_sin, int rope_cols, int L,
+                           const void* rope_cos, const void* rope_sin, int rope_cols, int L, int pos0,
                            void* stream);
+
+/* ---- decode loop (KV cache) -------------------------------------------------- */
+/* Append the k and v parts of packed rows [B*Ln, (q|k|v) of width HD each] to the caches
+ * [B, Lmax, HD] at positions pos0..pos0+Ln-1 (prefill: pos0=0, Ln=L; decode: Ln=1).  */
+int g4r_kv_append_bf16(const void* qkv, long long ld, void* kcache, void* vcache,
+                       int B, int Ln, int pos0, int Lmax, int HD, void* stream);
+/* One new query per sample against the first kv_len cached positions: out[b,h,:] =
+ * softmax(q.K^T*scale) V.  Replaces the decode-step attention of transformers' LlamaAttention with a
+ * DynamicCache (generate() in gpt4roi/app.py:293-300; vision branch skipped, spi_llava.py:47-48). */
+int g4r_decode_attention_bf16(const void* q, long long ldq, const void* kcache, const void* vcache,
+                              void* out, long long ldo, int B, int H, int head_dim, int kv_len,
+                              int Lmax, float scale, void* stream);
 
 /*
  * NHWC convolution as an implicit GEMM (stride 1, pad (ksize-1)/2, ksize 1 or 3):

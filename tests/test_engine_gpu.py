@@ -200,3 +200,33 @@ def test_zero_box_samples():
     got0 = eng.forward(ids0.to(DEV), images0.to(DEV, torch.bfloat16), boxes0).float()       # K = 0 overall
     none0 = eng.forward(ids0.to(DEV), images0.to(DEV, torch.bfloat16), None).float()        # bboxes=None
     assert torch.equal(got0, none0)
+
+
+def test_decode_loop_matches_prefill_logits():
+    """prefill + KV-cache decode steps reproduce the logits of a full prefill over the
+    extended sequence (teacher forcing); greedy generate() returns the same tokens as re-running prefill."""
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=17)
+    eng = PrefillEngine(cfg, sd, vit_sd, DEV)
+    ids, images, boxes = make_inputs(cfg, 2, [2, 1], 24, seed=8)
+    images = images.to(DEV, torch.bfloat16)
+    n_new = 5
+    full = eng.forward(ids.to(DEV), images, boxes).float()                   # [B, L, V]
+    L0 = ids.shape[1] - n_new
+    from gpt4roi_b200.engine import KVCache
+    cache = KVCache(cfg, 2, ids.shape[1], DEV)
+    # the <bbox> tokens must all be inside the prefix for this check
+    assert all(int(torch.where(ids[b] == cfg.bbox_token)[0].max()) < L0 for b in range(2))
+    plan = eng.plan_boxes(boxes)
+    pre = eng.forward_device(ids[:, :L0].contiguous().to(DEV), images, plan, last_only=True, cache=cache).float()
+    assert rel(pre[:, 0], full[:, L0 - 1]) < 5e-3
+    for t in range(n_new):
+        step = eng.decode_step(ids[:, L0 + t:L0 + t + 1].contiguous().to(DEV), cache).float()
+        e = rel(step[:, 0], full[:, L0 + t])
+        assert e < 1e-2, (t, e)
+    # generate(): greedy continuation is self-consistent with prefill
+    out = eng.generate(ids[:, :L0].contiguous(), images, boxes, max_new_tokens=3)
+    assert out.shape == (2, L0 + 3)
+    chk = eng.forward(out[:, :-1].contiguous(), images, boxes).float()
+    agree = (chk[:, L0 - 1:].argmax(-1) == out[:, L0:]).float().mean().item()
+    assert agree >= 0.8, agree
