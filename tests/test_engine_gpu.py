@@ -211,6 +211,7 @@ def test_decode_loop_matches_prefill_logits():
     ids, images, boxes = make_inputs(cfg, 2, [2, 1], 24, seed=8)
     images = images.to(DEV, torch.bfloat16)
     n_new = 5
+    ids = torch.cat([ids, torch.randint(3, 32000, (2, n_new), generator=torch.Generator().manual_seed(3))], 1)
     full = eng.forward(ids.to(DEV), images, boxes).float()                   # [B, L, V]
     L0 = ids.shape[1] - n_new
     from gpt4roi_b200.engine import KVCache
