@@ -41,6 +41,8 @@ struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_k_blocks;  // num_k_blocks: per split
   int k_splits;
+  int n_fast;  // tile order: 1 = n-tile index fastest (conv: the big NHWC input is read from DRAM once and
+               // its <= 4 weight panels stay in L2), 0 = m fastest (GEMM: weight panels stream once)
   // epilogue
   void* D;
   long long ldd;
@@ -371,7 +373,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int split = t / tiles_mn;
         const int mn = t % tiles_mn;
-        const int n_blk = mn / p.num_m_tiles, m_blk = mn % p.num_m_tiles;  // m fastest: weights stay in L2
+        const int n_blk = p.n_fast ? mn % p.num_n_tiles : mn / p.num_m_tiles;
+        const int m_blk = p.n_fast ? mn / p.num_n_tiles : mn % p.num_m_tiles;
         const int kb0 = split * p.num_k_blocks;
         int img = 0, y0 = 0, x0 = 0;
         if (CONV) {
@@ -440,7 +443,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t acc_phase = (it >> 1) & 1;
       const int split = t / tiles_mn;
       const int mn = t % tiles_mn;
-      const int n_blk = mn / p.num_m_tiles, m_blk = mn % p.num_m_tiles;
+      const int n_blk = p.n_fast ? mn % p.num_n_tiles : mn / p.num_m_tiles;
+      const int m_blk = p.n_fast ? mn / p.num_n_tiles : mn % p.num_m_tiles;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tcgen05_after_thread_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
@@ -534,7 +538,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const int split = t / tiles_mn;
         const int mn = t % tiles_mn;
-        const int n_blk = mn / num_m_pairs, m_blk = (mn % num_m_pairs) * 2 + (int)rank;
+        const int n_blk = p.n_fast ? mn % p.num_n_tiles : mn / num_m_pairs;
+        const int m_blk = (p.n_fast ? mn / p.num_n_tiles : mn % num_m_pairs) * 2 + (int)rank;
         const int kb0 = split * p.num_k_blocks;
         int img = 0, y0 = 0, x0 = 0;
         if (CONV) {
@@ -607,7 +612,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t acc_phase = (it >> 1) & 1;
       const int split = t / tiles_mn;
       const int mn = t % tiles_mn;
-      const int n_blk = mn / num_m_pairs, m_blk = (mn % num_m_pairs) * 2 + (int)rank;
+      const int n_blk = p.n_fast ? mn % p.num_n_tiles : mn / num_m_pairs;
+      const int m_blk = (p.n_fast ? mn / p.num_n_tiles : mn % num_m_pairs) * 2 + (int)rank;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tcgen05_after_thread_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
@@ -859,6 +865,11 @@ extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_
   p.k_splits = 1;
   p.D = Y; p.ldd = Cout; p.bias = bias; p.bias_f32 = bias_f32; p.act = act;
   p.conv = 1;
+  {
+    static int nf = -1;
+    if (nf < 0) { const char* e = getenv("G4R_CONV_NFAST"); nf = e ? atoi(e) : 1; }
+    p.n_fast = nf;
+  }
   p.gn_stats = gn_stats; p.gn_groups = gn_groups; p.gn_group_ch = gn_groups ? Cout / gn_groups : 0;
   const bool two = use_2sm(Cout, p.num_m_tiles, 1, true);
   const int bn = two ? 256 : pick_block_n(Cout, p.num_m_tiles, 1);

@@ -366,11 +366,8 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
     for (int i = threadIdx.x; i < PW * gw; i += blockDim.x)
       xtab[i] = pack_axis(axis_entry<float>(g.start_w, g.bin_w, i / gw, i % gw, gw, W), C);
     __syncthreads();
-    const int items = nrows * PW * lanes;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-      const int lane = it % lanes;
-      const int b = it / lanes;  // bin within this CTA's rows
-      const int prow = b / PW, pw = b % PW;
+    // Per-bin body: `prow`, `pw`, `lane` select the bin and the channel slice.
+    auto do_bin = [&](int prow, int pw, int lane, const PackedAxis* eyp) {
       const int coff = lane * CH;
       const Tin* mp = map + coff;
       float ga[CH], gb[CH];
@@ -385,7 +382,7 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
       for (int i = 0; i < CH; i++) acc[i] = 0.f;
 #pragma unroll
       for (int iy = 0; iy < (G > 0 ? G : gh); iy++) {
-        const PackedAxis ey = ytab[prow * gh + iy];
+        const PackedAxis ey = eyp ? eyp[iy] : ytab[prow * gh + iy];
 #pragma unroll
         for (int ix = 0; ix < (G > 0 ? G : gw); ix++) {
           const PackedAxis ex = xtab[pw * gw + ix];
@@ -427,6 +424,28 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
         for (int i = 0; i < VEC; i++) o[i] = acc[n * VEC + i];
         store_vec<Tout, VEC>(out + ((size_t)prow * PW + pw) * C + coff + n * VEC, o);
       }
+    };
+    if constexpr (G > 0) {
+      if (blockDim.x % lanes == 0 || lanes % blockDim.x == 0) {
+        // fixed channel slice per thread, y-axis entries hoisted out of the pw loop
+        const int ngrp = blockDim.x >= lanes ? blockDim.x / lanes : 1;
+        const int grp = blockDim.x >= lanes ? threadIdx.x / lanes : 0;
+        for (int lane = threadIdx.x % lanes; lane < lanes; lane += (blockDim.x >= lanes ? lanes : blockDim.x)) {
+          for (int prow = 0; prow < nrows; prow++) {
+            PackedAxis eyr[G];
+#pragma unroll
+            for (int iy = 0; iy < G; iy++) eyr[iy] = ytab[prow * G + iy];
+            for (int pw = grp; pw < PW; pw += ngrp) do_bin(prow, pw, lane, eyr);
+          }
+        }
+        return;
+      }
+    }
+    const int items = nrows * PW * lanes;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int lane = it % lanes;
+      const int b = it / lanes;  // bin within this CTA's rows
+      do_bin(b / PW, b % PW, lane, nullptr);
     }
     return;
   }
