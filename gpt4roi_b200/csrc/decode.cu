@@ -10,7 +10,9 @@ namespace g4r {
 // rows [B*Ln, 3*HD] packed (q|k|v) -> caches [B, Lmax, HD] at positions pos0 .. pos0+Ln-1
 __global__ void __launch_bounds__(256)
 kv_append_bf16(const __nv_bfloat16* __restrict__ qkv, long long ld, __nv_bfloat16* __restrict__ kc,
-               __nv_bfloat16* __restrict__ vc, int B, int Ln, int pos0, int Lmax, int HD) {
+               __nv_bfloat16* __restrict__ vc, int B, int Ln, int pos0, const int* __restrict__ pos_dev, int Lmax,
+               int HD) {
+  if (pos_dev) pos0 = *pos_dev;
   const int nvec = HD >> 3;
   const long long total = (long long)B * Ln * nvec * 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -32,7 +34,8 @@ template <int D>
 __global__ void __launch_bounds__(128)
 decode_attention_bf16(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kc,
                       const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, long long ldo,
-                      int H, int kv_len, int Lmax, float scale) {
+                      int H, int kv_len, const int* __restrict__ pos_dev, int Lmax, float scale) {
+  if (pos_dev) kv_len = *pos_dev + 1;
   extern __shared__ float sm[];  // [D] q | [kv_len] scores
   float* sq = sm;
   float* sc = sm + D;
@@ -106,7 +109,7 @@ decode_attention_bf16(const __nv_bfloat16* __restrict__ q, long long ldq, const 
 using namespace g4r;
 
 extern "C" int g4r_kv_append_bf16(const void* qkv, long long ld, void* kcache, void* vcache, int B, int Ln,
-                                  int pos0, int Lmax, int HD, void* stream) {
+                                  int pos0, const int* pos_dev, int Lmax, int HD, void* stream) {
   G4R_REQUIRE(qkv && kcache && vcache && B > 0 && Ln > 0 && pos0 >= 0 && pos0 + Ln <= Lmax && HD % 8 == 0 && ld % 8 == 0,
               "kv_append: bad arguments (pos0=%d Ln=%d Lmax=%d)", pos0, Ln, Lmax);
   const long long total = (long long)B * Ln * (HD / 8) * 2;
@@ -114,14 +117,14 @@ extern "C" int g4r_kv_append_bf16(const void* qkv, long long ld, void* kcache, v
   const long long cap = (long long)num_sms() * 16;
   if (grid > cap) grid = cap;
   kv_append_bf16<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)kcache,
-                                                                  (__nv_bfloat16*)vcache, B, Ln, pos0, Lmax, HD);
+                                                                  (__nv_bfloat16*)vcache, B, Ln, pos0, pos_dev, Lmax, HD);
   G4R_LAUNCH_CHECK("kv_append");
   return G4R_OK;
 }
 
 extern "C" int g4r_decode_attention_bf16(const void* q, long long ldq, const void* kcache, const void* vcache,
                                          void* out, long long ldo, int B, int H, int head_dim, int kv_len,
-                                         int Lmax, float scale, void* stream) {
+                                         const int* pos_dev, int Lmax, float scale, void* stream) {
   G4R_REQUIRE(q && kcache && vcache && out && B > 0 && H > 0 && kv_len > 0 && kv_len <= Lmax, "decode_attention: bad arguments");
   G4R_REQUIRE(head_dim == 64 || head_dim == 128, "decode_attention: head_dim %d", head_dim);
   const int smem = (head_dim + (kv_len > 2 * head_dim ? kv_len : 2 * head_dim) + 8) * 4 + (128 / (head_dim / 2)) * head_dim * 4;
@@ -132,12 +135,12 @@ extern "C" int g4r_decode_attention_bf16(const void* q, long long ldq, const voi
     static bool set = false;
     if (!set) { G4R_CUDA(cudaFuncSetAttribute(decode_attention_bf16<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
     decode_attention_bf16<128><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kcache,
-                                                         (const __nv_bfloat16*)vcache, (__nv_bfloat16*)out, ldo, H, kv_len, Lmax, scale);
+                                                         (const __nv_bfloat16*)vcache, (__nv_bfloat16*)out, ldo, H, kv_len, pos_dev, Lmax, scale);
   } else {
     static bool set = false;
     if (!set) { G4R_CUDA(cudaFuncSetAttribute(decode_attention_bf16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
     decode_attention_bf16<64><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kcache,
-                                                        (const __nv_bfloat16*)vcache, (__nv_bfloat16*)out, ldo, H, kv_len, Lmax, scale);
+                                                        (const __nv_bfloat16*)vcache, (__nv_bfloat16*)out, ldo, H, kv_len, pos_dev, Lmax, scale);
   }
   G4R_LAUNCH_CHECK("decode_attention");
   return G4R_OK;

@@ -1,0 +1,226 @@
+// gemm_skinny.cu -- weight-streaming GEMM for M <= 16 activation rows (the decode step behind
+// generate(), SURVEY.md 8(f1): one new token per sample, gpt4roi/models/spi_llava.py:47-48 skips the
+// vision branch so the step is the 7B LLaMA stack at M = batch).
+//
+// D[M, N] = A[M, K] . W[N, K]^T with the epilogues of gemm_tcgen05.cu (bias, residual, SwiGLU,
+// fused RoPE).  At M <= 16 a 128-row tcgen05 tile wastes the tensor pipe and, worse, gives one CTA
+// per 256 weight rows: too few CTAs to keep HBM busy (measured 1.7 TB/s).  This kernel is HBM-bound
+// by construction: every weight byte is read exactly once with 16-byte streaming loads
+// (ld.global.nc.L1::no_allocate), hundreds of CTAs each cover 16/32 weight rows over the whole K, and
+// the warps of a CTA split K.  The arithmetic rides on mma.sync m16n8k16 with the weight rows as the
+// 16-row operand and the (<= 8) activation rows as the 8-column operand -- tcgen05 has no shape this
+// small (M >= 64) and the kernel is nowhere near compute-bound (2*M flop per weight byte pair).
+//
+// k-permutation trick: the MMA contracts over "logical" k and does not care which physical k each
+// slot holds as long as A and B agree.  Thread (g, t) therefore takes its 8 slots of two consecutive
+// k16 steps from ONE 16-byte load at physical k0 + 8t .. 8t+7, from the weight row and from the
+// activation row alike -- no shuffles, no shared-memory staging, full-sector global loads.
+//
+// Deterministic: partial sums of the WARPS k-slices are reduced through shared memory in fixed order.
+#include "common.cuh"
+
+namespace g4r {
+
+enum { SK_ACT_NONE = 0, SK_ACT_RELU = 1, SK_ACT_QUICK_GELU = 2, SK_ACT_SWIGLU = 3 };
+
+struct SkinnyParams {
+  const __nv_bfloat16* A; long long lda;
+  const __nv_bfloat16* W; long long ldb;
+  __nv_bfloat16* D; long long ldd;
+  int M, N, K;
+  const void* bias; int bias_f32;
+  const __nv_bfloat16* residual; long long ldr;
+  int act;
+  const __nv_bfloat16* rope_cos; const __nv_bfloat16* rope_sin;
+  int rope_cols, rope_L, rope_pos0;
+  const int* rope_pos_dev;
+};
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* ptr) {
+  uint4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// MT: 16-row weight tiles per CTA (1 or 2); MB: 8-row activation blocks (1: M<=8, 2: M<=16);
+// ROPE: the two tiles are 64 rows apart (dims d and d+64 of one 128-dim head) so the rotation has
+// both partners in the CTA.
+template <int MT, int MB, int WARPS, bool ROPE>
+__global__ void __launch_bounds__(WARPS * 32)
+gemm_skinny_bf16(const SkinnyParams p) {
+  constexpr int KB = 128;        // k per warp iteration: 4 sub-blocks of 32 (one 16-byte load per row each)
+  constexpr int NT = MT * 16;
+  constexpr int MC = MB * 8;
+  __shared__ float red[WARPS][NT][MC + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tile_stride = ROPE ? 64 : 16;
+  const int n_base = ROPE ? (int)(blockIdx.x >> 2) * 128 + (int)(blockIdx.x & 3) * 16 : (int)blockIdx.x * NT;
+
+  float acc[MT][MB][4];
+#pragma unroll
+  for (int j = 0; j < MT; j++)
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[j][i][c] = 0.f;
+
+  const __nv_bfloat16* wrow[MT][2];
+  bool wok[MT][2];
+#pragma unroll
+  for (int j = 0; j < MT; j++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int n = n_base + j * tile_stride + g + 8 * h;
+      wok[j][h] = n < p.N;
+      wrow[j][h] = p.W + (long long)(wok[j][h] ? n : 0) * p.ldb + 8 * t;
+    }
+  const __nv_bfloat16* xrow[MB];
+  bool xok[MB];
+#pragma unroll
+  for (int i = 0; i < MB; i++) {
+    const int m = i * 8 + g;
+    xok[i] = m < p.M;
+    xrow[i] = p.A + (long long)(xok[i] ? m : 0) * p.lda + 8 * t;
+  }
+
+#pragma unroll 1
+  for (int k0 = warp * KB; k0 < p.K; k0 += WARPS * KB) {
+    uint4 a[4][MT][2], b[4][MB];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int kk = k0 + 32 * s;
+      const bool kok = kk < p.K;   // K % 32 == 0: a sub-block is whole or absent
+#pragma unroll
+      for (int j = 0; j < MT; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+          a[s][j][h] = (kok && wok[j][h]) ? ldg_stream16(wrow[j][h] + kk) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < MB; i++)
+        b[s][i] = (kok && xok[i]) ? __ldg(reinterpret_cast<const uint4*>(xrow[i] + kk)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+      for (int j = 0; j < MT; j++)
+#pragma unroll
+        for (int i = 0; i < MB; i++) {
+          mma_16816(acc[j][i], a[s][j][0].x, a[s][j][1].x, a[s][j][0].y, a[s][j][1].y, b[s][i].x, b[s][i].y);
+          mma_16816(acc[j][i], a[s][j][0].z, a[s][j][1].z, a[s][j][0].w, a[s][j][1].w, b[s][i].z, b[s][i].w);
+        }
+  }
+
+  // accumulator fragment: c0,c1 = (weight row g, activation rows 2t, 2t+1); c2,c3 = (weight row g+8, ...)
+#pragma unroll
+  for (int j = 0; j < MT; j++)
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) red[warp][j * 16 + g + 8 * (c >> 1)][i * 8 + 2 * t + (c & 1)] = acc[j][i][c];
+  __syncthreads();
+
+  auto total = [&](int r, int m) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) v += red[w][r][m];
+    return v;
+  };
+
+  if (ROPE) {
+    // thread <-> (activation row m, d in [0,16) of this CTA's slice); partners r (dim d) and 16 + r (dim d+64)
+    for (int e = threadIdx.x; e < 16 * MC; e += WARPS * 32) {
+      const int r = e & 15, m = e >> 4;
+      if (m >= p.M) continue;
+      const int n1 = n_base + r, n2 = n1 + 64;
+      const float v1 = total(r, m), v2 = total(16 + r, m);
+      __nv_bfloat16* o = p.D + (long long)m * p.ldd;
+      if (n1 < p.rope_cols) {
+        // rounding points as in the tcgen05 epilogue / transformers modeling_llama.py:138-168
+        const int pos = (p.rope_pos_dev ? *p.rope_pos_dev : p.rope_pos0) + m % p.rope_L;
+        const int d = n1 & 127;
+        const __nv_bfloat16* ct = p.rope_cos + (long long)pos * 128;
+        const __nv_bfloat16* st = p.rope_sin + (long long)pos * 128;
+        const float x1 = bf16r(v1), x2 = bf16r(v2);
+        const float a1 = bf16r(x1 * __bfloat162float(ct[d])), b1 = bf16r(-x2 * __bfloat162float(st[d]));
+        const float a2 = bf16r(x2 * __bfloat162float(ct[d + 64])), b2 = bf16r(x1 * __bfloat162float(st[d + 64]));
+        o[n1] = __float2bfloat16_rn(a1 + b1);
+        o[n2] = __float2bfloat16_rn(a2 + b2);
+      } else {
+        o[n1] = __float2bfloat16_rn(v1);
+        o[n2] = __float2bfloat16_rn(v2);
+      }
+    }
+    return;
+  }
+
+  for (int e = threadIdx.x; e < NT * MC; e += WARPS * 32) {
+    const int r = e % NT, m = e / NT;
+    const int n = n_base + r;
+    if (m >= p.M || n >= p.N) continue;
+    if (p.act == SK_ACT_SWIGLU) {
+      if (r & 1) continue;   // even row = gate_j, odd row = up_j (interleaved weights) -> out[:, j]
+      float gt = total(r, m), up = total(r + 1, m);
+      if (p.bias != nullptr) {
+        gt += p.bias_f32 ? reinterpret_cast<const float*>(p.bias)[n] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+        up += p.bias_f32 ? reinterpret_cast<const float*>(p.bias)[n + 1] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n + 1]);
+      }
+      p.D[(long long)m * p.ldd + (n >> 1)] = __float2bfloat16_rn(gt / (1.f + __expf(-gt)) * up);
+      continue;
+    }
+    float v = total(r, m);
+    if (p.bias != nullptr)
+      v += p.bias_f32 ? reinterpret_cast<const float*>(p.bias)[n] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+    if (p.act == SK_ACT_RELU) v = fmaxf(v, 0.f);
+    if (p.act == SK_ACT_QUICK_GELU) v = v / (1.f + __expf(-1.702f * v));
+    if (p.residual != nullptr) v += __bfloat162float(p.residual[(long long)m * p.ldr + n]);
+    p.D[(long long)m * p.ldd + n] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int MT, int MB, int WARPS, bool ROPE>
+static int launch_skinny(const SkinnyParams& p, unsigned grid, cudaStream_t st) {
+  gemm_skinny_bf16<MT, MB, WARPS, ROPE><<<grid, WARPS * 32, 0, st>>>(p);
+  G4R_LAUNCH_CHECK("gemm_skinny");
+  return G4R_OK;
+}
+
+// Called by gemm_impl (gemm_tcgen05.cu) when the shape qualifies; returns -1 when it does not.
+int gemm_skinny_dispatch(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
+                         int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr, int act,
+                         const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, int rope_pos0,
+                         const int* rope_pos_dev, void* stream) {
+  if (M > 16 || K % 32 != 0) return -1;
+  if (act == SK_ACT_SWIGLU && (N % 2 != 0)) return -1;
+  SkinnyParams p{};
+  p.A = (const __nv_bfloat16*)A; p.lda = lda; p.W = (const __nv_bfloat16*)B; p.ldb = ldb;
+  p.D = (__nv_bfloat16*)D; p.ldd = ldd; p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.bias_f32 = bias_f32; p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act;
+  p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin;
+  p.rope_cols = rope_cols; p.rope_L = rope_L > 0 ? rope_L : 1; p.rope_pos0 = rope_pos0; p.rope_pos_dev = rope_pos_dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rope_cos != nullptr) {
+    if (N % 128 != 0) return -1;
+    const unsigned grid = (unsigned)(N / 128) * 4;
+    return M <= 8 ? launch_skinny<2, 1, 4, true>(p, grid, st) : launch_skinny<2, 2, 4, true>(p, grid, st);
+  }
+  // 32-row tiles halve the activation re-reads; use them once they still give >= 2 CTAs per SM
+  const bool wide = (N + 31) / 32 >= 2 * num_sms();
+  if (wide) {
+    const unsigned grid = (unsigned)((N + 31) / 32);
+    return M <= 8 ? launch_skinny<2, 1, 4, false>(p, grid, st) : launch_skinny<2, 2, 4, false>(p, grid, st);
+  }
+  const unsigned grid = (unsigned)((N + 15) / 16);
+  return M <= 8 ? launch_skinny<1, 1, 8, false>(p, grid, st) : launch_skinny<1, 2, 8, false>(p, grid, st);
+}
+
+}  // namespace g4r

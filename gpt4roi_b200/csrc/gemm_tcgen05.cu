@@ -65,6 +65,7 @@ struct GemmParams {
   const __nv_bfloat16* rope_cos;
   const __nv_bfloat16* rope_sin;
   int rope_cols, rope_L, rope_pos0;
+  const int* rope_pos_dev;  // optional device-side position base (CUDA-graph decode): pos0 = *rope_pos_dev
   float* gn_stats;       // optional [n_img, groups, 2] (sum, sumsq) of the bf16-rounded output
   int gn_group_ch;       // channels per group (16)
   int gn_groups;         // groups per image (64)
@@ -113,7 +114,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     // dims (d, d+64) of a head are 64 columns apart -> load both 32-column chunks, rotate, store.
     // Rounding as in the reference: q/k are bf16 GEMM outputs, each bf16 tensor op rounds:
     //   out = bf16( bf16(x*cos) + bf16(rot*sin) ),  rotate_half(x) = cat(-x2, x1).
-    const int pos = p.rope_pos0 + (int)(out_row % p.rope_L);
+    const int pos = (p.rope_pos_dev ? *p.rope_pos_dev : p.rope_pos0) + (int)(out_row % p.rope_L);
     const __nv_bfloat16* ct = p.rope_cos + (long long)pos * 128;
     const __nv_bfloat16* st = p.rope_sin + (long long)pos * 128;
 #pragma unroll 1
@@ -749,7 +750,20 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
                      int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr,
                      int residual_f32, int bias_round_bf16, int act, int out_f32, int k_splits,
                      const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream,
-                     int rope_pos0 = 0);
+                     int rope_pos0 = 0, const int* rope_pos_dev = nullptr);
+
+namespace g4r {
+// gemm_skinny.cu: M <= 16 weight-streaming path; returns -1 when the shape does not qualify
+int gemm_skinny_dispatch(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
+                         int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr, int act,
+                         const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, int rope_pos0,
+                         const int* rope_pos_dev, void* stream);
+}
+static bool skinny_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("G4R_SKINNY"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 
 extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, void* D,
                                 long long ldd, int M, int N, int K, const void* bias, int bias_f32,
@@ -764,18 +778,19 @@ extern "C" int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, lon
 // q_proj/k_proj/v_proj + apply_rotary_pos_emb (transformers modeling_llama.py:138-168,240-260).
 extern "C" int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* B, long long ldb, void* D,
                                       long long ldd, int M, int N, int K, const void* rope_cos,
-                                      const void* rope_sin, int rope_cols, int L, int pos0, void* stream) {
+                                      const void* rope_sin, int rope_cols, int L, int pos0, const int* pos0_dev,
+                                      void* stream) {
   G4R_REQUIRE(rope_cos && rope_sin && L > 0, "qkv_rope: null tables");
   G4R_REQUIRE(rope_cols % 256 == 0 && rope_cols <= N && N % 128 == 0 && ldd % 8 == 0, "qkv_rope: rope_cols must be a multiple of 256 (whole tiles of 128-dim heads)");
   return gemm_impl(A, lda, B, ldb, D, ldd, M, N, K, nullptr, 0, nullptr, 0, 0, 0, ACT_NONE, 0, 1, rope_cos, rope_sin,
-                   rope_cols, L, stream, pos0);
+                   rope_cols, L, stream, pos0, pos0_dev);
 }
 
 static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
                      int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr,
                      int residual_f32, int bias_round_bf16, int act, int out_f32, int k_splits,
                      const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream,
-                     int rope_pos0) {
+                     int rope_pos0, const int* rope_pos_dev) {
   G4R_REQUIRE(A && B && D, "null operand");
   G4R_REQUIRE(M > 0 && N > 0 && K > 0, "bad sizes M=%d N=%d K=%d", M, N, K);
   G4R_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "lda/ldb must be >= K and multiples of 8 (16-byte TMA strides)");
@@ -784,6 +799,12 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   G4R_REQUIRE(k_splits >= 1, "k_splits=%d", k_splits);
   if (act == ACT_SWIGLU) G4R_REQUIRE(N % 2 == 0 && !out_f32 && k_splits == 1 && !residual, "SwiGLU epilogue: even N, bf16 out, no split-K/residual");
   if (k_splits > 1) G4R_REQUIRE(out_f32 && act == ACT_NONE && !residual && !bias, "split-K writes fp32 partial slabs [k_splits][M][ldd]: out_f32, no bias/act/residual");
+  // M <= 16 (decode step): HBM-bound weight-streaming kernel instead of a mostly empty 128-row tile
+  if (M <= 16 && !out_f32 && k_splits == 1 && !residual_f32 && !bias_round_bf16 && skinny_enabled()) {
+    const int rc = gemm_skinny_dispatch(A, lda, B, ldb, D, ldd, M, N, K, bias, bias_f32, residual, ldr, act, rope_cos,
+                                        rope_sin, rope_cols, rope_L, rope_pos0, rope_pos_dev, stream);
+    if (rc >= 0) return rc;
+  }
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
@@ -795,7 +816,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.residual_f32 = residual_f32;
   p.round_branch = bias_round_bf16;
   p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin;
-  p.rope_cols = rope_cols; p.rope_L = rope_L; p.rope_pos0 = rope_pos0;
+  p.rope_cols = rope_cols; p.rope_L = rope_L; p.rope_pos0 = rope_pos0; p.rope_pos_dev = rope_pos_dev;
   p.act = act; p.out_f32 = out_f32; p.atomic = k_splits > 1;
   p.conv = 0; p.a_rows = kBlockM;
   const bool two = use_2sm(N, p.num_m_tiles, k_splits, false);

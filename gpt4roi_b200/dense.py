@@ -92,7 +92,7 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out
 
 
-def qkv_rope(x, wqkv, cos, sin, L, rope_cols, pos0=0):
+def qkv_rope(x, wqkv, cos, sin, L, rope_cols, pos0=0, pos_dev=None):
     """Fused LLaMA q/k/v projection + rotary embedding: x [M,K] bf16, wqkv [N,K] (q|k|v rows), cos/sin
     bf16 [L,128]; columns [0,rope_cols) (q and k heads, head_dim 128) are rotated at position row % L."""
     M, K = x.shape
@@ -103,7 +103,7 @@ def qkv_rope(x, wqkv, cos, sin, L, rope_cols, pos0=0):
         _ps = _prof_begin(dev)
         _L.check(_L.load().g4r_gemm_qkv_rope_bf16(
             _L.ptr(x), x.stride(0), _L.ptr(wqkv), wqkv.stride(0), _L.ptr(out), N, M, N, K, _L.ptr(cos), _L.ptr(sin),
-            int(rope_cols), int(L), int(pos0), _L.stream_ptr(dev)))
+            int(rope_cols), int(L), int(pos0), _L.ptr(pos_dev), _L.stream_ptr(dev)))
         _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
     return out
 

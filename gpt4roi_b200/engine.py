@@ -318,14 +318,17 @@ class KVCache:
         self.B, self.max_len, self.length = B, max_len, 0
 
 
-def _decode_step(self, token_ids, cache):
+def _decode_step(self, token_ids, cache, pos_dev=None):
     """One decode step: token_ids int64 [B,1] -> logits [B,1,V]; the vision / SPI branch
-    is skipped exactly as the reference does for input_ids.shape[1] == 1 (spi_llava.py:47-48)."""
+    is skipped exactly as the reference does for input_ids.shape[1] == 1 (spi_llava.py:47-48).
+    pos_dev: optional device int32 holding the current length (CUDA-graph replay: the kernels read the
+    position from memory instead of from a launch argument)."""
     c = self.cfg
     B = token_ids.shape[0]
     pos = cache.length
     if pos + 1 > cache.max_len:
         raise RuntimeError('KV cache is full (%d)' % cache.max_len)
+    kv_len = cache.max_len if pos_dev is not None else pos + 1   # sizes the score buffer when device-driven
     x = splice_region_tokens(token_ids, self.embed, None, None, 0, c.im_patch_token, c.im_start_token,
                              c.im_end_token, c.bbox_token, validate=False).view(B, c.hidden)
     cos, sin = self._rope(cache.max_len)
@@ -334,12 +337,14 @@ def _decode_step(self, token_ids, cache):
     for li, w in enumerate(self.layers):
         h = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
         if fused:
-            qkv = dense.qkv_rope(h, w['wqkv'], cos, sin, 1, 2 * c.hidden, pos0=pos)
+            qkv = dense.qkv_rope(h, w['wqkv'], cos, sin, 1, 2 * c.hidden, pos0=pos, pos_dev=pos_dev)
         else:
+            if pos_dev is not None:
+                raise NotImplementedError('graph decode needs the fused-RoPE QKV GEMM (head_dim 128)')
             qkv = dense.linear(h, w['wqkv'])
             kernels.rope_inplace(qkv, cos[pos:pos + 1].contiguous(), sin[pos:pos + 1].contiguous(), 1, 2 * c.n_heads, c.head_dim)
-        kernels.kv_append(qkv, cache.k[li], cache.v[li], B, 1, pos)
-        a = kernels.decode_attention(qkv, cache.k[li], cache.v[li], B, c.n_heads, c.head_dim, pos + 1, scale)
+        kernels.kv_append(qkv, cache.k[li], cache.v[li], B, 1, pos, pos_dev)
+        a = kernels.decode_attention(qkv, cache.k[li], cache.v[li], B, c.n_heads, c.head_dim, kv_len, scale, pos_dev)
         x = dense.linear(a, w['wo'], residual=x)
         h = kernels.rmsnorm(x, w['ln_post'], c.rms_eps)
         f = dense.linear(h, w['wgu'], act='swiglu')
@@ -353,7 +358,7 @@ def _decode_step(self, token_ids, cache):
 
 @torch.no_grad()
 def _generate(self, input_ids, images, bboxes, max_new_tokens=32, do_sample=False, temperature=1.0,
-              stopping_criteria=None, eos_token_id=None, generator=None):
+              stopping_criteria=None, eos_token_id=None, generator=None, use_graph=True):
     """Prefill + greedy / temperature-sampled decode (gpt4roi/app.py:286-300 calls
     model.generate(input_ids, images=..., do_sample=True, temperature=0.2, max_new_tokens=1024,
     stopping_criteria=[...]) with the boxes bound to forward).  Returns ids [B, L + new]."""
@@ -363,6 +368,9 @@ def _generate(self, input_ids, images, bboxes, max_new_tokens=32, do_sample=Fals
     ids = input_ids.to(self.dev)
     logits = self.forward_device(ids, images.to(self.dev, BF16), plan, validate=True, last_only=True, cache=cache)
     out = ids
+    stepper = None
+    if use_graph and max_new_tokens > 4 and self.cfg.head_dim == 128:
+        stepper = GraphedDecode(self, cache)
     for step in range(max_new_tokens):
         last = logits[:, -1].float()
         if do_sample and temperature > 0:
@@ -375,8 +383,41 @@ def _generate(self, input_ids, images, bboxes, max_new_tokens=32, do_sample=Fals
         if stopping_criteria is not None and any(bool(torch.as_tensor(sc(out, last)).all()) for sc in stopping_criteria):
             break
         if step + 1 < max_new_tokens:
-            logits = self.decode_step(nxt, cache)
+            logits = stepper.step(nxt) if stepper is not None else self.decode_step(nxt, cache)
     return out
+
+
+class GraphedDecode:
+    """CUDA-graph replay of one decode step: ~260 launches become one.  The current length lives in a
+    device int32 that the QKV-RoPE epilogue, kv_append and decode_attention read; `step` bumps it."""
+
+    def __init__(self, engine, cache):
+        self.eng, self.cache = engine, cache
+        dev = engine.dev
+        self.ids = torch.zeros((cache.B, 1), dtype=torch.int64, device=dev)
+        self.pos = torch.tensor([cache.length], dtype=torch.int32, device=dev)
+        start = cache.length
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up (writes slot `start`, overwritten by the first real step)
+                engine.decode_step(self.ids, cache, self.pos)
+                cache.length = start
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits = engine.decode_step(self.ids, cache, self.pos)
+        cache.length = start
+
+    def step(self, token_ids):
+        if self.cache.length + 1 > self.cache.max_len:
+            raise RuntimeError('KV cache is full (%d)' % self.cache.max_len)
+        self.ids.copy_(token_ids, non_blocking=True)
+        self.graph.replay()
+        self.pos.add_(1)
+        self.cache.length += 1
+        return self.logits
 
 
 PrefillEngine.decode_step = _decode_step

@@ -159,16 +159,16 @@ def add_bias_pos_cast(acc, bias, pos):
     return out
 
 
-def kv_append(qkv, kcache, vcache, B, Ln, pos0):
+def kv_append(qkv, kcache, vcache, B, Ln, pos0, pos_dev=None):
     """Copy the k|v parts of packed qkv rows [B*Ln, 3*HD] into caches [B, Lmax, HD] at pos0..pos0+Ln-1."""
     HD = kcache.shape[-1]
     _call('g4r_kv_append_bf16', qkv.device, _L.ptr(qkv), qkv.stride(0), _L.ptr(kcache), _L.ptr(vcache), B, Ln,
-          int(pos0), kcache.shape[1], HD)
+          int(pos0), _L.ptr(pos_dev), kcache.shape[1], HD)
 
 
-def decode_attention(qkv, kcache, vcache, B, n_heads, head_dim, kv_len, scale):
+def decode_attention(qkv, kcache, vcache, B, n_heads, head_dim, kv_len, scale, pos_dev=None):
     """qkv [B, 3*HD] (one new token per sample); caches [B, Lmax, HD]; returns [B, HD]."""
     out = torch.empty((B, n_heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
     _call('g4r_decode_attention_bf16', qkv.device, _L.ptr(qkv), qkv.stride(0), _L.ptr(kcache), _L.ptr(vcache),
-          _L.ptr(out), out.stride(0), B, n_heads, head_dim, int(kv_len), kcache.shape[1], float(scale))
+          _L.ptr(out), out.stride(0), B, n_heads, head_dim, int(kv_len), _L.ptr(pos_dev), kcache.shape[1], float(scale))
     return out

@@ -182,18 +182,21 @@ int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb,
 int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* B, long long ldb,
                            void* D, long long ldd, int M, int N, int K,
                            const void* rope_cos, const void* rope_sin, int rope_cols, int L, int pos0,
+                           const int* pos0_dev /* device int32 overriding pos0 (CUDA-graph decode) or NULL */,
                            void* stream);
 
 /* ---- decode loop (KV cache) -------------------------------------------------- */
 /* Append the k and v parts of packed rows [B*Ln, (q|k|v) of width HD each] to the caches
  * [B, Lmax, HD] at positions pos0..pos0+Ln-1 (prefill: pos0=0, Ln=L; decode: Ln=1).  */
 int g4r_kv_append_bf16(const void* qkv, long long ld, void* kcache, void* vcache,
-                       int B, int Ln, int pos0, int Lmax, int HD, void* stream);
+                       int B, int Ln, int pos0, const int* pos_dev /* overrides pos0 when non-NULL */,
+                       int Lmax, int HD, void* stream);
 /* One new query per sample against the first kv_len cached positions: out[b,h,:] =
  * softmax(q.K^T*scale) V.  Replaces the decode-step attention of transformers' LlamaAttention with a
  * DynamicCache (generate() in gpt4roi/app.py:293-300; vision branch skipped, spi_llava.py:47-48). */
 int g4r_decode_attention_bf16(const void* q, long long ldq, const void* kcache, const void* vcache,
                               void* out, long long ldo, int B, int H, int head_dim, int kv_len,
+                              const int* pos_dev /* kv_len = *pos_dev + 1 when non-NULL; kv_len then sizes smem */,
                               int Lmax, float scale, void* stream);
 
 /*

@@ -106,3 +106,68 @@ def test_qkv_rope_fused_equals_unfused():
     ref = dense.linear(x, w)
     kernels.rope_inplace(ref, cos, sin, L, 2 * H, D)
     assert torch.equal(fused, ref)
+
+
+# ---- M <= 16 weight-streaming path (gemm_skinny.cu: the decode step) ---------------------------------
+
+@pytest.mark.parametrize('M', [1, 3, 8, 9, 16])
+@pytest.mark.parametrize('N,K', [(4096, 4096), (4096, 11008), (32006, 4096), (200, 96), (16, 32)])
+def test_skinny_gemm_plain_matches_fp32_and_tile_path(M, N, K):
+    torch.manual_seed(M * 7 + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.5).bfloat16()
+    got = dense.linear(a, b)
+    _close(got, a.float() @ b.float().t())
+    # against the 128-row tcgen05 tile kernel on a padded copy (M=17 rows disables the skinny route)
+    a17 = torch.cat([a, torch.zeros(17 - M, K, device=DEV, dtype=torch.bfloat16)])
+    tile = dense.linear(a17, b)[:M]
+    assert (got.float() - tile.float()).abs().max() <= 2e-2 * tile.float().abs().max()
+    assert torch.equal(got, dense.linear(a, b))  # reproducible (fixed-order k-slice reduction)
+
+
+def test_skinny_gemm_epilogues():
+    torch.manual_seed(1)
+    M, N, K = 5, 1312, 640
+    a = (torch.randn(M, K, device=DEV) * 0.3).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.3).bfloat16()
+    bias = torch.randn(N, device=DEV).bfloat16()
+    res = torch.randn(M, N, device=DEV).bfloat16()
+    base = a.float() @ b.float().t()
+    z = base + bias.float()
+    _close(dense.linear(a, b, bias), z)
+    _close(dense.linear(a, b, bias.float()), z)
+    _close(dense.linear(a, b, bias, act='relu'), torch.relu(z))
+    _close(dense.linear(a, b, bias, act='quick_gelu'), z * torch.sigmoid(1.702 * z))
+    _close(dense.linear(a, b, bias, residual=res), z + res.float())
+    _close(dense.linear(a, b, act='swiglu'), F.silu(base[:, 0::2]) * base[:, 1::2])
+    # wide-N variant (32-row tiles) with SwiGLU, as the LLaMA gate/up projection at batch 8
+    M, N, K = 8, 22016, 4096
+    a = (torch.randn(M, K, device=DEV) * 0.3).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    base = a.float() @ b.float().t()
+    _close(dense.linear(a, b, act='swiglu'), F.silu(base[:, 0::2]) * base[:, 1::2])
+    # strided activation rows (lda > K); fp32 output falls through to the tile kernel and stays correct
+    big = (torch.randn(M, 2 * K, device=DEV) * 0.3).bfloat16()
+    _close(dense.linear(big[:, :K], b), big[:, :K].float() @ b.float().t())
+    _close(dense.linear(a, b, out_dtype=torch.float32), base, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize('B,L', [(1, 1), (8, 1), (2, 5), (16, 1)])
+def test_skinny_qkv_rope_equals_unfused(B, L):
+    """Fused-RoPE skinny QKV GEMM (host pos0 and device-side position) == plain GEMM + rope kernel, bitwise."""
+    from gpt4roi_b200 import kernels
+    torch.manual_seed(5 + B)
+    H, D, pos0, Lmax = 4, 128, 37, 64
+    hid = H * D
+    x = (torch.randn(B * L, hid, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(3 * hid, hid, device=DEV) * 0.05).bfloat16()
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+    emb = torch.cat([torch.arange(Lmax).float()[:, None] * inv[None]] * 2, -1)
+    cos, sin = emb.cos().to(DEV, torch.bfloat16).contiguous(), emb.sin().to(DEV, torch.bfloat16).contiguous()
+    ref = dense.linear(x, w)
+    kernels.rope_inplace(ref, cos[pos0:pos0 + L].contiguous(), sin[pos0:pos0 + L].contiguous(), L, 2 * H, D)
+    fused = dense.qkv_rope(x, w, cos, sin, L, 2 * hid, pos0=pos0)
+    assert torch.equal(fused, ref)
+    pos_dev = torch.tensor([pos0], dtype=torch.int32, device=DEV)
+    fused_dev = dense.qkv_rope(x, w, cos, sin, L, 2 * hid, pos0=0, pos_dev=pos_dev)
+    assert torch.equal(fused_dev, ref)

@@ -231,3 +231,36 @@ def test_decode_loop_matches_prefill_logits():
     chk = eng.forward(out[:, :-1].contiguous(), images, boxes).float()
     agree = (chk[:, L0 - 1:].argmax(-1) == out[:, L0:]).float().mean().item()
     assert agree >= 0.8, agree
+
+
+def test_graphed_decode_is_bitwise_equal_to_eager_decode():
+    """GraphedDecode (device-side position, one CUDA-graph replay per token) must produce exactly the
+    logits of the eager decode_step at every step: same kernels, same order, no atomics."""
+    from gpt4roi_b200.engine import GraphedDecode, KVCache
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=19)
+    eng = PrefillEngine(cfg, sd, vit_sd, DEV)
+    ids, images, boxes = make_inputs(cfg, 2, [1, 2], 20, seed=9)
+    images = images.to(DEV, torch.bfloat16)
+    plan = eng.plan_boxes(boxes)
+    n_new = 6
+    toks = torch.randint(3, 32000, (n_new, 2, 1), generator=torch.Generator().manual_seed(4)).to(DEV)
+    outs = []
+    for graphed in (False, True):
+        cache = KVCache(cfg, 2, ids.shape[1] + n_new + 2, DEV)
+        eng.forward_device(ids.to(DEV), images, plan, last_only=True, cache=cache)
+        stepper = GraphedDecode(eng, cache) if graphed else None
+        seq = []
+        for t in range(n_new):
+            lg = stepper.step(toks[t]) if graphed else eng.decode_step(toks[t], cache)
+            seq.append(lg.clone())
+        assert cache.length == ids.shape[1] + n_new
+        outs.append(torch.stack(seq))
+    assert torch.equal(outs[0], outs[1])
+    # the cache-full guard still fires in graph mode
+    cache = KVCache(cfg, 2, ids.shape[1] + 1, DEV)
+    eng.forward_device(ids.to(DEV), images, plan, last_only=True, cache=cache)
+    st = GraphedDecode(eng, cache)
+    st.step(toks[0])
+    with pytest.raises(RuntimeError):
+        st.step(toks[1])

@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bench import synthetic_inputs  # noqa: E402
-from gpt4roi_b200.engine import EngineConfig, KVCache, PrefillEngine, random_state_dicts  # noqa: E402
+from gpt4roi_b200.engine import EngineConfig, GraphedDecode, KVCache, PrefillEngine, random_state_dicts  # noqa: E402
 
 
 def main():
@@ -19,7 +19,7 @@ def main():
     sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
     eng = PrefillEngine(cfg, sd, vit_sd, dev)
     del sd, vit_sd
-    for B in (1, 8):
+    for B, graphed in ((1, False), (1, True), (8, False), (8, True)):
         ids, images, boxes = synthetic_inputs(cfg, B, 8, 128)
         ids, images = ids.to(dev), images.to(dev)
         L = ids.shape[1]
@@ -31,17 +31,21 @@ def main():
         e[0].record()
         logits = eng.forward_device(ids, images, plan, validate=False, last_only=True, cache=cache)
         e[1].record()
+        torch.cuda.synchronize()
+        pre = e[0].elapsed_time(e[1])
         nxt = logits[:, -1].float().argmax(-1, keepdim=True)
+        stepper = GraphedDecode(eng, cache) if graphed else None   # capture is outside the decode timing
+        e[1].record()
         for _ in range(n_new):
-            logits = eng.decode_step(nxt, cache)
+            logits = stepper.step(nxt) if graphed else eng.decode_step(nxt, cache)
             nxt = logits[:, -1].float().argmax(-1, keepdim=True)
         e[2].record()
         torch.cuda.synchronize()
-        pre, dec = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+        dec = e[1].elapsed_time(e[2])
         print(json.dumps(dict(batch=B, prompt_len=L, new_tokens=n_new, prefill_ms=pre, decode_ms_per_token=dec / n_new,
                               decode_tokens_per_s=B * n_new / (dec / 1e3),
                               weight_stream_floor_ms=13.5e9 / 6.579e12 * 1e3,
-                              note='eager launches (no CUDA graph for the decode step yet)')), flush=True)
+                              mode='cuda_graph' if graphed else 'eager_launches')), flush=True)
 
 
 if __name__ == '__main__':
