@@ -4,6 +4,7 @@
 // llava/model/llava.py:263-283 prepare_inputs_for_generation; gpt4roi/app.py:293-300).
 // Both kernels are HBM-bound: the step streams the whole KV cache of the batch once.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace g4r {
 
@@ -27,81 +28,154 @@ kv_append_bf16(const __nv_bfloat16* __restrict__ qkv, long long ld, __nv_bfloat1
   }
 }
 
-// One CTA per (batch, head): out = softmax(q . K^T * scale) V over the first kv_len cached positions.
-// 128 threads; phase 1: thread <-> key (fp32 dot over D), block max / sum; phase 2: thread <-> pair of
-// output dims, coalesced reads of V rows.
+// Single-query attention over the KV cache: out = softmax(q . K^T * scale) V for the first kv_len
+// cached positions.  Grid (H, B, S) with a thread-block cluster of S CTAs along z: each CTA of the
+// cluster owns a contiguous slice of the keys (split-KV), and the softmax statistics and the partial
+// outputs are combined through distributed shared memory -- no workspace, no atomics, and a fixed
+// summation order (bitwise reproducible).  S is chosen so that even batch 1 (32 heads) fills the GPU.
+// 256 threads; a half-warp owns one key/value row (16 lanes x 16 bytes = the 256-byte row, coalesced).
+// Rounding as the reference's eager attention: fp32 softmax, probabilities cast to bf16 before P.V.
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 decode_attention_bf16(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kc,
                       const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, long long ldo,
-                      int H, int kv_len, const int* __restrict__ pos_dev, int Lmax, float scale) {
+                      int H, int kv_len, const int* __restrict__ pos_dev, int Lmax, float scale, int per_max) {
+  static_assert(D == 128 || D == 64, "head_dim");
+  constexpr int LPR = D / 8;          // lanes per row (16 or 8)
+  constexpr int RPW = 32 / LPR;       // rows per warp instruction (2 or 4)
+  constexpr int GROUPS = 8 * RPW;     // row groups per CTA (16 or 32)
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   if (pos_dev) kv_len = *pos_dev + 1;
-  extern __shared__ float sm[];  // [D] q | [kv_len] scores
-  float* sq = sm;
-  float* sc = sm + D;
-  __shared__ float red[4];
+  extern __shared__ float sm[];
+  float* sc = sm;                       // [per_max] scores / probabilities of this CTA's slice
+  float* part = sm + per_max;           // [GROUPS][D] partial outputs, then [D] CTA total in part[0..D)
+  __shared__ float red[8];
+  __shared__ float cl_max, cl_sum;      // this CTA's slice statistics, read by the cluster peers
   const int h = blockIdx.x, b = blockIdx.y;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = lane % LPR, grp = warp * RPW + lane / LPR;
   const int HD = H * D;
-  const __nv_bfloat16* qrow = q + (long long)b * ldq + (long long)h * D;
-  for (int i = tid; i < D; i += 128) sq[i] = __bfloat162float(qrow[i]) * scale;
-  __syncthreads();
-  const __nv_bfloat16* kb = kc + (long long)b * Lmax * HD + (long long)h * D;
-  float mx = -INFINITY;
-  for (int key = tid; key < kv_len; key += 128) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)key * HD);
-    float acc = 0.f;
+  const int per = (kv_len + S - 1) / S;
+  const int k0 = rank * per;
+  const int n_loc = max(0, min(kv_len, k0 + per) - k0);
+
+  float qf[8];
+  {
+    const uint4 raw = *reinterpret_cast<const uint4*>(q + (long long)b * ldq + (long long)h * D + sub * 8);
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-    for (int v = 0; v < D / 8; v++) {
-      const uint4 raw = kr[v];
-      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    for (int j = 0; j < 4; j++) {
+      const float2 f = __bfloat1622float2(hh[j]);
+      qf[2 * j] = f.x * scale;
+      qf[2 * j + 1] = f.y * scale;
+    }
+  }
+  // ---- phase 1: scores of the slice
+  const __nv_bfloat16* kb = kc + ((long long)b * Lmax + k0) * HD + (long long)h * D + sub * 8;
+  float mx = -INFINITY;
+  for (int base = 0; base < n_loc; base += GROUPS * 4) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int key = base + u * GROUPS + grp;
+      raw[u] = key < n_loc ? *reinterpret_cast<const uint4*>(kb + (long long)key * HD) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+      float acc = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const float2 f = __bfloat1622float2(hh[j]);
-        acc += f.x * sq[v * 8 + 2 * j] + f.y * sq[v * 8 + 2 * j + 1];
+        acc += f.x * qf[2 * j] + f.y * qf[2 * j + 1];
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const int key = base + u * GROUPS + grp;
+      if (key < n_loc) {
+        if (sub == 0) sc[key] = acc;
+        mx = fmaxf(mx, acc);
       }
     }
-    sc[key] = acc;
-    mx = fmaxf(mx, acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  __syncthreads();
+  if (tid == 0) {
+    float m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) m = fmaxf(m, red[w]);
+    cl_max = m;
+  }
+  cluster.sync();
+  float gmax = -INFINITY;
+  for (int r = 0; r < S; r++) gmax = fmaxf(gmax, *cluster.map_shared_rank(&cl_max, r));
   float sum = 0.f;
-  for (int key = tid; key < kv_len; key += 128) {
-    const float p = __expf(sc[key] - mx);
+  for (int key = tid; key < n_loc; key += 256) {
+    const float p = __expf(sc[key] - gmax);
     sc[key] = p;
     sum += p;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  if (lane == 0) red[warp] = sum;
   __syncthreads();
-  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
-  // phase 2: probabilities are cast to bf16 before the PV product like the reference (P.to(q.dtype))
-  const __nv_bfloat16* vb = vc + (long long)b * Lmax * HD + (long long)h * D;
-  constexpr int PAIRS = D / 2;  // 64 (D=128) or 32 (D=64) dim pairs; 128 threads split the keys 128/PAIRS ways
-  const int pair = tid % PAIRS, part = tid / PAIRS, parts = 128 / PAIRS;
-  float ax = 0.f, ay = 0.f;
-  for (int key = part; key < kv_len; key += parts) {
-    const float p = __bfloat162float(__float2bfloat16_rn(sc[key] * inv));
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (long long)key * HD + 2 * pair));
-    ax += p * f.x;
-    ay += p * f.y;
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += red[w];
+    cl_sum = t;
+  }
+  cluster.sync();
+  float gsum = 0.f;
+  for (int r = 0; r < S; r++) gsum += *cluster.map_shared_rank(&cl_sum, r);
+  const float inv = 1.f / gsum;
+  // ---- phase 2: partial P.V of the slice (probabilities rounded to bf16 like P.to(q.dtype))
+  const __nv_bfloat16* vb = vc + ((long long)b * Lmax + k0) * HD + (long long)h * D + sub * 8;
+  float o8[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) o8[j] = 0.f;
+  for (int base = 0; base < n_loc; base += GROUPS * 4) {
+    uint4 raw[4];
+    float pk[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int key = base + u * GROUPS + grp;
+      const bool ok = key < n_loc;
+      raw[u] = ok ? *reinterpret_cast<const uint4*>(vb + (long long)key * HD) : make_uint4(0, 0, 0, 0);
+      pk[u] = ok ? __bfloat162float(__float2bfloat16_rn(sc[key] * inv)) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float2 f = __bfloat1622float2(hh[j]);
+        o8[2 * j] += pk[u] * f.x;
+        o8[2 * j + 1] += pk[u] * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) part[grp * D + sub * 8 + j] = o8[j];
+  __syncthreads();
+  float tot = 0.f;
+  if (tid < D) {
+#pragma unroll 4
+    for (int g2 = 0; g2 < GROUPS; g2++) tot += part[g2 * D + tid];
   }
   __syncthreads();
-  float* acc2 = sm;  // reuse: [parts][D]
-  acc2[part * D + 2 * pair] = ax;
-  acc2[part * D + 2 * pair + 1] = ay;
-  __syncthreads();
-  if (tid < PAIRS) {
-    float x = 0.f, y = 0.f;
-    for (int pp = 0; pp < parts; pp++) { x += acc2[pp * D + 2 * tid]; y += acc2[pp * D + 2 * tid + 1]; }
-    *reinterpret_cast<__nv_bfloat162*>(out + (long long)b * ldo + (long long)h * D + 2 * tid) = __floats2bfloat162_rn(x, y);
+  if (tid < D) part[tid] = tot;   // CTA total, visible to rank 0 after the cluster barrier
+  cluster.sync();
+  if (rank == 0 && tid < D) {
+    float v = 0.f;
+    for (int r = 0; r < S; r++) v += cluster.map_shared_rank(part, r)[tid];
+    out[(long long)b * ldo + (long long)h * D + tid] = __float2bfloat16_rn(v);
   }
+  cluster.sync();   // keep every CTA's shared memory alive until rank 0 has read it
 }
 
 }  // namespace g4r
@@ -122,26 +196,46 @@ extern "C" int g4r_kv_append_bf16(const void* qkv, long long ld, void* kcache, v
   return G4R_OK;
 }
 
+template <int D>
+static int launch_decode_attention(const void* q, long long ldq, const void* kcache, const void* vcache, void* out,
+                                   long long ldo, int B, int H, int kv_len, const int* pos_dev, int Lmax,
+                                   float scale, cudaStream_t st) {
+  // split-KV factor: enough CTAs for >= 2 per SM, slices of >= 64 keys, cluster size <= 8 (portable)
+  int S = 1;
+  while (S < 8 && H * B * S < 2 * num_sms() && kv_len / (2 * S) >= 64) S *= 2;
+  const int per_max = (kv_len + S - 1) / S;
+  const int groups = 8 * (32 / (D / 8));
+  const size_t smem = ((size_t)per_max + (size_t)groups * D) * sizeof(float);
+  G4R_REQUIRE(smem <= 200 * 1024, "decode_attention: kv_len %d too long for the shared-memory score buffer", kv_len);
+  static bool set = false;
+  if (!set) {
+    G4R_CUDA(cudaFuncSetAttribute(decode_attention_bf16<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(H, B, S);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  G4R_CUDA(cudaLaunchKernelEx(&cfg, decode_attention_bf16<D>, (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kcache,
+                              (const __nv_bfloat16*)vcache, (__nv_bfloat16*)out, ldo, H, kv_len, pos_dev, Lmax, scale,
+                              per_max));
+  return G4R_OK;
+}
+
 extern "C" int g4r_decode_attention_bf16(const void* q, long long ldq, const void* kcache, const void* vcache,
                                          void* out, long long ldo, int B, int H, int head_dim, int kv_len,
                                          const int* pos_dev, int Lmax, float scale, void* stream) {
   G4R_REQUIRE(q && kcache && vcache && out && B > 0 && H > 0 && kv_len > 0 && kv_len <= Lmax, "decode_attention: bad arguments");
   G4R_REQUIRE(head_dim == 64 || head_dim == 128, "decode_attention: head_dim %d", head_dim);
-  const int smem = (head_dim + (kv_len > 2 * head_dim ? kv_len : 2 * head_dim) + 8) * 4 + (128 / (head_dim / 2)) * head_dim * 4;
-  G4R_REQUIRE(smem <= 200 * 1024, "decode_attention: kv_len %d too long for the shared-memory score buffer", kv_len);
-  dim3 grid(H, B);
+  G4R_REQUIRE(ldq % 8 == 0 && ((uintptr_t)q & 15) == 0, "decode_attention: q rows must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (head_dim == 128) {
-    static bool set = false;
-    if (!set) { G4R_CUDA(cudaFuncSetAttribute(decode_attention_bf16<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
-    decode_attention_bf16<128><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kcache,
-                                                         (const __nv_bfloat16*)vcache, (__nv_bfloat16*)out, ldo, H, kv_len, pos_dev, Lmax, scale);
-  } else {
-    static bool set = false;
-    if (!set) { G4R_CUDA(cudaFuncSetAttribute(decode_attention_bf16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
-    decode_attention_bf16<64><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kcache,
-                                                        (const __nv_bfloat16*)vcache, (__nv_bfloat16*)out, ldo, H, kv_len, pos_dev, Lmax, scale);
-  }
-  G4R_LAUNCH_CHECK("decode_attention");
-  return G4R_OK;
+  if (head_dim == 128)
+    return launch_decode_attention<128>(q, ldq, kcache, vcache, out, ldo, B, H, kv_len, pos_dev, Lmax, scale, st);
+  return launch_decode_attention<64>(q, ldq, kcache, vcache, out, ldo, B, H, kv_len, pos_dev, Lmax, scale, st);
 }

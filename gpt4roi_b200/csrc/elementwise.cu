@@ -122,9 +122,98 @@ norm_rows_bf16(const TI* __restrict__ x, long long ldx, const __nv_bfloat16* __r
   }
 }
 
+// Few rows (the decode step, M = batch): one CTA per row so the row's latency is one load round, not
+// PER_LANE dependent rounds of a single warp.  Same rounding points as norm_rows_bf16.
+template <bool RMS, int PER>
+__global__ void __launch_bounds__(256)
+norm_row_cta_bf16(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, long long ldo, int D,
+                  float eps) {
+  __shared__ float red[8];
+  __shared__ float stat;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nvec = D >> 3;
+  const __nv_bfloat16* xr = x + (long long)blockIdx.x * ldx;
+  float v[PER][8];
+  float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; i++) {
+    const int vi = tid + i * 256;
+    if (vi < nvec) {
+      load8<__nv_bfloat16>(xr + vi * 8, v[i]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sum += v[i][j]; sumsq += v[i][j] * v[i][j]; }
+  }
+  auto block_sum = [&](float t) {
+    t = warp_sum(t);
+    __syncthreads();
+    if (lane == 0) red[warp] = t;
+    __syncthreads();
+    if (tid == 0) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; k++) a += red[k];
+      stat = a;
+    }
+    __syncthreads();
+    return stat;
+  };
+  float mean = 0.f, rstd;
+  if (RMS) {
+    rstd = rsqrtf(block_sum(sumsq) / D + eps);
+  } else {
+    mean = block_sum(sum) / D;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      if (tid + i * 256 < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const float d = v[i][j] - mean; var += d * d; }
+      }
+    }
+    rstd = rsqrtf(block_sum(var) / D + eps);
+  }
+  __nv_bfloat16* orow = out + (long long)blockIdx.x * ldo;
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  const uint4* bv = reinterpret_cast<const uint4*>(b);
+#pragma unroll
+  for (int i = 0; i < PER; i++) {
+    const int vi = tid + i * 256;
+    if (vi >= nvec) continue;
+    float wf[8], o[8];
+    unpack8(wv[vi], wf);
+    if (RMS) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = wf[j] * bf16_round(v[i][j] * rstd);
+    } else {
+      float bf[8];
+      unpack8(bv[vi], bf);
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = (v[i][j] - mean) * rstd * wf[j] + bf[j];
+    }
+    store8<__nv_bfloat16>(orow + vi * 8, o);
+  }
+}
+
 template <bool RMS>
 static int launch_norm(const void* x, long long ldx, const void* w, const void* b, void* out, long long ldo,
                        int M, int D, float eps, cudaStream_t st) {
+  if (M <= 64 && D <= 8192) {
+    const int per = (D / 8 + 255) / 256;
+#define G4R_NORM_ROW_CASE(PR)                                                                              \
+  norm_row_cta_bf16<RMS, PR><<<M, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,      \
+                                               (const __nv_bfloat16*)b, (__nv_bfloat16*)out, ldo, D, eps)
+    if (per <= 1) G4R_NORM_ROW_CASE(1);
+    else if (per <= 2) G4R_NORM_ROW_CASE(2);
+    else G4R_NORM_ROW_CASE(4);
+#undef G4R_NORM_ROW_CASE
+    G4R_LAUNCH_CHECK(RMS ? "rmsnorm" : "layernorm");
+    return G4R_OK;
+  }
   const int per_lane = (D / 8 + 31) / 32;
   const dim3 grid((M + 7) / 8);
 #define G4R_NORM_CASE(PL)                                                                              \

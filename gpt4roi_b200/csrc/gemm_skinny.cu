@@ -16,8 +16,13 @@
 // k16 steps from ONE 16-byte load at physical k0 + 8t .. 8t+7, from the weight row and from the
 // activation row alike -- no shuffles, no shared-memory staging, full-sector global loads.
 //
-// Deterministic: partial sums of the WARPS k-slices are reduced through shared memory in fixed order.
+// Optional split-K over a thread-block cluster (G4R_SKINNY_CTAS=<target CTA count>): the KS CTAs of a
+// cluster (gridDim.y) share one weight-row tile and interleave its k-blocks; partial sums meet in rank 0
+// through distributed shared memory.  Measured slower than KS=1 on B200 (profiles/r1_decode_kernels.md),
+// so it is off by default; bytes in flight per SM come from 16-warp CTAs on the narrow-N shapes instead.
+// Deterministic: partial sums of the warps and of the cluster ranks are added in fixed order.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace g4r {
 
@@ -62,6 +67,10 @@ gemm_skinny_bf16(const SkinnyParams p) {
   constexpr int NT = MT * 16;
   constexpr int MC = MB * 8;
   __shared__ float red[WARPS][NT][MC + 1];
+  __shared__ float ctot[NT][MC];   // this CTA's k-slice total, read by cluster rank 0
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int KS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int tile_stride = ROPE ? 64 : 16;
   const int n_base = ROPE ? (int)(blockIdx.x >> 2) * 128 + (int)(blockIdx.x & 3) * 16 : (int)blockIdx.x * NT;
@@ -94,7 +103,7 @@ gemm_skinny_bf16(const SkinnyParams p) {
   }
 
 #pragma unroll 1
-  for (int k0 = warp * KB; k0 < p.K; k0 += WARPS * KB) {
+  for (int k0 = (rank * WARPS + warp) * KB; k0 < p.K; k0 += KS * WARPS * KB) {
     uint4 a[4][MT][2], b[4][MB];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
@@ -129,10 +138,21 @@ gemm_skinny_bf16(const SkinnyParams p) {
       for (int c = 0; c < 4; c++) red[warp][j * 16 + g + 8 * (c >> 1)][i * 8 + 2 * t + (c & 1)] = acc[j][i][c];
   __syncthreads();
 
-  auto total = [&](int r, int m) {
+  for (int e = threadIdx.x; e < NT * MC; e += WARPS * 32) {
+    const int r = e % NT, m = e / NT;
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < WARPS; w++) v += red[w][r][m];
+    ctot[r][m] = v;
+  }
+  cluster.sync();
+  if (rank != 0) {
+    cluster.sync();   // stay resident until rank 0 has read this CTA's totals
+    return;
+  }
+  auto total = [&](int r, int m) {
+    float v = ctot[r][m];
+    for (int c = 1; c < KS; c++) v += (*cluster.map_shared_rank(&ctot, c))[r][m];
     return v;
   };
 
@@ -160,6 +180,7 @@ gemm_skinny_bf16(const SkinnyParams p) {
         o[n2] = __float2bfloat16_rn(v2);
       }
     }
+    cluster.sync();
     return;
   }
 
@@ -185,12 +206,34 @@ gemm_skinny_bf16(const SkinnyParams p) {
     if (p.residual != nullptr) v += __bfloat162float(p.residual[(long long)m * p.ldr + n]);
     p.D[(long long)m * p.ldd + n] = __float2bfloat16_rn(v);
   }
+  cluster.sync();
+}
+
+static int skinny_target_ctas() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("G4R_SKINNY_CTAS");
+    v = e ? atoi(e) : 0;   // default: no split-K (measured: cluster scheduling costs more than the tail it removes)
+  }
+  return v;
 }
 
 template <int MT, int MB, int WARPS, bool ROPE>
-static int launch_skinny(const SkinnyParams& p, unsigned grid, cudaStream_t st) {
-  gemm_skinny_bf16<MT, MB, WARPS, ROPE><<<grid, WARPS * 32, 0, st>>>(p);
-  G4R_LAUNCH_CHECK("gemm_skinny");
+static int launch_skinny(const SkinnyParams& p, unsigned tiles, cudaStream_t st) {
+  // cluster split-K factor: enough CTAs for several waves, every warp keeps >= 1 k-block of 128
+  int ks = 1;
+  while (ks < 8 && (int)tiles * ks < skinny_target_ctas() && p.K >= 2 * ks * WARPS * 128) ks *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles, ks, 1);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ks; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  G4R_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_bf16<MT, MB, WARPS, ROPE>, p));
   return G4R_OK;
 }
 
@@ -220,7 +263,8 @@ int gemm_skinny_dispatch(const void* A, long long lda, const void* B, long long 
     return M <= 8 ? launch_skinny<2, 1, 4, false>(p, grid, st) : launch_skinny<2, 2, 4, false>(p, grid, st);
   }
   const unsigned grid = (unsigned)((N + 15) / 16);
-  return M <= 8 ? launch_skinny<1, 1, 8, false>(p, grid, st) : launch_skinny<1, 2, 8, false>(p, grid, st);
+  // 16-row tiles give few CTAs (N/16): 16 warps each keep >= 100 KB of weight loads in flight per SM
+  return M <= 8 ? launch_skinny<1, 1, 16, false>(p, grid, st) : launch_skinny<1, 2, 16, false>(p, grid, st);
 }
 
 }  // namespace g4r

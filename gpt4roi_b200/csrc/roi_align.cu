@@ -285,6 +285,7 @@ struct MlvlParams {
   void* out;  // forward: output; backward: grad_output (const)
   int N, C, K, PH, PW, sampling_ratio, aligned, rows_per_cta, n_levels;
   int rows_per_cta_lvl[G4R_MAX_LEVELS];  // forward: bin rows handled by one CTA, per level
+  float one;  // 1.0f, passed at run time: see add2_unfused
 };
 
 template <typename Tout, int N>
@@ -314,8 +315,54 @@ __device__ __forceinline__ void store_vec(Tout* p, const float (&v)[N]) {
   }
 }
 
-// Packed axis entry for the hot path: element offsets pre-multiplied (y: lo*W*C, x: lo*C),
-// off_lo < 0 marks an out-of-range sample (contributes exactly 0, common_cuda_helper.hpp:33).
+// ---- packed fp32x2 arithmetic (Blackwell FMUL2 / FFMA2: two IEEE fp32 lanes per instruction) ----------
+// The forward is bound by the fma pipe, not by HBM: the reference association
+//   val = ((w1*v1 + w2*v2) + w3*v3) + w4*v4;  acc += val          (roi_align.cpp:70-78 / cuda_kernel.cuh:63-66)
+// is 8 dependent-rounding fp32 ops per channel-sample and must not be contracted into FMAs to stay
+// bit-exact with the reference CPU kernel.  Two channels per instruction halves the pipe time.
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (seen in SASS), so the
+// unfused add is spelled fma(a, one, b) with `one` == 1.0f supplied at run time: a*1 is exact, the single
+// rounding is that of a + b, and there is no multiply left to contract.
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2_unfused(f32x2 a, f32x2 b, f32x2 one) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(one), "l"(b));
+  return r;
+}
+
+// 16-byte read-only global load with an explicit state space (the hoisted row pointers pass through an
+// optimisation barrier and would otherwise become generic LD instead of LDG).
+template <typename T>
+__device__ __forceinline__ void load16_global(const void* p, float (&out)[16 / sizeof(T)]) {
+  uint4 raw;
+  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(p));
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 16 / (int)sizeof(T); i++) out[i] = to_f32<T>(e[i]);
+}
+
+// Packed axis entry for the hot path: element offsets pre-multiplied (y: lo*W*C, x: lo*C).
+// An out-of-range sample gets offsets 0 and weights 0, exactly what the reference's pre_calc stores for it
+// (cpu/roi_align.cpp:43-57: pos1..4 = 0, w1..4 = 0): its four products are (+-)0 and leave the accumulator unchanged,
+// and the hot loop needs no branch (the loads of all samples of a bin can be in flight together).
 struct PackedAxis {
   int off_lo, off_hi;
   float l, h;
@@ -323,17 +370,17 @@ struct PackedAxis {
 
 __device__ __forceinline__ PackedAxis pack_axis(const AxisEntry<float>& e, int mul) {
   PackedAxis a;
-  a.off_lo = e.valid ? e.lo * mul : -1;
-  a.off_hi = e.hi * mul;
-  a.l = e.l;
-  a.h = e.h;
+  a.off_lo = e.valid ? e.lo * mul : 0;
+  a.off_hi = e.valid ? e.hi * mul : 0;
+  a.l = e.valid ? e.l : 0.f;
+  a.h = e.valid ? e.h : 0.f;
   return a;
 }
 
 // NV = 16-byte channel vectors per thread (1 or 2): with 2, the per-bin table reads, address arithmetic
 // and weight products are amortised over twice the channels (the kernel is issue / L1 bound, not HBM bound).
 template <typename Tin, typename Tout, int G, bool AFFINE, int NV>
-__global__ void __launch_bounds__(kThreads, (NV == 1 ? 5 : 3))
+__global__ void __launch_bounds__(kThreads, (NV == 1 && sizeof(Tin) == 4 && !AFFINE ? 5 : 3))
 roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
   constexpr int VEC = 16 / (int)sizeof(Tin);
   constexpr int CH = VEC * NV;
@@ -359,17 +406,18 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
   Tout* out = reinterpret_cast<Tout*>(p.out) +
               (((size_t)lvl * p.K + k) * p.PH + ph0) * (size_t)PW * C;
   const bool quarter = (gh * gw == 4);  // x/4 == x*0.25f exactly: avoids an IEEE division per value
+  const f32x2 one2 = pack2(p.one, p.one);
 
   if (nrows * gh <= kTab && PW * gw <= kTab) {
     for (int i = threadIdx.x; i < nrows * gh; i += blockDim.x)
       ytab[i] = pack_axis(axis_entry<float>(g.start_h, g.bin_h, ph0 + i / gh, i % gh, gh, H), W * C);
     for (int i = threadIdx.x; i < PW * gw; i += blockDim.x)
-      xtab[i] = pack_axis(axis_entry<float>(g.start_w, g.bin_w, i / gw, i % gw, gw, W), C);
+      xtab[i] = pack_axis(axis_entry<float>(g.start_w, g.bin_w, i / gw, i % gw, gw, W), C * (int)sizeof(Tin) / 16);  // 16-byte units
     __syncthreads();
     // Per-bin body: `prow`, `pw`, `lane` select the bin and the channel slice.
-    auto do_bin = [&](int prow, int pw, int lane, const PackedAxis* eyp) {
+    auto do_bin = [&](int prow, int pw, int lane, const PackedAxis* eyp, const char* const* rows) {
       const int coff = lane * CH;
-      const Tin* mp = map + coff;
+      const char* mpb = reinterpret_cast<const char*>(map + coff);
       float ga[CH], gb[CH];
       if constexpr (AFFINE) {
         const float* sa = p.gn_scale[lvl] + (size_t)g.batch * C + coff;
@@ -377,44 +425,62 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
 #pragma unroll
         for (int i = 0; i < CH; i++) { ga[i] = sa[i]; gb[i] = sb[i]; }
       }
-      float acc[CH];
+      f32x2 acc2[CH / 2];
 #pragma unroll
-      for (int i = 0; i < CH; i++) acc[i] = 0.f;
+      for (int i = 0; i < CH / 2; i++) acc2[i] = 0ull;   // (+0.f, +0.f)
 #pragma unroll
       for (int iy = 0; iy < (G > 0 ? G : gh); iy++) {
         const PackedAxis ey = eyp ? eyp[iy] : ytab[prow * gh + iy];
+        // row base pointers (hoisted by the caller when `rows` is given); each tap is then one
+        // IMAD.WIDE.U32: row + x_offset * 16 (x entries are stored in 16-byte units)
+        const char* r_lo = rows ? rows[2 * iy] : mpb + (size_t)(unsigned)ey.off_lo * sizeof(Tin);
+        const char* r_hi = rows ? rows[2 * iy + 1] : mpb + (size_t)(unsigned)ey.off_hi * sizeof(Tin);
 #pragma unroll
         for (int ix = 0; ix < (G > 0 ? G : gw); ix++) {
           const PackedAxis ex = xtab[pw * gw + ix];
-          if (ey.off_lo >= 0 && ex.off_lo >= 0) {
+          {
             const float w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
             float v1[CH], v2[CH], v3[CH], v4[CH];
 #pragma unroll
             for (int n = 0; n < NV; n++) {
               float t1[VEC], t2[VEC], t3[VEC], t4[VEC];
-              load16<Tin>(mp + (ey.off_lo + ex.off_lo) + n * VEC, t1);
-              load16<Tin>(mp + (ey.off_lo + ex.off_hi) + n * VEC, t2);
-              load16<Tin>(mp + (ey.off_hi + ex.off_lo) + n * VEC, t3);
-              load16<Tin>(mp + (ey.off_hi + ex.off_hi) + n * VEC, t4);
+              load16_global<Tin>(r_lo + (size_t)(unsigned)ex.off_lo * 16 + n * 16, t1);
+              load16_global<Tin>(r_lo + (size_t)(unsigned)ex.off_hi * 16 + n * 16, t2);
+              load16_global<Tin>(r_hi + (size_t)(unsigned)ex.off_lo * 16 + n * 16, t3);
+              load16_global<Tin>(r_hi + (size_t)(unsigned)ex.off_hi * 16 + n * 16, t4);
 #pragma unroll
               for (int i = 0; i < VEC; i++) {
                 v1[n * VEC + i] = t1[i]; v2[n * VEC + i] = t2[i]; v3[n * VEC + i] = t3[i]; v4[n * VEC + i] = t4[i];
               }
             }
+            if constexpr (AFFINE) {
+              // fused GroupNorm affine + ReLU on every tap (this engine's own fusion, tolerance-tested):
+              // one FFMA2 per channel pair and tap
 #pragma unroll
-            for (int i = 0; i < CH; i++) {
-              if constexpr (AFFINE) {
-                v1[i] = fmaxf(v1[i] * ga[i] + gb[i], 0.f);
-                v2[i] = fmaxf(v2[i] * ga[i] + gb[i], 0.f);
-                v3[i] = fmaxf(v3[i] * ga[i] + gb[i], 0.f);
-                v4[i] = fmaxf(v4[i] * ga[i] + gb[i], 0.f);
+              for (int i = 0; i < CH; i += 2) {
+                const f32x2 GA = pack2(ga[i], ga[i + 1]), GB = pack2(gb[i], gb[i + 1]);
+                float a, b;
+                unpack2(fma2(pack2(v1[i], v1[i + 1]), GA, GB), a, b); v1[i] = fmaxf(a, 0.f); v1[i + 1] = fmaxf(b, 0.f);
+                unpack2(fma2(pack2(v2[i], v2[i + 1]), GA, GB), a, b); v2[i] = fmaxf(a, 0.f); v2[i + 1] = fmaxf(b, 0.f);
+                unpack2(fma2(pack2(v3[i], v3[i + 1]), GA, GB), a, b); v3[i] = fmaxf(a, 0.f); v3[i + 1] = fmaxf(b, 0.f);
+                unpack2(fma2(pack2(v4[i], v4[i + 1]), GA, GB), a, b); v4[i] = fmaxf(a, 0.f); v4[i + 1] = fmaxf(b, 0.f);
               }
-              const float val = w1 * v1[i] + w2 * v2[i] + w3 * v3[i] + w4 * v4[i];
-              acc[i] += val;
+            }
+            const f32x2 W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3), W4 = pack2(w4, w4);
+#pragma unroll
+            for (int i = 0; i < CH; i += 2) {
+              f32x2 t = mul2(W1, pack2(v1[i], v1[i + 1]));
+              t = add2_unfused(t, mul2(W2, pack2(v2[i], v2[i + 1])), one2);
+              t = add2_unfused(t, mul2(W3, pack2(v3[i], v3[i + 1])), one2);
+              t = add2_unfused(t, mul2(W4, pack2(v4[i], v4[i + 1])), one2);
+              acc2[i / 2] = add2_unfused(acc2[i / 2], t, one2);
             }
           }
         }
       }
+      float acc[CH];
+#pragma unroll
+      for (int i = 0; i < CH; i += 2) unpack2(acc2[i / 2], acc[i], acc[i + 1]);
 #pragma unroll
       for (int i = 0; i < CH; i++) acc[i] = quarter ? acc[i] * 0.25f : acc[i] / g.count;
 #pragma unroll
@@ -433,9 +499,18 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
         for (int lane = threadIdx.x % lanes; lane < lanes; lane += (blockDim.x >= lanes ? lanes : blockDim.x)) {
           for (int prow = 0; prow < nrows; prow++) {
             PackedAxis eyr[G];
+            const char* rows[2 * G];
+            const char* mpb = reinterpret_cast<const char*>(map + lane * CH);
 #pragma unroll
-            for (int iy = 0; iy < G; iy++) eyr[iy] = ytab[prow * G + iy];
-            for (int pw = grp; pw < PW; pw += ngrp) do_bin(prow, pw, lane, eyr);
+            for (int iy = 0; iy < G; iy++) {
+              eyr[iy] = ytab[prow * G + iy];
+              rows[2 * iy] = mpb + (size_t)(unsigned)eyr[iy].off_lo * sizeof(Tin);
+              rows[2 * iy + 1] = mpb + (size_t)(unsigned)eyr[iy].off_hi * sizeof(Tin);
+              // opaque to the optimiser: keeps the 64-bit row pointers in registers instead of
+              // re-deriving them (3 integer instructions) at every tap
+              asm volatile("" : "+l"(rows[2 * iy]), "+l"(rows[2 * iy + 1]));
+            }
+            for (int pw = grp; pw < PW; pw += ngrp) do_bin(prow, pw, lane, eyr, rows);
           }
         }
         return;
@@ -445,7 +520,7 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
       const int lane = it % lanes;
       const int b = it / lanes;  // bin within this CTA's rows
-      do_bin(b / PW, b % PW, lane, nullptr);
+      do_bin(b / PW, b % PW, lane, nullptr, nullptr);
     }
     return;
   }
@@ -490,6 +565,147 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
 #pragma unroll
     for (int i = 0; i < VEC; i++) acc[i] = acc[i] / g.count;
     store_vec<Tout, VEC>(out + ((size_t)prow * PW + pw) * C + coff, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// "Row walk" forward for the fixed 2x2 sampling grid (the SPI module's RoIAlign(14, sampling_ratio=2),
+// gpt4roi/models/layers.py:205-212, and the 7x7 microbench).
+//
+// The table kernel above is bound by L1 wavefronts: every bin-thread issues 16 16-byte tap loads for one
+// 16-byte store, although on the coarse levels consecutive samples of a bin row fall into the same or the
+// adjacent map column.  Here a thread owns a channel slice and a whole bin ROW: for each of the two sample
+// rows it walks the 2*PW x-samples left to right keeping the current (lo, hi) column pair of both map rows
+// in registers -- a sample whose columns are already held costs no load, a sample one column further
+// shifts hi -> lo and loads one column.  Loads drop to (distinct columns) x 2 rows per sample row; the
+// arithmetic (weights, association, accumulation order iy-major / ix-minor) is unchanged, so the result
+// stays bit-identical to the table kernel and to the reference CPU kernel.
+// ------------------------------------------------------------------------------------
+template <typename Tin, typename Tout, bool AFFINE>
+__global__ void __launch_bounds__(kThreads, (sizeof(Tin) == 4 ? 3 : 2))
+roi_align_fwd_nhwc_mlvl_walk(const __grid_constant__ MlvlParams p) {
+  constexpr int VEC = 16 / (int)sizeof(Tin);   // channels per thread
+  constexpr int NB = VEC == 4 ? 7 : 4;         // bins per walk segment (accumulators live in registers)
+  constexpr int G = 2;
+  __shared__ PackedAxis ytab[kTab];
+  __shared__ PackedAxis xtab[kTab];
+
+  const int lvl = blockIdx.y;
+  const int rpc = p.rows_per_cta_lvl[lvl];
+  const int row_groups = (p.PH + rpc - 1) / rpc;
+  const int k = blockIdx.x / row_groups;
+  if (k >= p.K) return;
+  const int ph0 = (blockIdx.x % row_groups) * rpc;
+  const int nrows = min(rpc, p.PH - ph0);
+  const int H = p.H[lvl], W = p.W[lvl], C = p.C, PW = p.PW;
+  const float* r = p.rois + (size_t)k * 5;
+  const RoiGeom<float> g = roi_geom<float>(r[0], r[1], r[2], r[3], r[4], p.scale[lvl], p.PH, PW, G, p.aligned != 0, true);
+  const int lanes = C / VEC;
+  const Tin* map = reinterpret_cast<const Tin*>(p.maps[lvl]) + (size_t)g.batch * H * W * C;
+  Tout* out = reinterpret_cast<Tout*>(p.out) + (((size_t)lvl * p.K + k) * p.PH + ph0) * (size_t)PW * C;
+  const f32x2 one2 = pack2(p.one, p.one);
+
+  for (int i = threadIdx.x; i < nrows * G; i += blockDim.x)
+    ytab[i] = pack_axis(axis_entry<float>(g.start_h, g.bin_h, ph0 + i / G, i % G, G, H), W * C);
+  for (int i = threadIdx.x; i < PW * G; i += blockDim.x)
+    xtab[i] = pack_axis(axis_entry<float>(g.start_w, g.bin_w, i / G, i % G, G, W), C * (int)sizeof(Tin) / 16);
+  __syncthreads();
+
+  // thread -> (channel slice, row group); blockDim.x is a multiple of lanes or lanes a multiple of blockDim.x
+  const int ngrp = blockDim.x >= lanes ? blockDim.x / lanes : 1;
+  const int rgrp = blockDim.x >= lanes ? threadIdx.x / lanes : 0;
+  for (int lane = threadIdx.x % lanes; lane < lanes; lane += (blockDim.x >= lanes ? lanes : blockDim.x)) {
+    const int coff = lane * VEC;
+    const char* mpb = reinterpret_cast<const char*>(map + coff);
+    f32x2 ga2[VEC / 2], gb2[VEC / 2];
+    if constexpr (AFFINE) {
+      const float* sa = p.gn_scale[lvl] + (size_t)g.batch * C + coff;
+      const float* sb = p.gn_shift[lvl] + (size_t)g.batch * C + coff;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) { ga2[i / 2] = pack2(sa[i], sa[i + 1]); gb2[i / 2] = pack2(sb[i], sb[i + 1]); }
+    }
+    // one map pixel (16 bytes of channels) -> VEC/2 packed pairs, GroupNorm affine + ReLU applied once
+    auto load_px = [&](const char* ptr, f32x2 (&dst)[VEC / 2]) {
+      float t[VEC];
+      load16_global<Tin>(ptr, t);
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        if constexpr (AFFINE) {
+          float a, b;
+          unpack2(fma2(pack2(t[i], t[i + 1]), ga2[i / 2], gb2[i / 2]), a, b);
+          dst[i / 2] = pack2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+        } else {
+          dst[i / 2] = pack2(t[i], t[i + 1]);
+        }
+      }
+    };
+    for (int prow = rgrp; prow < nrows; prow += ngrp) {
+      for (int pw0 = 0; pw0 < PW; pw0 += NB) {
+        f32x2 acc2[NB][VEC / 2];
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+          for (int i = 0; i < VEC / 2; i++) acc2[b][i] = 0ull;
+#pragma unroll
+        for (int iy = 0; iy < G; iy++) {
+          const PackedAxis ey = ytab[prow * G + iy];
+          const char* r_lo = mpb + (size_t)(unsigned)ey.off_lo * sizeof(Tin);
+          const char* r_hi = mpb + (size_t)(unsigned)ey.off_hi * sizeof(Tin);
+          unsigned c_lo = 0xffffffffu, c_hi = 0xffffffffu;        // columns currently held
+          f32x2 a_lo[VEC / 2], a_hi[VEC / 2], b_lo[VEC / 2], b_hi[VEC / 2];  // a: map row lo, b: map row hi
+#pragma unroll
+          for (int i = 0; i < VEC / 2; i++) a_lo[i] = a_hi[i] = b_lo[i] = b_hi[i] = 0ull;
+#pragma unroll
+          for (int j = 0; j < NB * G; j++) {
+            const int pw = pw0 + j / G;
+            if (pw < PW) {   // block-uniform
+              const PackedAxis ex = xtab[pw * G + (j % G)];
+              const unsigned xl = (unsigned)ex.off_lo, xh = (unsigned)ex.off_hi;
+              if (xl != c_lo || xh != c_hi) {   // warp-uniform: all lanes of a warp share the RoI and the row
+                if (xl == c_hi) {
+#pragma unroll
+                  for (int i = 0; i < VEC / 2; i++) { a_lo[i] = a_hi[i]; b_lo[i] = b_hi[i]; }
+                } else {
+                  load_px(r_lo + (size_t)xl * 16, a_lo);
+                  load_px(r_hi + (size_t)xl * 16, b_lo);
+                }
+                if (xh == xl) {
+#pragma unroll
+                  for (int i = 0; i < VEC / 2; i++) { a_hi[i] = a_lo[i]; b_hi[i] = b_lo[i]; }
+                } else {
+                  load_px(r_lo + (size_t)xh * 16, a_hi);
+                  load_px(r_hi + (size_t)xh * 16, b_hi);
+                }
+                c_lo = xl;
+                c_hi = xh;
+              }
+              // reference association: val = ((w1*v1 + w2*v2) + w3*v3) + w4*v4;  acc += val
+              const float w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
+              const f32x2 W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3), W4 = pack2(w4, w4);
+#pragma unroll
+              for (int i = 0; i < VEC / 2; i++) {
+                f32x2 t = mul2(W1, a_lo[i]);
+                t = add2_unfused(t, mul2(W2, a_hi[i]), one2);
+                t = add2_unfused(t, mul2(W3, b_lo[i]), one2);
+                t = add2_unfused(t, mul2(W4, b_hi[i]), one2);
+                acc2[j / G][i] = add2_unfused(acc2[j / G][i], t, one2);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+          if (pw0 + b < PW) {
+            float o[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; i += 2) unpack2(acc2[b][i / 2], o[i], o[i + 1]);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) o[i] = o[i] * 0.25f;   // count = 4: x/4 == x*0.25f exactly
+            store_vec<Tout, VEC>(out + ((size_t)prow * PW + pw0 + b) * C + coff, o);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -612,6 +828,9 @@ static int launch_fwd_mlvl(MlvlParams& p, bool affine, cudaStream_t st) {
     const double map_mb = (double)p.H[l] * p.W[l] * p.C * sizeof(Tin) / 1e6;
     int rows = map_mb > 8.0 ? 1 : pick_rows_per_cta(p.K, p.n_levels, p.PH);
     if (env && atoi(env) > 0) rows = atoi(env);
+    // the row-walk kernel gives each thread group (C/VEC lanes) its own bin row: keep every group busy
+    const int lanes_l = p.C / (16 / (int)sizeof(Tin));
+    if (lanes_l < kThreads && rows < kThreads / lanes_l) rows = kThreads / lanes_l;
     if (rows > p.PH) rows = p.PH;
     p.rows_per_cta_lvl[l] = rows;
     const int groups = (p.PH + rows - 1) / rows;
@@ -629,6 +848,22 @@ static int launch_fwd_mlvl(MlvlParams& p, bool affine, cudaStream_t st) {
   // measured on B200 (profiles/r1_roialign_microbench_v3.jsonl): 2 vectors/thread is 25 % SLOWER (fewer
   // threads per bin => less latency hiding), so it stays opt-in (G4R_ROI_NV=2)
   const bool nv2 = sizeof(Tin) == 4 && p.C % (2 * VEC) == 0 && p.C / (2 * VEC) >= 32 && nv_env == 2;
+  // The row-walk kernel (fewer L1 wavefronts, but on-demand loads at 3 CTAs/SM) measured 9.7 ms against the
+  // table kernel's 7.6 ms on the BASELINE microbench (profiles/r1_roialign_microbench_v5.jsonl); an in-bin
+  // tap-dedup variant of the table kernel measured 10.7 ms.  Both lose to plain occupancy, so the walk kernel
+  // is opt-in (G4R_ROI_WALK=1) and the dedup variant was dropped.
+  static int walk_env = -1;
+  if (walk_env < 0) {
+    const char* e = getenv("G4R_ROI_WALK");
+    walk_env = e ? atoi(e) : 0;
+  }
+  const int lanes = p.C / VEC;
+  if (g2 && walk_env == 1 && !nv2 && (kThreads % lanes == 0 || lanes % kThreads == 0)) {
+    if (affine) roi_align_fwd_nhwc_mlvl_walk<Tin, Tout, true><<<grid, kThreads, 0, st>>>(p);
+    else roi_align_fwd_nhwc_mlvl_walk<Tin, Tout, false><<<grid, kThreads, 0, st>>>(p);
+    G4R_LAUNCH_CHECK("roi_align_fwd_nhwc_mlvl_walk");
+    return G4R_OK;
+  }
   if (g2) {
     if constexpr (sizeof(Tin) == 4) {
       if (nv2) {
@@ -669,6 +904,7 @@ extern "C" int g4r_roi_align_mlvl_forward(const void* const* maps, const int* H,
   if (K == 0) return G4R_OK;
   G4R_REQUIRE(rois, "rois is NULL with K=%d", K);
   MlvlParams p{};
+  p.one = 1.0f;
   for (int l = 0; l < n_levels; l++) {
     G4R_REQUIRE(maps[l] && H[l] > 0 && W[l] > 0, "level %d: bad map", l);
     G4R_REQUIRE(((uintptr_t)maps[l] & 15) == 0, "level %d: map not 16-byte aligned", l);

@@ -29,6 +29,20 @@ def test_layernorm_rmsnorm(D):
     close(kernels.rmsnorm(x, w, 1e-6), want, rtol=8e-3, atol=8e-3)
 
 
+@pytest.mark.parametrize('M', [1, 8, 64])
+@pytest.mark.parametrize('D', [1024, 4096, 8192, 520])
+def test_norm_few_rows_cta_per_row_variant(M, D):
+    """M <= 64 takes the CTA-per-row kernel (decode step); same reference as the warp-per-row one."""
+    torch.manual_seed(D + M)
+    x = (torch.randn(M, D, device=DEV) * 2 + 0.5).to(BF)
+    w = (torch.rand(D, device=DEV) + 0.5).to(BF)
+    b = torch.randn(D, device=DEV).to(BF)
+    close(kernels.layernorm(x, w, b, 1e-5), F.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-5))
+    xf = x.float()
+    want = w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(BF).float()
+    close(kernels.rmsnorm(x, w, 1e-6), want, rtol=8e-3, atol=8e-3)
+
+
 def test_rope_matches_hf_formula():
     torch.manual_seed(0)
     B, L, H, D = 2, 37, 4, 128
@@ -165,3 +179,51 @@ def test_attention_seqlens(impl):
         solo = qkv.view(B, L, -1)[b, :n].contiguous()
         ref = kernels.attention(solo, 1, n, H, D, True, D ** -0.5, impl=impl).view(n, H, D)
         torch.testing.assert_close(out[b, :n].float(), ref.float(), rtol=1e-2, atol=1e-2)
+
+
+# ---- decode step kernels ----------------------------------------------------------------
+
+@pytest.mark.parametrize('B,H,D', [(1, 32, 128), (8, 32, 128), (3, 4, 64), (2, 5, 128)])
+@pytest.mark.parametrize('kv_len', [1, 5, 63, 64, 129, 706, 1300])
+def test_decode_attention_matches_fp32_reference(B, H, D, kv_len):
+    """Cluster split-KV single-query attention vs a plain fp32 softmax(q.K^T)V with the reference's
+    rounding point (probabilities cast to bf16 before P.V).  Tolerance: bf16 output, rel-L2 <= 4e-3."""
+    torch.manual_seed(B * 1000 + H + kv_len)
+    HD, Lmax = H * D, kv_len + 7
+    qkv = (torch.randn(B, 3 * HD, device=DEV)).bfloat16()
+    kc = torch.randn(B, Lmax, HD, device=DEV).bfloat16()
+    vc = torch.randn(B, Lmax, HD, device=DEV).bfloat16()
+    scale = D ** -0.5
+    got = kernels.decode_attention(qkv, kc, vc, B, H, D, kv_len, scale).float()
+    q = qkv[:, :HD].float().view(B, H, 1, D)
+    k = kc[:, :kv_len].float().view(B, kv_len, H, D).permute(0, 2, 1, 3)
+    v = vc[:, :kv_len].float().view(B, kv_len, H, D).permute(0, 2, 1, 3)
+    p = torch.softmax(q @ k.transpose(-1, -2) * scale, -1).bfloat16().float()
+    want = (p @ v).permute(0, 2, 1, 3).reshape(B, HD)
+    rel = ((got - want).norm() / want.norm()).item()
+    assert rel < 4e-3, rel
+    # device-side length (CUDA-graph replay): kv_len argument only sizes the score buffer
+    pos_dev = torch.tensor([kv_len - 1], dtype=torch.int32, device=DEV)
+    got_dev = kernels.decode_attention(qkv, kc, vc, B, H, D, Lmax, scale, pos_dev=pos_dev).float()
+    rel = ((got_dev - want).norm() / want.norm()).item()
+    assert rel < 4e-3, rel
+    assert torch.equal(kernels.decode_attention(qkv, kc, vc, B, H, D, kv_len, scale).float(), got)  # reproducible
+
+
+def test_kv_append_places_rows():
+    torch.manual_seed(0)
+    B, Ln, HD, Lmax, pos0 = 3, 4, 256, 20, 9
+    qkv = torch.randn(B * Ln, 3 * HD, device=DEV).bfloat16()
+    kc = torch.zeros(B, Lmax, HD, device=DEV, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    kernels.kv_append(qkv, kc, vc, B, Ln, pos0)
+    want_k = torch.zeros_like(kc)
+    want_v = torch.zeros_like(kc)
+    want_k[:, pos0:pos0 + Ln] = qkv[:, HD:2 * HD].view(B, Ln, HD)
+    want_v[:, pos0:pos0 + Ln] = qkv[:, 2 * HD:].view(B, Ln, HD)
+    assert torch.equal(kc, want_k) and torch.equal(vc, want_v)
+    kc2, vc2 = torch.zeros_like(kc), torch.zeros_like(kc)
+    kernels.kv_append(qkv, kc2, vc2, B, Ln, 0, pos_dev=torch.tensor([pos0], dtype=torch.int32, device=DEV))
+    assert torch.equal(kc2, want_k) and torch.equal(vc2, want_v)
+    with pytest.raises(RuntimeError):
+        kernels.kv_append(qkv, kc, vc, B, Ln, Lmax - 1)

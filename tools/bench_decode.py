@@ -1,5 +1,5 @@
 """Decode-loop throughput: region-token prefill + KV-cache decode steps, 7B, bf16.
-Prints one JSON line per batch size.  usage: python tools/bench_decode.py [new_tokens]"""
+Prints one JSON line per batch size.  usage: python tools/bench_decode.py [new_tokens] [graph]"""
 import json
 import os
 import sys
@@ -19,7 +19,8 @@ def main():
     sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
     eng = PrefillEngine(cfg, sd, vit_sd, dev)
     del sd, vit_sd
-    for B, graphed in ((1, False), (1, True), (8, False), (8, True)):
+    modes = (True,) if 'graph' in sys.argv[2:] else (False, True)
+    for B, graphed in [(b, g) for b in (1, 8) for g in modes]:
         ids, images, boxes = synthetic_inputs(cfg, B, 8, 128)
         ids, images = ids.to(dev), images.to(dev)
         L = ids.shape[1]
