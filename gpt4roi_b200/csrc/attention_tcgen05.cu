@@ -47,17 +47,7 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// MN-major B operand (V tile [keys][d], d contiguous), 128-byte swizzle: rows (= k index) are 128 B
-// apart, 8-row groups 1024 B apart (SBO), 64-element MN atoms `lbo` bytes apart (LBO).
-__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
+using ptx::make_smem_desc_mn_sw128;  // V tile [keys][d] (d contiguous) is an MN-major B operand
 
 // BN = keys per block.  BN=64 keeps a CTA at 112 KB of shared memory and 256 TMEM columns (D=128), so
 // TWO CTAs share an SM: one CTA's prologue / epilogue overlaps the other's MMAs and 8 softmax warps

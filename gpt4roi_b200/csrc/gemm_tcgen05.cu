@@ -66,6 +66,8 @@ struct GemmParams {
   const __nv_bfloat16* rope_sin;
   int rope_cols, rope_L, rope_pos0;
   const int* rope_pos_dev;  // optional device-side position base (CUDA-graph decode): pos0 = *rope_pos_dev
+  // operand majorness (backward GEMMs): a_mn: A is stored [K][M] (M contiguous); b_mn: B is stored [K][N]
+  int a_mn, b_mn;
   float* gn_stats;       // optional [n_img, groups, 2] (sum, sumsq) of the bf16-rounded output
   int gn_group_ch;       // channels per group (16)
   int gn_groups;         // groups per image (64)
@@ -395,18 +397,31 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
             ptx::tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], cc * kBlockK, x0 + dx,
                              y0 + dy, img + lvl * p.lvl_img_stride);
+          } else if (p.a_mn) {
+            // MN-major A: two [64 k][64 m] boxes (one 128-byte swizzle atom of m each)
+#pragma unroll
+            for (int a = 0; a < kBlockM / 64; a++)
+              ptx::tma_load_2d(smem_a + stage * Cfg::kABytes + a * (kBlockK * 128), &tmap_a, &full[stage],
+                               m_blk * kBlockM + a * 64, kg * kBlockK);
           } else {
             ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], kg * kBlockK,
                              m_blk * kBlockM);
           }
-          ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full[stage], kg * kBlockK, n_blk * BLOCK_N);
+          if (!CONV && p.b_mn) {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; a++)
+              ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes + a * (kBlockK * 128), &tmap_b, &full[stage],
+                               n_blk * BLOCK_N + a * 64, kg * kBlockK);
+          } else {
+            ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full[stage], kg * kBlockK, n_blk * BLOCK_N);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, BLOCK_N);
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, BLOCK_N) | (p.a_mn ? 1u << 15 : 0u) | (p.b_mn ? 1u << 16 : 0u);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -420,12 +435,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::mbar_wait(&full[stage], phase);
         ptx::tcgen05_after_thread_sync();
         if (lane == 0) {
-          const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+          // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (>>4) address field.
+          // MN-major: advance 16 k-rows of 128 B: +128 in the address field; LBO = the 8 KB mn-atom stride.
+          const uint32_t sa = ptx::smem_u32(smem_a + stage * Cfg::kABytes), sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
+          const uint64_t da = p.a_mn ? ptx::make_smem_desc_mn_sw128(sa, kBlockK * 128) : ptx::make_smem_desc_sw128(sa);
+          const uint64_t db = p.b_mn ? ptx::make_smem_desc_mn_sw128(sb, kBlockK * 128) : ptx::make_smem_desc_sw128(sb);
+          const uint64_t ia = p.a_mn ? 128 : 2, ib = p.b_mn ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; k++) {
-            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (>>4) address field
-            ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            ptx::umma_f16_ss(tmem_d, da + ia * k, db + ib * k, idesc, (kb | k) != 0);
           }
           ptx::umma_commit(&empty[stage]);
           if (kb == p.num_k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
@@ -784,6 +802,50 @@ extern "C" int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* 
   G4R_REQUIRE(rope_cols % 256 == 0 && rope_cols <= N && N % 128 == 0 && ldd % 8 == 0, "qkv_rope: rope_cols must be a multiple of 256 (whole tiles of 128-dim heads)");
   return gemm_impl(A, lda, B, ldb, D, ldd, M, N, K, nullptr, 0, nullptr, 0, 0, 0, ACT_NONE, 0, 1, rope_cos, rope_sin,
                    rope_cols, L, stream, pos0, pos0_dev);
+}
+
+// Backward-pass GEMM: D[M, N] = op(A) . op(B)^T with either operand optionally stored "MN-major":
+//   a_mn = 0: A is [M, K] (K contiguous, row stride lda);  a_mn = 1: A is stored [K, M] (M contiguous, lda >= M)
+//   b_mn = 0: B is [N, K] (K contiguous, row stride ldb);  b_mn = 1: B is stored [K, N] (N contiguous, ldb >= N)
+// so that for y = x W^T (W [N_out, K_in], nn.Linear):
+//   dX[M, K_in]      = dY[M, N_out] . W          -> A = dY (a_mn 0), B = W  (b_mn 1, contraction N_out)
+//   dW[N_out, K_in]  = dY^T . X                  -> A = dY (a_mn 1), B = X  (b_mn 1, contraction M tokens)
+// The transposes happen in the tensor-core operand descriptors (UMMA major bits), never in memory.
+// Replaces the autograd of F.linear inside the stage-2 training step (gpt4roi/train/train.py:698-712).
+extern "C" int g4r_gemm_bf16_t(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D,
+                               long long ldd, int M, int N, int K, int out_f32, void* stream) {
+  G4R_REQUIRE(A && B && D, "null operand");
+  G4R_REQUIRE(M > 0 && N > 0 && K > 0, "bad sizes M=%d N=%d K=%d", M, N, K);
+  G4R_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 (16-byte TMA strides)");
+  G4R_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), "lda/ldb smaller than the contiguous extent");
+  G4R_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "A/B must be 16-byte aligned");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.k_splits = 1;
+  p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  p.D = D; p.ldd = ldd; p.out_f32 = out_f32;
+  p.a_rows = kBlockM;
+  p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
+  const int bn = pick_block_n(N, p.num_m_tiles, 1);
+  p.num_n_tiles = (N + bn - 1) / bn;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(a_mn ? M : K), (cuuint64_t)(a_mn ? K : M)};
+    cuuint64_t str[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(a_mn ? kBlockK : kBlockM)};
+    int rc = make_tmap(&ta, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(b_mn ? N : K), (cuuint64_t)(b_mn ? K : N)};
+    cuuint64_t str[1] = {(cuuint64_t)ldb * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(b_mn ? kBlockK : bn)};
+    int rc = make_tmap(&tb, B, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return bn == 256 ? launch_gemm<256, false>(ta, tb, p, st) : launch_gemm<128, false>(ta, tb, p, st);
 }
 
 static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,

@@ -140,7 +140,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major.
+// MN-major operand (stored [k][mn] with mn contiguous), 128-byte swizzle: one swizzle atom is
+// [k rows of 128 B] x [64 mn elements]; 8-row groups are 1024 B apart (SBO) and consecutive 64-element
+// mn atoms `lbo_bytes` apart (LBO).  Advancing k by one UMMA_K (16 rows) moves the start by 16*128 B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major (OR in bit 15 / 16 for an MN-major A / B).
 //   [4,6) c_format=1(F32) | [7,10) a_format=1(BF16) | [10,13) b_format=1 | [15] a_major=0 | [16] b_major=0
 //   [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {

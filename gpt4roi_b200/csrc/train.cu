@@ -1,0 +1,387 @@
+// train.cu -- the non-GEMM kernels of the stage-2 training step (SURVEY.md 8(a) row 14:
+// gpt4roi/train/train.py:698-712 drives HF Trainer over SPILlavaMPTForCausalLM; the loss is
+// llava/model/llava.py:238-249: shift logits/labels, CrossEntropyLoss() = mean over labels != -100).
+// Backward GEMMs are g4r_gemm_bf16_t (gemm_tcgen05.cu).  Everything here is HBM-bound elementwise /
+// row-reduction work: 16-byte vector loads, fp32 math, fixed-order reductions (no atomics, bitwise
+// reproducible), bf16 storage like the reference's bf16 autocast.
+#include "common.cuh"
+
+namespace g4r {
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void unpack8f(const uint4& raw, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
+  uint4 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return raw;
+}
+
+// block-wide sum / max over 256 threads; every thread gets the result
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum_f(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; w++) t += red[w];
+  return t;
+}
+__device__ __forceinline__ float block_max_256(float v, float* red) {
+  v = warp_max_f(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; w++) t = fmaxf(t, red[w]);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross entropy over rows of logits [M, V] (bf16, row stride ld) against int64 targets (-100 = ignore).
+// Pass 1 (one CTA per row): row max, log-sum-exp, loss_row = lse - x[target].
+// Pass 2 (one CTA): loss = sum(loss_row over valid rows) / count, in a fixed order.
+// Pass 3 (one CTA per row): dlogits = (softmax - onehot) * gscale / count, zero for ignored rows.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ce_rows_fwd(const __nv_bfloat16* __restrict__ logits, long long ld, const long long* __restrict__ targets,
+            float* __restrict__ row_loss, float* __restrict__ row_lse, int V) {
+  __shared__ float red[8];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const long long tgt = targets[r];
+  const __nv_bfloat16* x = logits + (long long)r * ld;
+  const bool vec = (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int V8 = vec ? (V & ~7) : 0;
+  float mx = -INFINITY;
+  for (int v = tid * 8; v < V8; v += 256 * 8) {
+    float f[8];
+    unpack8f(*reinterpret_cast<const uint4*>(x + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) mx = fmaxf(mx, f[j]);
+  }
+  for (int v = V8 + tid; v < V; v += 256) mx = fmaxf(mx, __bfloat162float(x[v]));
+  mx = block_max_256(mx, red);
+  float s = 0.f;
+  for (int v = tid * 8; v < V8; v += 256 * 8) {
+    float f[8];
+    unpack8f(*reinterpret_cast<const uint4*>(x + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += __expf(f[j] - mx);
+  }
+  for (int v = V8 + tid; v < V; v += 256) s += __expf(__bfloat162float(x[v]) - mx);
+  s = block_sum_256(s, red);
+  if (tid == 0) {
+    const float lse = mx + logf(s);
+    row_lse[r] = lse;
+    row_loss[r] = (tgt >= 0 && tgt < V) ? lse - __bfloat162float(x[tgt]) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ce_reduce(const float* __restrict__ row_loss, const long long* __restrict__ targets, int M, int V,
+          float* __restrict__ out /* [0] mean loss, [1] valid count */) {
+  __shared__ float red[8];
+  float s = 0.f, c = 0.f;
+  // fixed assignment of rows to threads + fixed-order tree => bitwise reproducible
+  for (int r = threadIdx.x; r < M; r += 256) {
+    const long long t = targets[r];
+    if (t >= 0 && t < V) { s += row_loss[r]; c += 1.f; }
+  }
+  s = block_sum_256(s, red);
+  c = block_sum_256(c, red);
+  if (threadIdx.x == 0) {
+    out[0] = c > 0.f ? s / c : 0.f;
+    out[1] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ce_rows_bwd(const __nv_bfloat16* __restrict__ logits, long long ld, const long long* __restrict__ targets,
+            const float* __restrict__ row_lse, const float* __restrict__ loss_count,
+            __nv_bfloat16* __restrict__ dlogits, long long ldd, int V, float gscale) {
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const long long tgt = targets[r];
+  const bool valid = tgt >= 0 && tgt < V;
+  const float cnt = loss_count[1];
+  const float k = (valid && cnt > 0.f) ? gscale / cnt : 0.f;
+  const float lse = row_lse[r];
+  const __nv_bfloat16* x = logits + (long long)r * ld;
+  __nv_bfloat16* d = dlogits + (long long)r * ldd;
+  const bool vec = (ld % 8 == 0) && (ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dlogits) & 15) == 0);
+  const int V8 = vec ? (V & ~7) : 0;
+  for (int v = tid * 8; v < V8; v += 256 * 8) {
+    float f[8];
+    unpack8f(*reinterpret_cast<const uint4*>(x + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = (__expf(f[j] - lse) - ((long long)(v + j) == tgt ? 1.f : 0.f)) * k;
+    *reinterpret_cast<uint4*>(d + v) = pack8f(f);
+  }
+  for (int v = V8 + tid; v < V; v += 256)
+    d[v] = __float2bfloat16_rn((__expf(__bfloat162float(x[v]) - lse) - ((long long)v == tgt ? 1.f : 0.f)) * k);
+}
+
+// ------------------------------------------------------------------------------------------
+// RMSNorm backward (transformers LlamaRMSNorm: y = w * (x * rsqrt(mean(x^2) + eps)).to(bf16)).
+// g = dy * w;  xh = x * r;  dx = r * (g - xh * mean(g * xh));  dw = sum_rows dy * xh.
+// One CTA walks rows r = blockIdx.x, blockIdx.x + gridDim.x, ...; each thread keeps its channel slice of
+// dw in fp32 registers and writes it to a per-CTA slab; rms_dw_reduce sums the slabs in CTA order.
+// ------------------------------------------------------------------------------------------
+template <int PER>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_rows(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                 const __nv_bfloat16* __restrict__ dy, long long ldy, __nv_bfloat16* __restrict__ dx, long long ldd,
+                 float* __restrict__ dw_slabs, int M, int D, float eps) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x;
+  const int nvec = D >> 3;
+  float wf[PER][8], dwacc[PER][8];
+#pragma unroll
+  for (int i = 0; i < PER; i++) {
+    const int vi = tid + i * 256;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { wf[i][j] = 0.f; dwacc[i][j] = 0.f; }
+    if (vi < nvec) unpack8f(reinterpret_cast<const uint4*>(w)[vi], wf[i]);
+  }
+  for (int r = blockIdx.x; r < M; r += gridDim.x) {
+    float xv[PER][8], gv[PER][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      const int vi = tid + i * 256;
+      if (vi < nvec) {
+        unpack8f(*reinterpret_cast<const uint4*>(x + (long long)r * ldx + vi * 8), xv[i]);
+        unpack8f(*reinterpret_cast<const uint4*>(dy + (long long)r * ldy + vi * 8), gv[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { xv[i][j] = 0.f; gv[i][j] = 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) ss += xv[i][j] * xv[i][j];
+    }
+    ss = block_sum_256(ss, red);
+    const float rs = rsqrtf(ss / D + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float xh = xv[i][j] * rs;
+        dwacc[i][j] += gv[i][j] * __bfloat162float(__float2bfloat16_rn(xh));  // dy * xhat (xhat as stored: bf16)
+        gv[i][j] *= wf[i][j];                                                // g = dy * w
+        xv[i][j] = xh;
+        dot += gv[i][j] * xh;
+      }
+    dot = block_sum_256(dot, red) / D;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      const int vi = tid + i * 256;
+      if (vi >= nvec) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = rs * (gv[i][j] - xv[i][j] * dot);
+      *reinterpret_cast<uint4*>(dx + (long long)r * ldd + vi * 8) = pack8f(o);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PER; i++) {
+    const int vi = tid + i * 256;
+    if (vi >= nvec) continue;
+    float* o = dw_slabs + (long long)blockIdx.x * D + vi * 8;
+    reinterpret_cast<float4*>(o)[0] = make_float4(dwacc[i][0], dwacc[i][1], dwacc[i][2], dwacc[i][3]);
+    reinterpret_cast<float4*>(o)[1] = make_float4(dwacc[i][4], dwacc[i][5], dwacc[i][6], dwacc[i][7]);
+  }
+}
+
+// out[d] = sum_s slabs[s][d] in slab order (fp32)
+__global__ void __launch_bounds__(256)
+slab_reduce_f32(const float* __restrict__ slabs, int S, int D, float* __restrict__ out) {
+  const int d = blockIdx.x * 256 + threadIdx.x;
+  if (d >= D) return;
+  float a = 0.f;
+  for (int s = 0; s < S; s++) a += slabs[(long long)s * D + d];
+  out[d] = a;
+}
+
+// ------------------------------------------------------------------------------------------
+// SwiGLU on an interleaved gate/up buffer gu [M, 2F] (column 2j = gate_j, 2j+1 = up_j; the layout the
+// fused weight of engine.py produces): f = silu(g) * u, and its backward
+//   dg = df * u * s * (1 + g * (1 - s)),  du = df * g * s,  s = sigmoid(g).
+// (transformers LlamaMLP: down_proj(act_fn(gate_proj(x)) * up_proj(x)).)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+swiglu_fwd(const __nv_bfloat16* __restrict__ gu, long long ldg, __nv_bfloat16* __restrict__ f, long long ldf,
+           long long M, int F) {
+  const int nv = F >> 2;  // 4 outputs (= 8 interleaved inputs, 16 bytes) per thread-step
+  const long long total = M * nv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long r = i / nv;
+    const int c = (int)(i % nv);
+    float v[8];
+    unpack8f(*reinterpret_cast<const uint4*>(gu + r * ldg + c * 8), v);
+    __nv_bfloat162 o[2];
+    float t[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) t[j] = v[2 * j] / (1.f + __expf(-v[2 * j])) * v[2 * j + 1];
+    o[0] = __floats2bfloat162_rn(t[0], t[1]);
+    o[1] = __floats2bfloat162_rn(t[2], t[3]);
+    *reinterpret_cast<uint2*>(f + r * ldf + c * 4) = *reinterpret_cast<uint2*>(o);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+swiglu_bwd(const __nv_bfloat16* __restrict__ gu, long long ldg, const __nv_bfloat16* __restrict__ df, long long ldf,
+           __nv_bfloat16* __restrict__ dgu, long long ldd, long long M, int F) {
+  const int nv = F >> 2;
+  const long long total = M * nv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long r = i / nv;
+    const int c = (int)(i % nv);
+    float v[8], o[8];
+    unpack8f(*reinterpret_cast<const uint4*>(gu + r * ldg + c * 8), v);
+    const uint2 draw = *reinterpret_cast<const uint2*>(df + r * ldf + c * 4);
+    const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&draw);
+    const float2 d01 = __bfloat1622float2(dh[0]), d23 = __bfloat1622float2(dh[1]);
+    const float d[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float g = v[2 * j], u = v[2 * j + 1];
+      const float s = 1.f / (1.f + __expf(-g));
+      o[2 * j] = d[j] * u * s * (1.f + g * (1.f - s));
+      o[2 * j + 1] = d[j] * g * s;
+    }
+    *reinterpret_cast<uint4*>(dgu + r * ldd + c * 8) = pack8f(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// AdamW (torch.optim.AdamW, the HF Trainer default `adamw_torch`): fp32 master weights and moments, gradient
+// bf16 or fp32, optional bf16 copy of the updated weight for the next forward.  bias corrections on the host.
+// ------------------------------------------------------------------------------------------
+template <typename TG>
+__global__ void __launch_bounds__(256)
+adamw_step(float* __restrict__ p, const TG* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+           __nv_bfloat16* __restrict__ p16, long long n, float lr, float b1, float b2, float eps, float wd,
+           float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float gi;
+    if constexpr (sizeof(TG) == 2) gi = __bfloat162float(g[i]) * gscale; else gi = (float)g[i] * gscale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (p16) p16[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+static unsigned grid_for(long long work_items) {
+  long long g = (work_items + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace g4r
+
+using namespace g4r;
+
+extern "C" int g4r_cross_entropy_bf16(const void* logits, long long ld, const long long* targets, int M, int V,
+                                      float* row_lse, float* row_loss, float* loss_count, void* dlogits,
+                                      long long ldd, float grad_scale, void* stream) {
+  G4R_REQUIRE(logits && targets && row_lse && row_loss && loss_count && M > 0 && V > 0 && ld >= V,
+              "cross_entropy: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ce_rows_fwd<<<M, 256, 0, st>>>((const __nv_bfloat16*)logits, ld, targets, row_loss, row_lse, V);
+  G4R_LAUNCH_CHECK("ce_rows_fwd");
+  ce_reduce<<<1, 256, 0, st>>>(row_loss, targets, M, V, loss_count);
+  G4R_LAUNCH_CHECK("ce_reduce");
+  if (dlogits) {
+    G4R_REQUIRE(ldd >= V, "cross_entropy: ldd < V");
+    ce_rows_bwd<<<M, 256, 0, st>>>((const __nv_bfloat16*)logits, ld, targets, row_lse, loss_count,
+                                   (__nv_bfloat16*)dlogits, ldd, V, grad_scale);
+    G4R_LAUNCH_CHECK("ce_rows_bwd");
+  }
+  return G4R_OK;
+}
+
+extern "C" int g4r_rmsnorm_bwd_slabs(int M) {
+  const int cap = 2 * num_sms();
+  return M < cap ? M : cap;
+}
+
+extern "C" int g4r_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* w, const void* dy, long long ldy,
+                                    void* dx, long long ldd, float* dw, float* dw_slabs, int M, int D, float eps,
+                                    void* stream) {
+  G4R_REQUIRE(x && w && dy && dx && dw && dw_slabs && M > 0, "rmsnorm_bwd: null operand");
+  G4R_REQUIRE(D % 8 == 0 && D <= 8192 && ldx % 8 == 0 && ldy % 8 == 0 && ldd % 8 == 0, "rmsnorm_bwd: D=%d (multiple of 8, <= 8192), 16-byte rows", D);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = g4r_rmsnorm_bwd_slabs(M);
+  const int per = (D / 8 + 255) / 256;
+#define G4R_RMSB(P)                                                                                              \
+  rmsnorm_bwd_rows<P><<<S, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,                  \
+                                         (const __nv_bfloat16*)dy, ldy, (__nv_bfloat16*)dx, ldd, dw_slabs, M, D, eps)
+  if (per <= 1) G4R_RMSB(1); else if (per <= 2) G4R_RMSB(2); else G4R_RMSB(4);
+#undef G4R_RMSB
+  G4R_LAUNCH_CHECK("rmsnorm_bwd_rows");
+  slab_reduce_f32<<<(D + 255) / 256, 256, 0, st>>>(dw_slabs, S, D, dw);
+  G4R_LAUNCH_CHECK("slab_reduce_f32");
+  return G4R_OK;
+}
+
+extern "C" int g4r_swiglu_fwd_bf16(const void* gu, long long ldg, void* f, long long ldf, long long M, int F,
+                                   void* stream) {
+  G4R_REQUIRE(gu && f && M > 0 && F > 0 && F % 4 == 0 && ldg % 8 == 0 && ldf % 4 == 0, "swiglu_fwd: bad arguments");
+  swiglu_fwd<<<grid_for(M * (F / 4)), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)gu, ldg, (__nv_bfloat16*)f, ldf, M, F);
+  G4R_LAUNCH_CHECK("swiglu_fwd");
+  return G4R_OK;
+}
+
+extern "C" int g4r_swiglu_bwd_bf16(const void* gu, long long ldg, const void* df, long long ldf, void* dgu,
+                                   long long ldd, long long M, int F, void* stream) {
+  G4R_REQUIRE(gu && df && dgu && M > 0 && F > 0 && F % 4 == 0 && ldg % 8 == 0 && ldf % 4 == 0 && ldd % 8 == 0,
+              "swiglu_bwd: bad arguments");
+  swiglu_bwd<<<grid_for(M * (F / 4)), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)gu, ldg, (const __nv_bfloat16*)df, ldf,
+                                                                    (__nv_bfloat16*)dgu, ldd, M, F);
+  G4R_LAUNCH_CHECK("swiglu_bwd");
+  return G4R_OK;
+}
+
+extern "C" int g4r_adamw_step(float* p, const void* g, int g_bf16, float* m, float* v, void* p_bf16, long long n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                              float grad_scale, void* stream) {
+  G4R_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_bf16)
+    adamw_step<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(p, (const __nv_bfloat16*)g, m, v, (__nv_bfloat16*)p_bf16, n, lr,
+                                                            beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale);
+  else
+    adamw_step<float><<<grid_for(n), 256, 0, st>>>(p, (const float*)g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2,
+                                                   eps, weight_decay, bc1, bc2s, grad_scale);
+  G4R_LAUNCH_CHECK("adamw_step");
+  return G4R_OK;
+}

@@ -92,6 +92,29 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out
 
 
+def matmul_t(a, b, a_mn=False, b_mn=False, out_dtype=torch.bfloat16):
+    """D[M,N] = op(a) @ op(b).T on the tensor cores with the transposes folded into the operand descriptors.
+    a: [M,K] (a_mn=False) or stored [K,M] (a_mn=True); b: [N,K] (b_mn=False) or stored [K,N] (b_mn=True).
+    Linear backward:  grad_x = matmul_t(grad_y, W, b_mn=True);  grad_W = matmul_t(grad_y, x, a_mn=True, b_mn=True)."""
+    dev = _L.require_cuda_same_device([('a', a), ('b', b)])
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 2 or b.dim() != 2:
+        raise TypeError('matmul_t: 2-D bf16 operands required')
+    if a.stride(1) != 1 or b.stride(1) != 1:
+        raise RuntimeError('matmul_t: operands must have unit stride on the last dim')
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise RuntimeError('matmul_t: contraction mismatch %d vs %d' % (K, Kb))
+    out = torch.empty((M, N), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        _ps = _prof_begin(dev)
+        _L.check(_L.load().g4r_gemm_bf16_t(_L.ptr(a), a.stride(0), int(a_mn), _L.ptr(b), b.stride(0), int(b_mn),
+                                           _L.ptr(out), out.stride(0), M, N, K, int(out_dtype == torch.float32),
+                                           _L.stream_ptr(dev)))
+        _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
+    return out
+
+
 def qkv_rope(x, wqkv, cos, sin, L, rope_cols, pos0=0, pos_dev=None):
     """Fused LLaMA q/k/v projection + rotary embedding: x [M,K] bf16, wqkv [N,K] (q|k|v rows), cos/sin
     bf16 [L,128]; columns [0,rope_cols) (q and k heads, head_dim 128) are rotated at position row % L."""

@@ -1,0 +1,98 @@
+"""Host wrappers of the training-step kernels: cross entropy, RMSNorm / SwiGLU /
+attention backward, AdamW.  Same rules as kernels.py: CUDA tensors in, raw pointers + current stream to the
+C ABI, no fallback."""
+import torch
+
+from . import lib as _L
+
+BF16 = torch.bfloat16
+
+
+def _call(name, dev, *args):
+    with torch.cuda.device(dev):
+        _L.check(getattr(_L.load(), name)(*args, _L.stream_ptr(dev)))
+
+
+def cross_entropy(logits, targets, grad_scale=1.0, want_grad=True):
+    """logits [M, V] bf16 (unit stride on V); targets int64 [M] already shifted, -100 = ignore
+    (llava/model/llava.py:238-249).  Returns (loss fp32 scalar tensor, valid count tensor, dlogits or None)."""
+    dev = _L.require_cuda_same_device([('logits', logits), ('targets', targets)])
+    if logits.dtype != BF16 or targets.dtype != torch.int64 or logits.dim() != 2 or logits.stride(1) != 1:
+        raise TypeError('cross_entropy: logits [M,V] bf16 and int64 targets required')
+    M, V = logits.shape
+    if targets.numel() != M or not targets.is_contiguous():
+        raise RuntimeError('cross_entropy: targets must be contiguous with one entry per logits row')
+    row = torch.empty((2, M), dtype=torch.float32, device=dev)
+    lc = torch.empty(2, dtype=torch.float32, device=dev)
+    dl = torch.empty((M, V), dtype=BF16, device=dev) if want_grad else None
+    _call('g4r_cross_entropy_bf16', dev, _L.ptr(logits), logits.stride(0), _L.ptr(targets), M, V, _L.ptr(row[0]),
+          _L.ptr(row[1]), _L.ptr(lc), _L.ptr(dl), dl.stride(0) if want_grad else 0, float(grad_scale))
+    _L.count_launches(2 if want_grad else 1)
+    return lc[0], lc[1], dl
+
+
+def rmsnorm_bwd(x, w, dy, eps):
+    """-> (dx bf16 [M,D], dw fp32 [D]) for y = w * (x * rsqrt(mean(x^2)+eps)).to(bf16)."""
+    dev = _L.require_cuda_same_device([('x', x), ('w', w), ('dy', dy)])
+    M, D = x.shape
+    dx = torch.empty((M, D), dtype=BF16, device=dev)
+    dw = torch.empty(D, dtype=torch.float32, device=dev)
+    S = _L.load().g4r_rmsnorm_bwd_slabs(M)
+    slabs = torch.empty((S, D), dtype=torch.float32, device=dev)
+    _call('g4r_rmsnorm_bwd_bf16', dev, _L.ptr(x), x.stride(0), _L.ptr(w), _L.ptr(dy), dy.stride(0), _L.ptr(dx),
+          dx.stride(0), _L.ptr(dw), _L.ptr(slabs), M, D, float(eps))
+    _L.count_launches(1)
+    return dx, dw
+
+
+def swiglu_fwd(gu):
+    """gu [M, 2F] interleaved (gate_j, up_j) -> silu(gate) * up  [M, F]."""
+    M, F2 = gu.shape
+    f = torch.empty((M, F2 // 2), dtype=BF16, device=gu.device)
+    _call('g4r_swiglu_fwd_bf16', gu.device, _L.ptr(gu), gu.stride(0), _L.ptr(f), f.stride(0), M, F2 // 2)
+    return f
+
+
+def swiglu_bwd(gu, df):
+    M, F2 = gu.shape
+    dgu = torch.empty((M, F2), dtype=BF16, device=gu.device)
+    _call('g4r_swiglu_bwd_bf16', gu.device, _L.ptr(gu), gu.stride(0), _L.ptr(df), df.stride(0), _L.ptr(dgu),
+          dgu.stride(0), M, F2 // 2)
+    return dgu
+
+
+def attention_fwd_lse(qkv, B, L, n_heads, head_dim, causal, scale):
+    """Training forward on packed qkv rows [B*L, 3*H*D]: returns (out [B*L, H*D] bf16, lse [B,H,L] fp32)."""
+    hid = n_heads * head_dim
+    out = torch.empty((B * L, hid), dtype=BF16, device=qkv.device)
+    lse = torch.empty((B, n_heads, L), dtype=torch.float32, device=qkv.device)
+    ld = qkv.stride(0)
+    _call('g4r_attention_fwd_lse_bf16', qkv.device, _L.ptr(qkv), _L.ptr(qkv[:, hid:]), _L.ptr(qkv[:, 2 * hid:]),
+          _L.ptr(out), ld, L * ld, hid, L * hid, B, n_heads, L, head_dim, int(causal), float(scale), _L.ptr(lse))
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, B, L, n_heads, head_dim, causal, scale):
+    """-> dqkv [B*L, 3*H*D] bf16 (dQ | dK | dV), gradients w.r.t. the post-RoPE q, k and v."""
+    hid = n_heads * head_dim
+    dqkv = torch.empty((B * L, 3 * hid), dtype=BF16, device=qkv.device)
+    delta = torch.empty((B, n_heads, L), dtype=torch.float32, device=qkv.device)
+    ld = qkv.stride(0)
+    _call('g4r_attention_bwd_bf16', qkv.device, _L.ptr(qkv), _L.ptr(qkv[:, hid:]), _L.ptr(qkv[:, 2 * hid:]),
+          _L.ptr(out), _L.ptr(dout), _L.ptr(lse), _L.ptr(delta), _L.ptr(dqkv), _L.ptr(dqkv[:, hid:]),
+          _L.ptr(dqkv[:, 2 * hid:]), ld, L * ld, out.stride(0), L * out.stride(0), dqkv.stride(0),
+          L * dqkv.stride(0), B, n_heads, L, head_dim, int(causal), float(scale))
+    _L.count_launches(2)
+    return dqkv
+
+
+def adamw_step(p32, grad, m, v, p16, lr, betas, eps, weight_decay, step, grad_scale=1.0):
+    """In-place torch.optim.AdamW update of the fp32 master `p32` (+ bf16 copy `p16`, optional)."""
+    n = p32.numel()
+    if not (p32.is_contiguous() and grad.is_contiguous() and m.is_contiguous() and v.is_contiguous()):
+        raise RuntimeError('adamw_step: contiguous tensors required')
+    if grad.dtype not in (BF16, torch.float32) or grad.numel() != n:
+        raise TypeError('adamw_step: grad must be bf16 or fp32 with the parameter\'s size')
+    _call('g4r_adamw_step', p32.device, _L.ptr(p32), _L.ptr(grad), int(grad.dtype == BF16), _L.ptr(m), _L.ptr(v),
+          _L.ptr(p16), n, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+          float(grad_scale))

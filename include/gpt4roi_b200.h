@@ -175,6 +175,17 @@ int g4r_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb,
                      const void* residual, long long ldr, int residual_f32, int bias_round_bf16,
                      int act, int out_f32, int k_splits, void* stream);
 
+/* Backward-pass GEMM with operand transposes done in the tensor-core descriptors:
+ *   D[M,N] = op(A) . op(B)^T ;  a_mn=0: A [M,K] K-contiguous, a_mn=1: A stored [K,M] M-contiguous (lda >= M)
+ *                               b_mn=0: B [N,K] K-contiguous, b_mn=1: B stored [K,N] N-contiguous (ldb >= N)
+ * For y = x.W^T (torch.nn.functional.linear; every Linear of the LLaMA stack the stage-2 step trains,
+ * gpt4roi/train/train.py:698-712 + llava_trainer.py:59-144):
+ *   grad_x = grad_y . W      -> g4r_gemm_bf16_t(grad_y, ., 0, W, ., 1, grad_x, ., M, K_in, N_out, ...)
+ *   grad_W = grad_y^T . x    -> g4r_gemm_bf16_t(grad_y, ., 1, x, ., 1, grad_W, ., N_out, K_in, M, ...)
+ * bf16 operands, fp32 accumulation, bf16 or fp32 (out_f32) output. */
+int g4r_gemm_bf16_t(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn,
+                    void* D, long long ldd, int M, int N, int K, int out_f32, void* stream);
+
 /* LLaMA QKV projection with apply_rotary_pos_emb fused into the epilogue (transformers
  * modeling_llama.py:138-168): D[M,N] = A.B^T; columns [0,rope_cols) are 128-dim heads rotated with the
  * bf16 cos/sin tables [>= pos0+L, 128] at position pos0 + (row % L) (pos0 > 0: decode steps);
@@ -298,6 +309,46 @@ int g4r_pos_embed_mlp(const float* boxes, const void* w0, const void* b0, const 
  * (split-K slabs of flatten_linear), pos fp32 [K,D]. */
 int g4r_add_bias_pos_cast(const float* acc, int splits, const void* bias, const float* pos, void* out,
                           int K, int D, void* stream);
+
+/* ---- training step (gpt4roi/train/train.py:698-712 + HF Trainer) ----------------
+ * Cross entropy of llava/model/llava.py:238-249 (CrossEntropyLoss(): mean over targets != -100) on rows of
+ * bf16 logits [M,V]; `targets` are the already shifted labels (labels[..., 1:], last position -100).
+ * Writes row_lse[M], row_loss[M], loss_count[2] = {mean loss, #valid rows} and, if dlogits != NULL,
+ * dlogits = (softmax - onehot) * grad_scale / count (bf16, a separate buffer).  No atomics. */
+int g4r_cross_entropy_bf16(const void* logits, long long ld, const long long* targets, int M, int V,
+                           float* row_lse, float* row_loss, float* loss_count, void* dlogits, long long ldd,
+                           float grad_scale, void* stream);
+
+/* LlamaRMSNorm backward (transformers modeling_llama.py LlamaRMSNorm.forward): dx bf16 [M,D], dw fp32 [D].
+ * dw_slabs: fp32 scratch [g4r_rmsnorm_bwd_slabs(M)][D] (per-CTA partial sums, reduced in fixed order). */
+int g4r_rmsnorm_bwd_slabs(int M);
+int g4r_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* w, const void* dy, long long ldy,
+                         void* dx, long long ldd, float* dw, float* dw_slabs, int M, int D, float eps, void* stream);
+
+/* SwiGLU on an interleaved gate/up buffer gu [M,2F] (col 2j gate_j, 2j+1 up_j): f = silu(g)*u [M,F], and its
+ * backward dgu [M,2F] from df [M,F] (transformers LlamaMLP.forward). */
+int g4r_swiglu_fwd_bf16(const void* gu, long long ldg, void* f, long long ldf, long long M, int F, void* stream);
+int g4r_swiglu_bwd_bf16(const void* gu, long long ldg, const void* df, long long ldf, void* dgu, long long ldd,
+                        long long M, int F, void* stream);
+
+/* Causal attention for training: forward that also writes lse[B,H,L] (fp32 log-sum-exp of the scaled scores),
+ * and the backward (autograd of transformers modeling_llama.py:199-222 eager attention): packed dQ|dK|dV rows
+ * from q,k,v (after RoPE), the forward output `out`, `dout` and `lse`.  delta: fp32 scratch [B,H,L].
+ * q/k/v: row stride ld, batch stride bs (elements); out/dout: ldo, bso; dq/dk/dv: ldg, bsg.  No atomics. */
+int g4r_attention_fwd_lse_bf16(const void* q, const void* k, const void* v, void* out, long long ld,
+                               long long bs, long long ldo, long long bso, int B, int H, int L,
+                               int head_dim, int causal, float scale, float* lse, void* stream);
+int g4r_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                           const float* lse, float* delta, void* dq, void* dk, void* dv, long long ld,
+                           long long bs, long long ldo, long long bso, long long ldg, long long bsg, int B,
+                           int H, int L, int head_dim, int causal, float scale, void* stream);
+
+/* torch.optim.AdamW step (HF Trainer optim="adamw_torch"; param groups llava_trainer.py:59-144): fp32 master
+ * weights p and moments m, v; gradient bf16 (g_bf16=1) or fp32, multiplied by grad_scale (1/world, clip factor);
+ * p_bf16 (optional) receives the bf16 copy used by the next forward.  step counts from 1. */
+int g4r_adamw_step(float* p, const void* g, int g_bf16, float* m, float* v, void* p_bf16, long long n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -171,3 +171,36 @@ def test_skinny_qkv_rope_equals_unfused(B, L):
     pos_dev = torch.tensor([pos0], dtype=torch.int32, device=DEV)
     fused_dev = dense.qkv_rope(x, w, cos, sin, L, 2 * hid, pos0=0, pos_dev=pos_dev)
     assert torch.equal(fused_dev, ref)
+
+
+# ---- backward-pass GEMMs: operand transposes in the UMMA descriptors ---------------------
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 640, 512), (706, 4096, 4096), (4096, 1024, 706),
+                                   (200, 72, 136), (5648, 4096, 11008)])
+@pytest.mark.parametrize('a_mn,b_mn', [(False, True), (True, True), (True, False)])
+def test_gemm_transposed_operands(M, N, K, a_mn, b_mn):
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.5).bfloat16()
+    want = a.float() @ b.float().t()
+    a_st = a.t().contiguous() if a_mn else a      # stored [K, M]
+    b_st = b.t().contiguous() if b_mn else b      # stored [K, N]
+    if (M % 8 if a_mn else K % 8) or (N % 8 if b_mn else K % 8):   # 16-byte row strides (TMA)
+        with pytest.raises(RuntimeError):
+            dense.matmul_t(a_st, b_st, a_mn, b_mn)
+        return
+    _close(dense.matmul_t(a_st, b_st, a_mn, b_mn), want)
+    _close(dense.matmul_t(a_st, b_st, a_mn, b_mn, out_dtype=torch.float32), want, rtol=1e-4, atol=1e-3)
+
+
+def test_linear_backward_matches_autograd():
+    """grad_x = grad_y.W and grad_W = grad_y^T.x through matmul_t == torch autograd of F.linear (fp32 reference)."""
+    torch.manual_seed(2)
+    M, N, K = 1412, 4096, 1024
+    x = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    gy = (torch.randn(M, N, device=DEV) * 0.1).bfloat16()
+    xf, wf = x.float().requires_grad_(), w.float().requires_grad_()
+    (F.linear(xf, wf) * gy.float()).sum().backward()
+    _close(dense.matmul_t(gy, w, b_mn=True), xf.grad)
+    _close(dense.matmul_t(gy, x, a_mn=True, b_mn=True), wf.grad)
