@@ -150,8 +150,9 @@ ce_rows_bwd(const __nv_bfloat16* __restrict__ logits, long long ld, const long l
 template <int PER>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_rows(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
-                 const __nv_bfloat16* __restrict__ dy, long long ldy, __nv_bfloat16* __restrict__ dx, long long ldd,
-                 float* __restrict__ dw_slabs, int M, int D, float eps) {
+                 const __nv_bfloat16* __restrict__ dy, long long ldy, const __nv_bfloat16* __restrict__ dres,
+                 long long ldr, __nv_bfloat16* __restrict__ dx, long long ldd, float* __restrict__ dw_slabs, int M,
+                 int D, float eps) {
   __shared__ float red[8];
   const int tid = threadIdx.x;
   const int nvec = D >> 3;
@@ -197,9 +198,13 @@ rmsnorm_bwd_rows(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_
     for (int i = 0; i < PER; i++) {
       const int vi = tid + i * 256;
       if (vi >= nvec) continue;
-      float o[8];
+      float o[8], rr[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) o[j] = rs * (gv[i][j] - xv[i][j] * dot);
+      for (int j = 0; j < 8; j++) rr[j] = 0.f;
+      // gradient arriving through the residual connection that bypasses the norm (x -> x + f(norm(x)))
+      if (dres != nullptr) unpack8f(*reinterpret_cast<const uint4*>(dres + (long long)r * ldr + vi * 8), rr);
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = rr[j] + rs * (gv[i][j] - xv[i][j] * dot);
       *reinterpret_cast<uint4*>(dx + (long long)r * ldd + vi * 8) = pack8f(o);
     }
   }
@@ -333,8 +338,9 @@ extern "C" int g4r_rmsnorm_bwd_slabs(int M) {
 }
 
 extern "C" int g4r_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* w, const void* dy, long long ldy,
-                                    void* dx, long long ldd, float* dw, float* dw_slabs, int M, int D, float eps,
-                                    void* stream) {
+                                    const void* dres, long long ldr, void* dx, long long ldd, float* dw,
+                                    float* dw_slabs, int M, int D, float eps, void* stream) {
+  G4R_REQUIRE(dres == nullptr || ldr % 8 == 0, "rmsnorm_bwd: dres rows must be 16-byte aligned");
   G4R_REQUIRE(x && w && dy && dx && dw && dw_slabs && M > 0, "rmsnorm_bwd: null operand");
   G4R_REQUIRE(D % 8 == 0 && D <= 8192 && ldx % 8 == 0 && ldy % 8 == 0 && ldd % 8 == 0, "rmsnorm_bwd: D=%d (multiple of 8, <= 8192), 16-byte rows", D);
   cudaStream_t st = (cudaStream_t)stream;
@@ -342,7 +348,8 @@ extern "C" int g4r_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* w,
   const int per = (D / 8 + 255) / 256;
 #define G4R_RMSB(P)                                                                                              \
   rmsnorm_bwd_rows<P><<<S, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,                  \
-                                         (const __nv_bfloat16*)dy, ldy, (__nv_bfloat16*)dx, ldd, dw_slabs, M, D, eps)
+                                         (const __nv_bfloat16*)dy, ldy, (const __nv_bfloat16*)dres, ldr,          \
+                                         (__nv_bfloat16*)dx, ldd, dw_slabs, M, D, eps)
   if (per <= 1) G4R_RMSB(1); else if (per <= 2) G4R_RMSB(2); else G4R_RMSB(4);
 #undef G4R_RMSB
   G4R_LAUNCH_CHECK("rmsnorm_bwd_rows");

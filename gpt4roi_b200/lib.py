@@ -60,7 +60,7 @@ SIGNATURES = {
     'g4r_pos_embed_mlp': (_i, [_vp] * 10 + [_i, _f, _vp]),
     'g4r_cross_entropy_bf16': (_i, [_vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _ll, _f, _vp]),
     'g4r_rmsnorm_bwd_slabs': (_i, [_i]),
-    'g4r_rmsnorm_bwd_bf16': (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _f, _vp]),
+    'g4r_rmsnorm_bwd_bf16': (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _f, _vp]),
     'g4r_swiglu_fwd_bf16': (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp]),
     'g4r_swiglu_bwd_bf16': (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _vp]),
     'g4r_attention_fwd_lse_bf16': (_i, [_vp] * 4 + [_ll] * 4 + [_i] * 5 + [_f, _vp, _vp]),

@@ -1,0 +1,218 @@
+"""Training step of the LLaMA stack (SURVEY.md 8(a) row 14 -- first slice).
+
+The reference's stage-2 step (gpt4roi/train/train.py:698-712: HF Trainer over SPILlavaMPTForCausalLM under
+bf16 autocast, DDP gradient all-reduce, AdamW with the parameter groups of llava_trainer.py:59-144) spends
+6.48 B of its 7.04 B trainable parameters in the 32 LLaMA decoder layers.  This module is that part, built on
+the sm_100a kernels only:
+
+    inputs_embeds (from the region-token prefill front end: engine.PrefillEngine splice)
+      -> 32 x [RMSNorm -> fused QKV GEMM + RoPE -> causal attention (saves LSE) -> o_proj + residual
+               -> RMSNorm -> gate/up GEMM -> SwiGLU -> down_proj + residual]
+      -> RMSNorm -> lm_head -> shifted cross entropy (llava/model/llava.py:238-249)
+    backward: cross-entropy gradient -> lm_head -> ... every Linear through g4r_gemm_bf16_t
+              (grad_x = grad_y.W, grad_W = grad_y^T.x, transposes in the UMMA descriptors), flash-attention
+              backward, RoPE^T (= RoPE with -sin), SwiGLU / RMSNorm backward
+    step: gradient all-reduce over NCCL (bucket = one decoder layer, overlapped with the rest of the
+          backward on a side stream) + fused AdamW on fp32 master weights, bf16 copies for the next forward.
+
+Returned beside the loss: the gradient w.r.t. inputs_embeds, which is what the not-yet-built backward of the
+splice / projector / SPI module (RoIAlign backward kernels exist) will consume.
+
+Precision: fp32 master weights and optimizer moments, bf16 weights/activations/gradients, fp32 accumulation
+in every GEMM and reduction.  The reference keeps the residual stream in fp32 under autocast (fp32 embeddings,
+`residual + bf16_branch` promotes); this first slice keeps it in bf16 like the inference path -- a stated
+deviation, covered by the tolerance of the parity test (tests/test_train_gpu.py).
+No PyTorch autograd, no torch.nn ops on the compute path: torch supplies device memory, streams and NCCL.
+"""
+import torch
+
+from . import dense, kernels, train_ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+LAYER_KEYS = ('ln_in', 'wqkv', 'wo', 'ln_post', 'wgu', 'wdown')
+
+
+class LlamaTrainStack:
+    """LLaMA decoder stack with explicit forward / backward / AdamW on the sm_100a kernels."""
+
+    def __init__(self, cfg, state_dict, device, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """cfg: engine.EngineConfig; state_dict: HF names (model.layers.N..., model.norm.weight, lm_head.weight).
+        weight_decay follows llava_trainer.py:59-144: decay on matrices, none on norm weights."""
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.step_count = 0
+        if cfg.head_dim != 128:
+            raise ValueError('LlamaTrainStack: head_dim 128 required (fused-RoPE QKV GEMM)')
+        f32 = lambda t: t.detach().to(self.dev, F32).contiguous()
+        self.master = []          # per layer: dict name -> fp32 master
+        for i in range(cfg.n_layers):
+            q = 'model.layers.%d.' % i
+            wqkv = torch.cat([f32(state_dict[q + 'self_attn.%s_proj.weight' % n]) for n in 'qkv'], 0)
+            g, u = f32(state_dict[q + 'mlp.gate_proj.weight']), f32(state_dict[q + 'mlp.up_proj.weight'])
+            wgu = torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]).contiguous()   # rows g0,u0,g1,u1,...
+            self.master.append(dict(ln_in=f32(state_dict[q + 'input_layernorm.weight']), wqkv=wqkv.contiguous(),
+                                    wo=f32(state_dict[q + 'self_attn.o_proj.weight']),
+                                    ln_post=f32(state_dict[q + 'post_attention_layernorm.weight']), wgu=wgu,
+                                    wdown=f32(state_dict[q + 'mlp.down_proj.weight'])))
+        self.master_top = dict(norm=f32(state_dict['model.norm.weight']), lm_head=f32(state_dict['lm_head.weight']))
+        self.w = [{k: v.to(BF16) for k, v in m.items()} for m in self.master]      # bf16 compute copies
+        self.w_top = {k: v.to(BF16) for k, v in self.master_top.items()}
+        zeros = lambda t: torch.zeros_like(t)
+        self.m1 = [{k: zeros(v) for k, v in m.items()} for m in self.master]
+        self.m2 = [{k: zeros(v) for k, v in m.items()} for m in self.master]
+        self.m1_top = {k: zeros(v) for k, v in self.master_top.items()}
+        self.m2_top = {k: zeros(v) for k, v in self.master_top.items()}
+        self._rope_cache = {}
+        self.saved = None
+        self.grads = None
+
+    # ------------------------------------------------------------------ helpers
+    def _rope(self, L):
+        if L not in self._rope_cache:
+            c = self.cfg
+            inv = 1.0 / (c.rope_theta ** (torch.arange(0, c.head_dim, 2, dtype=torch.int64).float() / c.head_dim))
+            emb = torch.cat([torch.arange(L, dtype=F32)[:, None] * inv[None, :]] * 2, -1)
+            cos, sin = emb.cos().to(self.dev, BF16).contiguous(), emb.sin().to(self.dev, BF16).contiguous()
+            self._rope_cache[L] = (cos, sin, (-sin).contiguous())
+        return self._rope_cache[L]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, inputs_embeds, targets):
+        """inputs_embeds [B, L, hidden] bf16; targets int64 [B, L]: labels shifted left by one
+        (targets[:, t] = labels[:, t+1], targets[:, -1] = -100).  Returns the mean loss (0-d fp32 tensor)."""
+        c = self.cfg
+        B, L, Hd = inputs_embeds.shape
+        M = B * L
+        cos, sin, _ = self._rope(L)
+        scale = c.head_dim ** -0.5
+        x = inputs_embeds.reshape(M, Hd).contiguous()
+        saved = []
+        for w in self.w:
+            h1 = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
+            qkv = dense.qkv_rope(h1, w['wqkv'], cos, sin, L, 2 * c.hidden)
+            a, lse = train_ops.attention_fwd_lse(qkv, B, L, c.n_heads, c.head_dim, True, scale)
+            x_mid = dense.linear(a, w['wo'], residual=x)
+            h2 = kernels.rmsnorm(x_mid, w['ln_post'], c.rms_eps)
+            gu = dense.linear(h2, w['wgu'])
+            f = train_ops.swiglu_fwd(gu)
+            x_out = dense.linear(f, w['wdown'], residual=x_mid)
+            saved.append(dict(x_in=x, h1=h1, qkv=qkv, a=a, lse=lse, x_mid=x_mid, h2=h2, gu=gu, f=f))
+            x = x_out
+        hn = kernels.rmsnorm(x, self.w_top['norm'], c.rms_eps)
+        vpad = (c.vocab + 63) // 64 * 64                       # 16-byte-aligned logits rows
+        logits = torch.empty((M, vpad), dtype=BF16, device=self.dev)[:, :c.vocab]
+        dense.linear(hn, self.w_top['lm_head'], out=logits)
+        self.saved = dict(layers=saved, x_last=x, hn=hn, logits=logits, targets=targets.reshape(M).contiguous(), B=B, L=L)
+        loss, count, _ = train_ops.cross_entropy(logits, self.saved['targets'], want_grad=False)
+        return loss
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, loss_scale=1.0, on_layer_grads=None):
+        """Gradients of loss_scale * loss.  Fills self.grads (bf16 matrices, fp32 norm weights) and returns the
+        gradient w.r.t. inputs_embeds [B, L, hidden] (bf16).  on_layer_grads(i, grads_i) is called as soon as
+        decoder layer i's gradients are complete (DDP bucket hook)."""
+        c, s = self.cfg, self.saved
+        B, L = s['B'], s['L']
+        _, _, nsin = self._rope(L)
+        cos = self._rope(L)[0]
+        scale = c.head_dim ** -0.5
+        _, _, dlogits = train_ops.cross_entropy(s['logits'], s['targets'], grad_scale=loss_scale, want_grad=True)
+        g_top = {}
+        g_top['lm_head'] = dense.matmul_t(dlogits, s['hn'], a_mn=True, b_mn=True)           # dW = dY^T X
+        dhn = dense.matmul_t(dlogits, self.w_top['lm_head'], b_mn=True)                      # dX = dY W
+        del dlogits
+        dx, g_top['norm'] = train_ops.rmsnorm_bwd(s['x_last'], self.w_top['norm'], dhn, c.rms_eps)
+        grads = [None] * len(self.w)
+        for i in range(len(self.w) - 1, -1, -1):
+            w, a = self.w[i], s['layers'][i]
+            g = {}
+            # x_out = x_mid + down(f)
+            g['wdown'] = dense.matmul_t(dx, a['f'], a_mn=True, b_mn=True)
+            df = dense.matmul_t(dx, w['wdown'], b_mn=True)
+            dgu = train_ops.swiglu_bwd(a['gu'], df)
+            g['wgu'] = dense.matmul_t(dgu, a['h2'], a_mn=True, b_mn=True)
+            dh2 = dense.matmul_t(dgu, w['wgu'], b_mn=True)
+            dx_mid, g['ln_post'] = train_ops.rmsnorm_bwd(a['x_mid'], w['ln_post'], dh2, c.rms_eps, dres=dx)
+            # x_mid = x_in + o_proj(attn)
+            g['wo'] = dense.matmul_t(dx_mid, a['a'], a_mn=True, b_mn=True)
+            da = dense.matmul_t(dx_mid, w['wo'], b_mn=True)
+            dqkv = train_ops.attention_bwd(a['qkv'], a['a'], da, a['lse'], B, L, c.n_heads, c.head_dim, True, scale)
+            kernels.rope_inplace(dqkv, cos, nsin, L, 2 * c.n_heads, c.head_dim)             # RoPE^T = RoPE(-theta)
+            g['wqkv'] = dense.matmul_t(dqkv, a['h1'], a_mn=True, b_mn=True)
+            dh1 = dense.matmul_t(dqkv, w['wqkv'], b_mn=True)
+            dx, g['ln_in'] = train_ops.rmsnorm_bwd(a['x_in'], w['ln_in'], dh1, c.rms_eps, dres=dx_mid)
+            grads[i] = g
+            s['layers'][i] = None                                                            # free activations
+            if on_layer_grads is not None:
+                on_layer_grads(i, g)
+        self.grads = dict(layers=grads, top=g_top)
+        self.saved = None
+        return dx.view(B, L, c.hidden)
+
+    # ------------------------------------------------------------------ optimizer
+    def optimizer_step(self, grad_scale=1.0):
+        """Fused AdamW on every tensor (fp32 master + moments, refreshes the bf16 compute copy)."""
+        self.step_count += 1
+        t = self.step_count
+
+        def upd(master, m1, m2, w16, grad, name):
+            wd = 0.0 if name.startswith('ln') or name == 'norm' else self.wd
+            train_ops.adamw_step(master.view(-1), grad.reshape(-1), m1.view(-1), m2.view(-1), w16.view(-1), self.lr,
+                                 self.betas, self.eps, wd, t, grad_scale)
+        for i, g in enumerate(self.grads['layers']):
+            for k in LAYER_KEYS:
+                upd(self.master[i][k], self.m1[i][k], self.m2[i][k], self.w[i][k], g[k], k)
+        for k in ('norm', 'lm_head'):
+            upd(self.master_top[k], self.m1_top[k], self.m2_top[k], self.w_top[k], self.grads['top'][k], k)
+        self.grads = None
+
+
+class LayerBucketAllReduce:
+    """DDP gradient all-reduce, one bucket per decoder layer, launched from the backward hook on a side stream so
+    the collective of layer i overlaps the backward of layers < i (NCCL over NVLink; gloo in the CPU tests).
+    Sums in place; the 1/world average is folded into AdamW's grad_scale."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.handles = []
+        self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+
+    def hook(self, i, grads):
+        if not (self.dist.is_available() and self.dist.is_initialized()) or self.dist.get_world_size(self.group) == 1:
+            return
+        tensors = [grads[k] for k in LAYER_KEYS]
+        if self.stream is not None and tensors[0].is_cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                for t in tensors:
+                    self.handles.append(self.dist.all_reduce(t, group=self.group, async_op=True))
+        else:
+            for t in tensors:
+                self.handles.append(self.dist.all_reduce(t, group=self.group, async_op=True))
+
+    def reduce_now(self, tensors):
+        if self.dist.is_available() and self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1:
+            for t in tensors:
+                self.handles.append(self.dist.all_reduce(t, group=self.group, async_op=True))
+
+    def wait(self):
+        for h in self.handles:
+            h.wait()
+        self.handles = []
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def train_step(stack, inputs_embeds, targets, reducer=None, world_size=1):
+    """One optimisation step of the LLaMA stack: forward, backward (+ overlapped gradient all-reduce), AdamW.
+    Returns (loss tensor, d_inputs_embeds)."""
+    loss = stack.forward(inputs_embeds, targets)
+    d_in = stack.backward(on_layer_grads=reducer.hook if reducer is not None else None)
+    if reducer is not None:
+        reducer.reduce_now([stack.grads['top']['lm_head'], stack.grads['top']['norm']])
+        reducer.wait()
+    stack.optimizer_step(grad_scale=1.0 / world_size)
+    return loss, d_in

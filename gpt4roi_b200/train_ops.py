@@ -24,23 +24,26 @@ def cross_entropy(logits, targets, grad_scale=1.0, want_grad=True):
         raise RuntimeError('cross_entropy: targets must be contiguous with one entry per logits row')
     row = torch.empty((2, M), dtype=torch.float32, device=dev)
     lc = torch.empty(2, dtype=torch.float32, device=dev)
-    dl = torch.empty((M, V), dtype=BF16, device=dev) if want_grad else None
+    # rows padded to a multiple of 64 elements: 16-byte-aligned rows for the dW / dX GEMMs that consume dlogits
+    dl = torch.empty((M, (V + 63) // 64 * 64), dtype=BF16, device=dev)[:, :V] if want_grad else None
     _call('g4r_cross_entropy_bf16', dev, _L.ptr(logits), logits.stride(0), _L.ptr(targets), M, V, _L.ptr(row[0]),
           _L.ptr(row[1]), _L.ptr(lc), _L.ptr(dl), dl.stride(0) if want_grad else 0, float(grad_scale))
     _L.count_launches(2 if want_grad else 1)
     return lc[0], lc[1], dl
 
 
-def rmsnorm_bwd(x, w, dy, eps):
-    """-> (dx bf16 [M,D], dw fp32 [D]) for y = w * (x * rsqrt(mean(x^2)+eps)).to(bf16)."""
+def rmsnorm_bwd(x, w, dy, eps, dres=None):
+    """-> (dx bf16 [M,D], dw fp32 [D]) for y = w * (x * rsqrt(mean(x^2)+eps)).to(bf16); dres (optional, bf16
+    [M,D]) is added to dx: the gradient that reaches x through the residual connection around the block."""
     dev = _L.require_cuda_same_device([('x', x), ('w', w), ('dy', dy)])
     M, D = x.shape
     dx = torch.empty((M, D), dtype=BF16, device=dev)
     dw = torch.empty(D, dtype=torch.float32, device=dev)
     S = _L.load().g4r_rmsnorm_bwd_slabs(M)
     slabs = torch.empty((S, D), dtype=torch.float32, device=dev)
-    _call('g4r_rmsnorm_bwd_bf16', dev, _L.ptr(x), x.stride(0), _L.ptr(w), _L.ptr(dy), dy.stride(0), _L.ptr(dx),
-          dx.stride(0), _L.ptr(dw), _L.ptr(slabs), M, D, float(eps))
+    _call('g4r_rmsnorm_bwd_bf16', dev, _L.ptr(x), x.stride(0), _L.ptr(w), _L.ptr(dy), dy.stride(0), _L.ptr(dres),
+          dres.stride(0) if dres is not None else 0, _L.ptr(dx), dx.stride(0), _L.ptr(dw), _L.ptr(slabs), M, D,
+          float(eps))
     _L.count_launches(1)
     return dx, dw
 

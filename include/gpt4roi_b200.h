@@ -323,7 +323,9 @@ int g4r_cross_entropy_bf16(const void* logits, long long ld, const long long* ta
  * dw_slabs: fp32 scratch [g4r_rmsnorm_bwd_slabs(M)][D] (per-CTA partial sums, reduced in fixed order). */
 int g4r_rmsnorm_bwd_slabs(int M);
 int g4r_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* w, const void* dy, long long ldy,
-                         void* dx, long long ldd, float* dw, float* dw_slabs, int M, int D, float eps, void* stream);
+                         const void* dres /* optional bf16 [M,D]: added to dx (gradient of the residual branch) */,
+                         long long ldr, void* dx, long long ldd, float* dw, float* dw_slabs, int M, int D, float eps,
+                         void* stream);
 
 /* SwiGLU on an interleaved gate/up buffer gu [M,2F] (col 2j gate_j, 2j+1 up_j): f = silu(g)*u [M,F], and its
  * backward dgu [M,2F] from df [M,F] (transformers LlamaMLP.forward). */

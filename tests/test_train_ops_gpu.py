@@ -61,6 +61,9 @@ def test_rmsnorm_bwd_matches_autograd(M, D):
     assert rel(dw, wf.grad) < 6e-3
     dx2, dw2 = train_ops.rmsnorm_bwd(x, w, dy, 1e-6)
     assert torch.equal(dx, dx2) and torch.equal(dw, dw2)
+    dres = torch.randn(M, D, device=DEV).to(BF)
+    dx3, _ = train_ops.rmsnorm_bwd(x, w, dy, 1e-6, dres=dres)
+    assert rel(dx3, xf.grad + dres.float()) < 6e-3
 
 
 def test_swiglu_fwd_bwd_match_autograd():
