@@ -71,3 +71,44 @@ def test_reference_arm_runs_on_rank0_only():
     line = json.loads(outs[0].splitlines()[-1])
     assert line['impl'] == 'reference' and line['unit'] == 'samples/s' and line['value'] > 0
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['cpu_baseline']['cores'] >= 1
+
+
+def _reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from gpt4roi_b200.train import LAYER_KEYS, LayerBucketAllReduce
+    red = LayerBucketAllReduce()
+    layers = []
+    for i in (1, 0):                                  # backward order: last layer first
+        g = {k: torch.full((3, 2), float(10 * i + j + rank)) for j, k in enumerate(LAYER_KEYS)}
+        layers.append((i, g))
+        red.hook(i, g)                                # async all-reduce of the layer's bucket
+    top = [torch.full((4,), float(100 + rank))]
+    red.reduce_now(top)
+    red.wait()
+    out = {i: {k: float(v[0, 0]) for k, v in g.items()} for i, g in layers}
+    q.put((rank, out, float(top[0][0])))
+    dist.destroy_process_group()
+
+
+def test_layer_bucket_allreduce_sums_over_ranks():
+    """DDP gradient all-reduce of the training step: one bucket per decoder layer, summed in place
+    over the ranks (the 1/world average is folded into AdamW's grad_scale)."""
+    from gpt4roi_b200.train import LAYER_KEYS
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_reducer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out, top in res:
+        for i in (0, 1):
+            for j, k in enumerate(LAYER_KEYS):
+                assert out[i][k] == 2 * (10 * i + j) + 1            # (v + 0) + (v + 1)
+        assert top == 201.0

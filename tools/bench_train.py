@@ -1,0 +1,90 @@
+"""Training step of the 7B LLaMA stack (first slice; BASELINE config 4 shape: 336 px
+prompt of 706 tokens, per-GPU batch 4 = global batch 32 on 8 GPUs): forward + backward + gradient all-reduce +
+AdamW on the sm_100a kernels, synthetic inputs_embeds/labels, random-init weights.
+  python tools/bench_train.py [--batch 4] [--steps 5] [--warmup 2]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_train.py
+Prints one JSON line (rank 0).  The SPI / projector / embedding backward is not part of this slice."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gpt4roi_b200 import lib as L  # noqa: E402
+from gpt4roi_b200.engine import EngineConfig, random_state_dicts  # noqa: E402
+from gpt4roi_b200.train import LayerBucketAllReduce, LlamaTrainStack, train_step  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=4)
+    ap.add_argument('--seq', type=int, default=706)
+    ap.add_argument('--layers', type=int, default=32)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=2)
+    a = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    reducer = None
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get('NCCL_DEBUG', 'VERSION') in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+        reducer = LayerBucketAllReduce()
+    cfg = EngineConfig(image_size=336, vit_layers=0, n_layers=a.layers)
+    sd, _ = random_state_dicts(cfg, dev, seed=0)                 # same weights on every rank (same seed)
+    stack = LlamaTrainStack(cfg, sd, dev, lr=2e-5)
+    del sd
+    torch.cuda.empty_cache()
+    g = torch.Generator(device='cpu').manual_seed(100 + rank)    # a different micro-batch per rank
+    x = (torch.randn(a.batch, a.seq, cfg.hidden, generator=g) * 0.5).to(dev, torch.bfloat16)
+    labels = torch.randint(0, cfg.vocab, (a.batch, a.seq), generator=g).to(dev)
+    targets = torch.full_like(labels, -100)
+    targets[:, :-1] = labels[:, 1:]
+    losses = []
+    for _ in range(a.warmup):
+        loss, _ = train_step(stack, x, targets, reducer, world)
+        losses.append(loss.item())
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    l0 = L.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss, _ = train_step(stack, x, targets, reducer, world)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    losses.append(loss.item())
+    if rank == 0:
+        n_params = sum(v.numel() for m in stack.master for v in m.values()) + sum(v.numel() for v in stack.master_top.values())
+        tokens = a.batch * a.seq
+        # 6 flop / parameter / token (fwd 2 + bwd 4) + causal attention (fwd 2*2*L*hid/2, bwd 2.5x incl. recompute)
+        attn = a.layers * a.batch * (4.0 * a.seq * a.seq * cfg.hidden / 2) * 3.5
+        flops = 6.0 * n_params * tokens + attn
+        print(json.dumps(dict(metric='train_step_llama_stack_tokens_per_sec', value=world * tokens / (ms / 1e3), unit='tokens/s',
+                              n_gpus=world, ms_per_step=ms, steps=a.steps, warmup=a.warmup,
+                              config=dict(workload='7B LLaMA stack fwd+bwd+allreduce+AdamW, bf16, seq %d, per-GPU batch %d' % (a.seq, a.batch),
+                                          layers=a.layers, params=n_params, global_batch=world * a.batch),
+                              model_tflops_per_gpu=flops / (ms / 1e3) / 1e12, gpu_launches_per_step=(L.LAUNCHES - l0) // a.steps,
+                              peak_mem_GB=torch.cuda.max_memory_allocated() / 1e9, losses=[round(v, 4) for v in losses],
+                              scope='LLaMA decoder stack + lm_head + loss only (SPI/projector/embedding backward not built)')),
+              flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
