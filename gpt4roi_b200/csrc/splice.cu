@@ -113,9 +113,77 @@ splice_move(const int32_t* __restrict__ plan, const uint4* __restrict__ embed,
   for (; v < vec_per_row; v += TPR) dst[v] = src[v];
 }
 
+// ---- backward (training step) ----------------------------------------------------
+// d(inputs_embeds) rows go back where the forward took them from.  Image and region rows have exactly one
+// consumer each (a plain row copy); embedding rows are shared by every occurrence of a token id.
+template <int ROWS, int TPR>
+__global__ void __launch_bounds__(ROWS * TPR)
+splice_bwd_move(const int32_t* __restrict__ plan, const uint4* __restrict__ d_out, uint4* __restrict__ d_image,
+                uint4* __restrict__ d_region, int n_rows, int L, int P, int vec_per_row) {
+  const int row = blockIdx.x * ROWS + threadIdx.x / TPR;
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x % TPR;
+  const int code = plan[row];
+  const int b = row / L;
+  uint4* dst;
+  if ((code & kTagMask) == kTagImage) dst = d_image ? d_image + ((size_t)b * P + (code & ~kTagMask)) * vec_per_row : nullptr;
+  else if ((code & kTagMask) == kTagRegion) dst = d_region ? d_region + (size_t)(code & ~kTagMask) * vec_per_row : nullptr;
+  else return;
+  if (dst == nullptr) return;
+  const uint4* src = d_out + (size_t)row * vec_per_row;
+  for (int v = lane; v < vec_per_row; v += TPR) dst[v] = src[v];
+}
+
+// One CTA per distinct token id u: grad[id_u] = sum of the d_out rows at the positions order[seg[u] .. seg[u+1])
+// (positions sorted by id on the host side of the call: fixed order => bitwise reproducible, no atomics).
+__global__ void __launch_bounds__(256)
+embed_grad_rows(const __nv_bfloat16* __restrict__ d_out, const int32_t* __restrict__ order,
+                const int32_t* __restrict__ seg, const int32_t* __restrict__ ids, float* __restrict__ grad, int D) {
+  const int u = blockIdx.x;
+  const int j0 = seg[u], j1 = seg[u + 1];
+  float* g = grad + (size_t)ids[u] * D;
+  for (int v = threadIdx.x * 8; v < D; v += 256 * 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int j = j0; j < j1; j++) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(d_out + (size_t)order[j] * D + v);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float2 f = __bfloat1622float2(h[i]);
+        acc[2 * i] += f.x;
+        acc[2 * i + 1] += f.y;
+      }
+    }
+    reinterpret_cast<float4*>(g + v)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    reinterpret_cast<float4*>(g + v)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
 }  // namespace g4r
 
 using namespace g4r;
+
+extern "C" int g4r_splice_backward(const int32_t* plan, const void* d_out, void* d_image, void* d_region, int B, int L,
+                                   int P, int D, void* stream) {
+  G4R_REQUIRE(plan && d_out && B > 0 && L > 0 && D % 8 == 0, "splice_backward: bad arguments");
+  const int n_rows = B * L;
+  constexpr int ROWS = 4, TPR = 64;
+  splice_bwd_move<ROWS, TPR><<<(n_rows + ROWS - 1) / ROWS, ROWS * TPR, 0, (cudaStream_t)stream>>>(
+      plan, (const uint4*)d_out, (uint4*)d_image, (uint4*)d_region, n_rows, L, P, D / 8);
+  G4R_LAUNCH_CHECK("splice_bwd_move");
+  return G4R_OK;
+}
+
+extern "C" int g4r_embed_grad_rows(const void* d_out, const int32_t* order, const int32_t* seg, const int32_t* ids,
+                                   int n_unique, float* grad, int D, void* stream) {
+  G4R_REQUIRE(d_out && order && seg && ids && grad && D % 8 == 0, "embed_grad_rows: bad arguments");
+  if (n_unique <= 0) return G4R_OK;
+  embed_grad_rows<<<n_unique, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_out, order, seg, ids, grad, D);
+  G4R_LAUNCH_CHECK("embed_grad_rows");
+  return G4R_OK;
+}
 
 extern "C" int g4r_splice_region_tokens(const int64_t* input_ids, const void* embed_table,
                                         const void* image_rows, const void* region_rows,

@@ -218,6 +218,26 @@ rmsnorm_bwd_rows(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_
   }
 }
 
+// Column sums of a bf16 matrix (bias gradients): CTA (x, y) sums the rows r = y, y + S, ... of 2048 columns
+// into slab y; slab_reduce_f32 adds the S slabs in order.
+__global__ void __launch_bounds__(256)
+colsum_rows(const __nv_bfloat16* __restrict__ x, long long ld, int M, int N, float* __restrict__ slabs) {
+  const int c0 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c0 >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = 0.f;
+  for (int r = blockIdx.y; r < M; r += gridDim.y) {
+    float f[8];
+    unpack8f(*reinterpret_cast<const uint4*>(x + (long long)r * ld + c0), f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] += f[j];
+  }
+  float* o = slabs + (long long)blockIdx.y * N + c0;
+  reinterpret_cast<float4*>(o)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  reinterpret_cast<float4*>(o)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
 // out[d] = sum_s slabs[s][d] in slab order (fp32)
 __global__ void __launch_bounds__(256)
 slab_reduce_f32(const float* __restrict__ slabs, int S, int D, float* __restrict__ out) {
@@ -354,6 +374,20 @@ extern "C" int g4r_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* w,
 #undef G4R_RMSB
   G4R_LAUNCH_CHECK("rmsnorm_bwd_rows");
   slab_reduce_f32<<<(D + 255) / 256, 256, 0, st>>>(dw_slabs, S, D, dw);
+  G4R_LAUNCH_CHECK("slab_reduce_f32");
+  return G4R_OK;
+}
+
+extern "C" int g4r_colsum_slabs(int M) { return M < 64 ? (M > 0 ? M : 1) : 64; }
+
+extern "C" int g4r_colsum_bf16(const void* x, long long ld, int M, int N, float* out, float* slabs, void* stream) {
+  G4R_REQUIRE(x && out && slabs && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "colsum: bad arguments (N, ld multiples of 8)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = g4r_colsum_slabs(M);
+  dim3 grid((N + 2047) / 2048, S);
+  colsum_rows<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, M, N, slabs);
+  G4R_LAUNCH_CHECK("colsum_rows");
+  slab_reduce_f32<<<(N + 255) / 256, 256, 0, st>>>(slabs, S, N, out);
   G4R_LAUNCH_CHECK("slab_reduce_f32");
   return G4R_OK;
 }

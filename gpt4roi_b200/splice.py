@@ -24,7 +24,7 @@ _MESSAGES = {
 
 def splice_region_tokens(input_ids, embed_weight, image_features, region_features, num_patches,
                          im_patch_token, im_start_token, im_end_token, bbox_token,
-                         out=None, validate=True):
+                         out=None, validate=True, return_plan=False):
     """Build `inputs_embeds` [B,L,D].
 
     input_ids       int64 [B,L] (cuda)
@@ -77,4 +77,37 @@ def splice_region_tokens(input_ids, embed_weight, image_features, region_feature
         if bad.numel():
             b = int(bad[0])
             raise ValueError('%s (sample %d)' % (_MESSAGES.get(int(st[b]), 'splice error %d' % int(st[b])), b))
-    return out
+    return (out, plan) if return_plan else out
+
+
+_TAG_REGION = 0x20000000   # csrc/splice.cu: plan codes >= this are image / region rows
+
+
+def splice_backward(plan, d_out, num_patches, n_regions, vocab, want_embed_grad=True):
+    """Backward of splice_region_tokens: d_out [B,L,D] (bf16) -> (d_image [B,P,D], d_region [K,D],
+    d_embed fp32 [V,D] dense or None).  The positions of every token id are grouped on the host side of the
+    call (torch.sort on B*L indices -- index plumbing like plan_boxes); the sums run in the kernel."""
+    B, L, D = d_out.shape
+    dev = d_out.device
+    P, K = int(num_patches), int(n_regions)
+    d_out = d_out.contiguous()
+    d_image = torch.empty((B, P, D), dtype=d_out.dtype, device=dev) if P > 0 else None
+    d_region = torch.empty((K, D), dtype=d_out.dtype, device=dev) if K > 0 else None
+    with torch.cuda.device(dev):
+        _L.check(_L.load().g4r_splice_backward(_L.ptr(plan), _L.ptr(d_out), _L.ptr(d_image), _L.ptr(d_region),
+                                               B, L, P, D, _L.stream_ptr(dev)))
+    d_embed = None
+    if want_embed_grad:
+        codes = plan.reshape(-1)
+        rows = torch.nonzero(codes < _TAG_REGION).squeeze(1)
+        ids_sorted, perm = torch.sort(codes[rows], stable=True)
+        order = rows[perm].to(torch.int32).contiguous()
+        uniq, counts = torch.unique_consecutive(ids_sorted, return_counts=True)
+        seg = torch.zeros(uniq.numel() + 1, dtype=torch.int32, device=dev)
+        seg[1:] = counts.cumsum(0)
+        d_embed = torch.zeros((vocab, D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _L.check(_L.load().g4r_embed_grad_rows(_L.ptr(d_out), _L.ptr(order), _L.ptr(seg),
+                                                   _L.ptr(uniq.to(torch.int32).contiguous()), int(uniq.numel()),
+                                                   _L.ptr(d_embed), D, _L.stream_ptr(dev)))
+    return d_image, d_region, d_embed

@@ -216,3 +216,74 @@ def train_step(stack, inputs_embeds, targets, reducer=None, world_size=1):
         reducer.wait()
     stack.optimizer_step(grad_scale=1.0 / world_size)
     return loss, d_in
+
+
+class FrontEndTrain:
+    """Training-mode front end (second slice of row 14): the region-token forward up to `inputs_embeds` with the
+    tensors its backward needs, and the backward of everything downstream of the pconv output and of the ViT
+    features: splice (`spi_llava.py:99-196`), `embed_tokens`, `mm_projector`, and the SPI head
+    (`MlvlRoIExtractor.forward`, layers.py:318-335: flatten_linear, + pos, updims).
+
+    Frozen / not differentiated here: the CLIP tower (frozen in both stages, train.py:604-612) and -- not built
+    yet -- the pconvs, RoIAlign (backward kernels exist), the MLVLFuseModule conv/GroupNorm stack and the box
+    position MLP; their incoming gradients `d_pconv_out` and `d_pos` are returned."""
+
+    def __init__(self, engine):
+        self.eng = engine
+        self.saved = None
+
+    def forward(self, input_ids, images, bboxes):
+        from .roi_align import roi_align_mlvl
+        from .splice import splice_region_tokens
+        eng, c = self.eng, self.eng.cfg
+        dev = eng.dev
+        input_ids = input_ids.to(dev)
+        images = images.to(dev, BF16)
+        B, L = input_ids.shape
+        plan_b = eng.plan_boxes(bboxes)
+        taps = eng.vit(images)
+        feat = kernels.cast_tokens_f32_bf16(taps[c.select_index])
+        img_rows = dense.linear(feat, eng.proj_w, eng.proj_b).view(B, c.num_patches, c.hidden)
+        K = plan_b['K'] if plan_b is not None else 0
+        region, pc, t = None, None, None
+        if K > 0:
+            maps, ss = eng.fuse_maps(taps)
+            boxes, bidx = plan_b['boxes'], plan_b['bidx']
+            rois = torch.cat([bidx[:, None], boxes * float(c.image_size)], 1).contiguous()
+            scales = [float(torch.tensor(1.0 / s, dtype=F32)) for s in c.strides]
+            feats = roi_align_mlvl(maps, rois, c.roi_out, scales, c.roi_sampling, True, out_dtype=BF16,
+                                   gn_scale=[s for s, _ in ss], gn_shift=[b for _, b in ss])
+            R = c.roi_out
+            pc = dense.conv_nhwc(feats.view(c.num_levels * K, R, R, c.spi_dim), eng.pconv_w, eng.pconv_b,
+                                 act='relu', levels=c.num_levels).view(K, -1)
+            acc = dense.linear(pc, eng.flat_w, out_dtype=F32)
+            pos = kernels.pos_embed_mlp(boxes.contiguous(), *eng.pos)
+            t = kernels.add_bias_pos_cast(acc, eng.flat_b, pos)
+            region = (dense.linear(t, eng.up_w, eng.up_b), plan_b['offs'])
+        elif plan_b is not None:
+            region = (torch.zeros((1, c.hidden), dtype=BF16, device=dev), plan_b['offs'])
+        embeds, plan = splice_region_tokens(input_ids, eng.embed, img_rows, region, c.num_patches, c.im_patch_token,
+                                            c.im_start_token, c.im_end_token, c.bbox_token, return_plan=True)
+        self.saved = dict(feat=feat, plan=plan, pc=pc, t=t, K=K, B=B)
+        return embeds
+
+    def backward(self, d_embeds):
+        """d_embeds [B,L,hidden] bf16 -> dict of gradients (reference parameter names) + hand-over gradients."""
+        from .splice import splice_backward
+        eng, c, s = self.eng, self.eng.cfg, self.saved
+        d_image, d_region, d_embed = splice_backward(s['plan'], d_embeds, c.num_patches, s['K'], c.vocab)
+        out = {'model.embed_tokens.weight': d_embed}
+        _, gw, gb = train_ops.linear_bwd(s['feat'], eng.proj_w, d_image.view(-1, c.hidden), need_dx=False)
+        out['model.mm_projector.weight'], out['model.mm_projector.bias'] = gw, gb
+        if s['K'] > 0:
+            q = 'model.spi_module.roi_align.'
+            dt, out[q + 'updims.weight'], out[q + 'updims.bias'] = train_ops.linear_bwd(s['t'], eng.up_w, d_region)
+            out[q + 'flatten_linear.bias'] = train_ops.colsum(dt)
+            d_pc, gfw, _ = train_ops.linear_bwd(s['pc'], eng.flat_w, dt, has_bias=False)
+            # engine layout of flatten_linear.weight is [out, (ph, pw, c)]; the reference's is [out, (c, ph, pw)]
+            R, C = c.roi_out, c.spi_dim
+            out[q + 'flatten_linear.weight'] = gfw.view(-1, R, R, C).permute(0, 3, 1, 2).reshape(gfw.shape[0], -1)
+            out['d_pos'] = dt                 # gradient into pos_embedd(...) (layers.py:329-331), not built yet
+            out['d_pconv_out'] = d_pc         # gradient into relu(sum_l pconv_l(roi_feats_l)), not built yet
+        self.saved = None
+        return out

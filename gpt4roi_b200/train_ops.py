@@ -48,6 +48,25 @@ def rmsnorm_bwd(x, w, dy, eps, dres=None):
     return dx, dw
 
 
+def colsum(x):
+    """fp32 column sums of a bf16 matrix [M,N] (bias gradient of a Linear: sum over rows of grad_y)."""
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    slabs = torch.empty((_L.load().g4r_colsum_slabs(M), N), dtype=torch.float32, device=x.device)
+    _call('g4r_colsum_bf16', x.device, _L.ptr(x), x.stride(0), M, N, _L.ptr(out), _L.ptr(slabs))
+    _L.count_launches(1)
+    return out
+
+
+def linear_bwd(x, w, dy, need_dx=True, has_bias=True):
+    """Backward of y = x @ w.T + b (torch.nn.functional.linear): returns (dx or None, dw bf16 [N,K], db fp32 [N] or None)."""
+    from . import dense
+    dw = dense.matmul_t(dy, x, a_mn=True, b_mn=True)
+    db = colsum(dy) if has_bias else None
+    dx = dense.matmul_t(dy, w, b_mn=True) if need_dx else None
+    return dx, dw, db
+
+
 def swiglu_fwd(gu):
     """gu [M, 2F] interleaved (gate_j, up_j) -> silu(gate) * up  [M, F]."""
     M, F2 = gu.shape

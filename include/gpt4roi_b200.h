@@ -345,6 +345,21 @@ int g4r_attention_bwd_bf16(const void* q, const void* k, const void* v, const vo
                            long long bs, long long ldo, long long bso, long long ldg, long long bsg, int B,
                            int H, int L, int head_dim, int causal, float scale, void* stream);
 
+/* Backward of the splice (spi_llava.py:99-196): rows of d(inputs_embeds) [B*L, D] (16-bit) are copied back to
+ * d_image [B*P, D] and d_region [K, D] following the forward's `plan` (either may be NULL to skip it).
+ * g4r_embed_grad_rows accumulates the rows that came from the embedding table into a dense fp32 gradient
+ * [V, D] (zeroed by the caller): `ids[n_unique]` are the distinct token ids, `order[seg[u] .. seg[u+1])` the
+ * row indices (b*L + t) of id u.  One CTA per id, fixed summation order, no atomics. */
+int g4r_splice_backward(const int32_t* plan, const void* d_out, void* d_image, void* d_region, int B, int L,
+                        int P, int D, void* stream);
+int g4r_embed_grad_rows(const void* d_out, const int32_t* order, const int32_t* seg, const int32_t* ids,
+                        int n_unique, float* grad, int D, void* stream);
+
+/* Column sums of a bf16 matrix [M,N] into fp32 out[N] (bias gradients of nn.Linear / Conv2d).
+ * slabs: fp32 scratch [g4r_colsum_slabs(M)][N]. */
+int g4r_colsum_slabs(int M);
+int g4r_colsum_bf16(const void* x, long long ld, int M, int N, float* out, float* slabs, void* stream);
+
 /* torch.optim.AdamW step (HF Trainer optim="adamw_torch"; param groups llava_trainer.py:59-144): fp32 master
  * weights p and moments m, v; gradient bf16 (g_bf16=1) or fp32, multiplied by grad_scale (1/world, clip factor);
  * p_bf16 (optional) receives the bf16 copy used by the next forward.  step counts from 1. */

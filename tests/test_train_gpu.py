@@ -85,3 +85,65 @@ def test_backward_is_bitwise_reproducible_and_step_lowers_loss():
         loss, _ = train_step(stack, x, targets)
         losses.append(loss.item())
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+def test_frontend_backward_matches_autograd():
+    """Second slice: splice / embedding / mm_projector / SPI-head backward vs fp32 autograd of the same algebra
+    (index_put splice, F.linear) on the tensors the forward saved.  rel-L2 <= 1.5e-2 per gradient."""
+    import torch.nn.functional as F
+    from gpt4roi_b200.engine import PrefillEngine
+    from gpt4roi_b200.train import FrontEndTrain
+    from tests.test_engine_gpu import make_inputs
+    cfg = EngineConfig(image_size=224, vit_layers=24, n_layers=0)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=5)
+    eng = PrefillEngine(cfg, sd, vit_sd, DEV)
+    ids, images, boxes = make_inputs(cfg, 2, [3, 1], 40, seed=2)
+    ids[1, -1] = ids[1, -2] = ids[0, 5] if int(ids[0, 5]) < 32000 else 17     # repeated token ids share a row
+    fe = FrontEndTrain(eng)
+    embeds = fe.forward(ids, images, boxes)
+    saved = dict(fe.saved)
+    torch.manual_seed(0)
+    d = (torch.randn_like(embeds.float()) * 0.1).to(BF)
+    got = fe.backward(d)
+
+    # fp32 autograd reference of the same computation from the saved activations
+    B, L = ids.shape
+    P, Hd = cfg.num_patches, cfg.hidden
+    emb = eng.embed.float().requires_grad_()
+    pw, pb = eng.proj_w.float().requires_grad_(), eng.proj_b.float().requires_grad_()
+    uw, ub = eng.up_w.float().requires_grad_(), eng.up_b.float().requires_grad_()
+    fw, fb = eng.flat_w.float().requires_grad_(), eng.flat_b.float().requires_grad_()
+    pc = saved['pc'].float().requires_grad_()
+    boxes_dev = torch.cat([b for b in boxes]).to(DEV)
+    from gpt4roi_b200 import kernels
+    pos = kernels.pos_embed_mlp(boxes_dev.contiguous(), *eng.pos).float().requires_grad_()
+    img = F.linear(saved['feat'].float(), pw, pb).view(B, P, Hd)
+    t = (F.linear(pc, fw) + fb + pos)
+    region = F.linear(t.detach().to(BF).float() + (t - t.detach()), uw, ub)  # bf16 rounding of t, straight-through
+    codes = saved['plan'].reshape(-1).long()
+    rows = []
+    for r, code in enumerate(codes.tolist()):
+        b = r // L
+        if code & 0x40000000:
+            rows.append(img[b, code & 0x1FFFFFFF])
+        elif code & 0x20000000:
+            rows.append(region[code & 0x1FFFFFFF])
+        else:
+            rows.append(emb[code])
+    ref = torch.stack(rows).view(B, L, Hd)
+    assert rel(embeds, ref) < 6e-3
+    (ref * d.float()).sum().backward()
+    q = 'model.spi_module.roi_align.'
+    R, C = cfg.roi_out, cfg.spi_dim
+    want = {'model.embed_tokens.weight': emb.grad, 'model.mm_projector.weight': pw.grad, 'model.mm_projector.bias': pb.grad,
+            q + 'updims.weight': uw.grad, q + 'updims.bias': ub.grad, q + 'flatten_linear.bias': fb.grad,
+            q + 'flatten_linear.weight': fw.grad.view(-1, R, R, C).permute(0, 3, 1, 2).reshape(fw.shape[0], -1),
+            'd_pos': pos.grad, 'd_pconv_out': pc.grad}
+    errs = {k: rel(got[k], v) for k, v in want.items()}
+    print('front-end grads rel-L2:', {k.split('.')[-2] + '.' + k.split('.')[-1] if '.' in k else k: '%.2e' % v for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < 1.5e-2}
+    assert not bad, bad
+    # untouched embedding rows have exactly zero gradient
+    used = torch.zeros(cfg.vocab, dtype=torch.bool, device=DEV)
+    used[codes[codes < 0x20000000]] = True
+    assert torch.all(got['model.embed_tokens.weight'][~used] == 0)
