@@ -66,8 +66,11 @@ struct GemmParams {
   const __nv_bfloat16* rope_sin;
   int rope_cols, rope_L, rope_pos0;
   const int* rope_pos_dev;  // optional device-side position base (CUDA-graph decode): pos0 = *rope_pos_dev
-  // operand majorness (backward GEMMs): a_mn: A is stored [K][M] (M contiguous); b_mn: B is stored [K][N]
-  int a_mn, b_mn;
+  // operand majorness (backward GEMMs): a_mn: A is stored [K][M] (M contiguous); b_mn: B is stored [K][N];
+  // b_mn == 2 (conv weight gradient): B is the zero-padded NHWC input seen through a 4-D tensor map
+  // {Cin, kx, row, ky} whose kx / ky dimensions alias the row dimension (strides of 1 and W+2 rows), so that
+  // column block n = (tap, cin) of the virtual [rows, 9*Cin] matrix is the input shifted by that tap
+  int a_mn, b_mn, dw_cin;
   float* gn_stats;       // optional [n_img, groups, 2] (sum, sumsq) of the bf16-rounded output
   int gn_group_ch;       // channels per group (16)
   int gn_groups;         // groups per image (64)
@@ -407,7 +410,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], kg * kBlockK,
                              m_blk * kBlockM);
           }
-          if (!CONV && p.b_mn) {
+          if (!CONV && p.b_mn == 2) {
+            const int n0 = n_blk * BLOCK_N, tap = n0 / p.dw_cin, c0 = n0 % p.dw_cin;
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; a++)
+              ptx::tma_load_4d(smem_b + stage * Cfg::kBBytes + a * (kBlockK * 128), &tmap_b, &full[stage],
+                               c0 + a * 64, tap % 3, kg * kBlockK, tap / 3);
+          } else if (!CONV && p.b_mn) {
 #pragma unroll
             for (int a = 0; a < BLOCK_N / 64; a++)
               ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes + a * (kBlockK * 128), &tmap_b, &full[stage],
@@ -846,6 +855,49 @@ extern "C" int g4r_gemm_bf16_t(const void* A, long long lda, int a_mn, const voi
   }
   cudaStream_t st = (cudaStream_t)stream;
   return bn == 256 ? launch_gemm<256, false>(ta, tb, p, st) : launch_gemm<128, false>(ta, tb, p, st);
+}
+
+// Weight gradient of a 3x3 / stride 1 / pad 1 convolution (NHWC, bf16) as ONE tensor-core GEMM on the
+// zero-padded layout:  dW[co, ky, kx, ci] = sum_rows dz_pad[row, co] * x_pad[row + (ky-1)*(W+2) + (kx-1), ci]
+// where rows run over n_img*(H+2)*(W+2) padded pixels (dz_pad is zero on the padding ring, so wrapped
+// neighbours contribute nothing).  A = dz_pad as an MN-major operand; B = x_pad through an aliasing 4-D tensor
+// map (b_mn == 2), so all nine taps are column blocks of one launch (8 x 36 tiles for 1024 -> 1024).
+// x_pad_origin points at the row of x_pad that tap (0,0) pairs with row 0, i.e. (W+2)+1 rows before the first
+// real row; the caller keeps >= (W+2)+1 zero guard rows on both ends.  dW is fp32 [Cout, 9*Cin]; accumulate != 0
+// adds to it (the four pyramid levels of a fuse round share one weight, gpt4roi/models/layers.py:152-180).
+extern "C" int g4r_conv3x3_dw_bf16(const void* dz_pad, const void* x_pad_origin, float* dW, long long rows, int Wp,
+                                   int Cin, int Cout, int accumulate, void* stream) {
+  G4R_REQUIRE(dz_pad && x_pad_origin && dW && rows > 0 && Wp > 2, "conv3x3_dw: bad arguments");
+  G4R_REQUIRE(Cin % 256 == 0 && Cout % 8 == 0, "conv3x3_dw: Cin=%d must be a multiple of 256, Cout=%d of 8", Cin, Cout);
+  G4R_REQUIRE((((uintptr_t)dz_pad | (uintptr_t)x_pad_origin) & 15) == 0, "conv3x3_dw: misaligned operands");
+  GemmParams p{};
+  p.M = Cout; p.N = 9 * Cin; p.K = (int)rows;
+  p.num_m_tiles = (Cout + kBlockM - 1) / kBlockM;
+  p.k_splits = 1;
+  p.num_k_blocks = (int)((rows + kBlockK - 1) / kBlockK);
+  p.D = dW; p.ldd = 9LL * Cin; p.out_f32 = 1;
+  if (accumulate) { p.residual = reinterpret_cast<const __nv_bfloat16*>(dW); p.residual_f32 = 1; p.ldr = p.ldd; }
+  p.a_rows = kBlockM;
+  p.a_mn = 1; p.b_mn = 2; p.dw_cin = Cin;
+  const int bn = 256;
+  p.num_n_tiles = p.N / bn;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)Cout * 2};
+    cuuint32_t box[2] = {64, kBlockK};
+    int rc = make_tmap(&ta, dz_pad, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    // dimension order {ci, kx, row, ky}: every stride is a multiple of the previous one (driver requirement)
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, 3, (cuuint64_t)rows, 3};
+    cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2, (cuuint64_t)Wp * Cin * 2};
+    cuuint32_t box[4] = {64, 1, kBlockK, 1};
+    int rc = make_tmap(&tb, x_pad_origin, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  return launch_gemm<256, false>(ta, tb, p, (cudaStream_t)stream);
 }
 
 static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,

@@ -321,6 +321,47 @@ adamw_step(float* __restrict__ p, const TG* __restrict__ g, float* __restrict__ 
   }
 }
 
+// Zero-padded NHWC copy for the conv weight-gradient GEMM: x [n, H, W, C] -> rows [guard | n*(H+2)*(W+2) | guard]
+// of C channels, zero on the 1-pixel ring and in the guards.
+__global__ void __launch_bounds__(256)
+pad_nhwc_rows(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int n, int H, int W, int C, int guard) {
+  const int nvec = C >> 3;
+  const long long rows = 2LL * guard + (long long)n * (H + 2) * (W + 2);
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int v = (int)(i % nvec);
+    const long long r = i / nvec - guard;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r >= 0 && r < (long long)n * (H + 2) * (W + 2)) {
+      const int xp = (int)(r % (W + 2)), yp = (int)((r / (W + 2)) % (H + 2));
+      const long long b = r / ((long long)(W + 2) * (H + 2));
+      if (xp >= 1 && xp <= W && yp >= 1 && yp <= H)
+        val = *reinterpret_cast<const uint4*>(x + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)C) + v * 8);
+    }
+    reinterpret_cast<uint4*>(out)[i] = val;
+  }
+}
+
+// Conv weight for the input-gradient convolution: Wf[ci][ky][kx][co] = W[co][2-ky][2-kx][ci]
+// (grad_x = conv(grad_z, flipped and transposed W)).  W rows (one per co) are `w_ld` elements apart so that
+// one level of the stacked pconv weight [Cout, L, 3, 3, Cin] can be addressed in place.  32x32 smem transpose.
+__global__ void __launch_bounds__(256)
+conv_weight_flip_t(const __nv_bfloat16* __restrict__ w, long long w_ld, __nv_bfloat16* __restrict__ wf, int Cin, int Cout) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int tap = blockIdx.z;                    // source tap; destination tap 8 - tap
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int co = co0 + j, ci = ci0 + tx;
+    tile[j][tx] = (co < Cout && ci < Cin) ? w[(long long)co * w_ld + (long long)tap * Cin + ci] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int ci = ci0 + j, co = co0 + tx;
+    if (ci < Cin && co < Cout) wf[((long long)ci * 9 + (8 - tap)) * Cout + co] = tile[tx][j];
+  }
+}
+
 static unsigned grid_for(long long work_items) {
   long long g = (work_items + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -375,6 +416,22 @@ extern "C" int g4r_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* w,
   G4R_LAUNCH_CHECK("rmsnorm_bwd_rows");
   slab_reduce_f32<<<(D + 255) / 256, 256, 0, st>>>(dw_slabs, S, D, dw);
   G4R_LAUNCH_CHECK("slab_reduce_f32");
+  return G4R_OK;
+}
+
+extern "C" int g4r_pad_nhwc_bf16(const void* x, void* out, int n, int H, int W, int C, int guard_rows, void* stream) {
+  G4R_REQUIRE(x && out && n > 0 && H > 0 && W > 0 && C % 8 == 0 && guard_rows >= W + 3, "pad_nhwc: bad arguments (guard_rows >= W+3)");
+  const long long total = (2LL * guard_rows + (long long)n * (H + 2) * (W + 2)) * (C / 8);
+  pad_nhwc_rows<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n, H, W, C, guard_rows);
+  G4R_LAUNCH_CHECK("pad_nhwc_rows");
+  return G4R_OK;
+}
+
+extern "C" int g4r_conv_weight_flip_t_bf16(const void* w, long long w_ld, void* wf, int Cin, int Cout, void* stream) {
+  G4R_REQUIRE(w && wf && Cin > 0 && Cout > 0 && w_ld >= 9LL * Cin, "conv_weight_flip_t: bad arguments");
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, 9);
+  conv_weight_flip_t<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)w, w_ld, (__nv_bfloat16*)wf, Cin, Cout);
+  G4R_LAUNCH_CHECK("conv_weight_flip_t");
   return G4R_OK;
 }
 

@@ -67,6 +67,42 @@ def linear_bwd(x, w, dy, need_dx=True, has_bias=True):
     return dx, dw, db
 
 
+def pad_nhwc(x):
+    """x [n,H,W,C] bf16 -> (padded rows [2*guard + n*(H+2)*(W+2), C], guard) with a zero ring and zero guards."""
+    n, H, W, C = x.shape
+    guard = W + 3
+    out = torch.empty((2 * guard + n * (H + 2) * (W + 2), C), dtype=BF16, device=x.device)
+    _call('g4r_pad_nhwc_bf16', x.device, _L.ptr(x), _L.ptr(out), n, H, W, C, guard)
+    return out, guard
+
+
+def conv_weight_flip_t(w):
+    """w [Cout, 3, 3, Cin] (rows may be strided: a level slice of [Cout, L, 3, 3, Cin]) -> [Cin, 3, 3, Cout] flipped."""
+    Cout, Cin = w.shape[0], w.shape[-1]
+    wf = torch.empty((Cin, 3, 3, Cout), dtype=BF16, device=w.device)
+    _call('g4r_conv_weight_flip_t_bf16', w.device, _L.ptr(w), w.stride(0), _L.ptr(wf), Cin, Cout)
+    return wf
+
+
+def conv3x3_bwd(x, w, dz, dw_acc=None, need_dx=True, wf=None):
+    """Backward of z = conv3x3(x, w) (NHWC bf16, stride 1, pad 1, no bias): x [n,H,W,Cin], w [Cout,3,3,Cin],
+    dz [n,H,W,Cout].  Returns (dx bf16 or None, dW fp32 [Cout,3,3,Cin]); dw_acc (fp32) is accumulated into."""
+    from . import dense
+    n, H, W, Cin = x.shape
+    Cout = dz.shape[-1]
+    xp, guard = pad_nhwc(x)
+    dzp, _ = pad_nhwc(dz)
+    rows = n * (H + 2) * (W + 2)
+    acc = dw_acc is not None
+    dW = dw_acc if acc else torch.empty((Cout, 3, 3, Cin), dtype=torch.float32, device=x.device)
+    _call('g4r_conv3x3_dw_bf16', x.device, _L.ptr(dzp[guard:]), _L.ptr(xp[guard - (W + 2) - 1:]), _L.ptr(dW), rows, W + 2,
+          Cin, Cout, int(acc))
+    dx = None
+    if need_dx:
+        dx = dense.conv_nhwc(dz, wf if wf is not None else conv_weight_flip_t(w))
+    return dx, dW
+
+
 def swiglu_fwd(gu):
     """gu [M, 2F] interleaved (gate_j, up_j) -> silu(gate) * up  [M, F]."""
     M, F2 = gu.shape

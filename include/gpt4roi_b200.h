@@ -360,6 +360,19 @@ int g4r_embed_grad_rows(const void* d_out, const int32_t* order, const int32_t* 
 int g4r_colsum_slabs(int M);
 int g4r_colsum_bf16(const void* x, long long ld, int M, int N, float* out, float* slabs, void* stream);
 
+/* Backward of a 3x3 / stride 1 / pad 1 NHWC convolution (mmcv ConvModule of MLVLFuseModule, layers.py:133-145, and
+ * the pconvs of MlvlRoIExtractor, layers.py:262-268):
+ *   grad_x = g4r_conv_nhwc_bf16(grad_z, Wf) with Wf = g4r_conv_weight_flip_t_bf16(W): Wf[ci][ky][kx][co] = W[co][2-ky][2-kx][ci]
+ *            (W rows `w_ld` elements apart, so one level of a stacked [Cout, L, 3, 3, Cin] weight works in place);
+ *   grad_W = g4r_conv3x3_dw_bf16 on zero-padded copies (g4r_pad_nhwc_bf16: rows [guard | n*(H+2)*(W+2) | guard] x C,
+ *            guard_rows >= W+3): one GEMM over all padded pixels, the nine taps being column blocks reached through an
+ *            aliasing 4-D TMA tensor map.  x_pad_origin = x_pad + (guard_rows - (W+2) - 1) * Cin elements;
+ *            dz_pad = first real row of the padded grad_z (skip its guard).  dW fp32 [Cout, 9*Cin]. */
+int g4r_pad_nhwc_bf16(const void* x, void* out, int n, int H, int W, int C, int guard_rows, void* stream);
+int g4r_conv_weight_flip_t_bf16(const void* w, long long w_ld, void* wf, int Cin, int Cout, void* stream);
+int g4r_conv3x3_dw_bf16(const void* dz_pad, const void* x_pad_origin, float* dW, long long rows, int Wp,
+                        int Cin, int Cout, int accumulate, void* stream);
+
 /* torch.optim.AdamW step (HF Trainer optim="adamw_torch"; param groups llava_trainer.py:59-144): fp32 master
  * weights p and moments m, v; gradient bf16 (g_bf16=1) or fp32, multiplied by grad_scale (1/world, clip factor);
  * p_bf16 (optional) receives the bf16 copy used by the next forward.  step counts from 1. */

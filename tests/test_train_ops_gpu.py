@@ -127,3 +127,24 @@ def test_attention_fwd_lse_and_bwd_match_autograd(B, L, H, D, causal):
         e = rel(dqkv[:, sl], qf.grad[:, sl])
         assert e < 1.5e-2, (name, e)
     assert torch.equal(dqkv, train_ops.attention_bwd(qkv, out, dout, lse, B, L, H, D, causal, scale))  # no atomics
+
+
+@pytest.mark.parametrize('n,H,Cin,Cout', [(2, 12, 256, 128), (1, 24, 1024, 1024), (3, 14, 256, 256)])
+def test_conv3x3_backward_matches_autograd(n, H, Cin, Cout):
+    """grad_x (implicit-GEMM conv on flipped/transposed weights) and grad_W (one padded-layout GEMM with the nine
+    taps as column blocks) vs autograd of F.conv2d in fp32.  rel-L2 <= 6e-3 (bf16 operands, fp32 accumulation)."""
+    torch.manual_seed(H + Cin)
+    x = (torch.randn(n, H, H, Cin, device=DEV) * 0.5).to(BF)
+    w = (torch.randn(Cout, 3, 3, Cin, device=DEV) * 0.05).to(BF)
+    dz = (torch.randn(n, H, H, Cout, device=DEV) * 0.1).to(BF)
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_()
+    wf = w.float().permute(0, 3, 1, 2).requires_grad_()
+    (F.conv2d(xf, wf, padding=1) * dz.float().permute(0, 3, 1, 2)).sum().backward()
+    dx, dW = train_ops.conv3x3_bwd(x, w, dz)
+    assert rel(dx, xf.grad.permute(0, 2, 3, 1)) < 6e-3
+    assert rel(dW, wf.grad.permute(0, 2, 3, 1)) < 6e-3
+    _, dW2 = train_ops.conv3x3_bwd(x, w, dz, dw_acc=dW.clone(), need_dx=False)     # accumulation: 2x
+    assert rel(dW2, 2 * wf.grad.permute(0, 2, 3, 1)) < 6e-3
+    # a level slice of a stacked [Cout, L, 3, 3, Cin] weight (pconv layout) is flipped in place
+    stacked = torch.stack([w, w * 2], 1).contiguous()
+    assert torch.equal(train_ops.conv_weight_flip_t(stacked[:, 0]), train_ops.conv_weight_flip_t(w))
