@@ -488,6 +488,76 @@ fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restri
   }
 }
 
+// Adjoint of fuse_gather_bf16 (training step): gradient w.r.t. the ACTIVATED maps of the previous round at
+// pyramid level m, from the gradients d_in of the conv inputs of the levels that read level m:
+//   channels [0, C/2)      <- d_in_m[:, 0:C/2]                                (own)
+//   channels [C/2, 3C/4)   <- sum over levels l with down(l) = m of resize^T(d_in_l[:, 3C/4:C])
+//   channels [3C/4, C)     <- sum over levels l with top(l)  = m of resize^T(d_in_l[:, C/2:3C/4])
+// resize^T is the transpose of the align_corners bilinear resize from size H_m to H_l, evaluated as a GATHER
+// per source pixel (every destination pixel whose footprint contains it), so there are no atomics and the
+// summation order is fixed.  Same-size consumers are the identity.  Output fp32 [B, Hm, Hm, C].
+struct FuseGrad {
+  const __nv_bfloat16* __restrict__ p;   // d_in of a consumer level (bf16 NHWC), or null
+  int H;
+};
+__device__ __forceinline__ void adjoint_resize8(const FuseGrad& gsrc, int b, int ys, int xs, int Hs, int C, int ch,
+                                                float (&acc)[8]) {
+  const int Hd = gsrc.H;
+  const __nv_bfloat16* base = gsrc.p + (long long)b * Hd * Hd * C + ch;
+  if (Hd == Hs) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(base + ((long long)ys * Hd + xs) * C), f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] += f[j];
+    return;
+  }
+  const float r = Hs > 1 ? (float)(Hd - 1) / (float)(Hs - 1) : 0.f;
+  const int ylo = max(0, (int)floorf((ys - 1) * r) - 1), yhi = min(Hd - 1, (int)ceilf((ys + 1) * r) + 1);
+  const int xlo = max(0, (int)floorf((xs - 1) * r) - 1), xhi = min(Hd - 1, (int)ceilf((xs + 1) * r) + 1);
+  for (int yd = ylo; yd <= yhi; yd++) {
+    const Lerp ly = lerp_ac(yd, Hs, Hd);
+    const float wy = (ly.i0 == ys ? ly.l0 : 0.f) + (ly.i1 == ys ? ly.l1 : 0.f);
+    if (wy == 0.f) continue;
+    for (int xd = xlo; xd <= xhi; xd++) {
+      const Lerp lx = lerp_ac(xd, Hs, Hd);
+      const float wx = (lx.i0 == xs ? lx.l0 : 0.f) + (lx.i1 == xs ? lx.l1 : 0.f);
+      if (wx == 0.f) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + ((long long)yd * Hd + xd) * C), f);
+      const float wgt = wy * wx;
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] += wgt * f[j];
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+fuse_gather_bwd(FuseGrad own, FuseGrad dn0, FuseGrad dn1, FuseGrad tp0, FuseGrad tp1, float* __restrict__ out, int B, int C) {
+  const int H = own.H;
+  const int nvec = C >> 3, q = C >> 2;
+  const int ppb = blockDim.x / nvec;
+  const long long npix = (long long)B * H * H;
+  const int v = threadIdx.x % nvec;
+  for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / nvec; pix < npix; pix += (long long)gridDim.x * ppb) {
+    const int x = (int)(pix % H), y = (int)((pix / H) % H), b = (int)(pix / ((long long)H * H));
+    const int c = v * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    if (c < 2 * q) {
+      unpack8(*reinterpret_cast<const uint4*>(own.p + (((long long)b * H + y) * H + x) * C + c), acc);
+    } else if (c < 3 * q) {   // read as "down" source: consumer channel c + C/4
+      if (dn0.p) adjoint_resize8(dn0, b, y, x, H, C, c + q, acc);
+      if (dn1.p) adjoint_resize8(dn1, b, y, x, H, C, c + q, acc);
+    } else {                  // read as "top" source: consumer channel c - C/4
+      if (tp0.p) adjoint_resize8(tp0, b, y, x, H, C, c - q, acc);
+      if (tp1.p) adjoint_resize8(tp1, b, y, x, H, C, c - q, acc);
+    }
+    float* o = out + (((long long)b * H + y) * H + x) * C + c;
+    reinterpret_cast<float4*>(o)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    reinterpret_cast<float4*>(o)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
 // GroupNorm finalisation: stats [B,groups,2] (sum, sumsq over H*W*cpg elements) + gamma/beta ->
 // per-(image,channel) scale/shift so that GN(x) = x*scale + shift (eps inside the rsqrt, biased
 // variance, like torch.nn.GroupNorm).
@@ -716,6 +786,25 @@ extern "C" int g4r_fuse_gather_bf16(const void* own, const float* own_sc, const 
   if (blocks > cap) blocks = cap;
   fuse_gather_bf16<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(a, t, d, (__nv_bfloat16*)out, B, C);
   G4R_LAUNCH_CHECK("fuse_gather");
+  return G4R_OK;
+}
+
+extern "C" int g4r_fuse_gather_bwd(const void* d_own, int H, const void* dn0, int Hdn0, const void* dn1, int Hdn1,
+                                   const void* tp0, int Htp0, const void* tp1, int Htp1, float* out, int B, int C,
+                                   void* stream) {
+  G4R_REQUIRE(d_own && out && B > 0 && C % 32 == 0 && H > 1, "fuse_gather_bwd: bad arguments");
+  FuseGrad o{(const __nv_bfloat16*)d_own, H}, a{(const __nv_bfloat16*)dn0, Hdn0}, b{(const __nv_bfloat16*)dn1, Hdn1};
+  FuseGrad c{(const __nv_bfloat16*)tp0, Htp0}, d{(const __nv_bfloat16*)tp1, Htp1};
+  const int nvec = C / 8;
+  G4R_REQUIRE(nvec <= 1024, "fuse_gather_bwd: C too large");
+  const int threads = nvec >= 256 ? nvec : (256 / nvec) * nvec;
+  const long long npix = (long long)B * H * H;
+  const int ppb = threads / nvec;
+  long long blocks = (npix + ppb - 1) / ppb;
+  const long long cap = (long long)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  fuse_gather_bwd<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(o, a, b, c, d, out, B, C);
+  G4R_LAUNCH_CHECK("fuse_gather_bwd");
   return G4R_OK;
 }
 

@@ -362,6 +362,144 @@ conv_weight_flip_t(const __nv_bfloat16* __restrict__ w, long long w_ld, __nv_bfl
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// GroupNorm(64) + ReLU backward for the fuse convs (mmcv ConvModule: conv -> GN -> ReLU, conv_module.py:196-208).
+//   z: raw conv output (bf16 NHWC, saved by the forward), y = z*scale + shift (scale/shift from gn_finalize),
+//   dy = dA * [y > 0],  xh = (z - mean) * rstd
+//   dbeta_c = sum dy,  dgamma_c = sum dy*xh
+//   dz = rstd * (dy*gamma - mean_g(dy*gamma) - xh * mean_g(dy*gamma*xh))      (means over the group's H*W*cpg values)
+// Pass 1 (gn_bwd_partial): per (image, pixel slab) partial sums of dy and dy*xh per channel -> slabs.
+// Pass 2 (gn_bwd_reduce): slabs -> per-(image, channel) sums AB and per-(image, group) sums S1, S2; all in a
+//         fixed order.  Pass 3 (gn_bwd_apply): elementwise dz.  gn_param_grad sums AB over the images.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_mean_rstd(const float* __restrict__ stats, float* __restrict__ out, int B, int groups, int slots, float count, float eps) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= B * groups) return;
+  const int lane = threadIdx.x & 31;
+  const int b = w / groups, g = w % groups;
+  float s = 0.f, ss = 0.f;
+  for (int t = lane; t < slots; t += 32) {     // same order as gn_finalize (elementwise.cu): identical mean / rstd
+    const float2 v = *reinterpret_cast<const float2*>(stats + (((long long)b * slots + t) * groups + g) * 2);
+    s += v.x;
+    ss += v.y;
+  }
+  s = warp_sum_f(s);
+  ss = warp_sum_f(ss);
+  const float mean = s / count;
+  float var = ss / count - mean * mean;
+  var = var < 0.f ? 0.f : var;
+  if (lane == 0) {
+    out[(long long)w * 2] = mean;
+    out[(long long)w * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+template <typename TA>
+__device__ __forceinline__ void load8_any(const TA* p, float (&f)[8]) {
+  if constexpr (sizeof(TA) == 2) {
+    unpack8f(*reinterpret_cast<const uint4*>(p), f);
+  } else {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+}
+
+// grid (S, B), block = C/8 threads (one 8-channel vector each)
+template <typename TA>
+__global__ void gn_bwd_partial(const __nv_bfloat16* __restrict__ z, const TA* __restrict__ dA, const float* __restrict__ scale,
+                               const float* __restrict__ shift, const float* __restrict__ mean_rstd,
+                               float* __restrict__ slabs, int HW, int C, int groups) {
+  const int b = blockIdx.y, s = blockIdx.x, S = gridDim.x;
+  const int c0 = threadIdx.x * 8;
+  const int cpg = C / groups;
+  float sc[8], sh[8], a[8], bb[8];
+  const float mean = mean_rstd[((long long)b * groups + c0 / cpg) * 2], rstd = mean_rstd[((long long)b * groups + c0 / cpg) * 2 + 1];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { sc[j] = scale[(long long)b * C + c0 + j]; sh[j] = shift[(long long)b * C + c0 + j]; a[j] = 0.f; bb[j] = 0.f; }
+  for (int pix = s; pix < HW; pix += S) {
+    const long long off = ((long long)b * HW + pix) * C + c0;
+    float zf[8], df[8];
+    unpack8f(*reinterpret_cast<const uint4*>(z + off), zf);
+    load8_any<TA>(dA + off, df);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float dy = (zf[j] * sc[j] + sh[j] > 0.f) ? df[j] : 0.f;
+      a[j] += dy;
+      bb[j] += dy * ((zf[j] - mean) * rstd);
+    }
+  }
+  float* o = slabs + (((long long)b * S + s) * 2) * C + c0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { o[j] = a[j]; o[C + j] = bb[j]; }
+}
+
+// grid B, block 256: AB[b][0/1][c] = sum_s slabs;  gs[b][g] = (sum_c gamma*A, sum_c gamma*B) over the group's channels
+__global__ void __launch_bounds__(256)
+gn_bwd_reduce(const float* __restrict__ slabs, const __nv_bfloat16* __restrict__ gamma, float* __restrict__ AB,
+              float* __restrict__ gs, int S, int C, int groups) {
+  extern __shared__ float sm_ab[];   // [2][C]
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float acc = 0.f;
+    for (int s = 0; s < S; s++) acc += slabs[(((long long)b * S + s) * 2) * C + i];
+    sm_ab[i] = acc;
+    AB[(long long)b * 2 * C + i] = acc;
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += 256) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < cpg; j++) {
+      const float gm = __bfloat162float(gamma[g * cpg + j]);
+      s1 += gm * sm_ab[g * cpg + j];
+      s2 += gm * sm_ab[C + g * cpg + j];
+    }
+    gs[((long long)b * groups + g) * 2] = s1;
+    gs[((long long)b * groups + g) * 2 + 1] = s2;
+  }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(256)
+gn_bwd_apply(const __nv_bfloat16* __restrict__ z, const TA* __restrict__ dA, const float* __restrict__ scale,
+             const float* __restrict__ shift, const float* __restrict__ mean_rstd, const float* __restrict__ gs,
+             const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ dz, int B, int HW, int C, int groups) {
+  const int nvec = C >> 3, cpg = C / groups;
+  const long long total = (long long)B * HW * nvec;
+  const float inv_n = 1.f / ((float)HW * cpg);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int v = (int)(i % nvec);
+    const int b = (int)(i / ((long long)nvec * HW));
+    const int c0 = v * 8, g = c0 / cpg;
+    const float mean = mean_rstd[((long long)b * groups + g) * 2], rstd = mean_rstd[((long long)b * groups + g) * 2 + 1];
+    const float m1 = gs[((long long)b * groups + g) * 2] * inv_n, m2 = gs[((long long)b * groups + g) * 2 + 1] * inv_n;
+    float zf[8], df[8], gm[8], o[8];
+    unpack8f(*reinterpret_cast<const uint4*>(z + i * 8), zf);
+    load8_any<TA>(dA + i * 8, df);
+    unpack8f(*reinterpret_cast<const uint4*>(gamma + c0), gm);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float y = zf[j] * scale[(long long)b * C + c0 + j] + shift[(long long)b * C + c0 + j];
+      const float dy = y > 0.f ? df[j] : 0.f;
+      const float xh = (zf[j] - mean) * rstd;
+      o[j] = rstd * (dy * gm[j] - m1 - xh * m2);
+    }
+    *reinterpret_cast<uint4*>(dz + i * 8) = pack8f(o);
+  }
+}
+
+// dbeta[c] (+)= sum_b AB[b][0][c];  dgamma[c] (+)= sum_b AB[b][1][c]
+__global__ void __launch_bounds__(256)
+gn_param_grad(const float* __restrict__ AB, int B, int C, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, bsum = 0.f;
+  for (int b = 0; b < B; b++) { a += AB[(long long)b * 2 * C + c]; bsum += AB[(long long)b * 2 * C + C + c]; }
+  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + a;
+  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + bsum;
+}
+
 static unsigned grid_for(long long work_items) {
   long long g = (work_items + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -416,6 +554,44 @@ extern "C" int g4r_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* w,
   G4R_LAUNCH_CHECK("rmsnorm_bwd_rows");
   slab_reduce_f32<<<(D + 255) / 256, 256, 0, st>>>(dw_slabs, S, D, dw);
   G4R_LAUNCH_CHECK("slab_reduce_f32");
+  return G4R_OK;
+}
+
+static int gn_bwd_slabs(int HW) { return HW < 64 ? HW : 64; }
+
+extern "C" long long g4r_gn_relu_bwd_workspace(int B, int HW, int C, int groups) {
+  return (long long)B * gn_bwd_slabs(HW) * 2 * C + (long long)B * 2 * C + (long long)B * groups * 4;
+}
+
+extern "C" int g4r_gn_relu_bwd_bf16(const void* z, const void* dA, int dA_f32, const float* scale, const float* shift,
+                                    const float* stats, int slots, float count, float eps, const void* gamma, void* dz,
+                                    float* dgamma, float* dbeta, int accumulate, float* workspace, int B, int HW, int C,
+                                    int groups, void* stream) {
+  G4R_REQUIRE(z && dA && scale && shift && stats && gamma && dz && dgamma && dbeta && workspace, "gn_relu_bwd: null argument");
+  G4R_REQUIRE(B > 0 && HW > 0 && groups > 0 && C % groups == 0 && (C / groups) % 8 == 0 && C / 8 <= 1024,
+              "gn_relu_bwd: C=%d groups=%d (channels per group must be a multiple of 8)", C, groups);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = gn_bwd_slabs(HW);
+  float* slabs = workspace;
+  float* AB = slabs + (long long)B * S * 2 * C;
+  float* gs = AB + (long long)B * 2 * C;
+  float* mr = gs + (long long)B * groups * 2;
+  gn_mean_rstd<<<(B * groups + 7) / 8, 256, 0, st>>>(stats, mr, B, groups, slots, count, eps);
+  G4R_LAUNCH_CHECK("gn_mean_rstd");
+  dim3 grid(S, B);
+  if (dA_f32) gn_bwd_partial<float><<<grid, C / 8, 0, st>>>((const __nv_bfloat16*)z, (const float*)dA, scale, shift, mr, slabs, HW, C, groups);
+  else gn_bwd_partial<__nv_bfloat16><<<grid, C / 8, 0, st>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dA, scale, shift, mr, slabs, HW, C, groups);
+  G4R_LAUNCH_CHECK("gn_bwd_partial");
+  gn_bwd_reduce<<<B, 256, 2 * C * sizeof(float), st>>>(slabs, (const __nv_bfloat16*)gamma, AB, gs, S, C, groups);
+  G4R_LAUNCH_CHECK("gn_bwd_reduce");
+  const long long total = (long long)B * HW * (C / 8);
+  if (dA_f32) gn_bwd_apply<float><<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)z, (const float*)dA, scale, shift, mr, gs,
+                                                                   (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dz, B, HW, C, groups);
+  else gn_bwd_apply<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dA, scale, shift, mr, gs,
+                                                                     (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dz, B, HW, C, groups);
+  G4R_LAUNCH_CHECK("gn_bwd_apply");
+  gn_param_grad<<<(C + 255) / 256, 256, 0, st>>>(AB, B, C, dgamma, dbeta, accumulate);
+  G4R_LAUNCH_CHECK("gn_param_grad");
   return G4R_OK;
 }
 

@@ -72,6 +72,9 @@ SIGNATURES = {
     'g4r_pad_nhwc_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'g4r_conv_weight_flip_t_bf16': (_i, [_vp, _ll, _vp, _i, _i, _vp]),
     'g4r_conv3x3_dw_bf16': (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
+    'g4r_gn_relu_bwd_workspace': (_ll, [_i, _i, _i, _i]),
+    'g4r_gn_relu_bwd_bf16': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    'g4r_fuse_gather_bwd': (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp]),
     'g4r_adamw_step': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp]),
     'g4r_add_bias_pos_cast': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
 }

@@ -103,6 +103,37 @@ def conv3x3_bwd(x, w, dz, dw_acc=None, need_dx=True, wf=None):
     return dx, dW
 
 
+def gn_relu_bwd(z, dA, scale, shift, stats, count, gamma, dgamma, dbeta, accumulate, eps=1e-5):
+    """z bf16 [B,H,W,C]; dA fp32 or bf16 (gradient w.r.t. relu(gn(z))); stats fp32 [B,slots,groups,2] of the forward.
+    Returns dz bf16; dgamma / dbeta (fp32 [C]) are written or accumulated in place."""
+    B, H, W, C = z.shape
+    _, slots, groups, _ = stats.shape
+    dz = torch.empty_like(z)
+    ws = torch.empty(_L.load().g4r_gn_relu_bwd_workspace(B, H * W, C, groups), dtype=torch.float32, device=z.device)
+    _call('g4r_gn_relu_bwd_bf16', z.device, _L.ptr(z), _L.ptr(dA), int(dA.dtype == torch.float32), _L.ptr(scale),
+          _L.ptr(shift), _L.ptr(stats), slots, float(count), float(eps), _L.ptr(gamma), _L.ptr(dz), _L.ptr(dgamma),
+          _L.ptr(dbeta), int(accumulate), _L.ptr(ws), B, H * W, C, groups)
+    _L.count_launches(4)
+    return dz
+
+
+def fuse_gather_bwd(d_in, m):
+    """d_in: list (per level) of conv-input gradients bf16 [B,H_l,H_l,C] of one fuse round; returns the fp32 gradient
+    w.r.t. the previous round's activated maps of level m (adjoint of kernels.fuse_gather)."""
+    n = len(d_in)
+    B, H, _, C = d_in[m].shape
+    dn = [l for l in range(n) if max(l - 1, 0) == m]        # levels whose `down` source is m
+    tp = [l for l in range(n) if min(l + 1, n - 1) == m]    # levels whose `top` source is m
+    out = torch.empty((B, H, H, C), dtype=torch.float32, device=d_in[m].device)
+
+    def pair(ls, i):
+        return (_L.ptr(d_in[ls[i]]), d_in[ls[i]].shape[1]) if i < len(ls) else (None, 0)
+    a, b, c, d = pair(dn, 0), pair(dn, 1), pair(tp, 0), pair(tp, 1)
+    _call('g4r_fuse_gather_bwd', out.device, _L.ptr(d_in[m]), H, a[0], a[1], b[0], b[1], c[0], c[1], d[0], d[1],
+          _L.ptr(out), B, C)
+    return out
+
+
 def swiglu_fwd(gu):
     """gu [M, 2F] interleaved (gate_j, up_j) -> silu(gate) * up  [M, F]."""
     M, F2 = gu.shape

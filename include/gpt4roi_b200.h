@@ -373,6 +373,25 @@ int g4r_conv_weight_flip_t_bf16(const void* w, long long w_ld, void* wf, int Cin
 int g4r_conv3x3_dw_bf16(const void* dz_pad, const void* x_pad_origin, float* dW, long long rows, int Wp,
                         int Cin, int Cout, int accumulate, void* stream);
 
+/* GroupNorm(64) + ReLU backward of the fuse ConvModules (mmcv cnn/bricks/conv_module.py:196-208): z = raw conv output
+ * (bf16 [B,HW,C], saved), dA = gradient w.r.t. relu(gn(z)) (fp32 when dA_f32, else bf16), scale/shift = g4r_gn_finalize
+ * outputs, stats/slots/count/eps = the forward's GroupNorm statistics (mean / rstd are re-derived in the same order).
+ * Writes dz (bf16) and dgamma / dbeta (fp32 [C]; accumulate != 0 adds: the four pyramid levels share one GN).
+ * workspace: fp32 scratch of g4r_gn_relu_bwd_workspace(B, HW, C, groups) elements.  Fixed-order reductions only. */
+long long g4r_gn_relu_bwd_workspace(int B, int HW, int C, int groups);
+int g4r_gn_relu_bwd_bf16(const void* z, const void* dA, int dA_f32, const float* scale, const float* shift,
+                         const float* stats, int slots, float count, float eps, const void* gamma, void* dz,
+                         float* dgamma, float* dbeta, int accumulate, float* workspace, int B, int HW, int C,
+                         int groups, void* stream);
+
+/* Adjoint of g4r_fuse_gather_bf16 (MLVLFuseModule._single_shuffle, layers.py:152-180) for pyramid level m:
+ * out fp32 [B,H,H,C] = gradient w.r.t. the previous round's activated maps of level m.  d_own = gradient of level
+ * m's own conv input; dn0/dn1 = gradients of the conv inputs of the (<= 2) levels that read level m as their
+ * `down` source, tp0/tp1 = of those that read it as their `top` source (NULL when absent), each bf16
+ * [B,Hx,Hx,C].  Transposed bilinear resize evaluated as a gather (no atomics). */
+int g4r_fuse_gather_bwd(const void* d_own, int H, const void* dn0, int Hdn0, const void* dn1, int Hdn1,
+                        const void* tp0, int Htp0, const void* tp1, int Htp1, float* out, int B, int C, void* stream);
+
 /* torch.optim.AdamW step (HF Trainer optim="adamw_torch"; param groups llava_trainer.py:59-144): fp32 master
  * weights p and moments m, v; gradient bf16 (g_bf16=1) or fp32, multiplied by grad_scale (1/world, clip factor);
  * p_bf16 (optional) receives the bf16 copy used by the next forward.  step counts from 1. */

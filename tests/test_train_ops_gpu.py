@@ -148,3 +148,53 @@ def test_conv3x3_backward_matches_autograd(n, H, Cin, Cout):
     # a level slice of a stacked [Cout, L, 3, 3, Cin] weight (pconv layout) is flipped in place
     stacked = torch.stack([w, w * 2], 1).contiguous()
     assert torch.equal(train_ops.conv_weight_flip_t(stacked[:, 0]), train_ops.conv_weight_flip_t(w))
+
+
+def test_gn_relu_bwd_matches_autograd():
+    """GroupNorm(64)+ReLU backward on a conv output with the forward's own statistics vs autograd of
+    relu(group_norm(z.float())).  dz rel-L2 <= 6e-3, dgamma/dbeta <= 2e-3; accumulation doubles the param grads."""
+    from gpt4roi_b200 import dense, kernels
+    torch.manual_seed(0)
+    B, H, C, G = 2, 24, 1024, 64
+    x = (torch.randn(B, H, H, C, device=DEV) * 0.5).to(BF)
+    w = (torch.randn(C, 3, 3, C, device=DEV) * 0.02).to(BF)
+    gamma = (torch.rand(C, device=DEV) + 0.5).to(BF)
+    beta = (torch.randn(C, device=DEV) * 0.2).to(BF)
+    st = torch.zeros((B, dense.gn_slots(H, H), G, 2), dtype=torch.float32, device=DEV)
+    z = dense.conv_nhwc(x, w, gn_stats=st)
+    count = H * H * (C // G)
+    scale, shift = kernels.gn_finalize(st, gamma, beta, count=count)
+    for dt in (torch.float32, BF):
+        dA = torch.randn(B, H, H, C, device=DEV).to(dt)
+        zf = z.float().permute(0, 3, 1, 2).requires_grad_()
+        gf, bf = gamma.float().requires_grad_(), beta.float().requires_grad_()
+        a = F.relu(F.group_norm(zf, G, gf, bf, 1e-5))
+        (a * dA.float().permute(0, 3, 1, 2)).sum().backward()
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dz = train_ops.gn_relu_bwd(z, dA, scale, shift, st, count, gamma, dg, db, accumulate=False)
+        assert rel(dz, zf.grad.permute(0, 2, 3, 1)) < 6e-3
+        assert rel(dg, gf.grad) < 2e-3 and rel(db, bf.grad) < 2e-3
+        train_ops.gn_relu_bwd(z, dA, scale, shift, st, count, gamma, dg, db, accumulate=True)
+        assert rel(dg, 2 * gf.grad) < 2e-3 and rel(db, 2 * bf.grad) < 2e-3
+
+
+def test_fuse_gather_bwd_is_the_adjoint_of_fuse_gather():
+    """<fuse_gather(a), d_in> == <a, fuse_gather_bwd(d_in)> checked through autograd of the torch restatement
+    (own | resize(top[3C/4:]) | resize(down[C/2:3C/4]), align_corners bilinear).  rel-L2 <= 4e-3 per level."""
+    torch.manual_seed(1)
+    B, C, n = 2, 256, 4
+    sizes = [32, 16, 8, 4]
+    q = C // 4
+    a = [torch.randn(B, C, h, h, device=DEV, requires_grad=True) for h in sizes]
+    d_in = [(torch.randn(B, h, h, C, device=DEV) * 0.3).to(BF) for h in sizes]
+    loss = 0
+    for l in range(n):
+        top, down = min(l + 1, n - 1), max(l - 1, 0)
+        ft = F.interpolate(a[top][:, 3 * q:], size=(sizes[l],) * 2, mode='bilinear', align_corners=True)
+        fd = F.interpolate(a[down][:, 2 * q:3 * q], size=(sizes[l],) * 2, mode='bilinear', align_corners=True)
+        zin = torch.cat([a[l][:, :2 * q], ft, fd], 1)
+        loss = loss + (zin * d_in[l].float().permute(0, 3, 1, 2)).sum()
+    loss.backward()
+    for m in range(n):
+        got = train_ops.fuse_gather_bwd(d_in, m)
+        assert rel(got, a[m].grad.permute(0, 2, 3, 1)) < 4e-3, m
