@@ -660,6 +660,108 @@ pos_embed_mlp(const float* __restrict__ boxes, const __nv_bfloat16* __restrict__
   }
 }
 
+// Backward of pos_embed_mlp (training step): one CTA per RoI recomputes the forward and writes that RoI's
+// parameter-gradient slab [w0 4x256 | b0 | g2 | be2 | w3 1024x256 | b3 | g5 | be5] (fp32, kPosSlab floats);
+// pos_slab_reduce sums the slabs over the RoIs in order.  Rounding points of the forward are treated as identity.
+constexpr int kPosSlab = 1024 + 256 * 3 + 1024 * 256 + 1024 * 3;
+__global__ void __launch_bounds__(256)
+pos_embed_mlp_bwd(const float* __restrict__ boxes, const __nv_bfloat16* __restrict__ w0,
+                  const __nv_bfloat16* __restrict__ b0, const __nv_bfloat16* __restrict__ g2,
+                  const __nv_bfloat16* __restrict__ be2, const __nv_bfloat16* __restrict__ w3,
+                  const __nv_bfloat16* __restrict__ b3, const __nv_bfloat16* __restrict__ g5,
+                  const __nv_bfloat16* __restrict__ dout, long long ldd, float* __restrict__ slabs, float eps) {
+  __shared__ float h1[256];
+  __shared__ float du2s[1024];
+  __shared__ float red[8];
+  const int k = blockIdx.x, t = threadIdx.x;
+  float* sl = slabs + (long long)k * kPosSlab;
+  float bx[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) bx[j] = bf16_round(boxes[k * 4 + j]);
+  float u1 = __bfloat162float(b0[t]);
+#pragma unroll
+  for (int j = 0; j < 4; j++) u1 += bx[j] * __bfloat162float(w0[t * 4 + j]);
+  const float r1 = fmaxf(bf16_round(u1), 0.f);
+  const float mean1 = block_sum_256(r1, red) / 256.f;
+  const float d1 = r1 - mean1;
+  const float rstd1 = rsqrtf(block_sum_256(d1 * d1, red) / 256.f + eps);
+  const float xh1 = d1 * rstd1;
+  const float g2f = __bfloat162float(g2[t]);
+  h1[t] = bf16_round(xh1 * g2f + __bfloat162float(be2[t]));
+  __syncthreads();
+  float u2[4], r2[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int n = t + r * 256;
+    float acc = 0.f;
+    const uint4* wr = reinterpret_cast<const uint4*>(w3 + (long long)n * 256);
+    for (int v = 0; v < 32; v++) {
+      float wf[8];
+      unpack8(wr[v], wf);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc += wf[j] * h1[v * 8 + j];
+    }
+    u2[r] = bf16_round(acc + __bfloat162float(b3[n]));
+    r2[r] = fmaxf(u2[r], 0.f);
+  }
+  const float mean2 = block_sum_256(r2[0] + r2[1] + r2[2] + r2[3], red) / 1024.f;
+  float vs = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; r++) { const float dd = r2[r] - mean2; vs += dd * dd; }
+  const float rstd2 = rsqrtf(block_sum_256(vs, red) / 1024.f + eps);
+  // ---- LayerNorm(1024) backward
+  float dxh[4], xh2[4], s1 = 0.f, s2 = 0.f;
+  float* o_w3 = sl + 1024 + 768;
+  float* o_b3 = o_w3 + 1024 * 256;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int n = t + r * 256;
+    const float dy = __bfloat162float(dout[(long long)k * ldd + n]);
+    xh2[r] = (r2[r] - mean2) * rstd2;
+    o_b3[1024 + n] = dy * xh2[r];          // dg5
+    o_b3[2048 + n] = dy;                   // dbe5
+    dxh[r] = dy * __bfloat162float(g5[n]);
+    s1 += dxh[r];
+    s2 += dxh[r] * xh2[r];
+  }
+  s1 = block_sum_256(s1, red) / 1024.f;
+  s2 = block_sum_256(s2, red) / 1024.f;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int n = t + r * 256;
+    const float dr2 = rstd2 * (dxh[r] - s1 - xh2[r] * s2);
+    const float du2 = u2[r] > 0.f ? dr2 : 0.f;
+    du2s[n] = du2;
+    o_b3[n] = du2;                         // db3
+    float* row = o_w3 + (long long)n * 256;
+    for (int i = 0; i < 256; i++) row[i] = du2 * h1[i];   // dW3[n, :]
+  }
+  __syncthreads();
+  // dn1[t] = sum_n W3[n, t] * du2[n]
+  float dn1 = 0.f;
+  for (int n = 0; n < 1024; n++) dn1 += __bfloat162float(w3[(long long)n * 256 + t]) * du2s[n];
+  // ---- LayerNorm(256) backward
+  sl[1024 + 256 + t] = dn1 * xh1;          // dg2
+  sl[1024 + 512 + t] = dn1;                // dbe2
+  const float dx1 = dn1 * g2f;
+  const float m1 = block_sum_256(dx1, red) / 256.f;
+  const float m2 = block_sum_256(dx1 * xh1, red) / 256.f;
+  const float dr1 = rstd1 * (dx1 - m1 - xh1 * m2);
+  const float du1 = bf16_round(u1) > 0.f ? dr1 : 0.f;
+  sl[1024 + t] = du1;                      // db0
+#pragma unroll
+  for (int j = 0; j < 4; j++) sl[t * 4 + j] = du1 * bx[j];   // dW0[t, :]
+}
+
+__global__ void __launch_bounds__(256)
+pos_slab_reduce(const float* __restrict__ slabs, int K, float* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= kPosSlab) return;
+  float a = 0.f;
+  for (int k = 0; k < K; k++) a += slabs[(long long)k * kPosSlab + i];
+  out[i] = a;
+}
+
 // t[k,:] = bf16( bf16(acc[k,:] + bias) + pos[k,:] )   (gpt4roi/models/layers.py:327-328: flatten_linear
 // output is bf16 under autocast, `+ pos_embedd` promotes to fp32, updims casts its input to bf16)
 __global__ void add_bias_pos_cast(const float* __restrict__ acc, int splits, const __nv_bfloat16* __restrict__ bias,
@@ -826,6 +928,22 @@ extern "C" int g4r_pos_embed_mlp(const float* boxes, const void* w0, const void*
       (const __nv_bfloat16*)g2, (const __nv_bfloat16*)be2, (const __nv_bfloat16*)w3, (const __nv_bfloat16*)b3,
       (const __nv_bfloat16*)g5, (const __nv_bfloat16*)be5, out, eps);
   G4R_LAUNCH_CHECK("pos_embed_mlp");
+  return G4R_OK;
+}
+
+extern "C" int g4r_pos_embed_mlp_grad_size(void) { return kPosSlab; }
+
+extern "C" int g4r_pos_embed_mlp_bwd(const float* boxes, const void* w0, const void* b0, const void* g2, const void* be2,
+                                     const void* w3, const void* b3, const void* g5, const void* dout, long long ldd,
+                                     float* grads, float* slabs, int K, float eps, void* stream) {
+  G4R_REQUIRE(boxes && w0 && b0 && g2 && be2 && w3 && b3 && g5 && dout && grads && slabs && K > 0, "pos_embed_mlp_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  pos_embed_mlp_bwd<<<K, 256, 0, st>>>(boxes, (const __nv_bfloat16*)w0, (const __nv_bfloat16*)b0, (const __nv_bfloat16*)g2,
+      (const __nv_bfloat16*)be2, (const __nv_bfloat16*)w3, (const __nv_bfloat16*)b3, (const __nv_bfloat16*)g5,
+      (const __nv_bfloat16*)dout, ldd, slabs, eps);
+  G4R_LAUNCH_CHECK("pos_embed_mlp_bwd");
+  pos_slab_reduce<<<(kPosSlab + 255) / 256, 256, 0, st>>>(slabs, K, grads);
+  G4R_LAUNCH_CHECK("pos_slab_reduce");
   return G4R_OK;
 }
 

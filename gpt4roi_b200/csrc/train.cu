@@ -500,6 +500,19 @@ gn_param_grad(const float* __restrict__ AB, int B, int C, float* __restrict__ dg
   dgamma[c] = (accumulate ? dgamma[c] : 0.f) + bsum;
 }
 
+// out = y > 0 ? dy : 0   (ReLU backward from the saved OUTPUT y; bf16, n multiple of 8)
+__global__ void __launch_bounds__(256)
+relu_bwd_rows(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, long long nvec) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += (long long)gridDim.x * 256) {
+    float d[8], v[8];
+    unpack8f(reinterpret_cast<const uint4*>(dy)[i], d);
+    unpack8f(reinterpret_cast<const uint4*>(y)[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) d[j] = v[j] > 0.f ? d[j] : 0.f;
+    reinterpret_cast<uint4*>(out)[i] = pack8f(d);
+  }
+}
+
 static unsigned grid_for(long long work_items) {
   long long g = (work_items + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -592,6 +605,13 @@ extern "C" int g4r_gn_relu_bwd_bf16(const void* z, const void* dA, int dA_f32, c
   G4R_LAUNCH_CHECK("gn_bwd_apply");
   gn_param_grad<<<(C + 255) / 256, 256, 0, st>>>(AB, B, C, dgamma, dbeta, accumulate);
   G4R_LAUNCH_CHECK("gn_param_grad");
+  return G4R_OK;
+}
+
+extern "C" int g4r_relu_bwd_bf16(const void* dy, const void* y, void* out, long long n, void* stream) {
+  G4R_REQUIRE(dy && y && out && n > 0 && n % 8 == 0, "relu_bwd: n must be a positive multiple of 8");
+  relu_bwd_rows<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)out, n / 8);
+  G4R_LAUNCH_CHECK("relu_bwd_rows");
   return G4R_OK;
 }
 

@@ -287,3 +287,117 @@ class FrontEndTrain:
             out['d_pconv_out'] = d_pc         # gradient into relu(sum_l pconv_l(roi_feats_l)), not built yet
         self.saved = None
         return out
+
+
+class SpiTrain:
+    """Forward (with saved activations) and complete backward of the SPI module -- MLVLROIQueryModule
+    (gpt4roi/models/layers.py:198-236): pyramid upsampling, MLVLFuseModule (4 input 1x1 convs + 5 shared
+    ConvModule(3x3, GN(64), ReLU) rounds with the channel shuffle between levels), MlvlRoIExtractor (4 RoIAligns,
+    4 pconvs, flatten_linear, box position MLP, updims) -- on the sm_100a kernels, no autograd.
+    Inputs: the CLIP hidden states (frozen tower) and the boxes; output: one region token per box.
+    `backward(d_region)` returns gradients under the reference's parameter names and layouts (fp32 or bf16)."""
+
+    def __init__(self, engine):
+        self.eng = engine
+        self.saved = None
+
+    def forward(self, taps, plan_b):
+        from .roi_align import roi_align_mlvl
+        eng, c = self.eng, self.eng.cfg
+        C, n = c.spi_dim, c.num_levels
+        B = next(iter(taps.values())).shape[0]
+        ups, maps = [], []
+        for l, layer in enumerate(c.level_layers):
+            H = c.level_sizes[l]
+            up = kernels.upsample_tokens_coords(taps[layer], c.grid, H, eng.spi_cpad)
+            ups.append(up)
+            maps.append(dense.linear(up.view(-1, eng.spi_cpad), eng.in_w[l], eng.in_b[l]).view(B, H, H, C))
+        zs, sts, sss = [maps], [None], [[None] * n]
+        for r in range(5):
+            new, stats = [], []
+            prev, ss = zs[-1], sss[-1]
+            for l in range(n):
+                top, down = min(l + 1, n - 1), max(l - 1, 0)
+                x_in = kernels.fuse_gather(prev[l], prev[top], prev[down], ss[l], ss[top], ss[down])
+                st = torch.zeros((B, dense.gn_slots(c.level_sizes[l], c.level_sizes[l]), c.gn_groups, 2), dtype=F32, device=eng.dev)
+                new.append(dense.conv_nhwc(x_in, eng.fuse[r]['w'], gn_stats=st))
+                stats.append(st)
+            zs.append(new)
+            sts.append(stats)
+            sss.append([kernels.gn_finalize(stats[l], eng.fuse[r]['gamma'], eng.fuse[r]['beta'],
+                                            count=c.level_sizes[l] ** 2 * (C // c.gn_groups)) for l in range(n)])
+        boxes, bidx = plan_b['boxes'], plan_b['bidx']
+        K = boxes.shape[0]
+        rois = torch.cat([bidx[:, None], boxes * float(c.image_size)], 1).contiguous()
+        scales = [float(torch.tensor(1.0 / s, dtype=F32)) for s in c.strides]
+        ss = sss[-1]
+        feats = roi_align_mlvl(zs[-1], rois, c.roi_out, scales, c.roi_sampling, True, out_dtype=BF16,
+                               gn_scale=[s for s, _ in ss], gn_shift=[b for _, b in ss])
+        R = c.roi_out
+        pc = dense.conv_nhwc(feats.view(n * K, R, R, C), eng.pconv_w, eng.pconv_b, act='relu', levels=n)
+        acc = dense.linear(pc.view(K, -1), eng.flat_w, out_dtype=F32)
+        pos = kernels.pos_embed_mlp(boxes.contiguous(), *eng.pos)
+        t = kernels.add_bias_pos_cast(acc, eng.flat_b, pos)
+        region = dense.linear(t, eng.up_w, eng.up_b)
+        self.saved = dict(ups=ups, zs=zs, sts=sts, sss=sss, rois=rois, scales=scales, feats=feats, pc=pc, t=t,
+                          boxes=boxes.contiguous(), K=K, B=B)
+        return region
+
+    def backward(self, d_region):
+        from .roi_align import roi_align_mlvl_backward
+        eng, c, s = self.eng, self.eng.cfg, self.saved
+        C, n, R, K, B = c.spi_dim, c.num_levels, c.roi_out, s['K'], s['B']
+        p = 'model.spi_module.'
+        q = p + 'roi_align.'
+        g = {}
+        # ---- head: updims, + pos, flatten_linear (layers.py:326-335)
+        dt, g[q + 'updims.weight'], g[q + 'updims.bias'] = train_ops.linear_bwd(s['t'], eng.up_w, d_region)
+        g[q + 'flatten_linear.bias'] = train_ops.colsum(dt)
+        for name, v in train_ops.pos_embed_mlp_bwd(s['boxes'], eng.pos, dt).items():
+            g[q + 'pos_embedd.' + name] = v
+        pcf = s['pc'].view(K, -1)
+        d_pc, gfw, _ = train_ops.linear_bwd(pcf, eng.flat_w, dt, has_bias=False)
+        g[q + 'flatten_linear.weight'] = gfw.view(-1, R, R, C).permute(0, 3, 1, 2).reshape(gfw.shape[0], -1)
+        # ---- relu(sum_l pconv_l(roi_feats_l))  (layers.py:318-325)
+        dZ = train_ops.relu_bwd(d_pc, pcf).view(K, R, R, C)
+        gb = train_ops.colsum(dZ.view(-1, C))
+        feats = s['feats'].view(n, K, R, R, C)
+        d_feats = torch.empty_like(feats)
+        for l in range(n):
+            wl = eng.pconv_w[:, l]                                       # [Cout, 3, 3, Cin], rows n*9*Cin apart
+            dx, dW = train_ops.conv3x3_bwd(feats[l], wl, dZ)
+            d_feats[l] = dx
+            g[q + 'pconvs.%d.weight' % l] = dW.permute(0, 3, 1, 2)
+            g[q + 'pconvs.%d.bias' % l] = gb
+        # ---- 4 x RoIAlign (the forward fused the last GroupNorm+ReLU into its taps)
+        shapes = [tuple(z.shape) for z in s['zs'][-1]]
+        dA = roi_align_mlvl_backward(d_feats, s['rois'], shapes, s['scales'], c.roi_sampling, True)
+        # ---- MLVLFuseModule, rounds 4 .. 0 (layers.py:152-195)
+        for r in range(4, -1, -1):
+            gamma = eng.fuse[r]['gamma']
+            dg, db = torch.empty(C, dtype=F32, device=eng.dev), torch.empty(C, dtype=F32, device=eng.dev)
+            zr, st, ss = s['zs'][r + 1], s['sts'][r + 1], s['sss'][r + 1]
+            dz = [train_ops.gn_relu_bwd(zr[l], dA[l], ss[l][0], ss[l][1], st[l], c.level_sizes[l] ** 2 * (C // c.gn_groups),
+                                        gamma, dg, db, accumulate=l > 0) for l in range(n)]
+            prev, pss = s['zs'][r], s['sss'][r]
+            wf = train_ops.conv_weight_flip_t(eng.fuse[r]['w'])
+            dW, d_in = None, []
+            for l in range(n):
+                top, down = min(l + 1, n - 1), max(l - 1, 0)
+                x_in = kernels.fuse_gather(prev[l], prev[top], prev[down], pss[l], pss[top], pss[down])
+                dx, dW = train_ops.conv3x3_bwd(x_in, eng.fuse[r]['w'], dz[l], dw_acc=dW, wf=wf)
+                d_in.append(dx)
+            g[p + 'mlvl_fuse.fuse_convs.%d.conv.weight' % r] = dW.permute(0, 3, 1, 2)
+            g[p + 'mlvl_fuse.fuse_convs.%d.gn.weight' % r] = dg
+            g[p + 'mlvl_fuse.fuse_convs.%d.gn.bias' % r] = db
+            dA = [train_ops.fuse_gather_bwd(d_in, m) for m in range(n)]
+            s['zs'][r + 1] = None
+        # ---- input 1x1 convs on [tokens | coords] (layers.py:185-191); the CLIP tower is frozen: no grad_x
+        for l in range(n):
+            dm = train_ops.cast_f32_bf16(dA[l].view(-1, C))
+            up = s['ups'][l].view(-1, eng.spi_cpad)
+            gw = dense.matmul_t(dm, up, a_mn=True, b_mn=True)            # [C, cpad]
+            g[p + 'mlvl_fuse.input_conv.%d.weight' % l] = gw[:, :C + 2].reshape(C, C + 2, 1, 1)
+            g[p + 'mlvl_fuse.input_conv.%d.bias' % l] = train_ops.colsum(dm)
+        self.saved = None
+        return g

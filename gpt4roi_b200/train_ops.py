@@ -134,6 +134,41 @@ def fuse_gather_bwd(d_in, m):
     return out
 
 
+def pos_embed_mlp_bwd(boxes, params, dout, eps=1e-5):
+    """boxes fp32 [K,4]; params = (w0, b0, g2, be2, w3, b3, g5, be5) bf16; dout bf16 [K,1024].
+    Returns a dict name -> fp32 gradient for pos_embedd.{0,2,3,5}.{weight,bias}."""
+    w0, b0, g2, be2, w3, b3, g5, be5 = params
+    K = boxes.shape[0]
+    n = _L.load().g4r_pos_embed_mlp_grad_size()
+    grads = torch.empty(n, dtype=torch.float32, device=boxes.device)
+    slabs = torch.empty((K, n), dtype=torch.float32, device=boxes.device)
+    _call('g4r_pos_embed_mlp_bwd', boxes.device, _L.ptr(boxes), _L.ptr(w0), _L.ptr(b0), _L.ptr(g2), _L.ptr(be2), _L.ptr(w3),
+          _L.ptr(b3), _L.ptr(g5), _L.ptr(dout), dout.stride(0), _L.ptr(grads), _L.ptr(slabs), K, float(eps))
+    o, out = 0, {}
+    for name, shape in (('0.weight', (256, 4)), ('0.bias', (256,)), ('2.weight', (256,)), ('2.bias', (256,)),
+                        ('3.weight', (1024, 256)), ('3.bias', (1024,)), ('5.weight', (1024,)), ('5.bias', (1024,))):
+        cnt = 1
+        for d in shape:
+            cnt *= d
+        out[name] = grads[o:o + cnt].view(shape)
+        o += cnt
+    return out
+
+
+def relu_bwd(dy, y):
+    out = torch.empty_like(dy)
+    _call('g4r_relu_bwd_bf16', dy.device, _L.ptr(dy), _L.ptr(y), _L.ptr(out), dy.numel())
+    return out
+
+
+def cast_f32_bf16(x):
+    """contiguous fp32 [N, D] -> bf16 [N, D] (g4r_cast_f32_bf16)."""
+    N, D = x.shape
+    out = torch.empty((N, D), dtype=BF16, device=x.device)
+    _call('g4r_cast_f32_bf16', x.device, _L.ptr(x), D, 0, _L.ptr(out), 1, N, D)
+    return out
+
+
 def swiglu_fwd(gu):
     """gu [M, 2F] interleaved (gate_j, up_j) -> silu(gate) * up  [M, F]."""
     M, F2 = gu.shape

@@ -392,6 +392,17 @@ int g4r_gn_relu_bwd_bf16(const void* z, const void* dA, int dA_f32, const float*
 int g4r_fuse_gather_bwd(const void* d_own, int H, const void* dn0, int Hdn0, const void* dn1, int Hdn1,
                         const void* tp0, int Htp0, const void* tp1, int Htp1, float* out, int B, int C, void* stream);
 
+/* Backward of g4r_pos_embed_mlp (pos_embedd of MlvlRoIExtractor, layers.py:260-267): dout bf16 [K,1024] -> fp32
+ * parameter gradients packed as [w0 256x4 | b0 256 | ln2.weight 256 | ln2.bias 256 | w3 1024x256 | b3 1024 |
+ * ln5.weight 1024 | ln5.bias 1024] (g4r_pos_embed_mlp_grad_size() floats).  slabs: fp32 scratch [K][that size]. */
+int g4r_pos_embed_mlp_grad_size(void);
+int g4r_pos_embed_mlp_bwd(const float* boxes, const void* w0, const void* b0, const void* g2, const void* be2,
+                          const void* w3, const void* b3, const void* g5, const void* dout, long long ldd,
+                          float* grads, float* slabs, int K, float eps, void* stream);
+
+/* ReLU backward from the saved output: out = y > 0 ? dy : 0 (bf16, n elements, n % 8 == 0). */
+int g4r_relu_bwd_bf16(const void* dy, const void* y, void* out, long long n, void* stream);
+
 /* torch.optim.AdamW step (HF Trainer optim="adamw_torch"; param groups llava_trainer.py:59-144): fp32 master
  * weights p and moments m, v; gradient bf16 (g_bf16=1) or fp32, multiplied by grad_scale (1/world, clip factor);
  * p_bf16 (optional) receives the bf16 copy used by the next forward.  step counts from 1. */
