@@ -219,17 +219,17 @@ def train_step(stack, inputs_embeds, targets, reducer=None, world_size=1):
 
 
 class FrontEndTrain:
-    """Training-mode front end (second slice of row 14): the region-token forward up to `inputs_embeds` with the
-    tensors its backward needs, and the backward of everything downstream of the pconv output and of the ViT
-    features: splice (`spi_llava.py:99-196`), `embed_tokens`, `mm_projector`, and the SPI head
-    (`MlvlRoIExtractor.forward`, layers.py:318-335: flatten_linear, + pos, updims).
+    """Training-mode front end: the region-token forward up to `inputs_embeds` with the tensors its backward needs,
+    and the backward of everything in front of the LLaMA stack that stage 2 trains: splice
+    (`spi_llava.py:99-196`), `embed_tokens`, `mm_projector` and the whole SPI module (`SpiTrain`).  The CLIP tower
+    is frozen in both stages (train.py:604-612) and is not differentiated.
+    head_only=True stops at the pconv output / position-MLP input and returns those hand-over gradients
+    (`d_pconv_out`, `d_pos`) instead of running SpiTrain (kept for the slice-level test)."""
 
-    Frozen / not differentiated here: the CLIP tower (frozen in both stages, train.py:604-612) and -- not built
-    yet -- the pconvs, RoIAlign (backward kernels exist), the MLVLFuseModule conv/GroupNorm stack and the box
-    position MLP; their incoming gradients `d_pconv_out` and `d_pos` are returned."""
-
-    def __init__(self, engine):
+    def __init__(self, engine, head_only=False):
         self.eng = engine
+        self.head_only = head_only
+        self.spi = SpiTrain(engine)
         self.saved = None
 
     def forward(self, input_ids, images, bboxes):
@@ -246,7 +246,9 @@ class FrontEndTrain:
         img_rows = dense.linear(feat, eng.proj_w, eng.proj_b).view(B, c.num_patches, c.hidden)
         K = plan_b['K'] if plan_b is not None else 0
         region, pc, t = None, None, None
-        if K > 0:
+        if K > 0 and not self.head_only:
+            region = (self.spi.forward(taps, plan_b), plan_b['offs'])
+        elif K > 0:
             maps, ss = eng.fuse_maps(taps)
             boxes, bidx = plan_b['boxes'], plan_b['bidx']
             rois = torch.cat([bidx[:, None], boxes * float(c.image_size)], 1).contiguous()
@@ -268,14 +270,16 @@ class FrontEndTrain:
         return embeds
 
     def backward(self, d_embeds):
-        """d_embeds [B,L,hidden] bf16 -> dict of gradients (reference parameter names) + hand-over gradients."""
+        """d_embeds [B,L,hidden] bf16 -> dict of gradients under the reference's parameter names."""
         from .splice import splice_backward
         eng, c, s = self.eng, self.eng.cfg, self.saved
         d_image, d_region, d_embed = splice_backward(s['plan'], d_embeds, c.num_patches, s['K'], c.vocab)
         out = {'model.embed_tokens.weight': d_embed}
         _, gw, gb = train_ops.linear_bwd(s['feat'], eng.proj_w, d_image.view(-1, c.hidden), need_dx=False)
         out['model.mm_projector.weight'], out['model.mm_projector.bias'] = gw, gb
-        if s['K'] > 0:
+        if s['K'] > 0 and not self.head_only:
+            out.update(self.spi.backward(d_region))
+        elif s['K'] > 0:
             q = 'model.spi_module.roi_align.'
             dt, out[q + 'updims.weight'], out[q + 'updims.bias'] = train_ops.linear_bwd(s['t'], eng.up_w, d_region)
             out[q + 'flatten_linear.bias'] = train_ops.colsum(dt)
@@ -283,8 +287,8 @@ class FrontEndTrain:
             # engine layout of flatten_linear.weight is [out, (ph, pw, c)]; the reference's is [out, (c, ph, pw)]
             R, C = c.roi_out, c.spi_dim
             out[q + 'flatten_linear.weight'] = gfw.view(-1, R, R, C).permute(0, 3, 1, 2).reshape(gfw.shape[0], -1)
-            out['d_pos'] = dt                 # gradient into pos_embedd(...) (layers.py:329-331), not built yet
-            out['d_pconv_out'] = d_pc         # gradient into relu(sum_l pconv_l(roi_feats_l)), not built yet
+            out['d_pos'] = dt
+            out['d_pconv_out'] = d_pc
         self.saved = None
         return out
 
@@ -401,3 +405,75 @@ class SpiTrain:
             g[p + 'mlvl_fuse.input_conv.%d.bias' % l] = train_ops.colsum(dm)
         self.saved = None
         return g
+
+
+class Stage2Trainer:
+    """One optimisation step of GPT4RoI stage 2 (scripts/train_stage2.sh -> gpt4roi/train/train.py:698-712): every
+    parameter except the frozen CLIP tower is trained -- embed_tokens, mm_projector, the SPI module, the 32 LLaMA
+    layers, final norm and lm_head -- with the loss of llava/model/llava.py:238-249, DDP gradient all-reduce and
+    torch.optim.AdamW semantics.  Forward, backward and optimizer run on the sm_100a kernels; no autograd.
+
+        front = FrontEndTrain(PrefillEngine without LLaMA layers)   ViT (frozen) -> projector / SPI -> splice
+        stack = LlamaTrainStack                                     decoder stack -> lm_head -> cross entropy
+    """
+
+    def __init__(self, cfg, state_dict, vit_state_dict, device, lr=2e-5, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, reducer=None, world_size=1):
+        import copy
+        from .engine import PrefillEngine
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.reducer, self.world = reducer, world_size
+        fcfg = copy.copy(cfg)
+        fcfg.n_layers = 0                                   # the front-end engine holds no decoder layers
+        self.eng = PrefillEngine(fcfg, state_dict, vit_state_dict, device)
+        self.front = FrontEndTrain(self.eng)
+        self.stack = LlamaTrainStack(cfg, state_dict, device, lr, betas, eps, weight_decay)
+        names = [k for k in state_dict if k.startswith('model.spi_module.') or k.startswith('model.mm_projector.')
+                 or k == 'model.embed_tokens.weight']
+        self.master = {k: state_dict[k].detach().to(self.dev, F32).contiguous() for k in names}
+        self.m1 = {k: torch.zeros_like(v) for k, v in self.master.items()}
+        self.m2 = {k: torch.zeros_like(v) for k, v in self.master.items()}
+        self.w16 = {k: v.to(BF16) for k, v in self.master.items()}
+        self.front_grads = None
+
+    @staticmethod
+    def shift_labels(labels):
+        """labels [B,L] (-100 = ignored) -> targets with targets[:, t] = labels[:, t+1] (llava.py:241-242)."""
+        t = torch.full_like(labels, -100)
+        t[:, :-1] = labels[:, 1:]
+        return t
+
+    def forward_backward(self, input_ids, images, bboxes, labels):
+        """Returns the loss; gradients are left in self.stack.grads and self.front_grads (already all-reduced)."""
+        embeds = self.front.forward(input_ids, images, bboxes)
+        loss = self.stack.forward(embeds, self.shift_labels(labels.to(self.dev)))
+        d_embeds = self.stack.backward(on_layer_grads=self.reducer.hook if self.reducer is not None else None)
+        self.front_grads = {k: v for k, v in self.front.backward(d_embeds).items() if k in self.master}
+        if self.reducer is not None:
+            top = self.stack.grads['top']
+            self.front_grads = {k: v.contiguous() for k, v in self.front_grads.items()}
+            self.reducer.reduce_now([top['lm_head'], top['norm']] + list(self.front_grads.values()))
+            self.reducer.wait()
+        return loss
+
+    def optimizer_step(self):
+        scale = 1.0 / self.world
+        self.stack.optimizer_step(grad_scale=scale)
+        t = self.stack.step_count
+        for k, gr in self.front_grads.items():
+            no_decay = k.endswith('.bias') or '.gn.' in k or 'pos_embedd.2.' in k or 'pos_embedd.5.' in k
+            gr = gr.reshape(-1)
+            if gr.dtype not in (BF16, F32):
+                gr = gr.float()
+            train_ops.adamw_step(self.master[k].view(-1), gr, self.m1[k].view(-1), self.m2[k].view(-1),
+                                 self.w16[k].view(-1), self.lr, self.betas, self.eps, 0.0 if no_decay else self.wd, t, scale)
+        self.front_grads = None
+        # refresh the engine's bf16 tensors (its own layouts: padded 1x1 weights, KHWC convs, stacked pconvs ...)
+        self.eng._prepare_spi(self.w16)
+        self.eng.embed = self.w16['model.embed_tokens.weight']
+
+    def step(self, input_ids, images, bboxes, labels):
+        loss = self.forward_backward(input_ids, images, bboxes, labels)
+        self.optimizer_step()
+        return loss

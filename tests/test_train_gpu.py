@@ -101,7 +101,7 @@ def test_frontend_backward_matches_autograd():
     eng = PrefillEngine(cfg, sd, vit_sd, DEV)
     ids, images, boxes = make_inputs(cfg, 2, [3, 1], 40, seed=2)
     ids[1, -1] = ids[1, -2] = ids[0, 5] if int(ids[0, 5]) < 32000 else 17     # repeated token ids share a row
-    fe = FrontEndTrain(eng)
+    fe = FrontEndTrain(eng, head_only=True)
     embeds = fe.forward(ids, images, boxes)
     saved = dict(fe.saved)
     torch.manual_seed(0)
@@ -207,3 +207,88 @@ def test_spi_module_backward_matches_oracle_autograd():
     # at least as close to the fp32 anchor as 1.5x the reference's own bf16-autocast run, or within 2e-2 outright
     bad = {k: (v, errs16[k]) for k, v in errs.items() if not (v < 2e-2 or v < 1.5 * errs16[k])}
     assert not bad, bad
+
+
+def test_stage2_step_end_to_end_matches_autograd():
+    """Whole stage-2 step (frozen CLIP tower -> projector / SPI module / embeddings -> splice -> LLaMA -> loss):
+    every trained parameter's gradient vs fp32 autograd through the oracle composition (spi_oracle + index splice +
+    transformers LlamaForCausalLM), calibrated like the SPI test against the same composition under bf16 autocast
+    (the reference's training mode).  Then one AdamW step must lower the loss of the batch."""
+    import torch.nn.functional as F
+    from gpt4roi_b200.train import Stage2Trainer
+    from oracle import spi_oracle
+    from tests.test_engine_gpu import make_inputs
+    cfg = EngineConfig(image_size=224, vit_layers=24, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=21)
+    sd = {k: v.to(BF).float() for k, v in sd.items()}
+    tr = Stage2Trainer(cfg, sd, vit_sd, DEV, lr=1e-3)
+    ids, images, boxes = make_inputs(cfg, 2, [2, 1], 24, seed=6)
+    labels = ids.clone()
+    labels[:, : cfg.num_patches + 8] = -100
+    labels[ids == cfg.bbox_token] = -100
+    loss = tr.forward_backward(ids, images, boxes, labels)
+    got = dict(tr.front_grads)
+    for i, gl in enumerate(tr.stack.grads['layers']):
+        for k in LAYER_KEYS:
+            got['L%d.%s' % (i, k)] = gl[k]
+    got['norm'], got['lm_head'] = tr.stack.grads['top']['norm'], tr.stack.grads['top']['lm_head']
+
+    # ---- oracle composition (CLIP outputs are constants: the tower is frozen)
+    eng = tr.eng
+    taps = eng.vit(images.to(DEV, BF))
+    toks = [taps[layer][:, 1:].float().contiguous() for layer in cfg.level_layers]
+    feat = taps[cfg.select_index][:, 1:].float()
+    B, L = ids.shape
+    P, Hd = cfg.num_patches, cfg.hidden
+    boxes_dev = [b.to(DEV) for b in boxes]
+    fe_plan = None
+
+    def reference(autocast):
+        ref = {k: v.clone().to(DEV).requires_grad_() for k, v in sd.items()
+               if k.startswith('model.spi_module.') or k.startswith('model.mm_projector.') or k == 'model.embed_tokens.weight'}
+        llm = model_oracle.build_llm(cfg, sd, DEV, torch.float32).train()
+        ctx = torch.autocast('cuda', dtype=BF) if autocast else contextlib.nullcontext()
+        with ctx:
+            region = torch.cat(spi_oracle.roi_query_forward(ref, toks, boxes_dev, cfg.image_size), 0)
+            img = F.linear(feat, ref['model.mm_projector.weight'], ref['model.mm_projector.bias'])
+            emb = ref['model.embed_tokens.weight']
+            rows, k = [], 0
+            for b in range(B):
+                s0 = int((ids[b] == cfg.im_start_token).nonzero()[0])
+                for t in range(L):
+                    tok = int(ids[b, t])
+                    if s0 < t <= s0 + P:
+                        rows.append(img[b, t - s0 - 1].float())
+                    elif tok == cfg.bbox_token:
+                        rows.append(region[k].float())
+                        k += 1
+                    else:
+                        rows.append(emb[tok])
+            embeds = torch.stack(rows).view(B, L, Hd)
+            out = llm(inputs_embeds=embeds, labels=labels.to(DEV))
+        out.loss.backward()
+        g = {k: v.grad for k, v in ref.items()}
+        for i, lyr in enumerate(llm.model.layers):
+            g['L%d.ln_in' % i] = lyr.input_layernorm.weight.grad
+            g['L%d.ln_post' % i] = lyr.post_attention_layernorm.weight.grad
+            g['L%d.wqkv' % i] = torch.cat([lyr.self_attn.q_proj.weight.grad, lyr.self_attn.k_proj.weight.grad, lyr.self_attn.v_proj.weight.grad], 0)
+            g['L%d.wo' % i] = lyr.self_attn.o_proj.weight.grad
+            g['L%d.wgu' % i] = torch.stack([lyr.mlp.gate_proj.weight.grad, lyr.mlp.up_proj.weight.grad], 1).reshape(2 * cfg.mlp, cfg.hidden)
+            g['L%d.wdown' % i] = lyr.mlp.down_proj.weight.grad
+        g['norm'], g['lm_head'] = llm.model.norm.weight.grad, llm.lm_head.weight.grad
+        return out.loss.item(), g
+
+    l32, g32 = reference(False)
+    l16, g16 = reference(True)
+    assert abs(loss.item() - l32) <= max(3e-3 * abs(l32), 1.5 * abs(l16 - l32)), (loss.item(), l32, l16)
+    assert set(got) == set(g32), set(got) ^ set(g32)
+    errs = {k: (rel(got[k].reshape(v.shape), v), rel(g16[k].float(), v)) for k, v in g32.items()}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1][0])[:8]
+    print('stage-2 step, loss %.4f (fp32 oracle %.4f, bf16-autocast oracle %.4f); worst gradient rel-L2 (ours | autocast):' % (loss.item(), l32, l16))
+    for k, (a, b) in worst:
+        print('   %-50s %.2e | %.2e' % (k, a, b))
+    bad = {k: v for k, v in errs.items() if not (v[0] < 2e-2 or v[0] < 1.5 * v[1])}
+    assert not bad, bad
+    tr.optimizer_step()
+    loss2 = tr.forward_backward(ids, images, boxes, labels)
+    assert loss2.item() < loss.item(), (loss.item(), loss2.item())
