@@ -25,6 +25,8 @@ def main():
     ap.add_argument('--layers', type=int, default=32)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=2)
+    ap.add_argument('--full', action='store_true', help='whole stage-2 step (BASELINE config 4): CLIP (frozen) + SPI + projector + '
+                    'embeddings + LLaMA, 336 px, 8 RoIs/img, 128 text tokens; default is the LLaMA stack only')
     a = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -38,6 +40,8 @@ def main():
             os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device(dev))
         reducer = LayerBucketAllReduce()
+    if a.full:
+        return full_step(a, world, rank, dev, reducer)
     cfg = EngineConfig(image_size=336, vit_layers=0, n_layers=a.layers)
     sd, _ = random_state_dicts(cfg, dev, seed=0)                 # same weights on every rank (same seed)
     stack = LlamaTrainStack(cfg, sd, dev, lr=2e-5)
@@ -82,6 +86,52 @@ def main():
                               peak_mem_GB=torch.cuda.max_memory_allocated() / 1e9, losses=[round(v, 4) for v in losses],
                               scope='LLaMA decoder stack + lm_head + loss only (SPI/projector/embedding backward not built)')),
               flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def full_step(a, world, rank, dev, reducer):
+    from bench import synthetic_inputs
+    from gpt4roi_b200.train import Stage2Trainer
+    cfg = EngineConfig(image_size=336, n_layers=a.layers)
+    sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
+    tr = Stage2Trainer(cfg, sd, vit_sd, dev, lr=2e-5, reducer=reducer, world_size=world)
+    del sd, vit_sd
+    torch.cuda.empty_cache()
+    ids, images, boxes = synthetic_inputs(cfg, a.batch, 8, 128, seed=100 + rank)   # a different micro-batch per rank
+    ids, images = ids.to(dev), images.to(dev)
+    labels = ids.clone()
+    labels[:, : cfg.num_patches + 3] = -100
+    labels[ids == cfg.bbox_token] = -100
+    losses = []
+    for _ in range(a.warmup):
+        losses.append(tr.step(ids, images, boxes, labels).item())
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    l0 = L.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = tr.step(ids, images, boxes, labels)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    losses.append(loss.item())
+    if rank == 0:
+        n_params = sum(v.numel() for m in tr.stack.master for v in m.values()) + sum(v.numel() for v in tr.stack.master_top.values()) \
+            + sum(v.numel() for v in tr.master.values())
+        print(json.dumps(dict(metric='train_step_stage2_samples_per_sec', value=world * a.batch / (ms / 1e3), unit='samples/s',
+                              n_gpus=world, ms_per_step=ms, steps=a.steps, warmup=a.warmup,
+                              config=dict(workload='stage-2 step (ViT frozen), 7B, bf16, 336 px, 8 RoIs/img, 128 text tokens (L=%d), per-GPU batch %d'
+                                          % (ids.shape[1], a.batch), layers=a.layers, trained_params=n_params, global_batch=world * a.batch),
+                              tokens_per_sec=world * a.batch * ids.shape[1] / (ms / 1e3), gpu_launches_per_step=(L.LAUNCHES - l0) // a.steps,
+                              peak_mem_GB=torch.cuda.max_memory_allocated() / 1e9, losses=[round(v, 4) for v in losses],
+                              data='synthetic images / boxes / tokens, random-init weights')), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
