@@ -452,7 +452,11 @@ class Stage2Trainer:
         self.front_grads = {k: v for k, v in self.front.backward(d_embeds).items() if k in self.master}
         if self.reducer is not None:
             top = self.stack.grads['top']
-            self.front_grads = {k: v.contiguous() for k, v in self.front_grads.items()}
+            # every rank must contribute the same tensors to the collective: a rank whose micro-batch has no boxes
+            # (no SPI gradients) contributes zeros, in the master's key order
+            self.front_grads = {k: (self.front_grads[k].reshape(self.master[k].shape).contiguous() if k in self.front_grads
+                                    else torch.zeros(self.master[k].shape, dtype=F32, device=self.dev)) for k in self.master}
+            self.front_grads = {k: (v if v.dtype == F32 else v.float()) for k, v in self.front_grads.items()}
             self.reducer.reduce_now([top['lm_head'], top['norm']] + list(self.front_grads.values()))
             self.reducer.wait()
         return loss

@@ -102,3 +102,20 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(ImportError, match='no CPU'):
         lib.load()
+
+
+def test_training_ops_fail_loudly_without_cuda():
+    """The training-step wrappers have no CPU path: CPU tensors raise (never a silent PyTorch fallback)."""
+    import pytest
+    import torch
+    from gpt4roi_b200 import dense, train, train_ops
+    x = torch.zeros(4, 8, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        train_ops.cross_entropy(x, torch.zeros(4, dtype=torch.int64))
+    with pytest.raises(RuntimeError):
+        dense.matmul_t(x, x, b_mn=True)
+    with pytest.raises(RuntimeError):
+        train_ops.rmsnorm_bwd(x, torch.zeros(8, dtype=torch.bfloat16), x, 1e-6)
+    # pure host logic: the label shift of llava/model/llava.py:241-242
+    lab = torch.tensor([[5, 6, -100, 7]])
+    assert train.Stage2Trainer.shift_labels(lab).tolist() == [[6, -100, 7, -100]]
