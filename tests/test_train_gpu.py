@@ -292,3 +292,33 @@ def test_stage2_step_end_to_end_matches_autograd():
     tr.optimizer_step()
     loss2 = tr.forward_backward(ids, images, boxes, labels)
     assert loss2.item() < loss.item(), (loss.item(), loss2.item())
+
+
+def test_right_padded_batch_needs_no_mask_in_causal_training():
+    """The collator right-pads (data_modules.py:33-44) and sets labels to -100 on the padding: with causal attention a
+    valid position never attends to a padded key and padded queries receive zero gradient, so the stack's gradients
+    equal those of transformers run WITH the attention mask.  Same tolerances as the unpadded test."""
+    cfg, sd, x, labels, targets = _setup(B=2, L=80, seed=5)
+    lens = [80, 53]
+    mask = torch.zeros(2, 80, dtype=torch.long, device=DEV)
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+    labels = labels.clone()
+    labels[mask == 0] = -100
+    targets = torch.full_like(labels, -100)
+    targets[:, :-1] = labels[:, 1:]
+    stack = LlamaTrainStack(cfg, sd, DEV)
+    loss = stack.forward(x, targets)
+    d_in = stack.backward()
+    llm = model_oracle.build_llm(cfg, sd, DEV, torch.float32).train()
+    xr = x.float().requires_grad_()
+    out = llm(inputs_embeds=xr, attention_mask=mask, labels=labels)
+    out.loss.backward()
+    assert abs(loss.item() - out.loss.item()) <= 2e-3 * abs(out.loss.item())
+    valid = mask.bool()
+    assert rel(d_in[valid], xr.grad[valid]) < 3e-2
+    assert torch.all(d_in[~valid] == 0)                       # padded positions: exactly zero gradient
+    for i, lyr in enumerate(llm.model.layers):
+        assert rel(stack.grads['layers'][i]['wo'], lyr.self_attn.o_proj.weight.grad) < 3e-2
+        assert rel(stack.grads['layers'][i]['wdown'], lyr.mlp.down_proj.weight.grad) < 3e-2
+    assert rel(stack.grads['top']['lm_head'], llm.lm_head.weight.grad) < 3e-2
