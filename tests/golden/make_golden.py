@@ -261,3 +261,102 @@ def full_model_golden():
 
 if __name__ == '__main__' and '--model' in sys.argv:
     full_model_golden()
+
+
+# ---------------------------------------------------------------------------------------
+# Training-step golden: the reference's OWN forward WITH labels + loss.backward() (the body of the HF Trainer step,
+# gpt4roi/train/train.py:698-712) on the same unmodified modules as the full-model golden, fp32 on CPU, CLIP tower
+# frozen as in stage 2.  Weights are rounded to bf16-representable values so that the sm_100a trainer starts from
+# identical parameters.  Stored: the loss and the gradients of a probe set of parameters (small tensors in full,
+# the first rows of the large ones).  Pins gpt4roi_b200.train.Stage2Trainer to the reference's autograd.
+# ---------------------------------------------------------------------------------------
+TRAIN_PROBES_FULL = [
+    'model.norm.weight', 'model.layers.1.input_layernorm.weight', 'model.layers.0.post_attention_layernorm.weight',
+    'model.mm_projector.bias', 'model.spi_module.roi_align.updims.bias', 'model.spi_module.roi_align.flatten_linear.bias',
+    'model.spi_module.mlvl_fuse.fuse_convs.0.gn.weight', 'model.spi_module.mlvl_fuse.fuse_convs.4.gn.bias',
+    'model.spi_module.roi_align.pos_embedd.5.weight', 'model.spi_module.roi_align.pos_embedd.0.weight',
+    'model.spi_module.mlvl_fuse.input_conv.3.bias', 'model.spi_module.roi_align.pconvs.1.bias',
+]
+TRAIN_PROBES_ROWS = {   # name -> number of leading rows kept
+    'lm_head.weight': 4, 'model.layers.0.self_attn.q_proj.weight': 4, 'model.layers.0.self_attn.v_proj.weight': 4,
+    'model.layers.1.self_attn.o_proj.weight': 4, 'model.layers.1.mlp.gate_proj.weight': 4,
+    'model.layers.1.mlp.down_proj.weight': 4, 'model.mm_projector.weight': 8,
+    'model.spi_module.roi_align.updims.weight': 8, 'model.spi_module.roi_align.pconvs.2.weight': 2,
+    'model.spi_module.mlvl_fuse.fuse_convs.2.conv.weight': 2, 'model.spi_module.mlvl_fuse.fuse_convs.0.conv.weight': 2,
+    'model.spi_module.mlvl_fuse.input_conv.0.weight': 8,
+}
+
+
+def train_inputs():
+    from gpt4roi_b200.engine import EngineConfig
+    cfg = EngineConfig(image_size=224, vit_layers=24, n_layers=2)
+    ids, images, boxes = model_inputs(cfg, [2, 1], 20, seed=77)
+    labels = ids.clone()
+    labels[:, : cfg.num_patches + 6] = -100                      # prompt / image part is not supervised
+    labels[ids == cfg.bbox_token] = -100
+    return cfg, ids, images, boxes, labels
+
+
+def train_step_golden():
+    sys.path.insert(0, HERE)
+    import importlib
+    import ref_shims
+    from gpt4roi_b200.engine import random_state_dicts
+    ref_shims.install()
+    spi_llava = importlib.import_module('gpt4roi.models.spi_llava')
+    llava = importlib.import_module('llava.model.llava')
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    cfg, ids, images, boxes, labels = train_inputs()
+    sd, vit_sd = random_state_dicts(cfg, 'cpu', seed=1234, dtype=torch.float32)
+    sd = {k: v.to(torch.bfloat16).float() for k, v in sd.items()}
+    vit_sd = {k: v.to(torch.bfloat16).float() for k, v in vit_sd.items()}
+    lc = llava.LlavaConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=2, num_attention_heads=32,
+                           num_key_value_heads=32, vocab_size=32006, rms_norm_eps=1e-6, max_position_embeddings=2048)
+    lc._attn_implementation = 'eager'
+    lc.mm_vision_select_layer = -2
+    lc.use_mm_proj = True
+    lc.mm_hidden_size = 1024
+    model = spi_llava.SPILlavaMPTForCausalLM(lc)
+    vc = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                          image_size=224, patch_size=14)
+    vc._attn_implementation = 'eager'
+    vt = CLIPVisionModel(vc)
+    missing, unexpected = vt.load_state_dict(vit_sd, strict=False)
+    assert not unexpected
+    vt.requires_grad_(False)                                     # frozen tower (train.py:604-612)
+    model.model.vision_tower = [vt.eval()]
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    model.train()
+    vconf = vt.config
+    vconf.im_patch_token, vconf.bbox_token = cfg.im_patch_token, cfg.bbox_token
+    vconf.im_start_token, vconf.im_end_token = cfg.im_start_token, cfg.im_end_token
+    vconf.use_im_start_end = True
+
+    class Tok:
+        def convert_tokens_to_ids(self, toks):
+            return [cfg.bbox_token for _ in toks]
+    for m in model.modules():
+        m.tokenizer = Tok()
+    out = model(input_ids=ids, images=images, img_metas=[None] * len(boxes), bboxes=boxes,
+                attention_mask=torch.ones_like(ids), labels=labels)
+    out.loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    trained = sorted(grads)
+    store = {'loss': np.array([float(out.loss)]), 'n_trained_tensors': np.array([len(trained)]),
+             'ids_checksum': np.array([int(ids.sum())]), 'w_checksum': np.array([float(sd['lm_head.weight'].double().sum())])}
+    for k in TRAIN_PROBES_FULL:
+        store['full/' + k] = grads[k].float().numpy()
+    for k, n in TRAIN_PROBES_ROWS.items():
+        store['rows/' + k] = grads[k][:n].float().numpy()
+    used = torch.unique(ids[(ids < 32000)])[:6]
+    store['embed_ids'] = used.numpy()
+    store['embed_rows'] = grads['model.embed_tokens.weight'][used].float().numpy()
+    store['norms'] = np.array([float(grads[k].double().norm()) for k in trained])
+    store['norm_names'] = np.array(trained)
+    np.savez_compressed(os.path.join(HERE, 'train_step_ref_224.npz'), **store)
+    print('wrote train_step_ref_224.npz: loss %.6f, %d trained tensors' % (float(out.loss), len(trained)))
+
+
+if __name__ == '__main__' and '--train' in sys.argv:
+    train_step_golden()
