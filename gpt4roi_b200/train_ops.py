@@ -117,13 +117,20 @@ def gn_relu_bwd(z, dA, scale, shift, stats, count, gamma, dgamma, dbeta, accumul
     return dz
 
 
+def fuse_consumers(n, m):
+    """Inverse of MLVLFuseModule's fuse_lvl_list (layers.py:105-112: level l reads top = min(l+1, n-1) and
+    down = max(l-1, 0)): the levels that read level m as their `down` source and as their `top` source."""
+    dn = [l for l in range(n) if max(l - 1, 0) == m]
+    tp = [l for l in range(n) if min(l + 1, n - 1) == m]
+    return dn, tp
+
+
 def fuse_gather_bwd(d_in, m):
     """d_in: list (per level) of conv-input gradients bf16 [B,H_l,H_l,C] of one fuse round; returns the fp32 gradient
     w.r.t. the previous round's activated maps of level m (adjoint of kernels.fuse_gather)."""
     n = len(d_in)
     B, H, _, C = d_in[m].shape
-    dn = [l for l in range(n) if max(l - 1, 0) == m]        # levels whose `down` source is m
-    tp = [l for l in range(n) if min(l + 1, n - 1) == m]    # levels whose `top` source is m
+    dn, tp = fuse_consumers(n, m)
     out = torch.empty((B, H, H, C), dtype=torch.float32, device=d_in[m].device)
 
     def pair(ls, i):

@@ -119,3 +119,19 @@ def test_training_ops_fail_loudly_without_cuda():
     # pure host logic: the label shift of llava/model/llava.py:241-242
     lab = torch.tensor([[5, 6, -100, 7]])
     assert train.Stage2Trainer.shift_labels(lab).tolist() == [[6, -100, 7, -100]]
+
+
+def test_fuse_consumers_inverts_the_shuffle_wiring():
+    """train_ops.fuse_consumers is the transpose of the forward wiring (level l reads top=min(l+1,n-1), down=max(l-1,0));
+    every (reader, source) edge appears exactly once and no level has more than two readers per role (the kernel's limit)."""
+    from gpt4roi_b200.train_ops import fuse_consumers
+    for n in (1, 2, 3, 4, 5):
+        edges_dn = {(l, max(l - 1, 0)) for l in range(n)}
+        edges_tp = {(l, min(l + 1, n - 1)) for l in range(n)}
+        got_dn, got_tp = set(), set()
+        for m in range(n):
+            dn, tp = fuse_consumers(n, m)
+            assert len(dn) <= 2 and len(tp) <= 2
+            got_dn |= {(l, m) for l in dn}
+            got_tp |= {(l, m) for l in tp}
+        assert got_dn == edges_dn and got_tp == edges_tp
