@@ -34,6 +34,72 @@ F32 = torch.float32
 LAYER_KEYS = ('ln_in', 'wqkv', 'wo', 'ln_post', 'wgu', 'wdown')
 
 
+def fuse_llama_layer(state_dict, i, device=None, dtype=F32):
+    """HF LLaMA layer i -> the engine's fused layout: wqkv = [q; k; v], wgu = rows (gate_0, up_0, gate_1, up_1, ...)."""
+    q = 'model.layers.%d.' % i
+    cvt = lambda t: t.detach().to(device=device if device is not None else t.device, dtype=dtype).contiguous()
+    wqkv = torch.cat([cvt(state_dict[q + 'self_attn.%s_proj.weight' % n]) for n in 'qkv'], 0).contiguous()
+    g, u = cvt(state_dict[q + 'mlp.gate_proj.weight']), cvt(state_dict[q + 'mlp.up_proj.weight'])
+    wgu = torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]).contiguous()
+    return dict(ln_in=cvt(state_dict[q + 'input_layernorm.weight']), wqkv=wqkv,
+                wo=cvt(state_dict[q + 'self_attn.o_proj.weight']),
+                ln_post=cvt(state_dict[q + 'post_attention_layernorm.weight']), wgu=wgu,
+                wdown=cvt(state_dict[q + 'mlp.down_proj.weight']))
+
+
+def unfuse_llama_layer(layer, i):
+    """Inverse of fuse_llama_layer: fused layer dict -> HF / reference parameter names (views, no copies)."""
+    q = 'model.layers.%d.' % i
+    H = layer['wqkv'].shape[0] // 3
+    return {q + 'self_attn.q_proj.weight': layer['wqkv'][:H], q + 'self_attn.k_proj.weight': layer['wqkv'][H:2 * H],
+            q + 'self_attn.v_proj.weight': layer['wqkv'][2 * H:], q + 'self_attn.o_proj.weight': layer['wo'],
+            q + 'mlp.gate_proj.weight': layer['wgu'][0::2], q + 'mlp.up_proj.weight': layer['wgu'][1::2],
+            q + 'mlp.down_proj.weight': layer['wdown'], q + 'input_layernorm.weight': layer['ln_in'],
+            q + 'post_attention_layernorm.weight': layer['ln_post']}
+
+
+def save_checkpoint(state_dict, out_dir, max_shard_bytes=10 * 1024 ** 3, dtype=None):
+    """Write `state_dict` (reference parameter names) the way the reference's trainer does
+    (train.py:88-98 -> Trainer._save -> save_pretrained): `pytorch_model-XXXXX-of-YYYYY.bin` shards plus
+    `pytorch_model.bin.index.json`, loadable by SPILlavaMPTForCausalLM.from_pretrained.  Returns the shard file names."""
+    import json
+    import os
+    os.makedirs(out_dir, exist_ok=True)
+    shards, cur, cur_bytes = [], {}, 0
+    for k, v in state_dict.items():
+        t = v.detach().to('cpu', dtype if dtype is not None else v.dtype).contiguous()
+        nbytes = t.numel() * t.element_size()
+        if cur and cur_bytes + nbytes > max_shard_bytes:
+            shards.append(cur)
+            cur, cur_bytes = {}, 0
+        cur[k] = t
+        cur_bytes += nbytes
+    if cur:
+        shards.append(cur)
+    names = ['pytorch_model-%05d-of-%05d.bin' % (i + 1, len(shards)) for i in range(len(shards))]
+    weight_map, total = {}, 0
+    for name, shard in zip(names, shards):
+        torch.save(shard, os.path.join(out_dir, name))
+        for k, t in shard.items():
+            weight_map[k] = name
+            total += t.numel() * t.element_size()
+    with open(os.path.join(out_dir, 'pytorch_model.bin.index.json'), 'w') as f:
+        json.dump({'metadata': {'total_size': total}, 'weight_map': weight_map}, f, indent=2, sort_keys=True)
+    return names
+
+
+def load_checkpoint(ckpt_dir):
+    """Read a sharded HF checkpoint directory written by save_checkpoint / save_pretrained into one state dict."""
+    import json
+    import os
+    with open(os.path.join(ckpt_dir, 'pytorch_model.bin.index.json')) as f:
+        index = json.load(f)
+    out = {}
+    for name in sorted(set(index['weight_map'].values())):
+        out.update(torch.load(os.path.join(ckpt_dir, name), map_location='cpu'))
+    return out
+
+
 class LlamaTrainStack:
     """LLaMA decoder stack with explicit forward / backward / AdamW on the sm_100a kernels."""
 
@@ -46,16 +112,7 @@ class LlamaTrainStack:
         if cfg.head_dim != 128:
             raise ValueError('LlamaTrainStack: head_dim 128 required (fused-RoPE QKV GEMM)')
         f32 = lambda t: t.detach().to(self.dev, F32).contiguous()
-        self.master = []          # per layer: dict name -> fp32 master
-        for i in range(cfg.n_layers):
-            q = 'model.layers.%d.' % i
-            wqkv = torch.cat([f32(state_dict[q + 'self_attn.%s_proj.weight' % n]) for n in 'qkv'], 0)
-            g, u = f32(state_dict[q + 'mlp.gate_proj.weight']), f32(state_dict[q + 'mlp.up_proj.weight'])
-            wgu = torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]).contiguous()   # rows g0,u0,g1,u1,...
-            self.master.append(dict(ln_in=f32(state_dict[q + 'input_layernorm.weight']), wqkv=wqkv.contiguous(),
-                                    wo=f32(state_dict[q + 'self_attn.o_proj.weight']),
-                                    ln_post=f32(state_dict[q + 'post_attention_layernorm.weight']), wgu=wgu,
-                                    wdown=f32(state_dict[q + 'mlp.down_proj.weight'])))
+        self.master = [fuse_llama_layer(state_dict, i, self.dev) for i in range(cfg.n_layers)]   # fp32 masters
         self.master_top = dict(norm=f32(state_dict['model.norm.weight']), lm_head=f32(state_dict['lm_head.weight']))
         self.w = [{k: v.to(BF16) for k, v in m.items()} for m in self.master]      # bf16 compute copies
         self.w_top = {k: v.to(BF16) for k, v in self.master_top.items()}
@@ -67,6 +124,14 @@ class LlamaTrainStack:
         self._rope_cache = {}
         self.saved = None
         self.grads = None
+
+    def state_dict(self):
+        """fp32 master weights under the reference's parameter names (views of the fused tensors)."""
+        out = {}
+        for i, m in enumerate(self.master):
+            out.update(unfuse_llama_layer(m, i))
+        out['model.norm.weight'], out['lm_head.weight'] = self.master_top['norm'], self.master_top['lm_head']
+        return out
 
     # ------------------------------------------------------------------ helpers
     def _rope(self, L):
@@ -481,3 +546,38 @@ class Stage2Trainer:
         loss = self.forward_backward(input_ids, images, bboxes, labels)
         self.optimizer_step()
         return loss
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """All trained parameters, fp32, reference names and layouts -- what the reference's trainer saves
+        (train.py:88-98); the CLIP tower is not part of the model's state dict (llava.py:47-48)."""
+        out = dict(self.master)
+        out.update(self.stack.state_dict())
+        return out
+
+    def save_pretrained(self, out_dir, dtype=None, max_shard_bytes=10 * 1024 ** 3):
+        return save_checkpoint(self.state_dict(), out_dir, max_shard_bytes, dtype)
+
+    def optimizer_state(self):
+        """AdamW step count and moments under reference names (resume: pass the saved weights to __init__, then
+        load_optimizer_state)."""
+        m1, m2 = dict(self.m1), dict(self.m2)
+        for i in range(len(self.stack.master)):
+            m1.update(unfuse_llama_layer(self.stack.m1[i], i))
+            m2.update(unfuse_llama_layer(self.stack.m2[i], i))
+        for k, name in (('norm', 'model.norm.weight'), ('lm_head', 'lm_head.weight')):
+            m1[name], m2[name] = self.stack.m1_top[k], self.stack.m2_top[k]
+        return dict(step=self.stack.step_count, exp_avg=m1, exp_avg_sq=m2)
+
+    def load_optimizer_state(self, state):
+        self.stack.step_count = int(state['step'])
+        for src, dst_front, dst_layers, dst_top in ((state['exp_avg'], self.m1, self.stack.m1, self.stack.m1_top),
+                                                    (state['exp_avg_sq'], self.m2, self.stack.m2, self.stack.m2_top)):
+            for k in dst_front:
+                dst_front[k].copy_(src[k])
+            for i in range(len(dst_layers)):
+                fused = fuse_llama_layer(src, i, self.dev)
+                for k in LAYER_KEYS:
+                    dst_layers[i][k].copy_(fused[k])
+            dst_top['norm'].copy_(src['model.norm.weight'])
+            dst_top['lm_head'].copy_(src['lm_head.weight'])

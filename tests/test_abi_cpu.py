@@ -135,3 +135,62 @@ def test_fuse_consumers_inverts_the_shuffle_wiring():
             got_dn |= {(l, m) for l in dn}
             got_tp |= {(l, m) for l in tp}
         assert got_dn == edges_dn and got_tp == edges_tp
+
+
+def test_checkpoint_layout_round_trip(tmp_path):
+    """fuse_llama_layer / unfuse_llama_layer are exact inverses, and save_checkpoint writes the sharded HF layout
+    (pytorch_model-XXXXX-of-YYYYY.bin + pytorch_model.bin.index.json, reference parameter names) the reference's
+    trainer produces (train.py:88-98) -- read back bit-identically by load_checkpoint."""
+    import json
+    import torch
+    from gpt4roi_b200 import train
+    g = torch.Generator().manual_seed(0)
+    H, Fd = 16, 40
+    sd = {}
+    for i in range(2):
+        q = 'model.layers.%d.' % i
+        for n in 'qkvo':
+            sd[q + 'self_attn.%s_proj.weight' % n] = torch.randn(H, H, generator=g)
+        sd[q + 'mlp.gate_proj.weight'] = torch.randn(Fd, H, generator=g)
+        sd[q + 'mlp.up_proj.weight'] = torch.randn(Fd, H, generator=g)
+        sd[q + 'mlp.down_proj.weight'] = torch.randn(H, Fd, generator=g)
+        sd[q + 'input_layernorm.weight'] = torch.randn(H, generator=g)
+        sd[q + 'post_attention_layernorm.weight'] = torch.randn(H, generator=g)
+    back = {}
+    for i in range(2):
+        fused = train.fuse_llama_layer(sd, i)
+        assert fused['wqkv'].shape == (3 * H, H) and fused['wgu'].shape == (2 * Fd, H)
+        assert torch.equal(fused['wgu'][0::2], sd['model.layers.%d.mlp.gate_proj.weight' % i])
+        back.update(train.unfuse_llama_layer(fused, i))
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    sd['lm_head.weight'] = torch.randn(50, H, generator=g)
+    names = train.save_checkpoint(sd, str(tmp_path), max_shard_bytes=6000)
+    assert len(names) > 1 and all(n.startswith('pytorch_model-') and n.endswith('-of-%05d.bin' % len(names)) for n in names)
+    index = json.load(open(tmp_path / 'pytorch_model.bin.index.json'))
+    assert set(index['weight_map']) == set(sd) and index['metadata']['total_size'] == sum(v.numel() * 4 for v in sd.values())
+    loaded = train.load_checkpoint(str(tmp_path))
+    assert set(loaded) == set(sd) and all(torch.equal(loaded[k], sd[k]) for k in sd)
+
+
+def test_llama_train_stack_state_dict_round_trip_on_cpu():
+    """Construction and checkpoint export of the training stack are pure tensor plumbing (no kernel runs):
+    state_dict() returns exactly the reference-named fp32 weights it was built from."""
+    import torch
+    from gpt4roi_b200.engine import EngineConfig
+    from gpt4roi_b200.train import LlamaTrainStack
+    cfg = EngineConfig(hidden=256, n_heads=2, n_layers=2, mlp=96, vocab=120)
+    g = torch.Generator().manual_seed(1)
+    sd = {'model.norm.weight': torch.randn(256, generator=g), 'lm_head.weight': torch.randn(120, 256, generator=g)}
+    for i in range(2):
+        q = 'model.layers.%d.' % i
+        for n in 'qkvo':
+            sd[q + 'self_attn.%s_proj.weight' % n] = torch.randn(256, 256, generator=g)
+        sd[q + 'mlp.gate_proj.weight'] = torch.randn(96, 256, generator=g)
+        sd[q + 'mlp.up_proj.weight'] = torch.randn(96, 256, generator=g)
+        sd[q + 'mlp.down_proj.weight'] = torch.randn(256, 96, generator=g)
+        sd[q + 'input_layernorm.weight'] = torch.randn(256, generator=g)
+        sd[q + 'post_attention_layernorm.weight'] = torch.randn(256, generator=g)
+    stack = LlamaTrainStack(cfg, sd, 'cpu')
+    out = stack.state_dict()
+    assert set(out) == set(sd) and all(torch.equal(out[k], sd[k]) for k in sd)
+    assert stack.w[0]['wqkv'].dtype == torch.bfloat16 and stack.w[0]['wqkv'].shape == (768, 256)
