@@ -947,6 +947,40 @@ extern "C" int g4r_pos_embed_mlp_bwd(const float* boxes, const void* w0, const v
   return G4R_OK;
 }
 
+// out = relu(z * scale[b, c] + shift[b, c]) on an NHWC bf16 map: applies a pending GroupNorm affine + ReLU
+// (mmcv ConvModule's norm + activation, conv_module.py:196-208) where a caller needs the activated map itself
+// (MLVLFuseModule.forward returns it, gpt4roi/models/layers.py:182-195; inside the engine the affine stays
+// folded into the consumer's taps instead).  8 channels (16 bytes) per thread.
+__global__ void __launch_bounds__(256)
+affine_relu_nhwc(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                 __nv_bfloat16* __restrict__ out, long long pix_per_img, int C, long long total_vec) {
+  const int nvec = C >> 3;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total_vec; i += (long long)gridDim.x * 256) {
+    const int v = (int)(i % nvec);
+    const long long b = (i / nvec) / pix_per_img;
+    float f[8];
+    load16<__nv_bfloat16>(z + i * 8, f);
+    const float* sc = scale + b * C + v * 8;
+    const float* sh = shift + b * C + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+    store16<__nv_bfloat16>(out + i * 8, f);
+  }
+}
+
+extern "C" int g4r_affine_relu_nhwc_bf16(const void* z, const float* scale, const float* shift, void* out, int B,
+                                         long long pix_per_img, int C, void* stream) {
+  G4R_REQUIRE(z && scale && shift && out && B > 0 && pix_per_img > 0 && C > 0 && C % 8 == 0, "affine_relu_nhwc: bad arguments");
+  const long long total = (long long)B * pix_per_img * (C / 8);
+  long long grid = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (grid > cap) grid = cap;
+  affine_relu_nhwc<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, scale, shift, (__nv_bfloat16*)out,
+                                                                    pix_per_img, C, total);
+  G4R_LAUNCH_CHECK("affine_relu_nhwc");
+  return G4R_OK;
+}
+
 extern "C" int g4r_add_bias_pos_cast(const float* acc, int splits, const void* bias, const float* pos, void* out,
                                      int K, int D, void* stream) {
   G4R_REQUIRE(acc && bias && pos && out && K > 0 && D > 0 && splits >= 1, "add_bias_pos_cast: bad arguments");

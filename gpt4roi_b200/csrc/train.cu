@@ -303,21 +303,92 @@ swiglu_bwd(const __nv_bfloat16* __restrict__ gu, long long ldg, const __nv_bfloa
 // AdamW (torch.optim.AdamW, the HF Trainer default `adamw_torch`): fp32 master weights and moments, gradient
 // bf16 or fp32, optional bf16 copy of the updated weight for the next forward.  bias corrections on the host.
 // ------------------------------------------------------------------------------------------
+// 4 elements per thread-iteration (16-byte p/m/v accesses, 8/16-byte gradient loads); `n4` = n / 4 vectors, the
+// (< 4) tail elements are handled by the scalar epilogue of the last CTA.  scale_dev (optional) is a device
+// float multiplied into the gradient scale: the global-norm clip coefficient written by grad_clip_coef, so
+// that clipping needs no host synchronisation (HF Trainer: clip_grad_norm_(max_grad_norm=1.0) before step()).
 template <typename TG>
 __global__ void __launch_bounds__(256)
 adamw_step(float* __restrict__ p, const TG* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
            __nv_bfloat16* __restrict__ p16, long long n, float lr, float b1, float b2, float eps, float wd,
-           float bc1, float bc2_sqrt, float gscale) {
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    float gi;
-    if constexpr (sizeof(TG) == 2) gi = __bfloat162float(g[i]) * gscale; else gi = (float)g[i] * gscale;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= (lr / bc1) * (mi / denom);
-    p[i] = pi; m[i] = mi; v[i] = vi;
-    if (p16) p16[i] = __float2bfloat16_rn(pi);
+           float bc1, float bc2_sqrt, float gscale, const float* __restrict__ scale_dev) {
+  if (scale_dev) gscale *= scale_dev[0];
+  const float decay = 1.f - lr * wd, step = lr / bc1, ib2 = 1.f / bc2_sqrt;
+  auto upd = [&](float& pi, float& mi, float& vi, float gi) {
+    gi *= gscale;
+    pi *= decay;
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    pi -= step * (mi / (sqrtf(vi) * ib2 + eps));
+  };
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    float g4[4];
+    if constexpr (sizeof(TG) == 2) {
+      const uint2 raw = reinterpret_cast<const uint2*>(g)[i];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+      g4[0] = a.x; g4[1] = a.y; g4[2] = b.x; g4[3] = b.y;
+    } else {
+      const float4 G = reinterpret_cast<const float4*>(g)[i];
+      g4[0] = G.x; g4[1] = G.y; g4[2] = G.z; g4[3] = G.w;
+    }
+    upd(P.x, M.x, V.x, g4[0]); upd(P.y, M.y, V.y, g4[1]); upd(P.z, M.z, V.z, g4[2]); upd(P.w, M.w, V.w, g4[3]);
+    reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V;
+    if (p16) {
+      uint2 o;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+      h[0] = __floats2bfloat162_rn(P.x, P.y); h[1] = __floats2bfloat162_rn(P.z, P.w);
+      reinterpret_cast<uint2*>(p16)[i] = o;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1) {
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += 256) {
+      float gi;
+      if constexpr (sizeof(TG) == 2) gi = __bfloat162float(g[i]); else gi = (float)g[i];
+      float pi = p[i], mi = m[i], vi = v[i];
+      upd(pi, mi, vi, gi);
+      p[i] = pi; m[i] = mi; v[i] = vi;
+      if (p16) p16[i] = __float2bfloat16_rn(pi);
+    }
+  }
+}
+
+// Sum of squares of one gradient tensor as kSumsqSlabs per-CTA partials (fixed order: bitwise reproducible).
+constexpr int kSumsqSlabs = 296;
+template <typename TG>
+__global__ void __launch_bounds__(256)
+sumsq_partial(const TG* __restrict__ g, long long n, float* __restrict__ slab) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  constexpr int V = 16 / (int)sizeof(TG);
+  const bool aligned = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  const long long nv = aligned ? n / V : 0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nv; i += (long long)gridDim.x * 256) {
+    float f[V];
+    load16<TG>(g + i * V, f);
+#pragma unroll
+    for (int j = 0; j < V; j++) acc += f[j] * f[j];
+  }
+  if (blockIdx.x == 0)
+    for (long long i = nv * V + threadIdx.x; i < n; i += 256) { const float x = to_f32<TG>(g[i]); acc += x * x; }
+  const float t = block_sum_256(acc, red);
+  if (threadIdx.x == 0) slab[blockIdx.x] = t;
+}
+
+// total norm and clip coefficient of torch.nn.utils.clip_grad_norm_ (norm_type 2): out[0] = ||g|| * pre_scale,
+// out[1] = min(1, max_norm / (out[0] + 1e-6)) (1 when max_norm <= 0).  One CTA, fixed summation order.
+__global__ void __launch_bounds__(256)
+grad_clip_coef(const float* __restrict__ slabs, long long n, float pre_scale, float max_norm, float* __restrict__ out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) acc += slabs[i];
+  const float t = block_sum_256(acc, red);
+  if (threadIdx.x == 0) {
+    const float norm = sqrtf(t) * pre_scale;
+    out[0] = norm;
+    out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
   }
 }
 
@@ -663,19 +734,54 @@ extern "C" int g4r_swiglu_bwd_bf16(const void* gu, long long ldg, const void* df
   return G4R_OK;
 }
 
-extern "C" int g4r_adamw_step(float* p, const void* g, int g_bf16, float* m, float* v, void* p_bf16, long long n,
-                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                              float grad_scale, void* stream) {
+static int adamw_launch(float* p, const void* g, int g_bf16, float* m, float* v, void* p_bf16, long long n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                        float grad_scale, const float* scale_dev, void* stream) {
   G4R_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
+  G4R_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0 &&
+              ((uintptr_t)g & (g_bf16 ? 7 : 15)) == 0 && ((uintptr_t)p_bf16 & 7) == 0,
+              "adamw: tensors must be 16-byte aligned (8 for the bf16 ones)");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for((n + 3) / 4);
   if (g_bf16)
-    adamw_step<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(p, (const __nv_bfloat16*)g, m, v, (__nv_bfloat16*)p_bf16, n, lr,
-                                                            beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale);
+    adamw_step<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (const __nv_bfloat16*)g, m, v, (__nv_bfloat16*)p_bf16, n, lr,
+                                                     beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale, scale_dev);
   else
-    adamw_step<float><<<grid_for(n), 256, 0, st>>>(p, (const float*)g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2,
-                                                   eps, weight_decay, bc1, bc2s, grad_scale);
+    adamw_step<float><<<grid, 256, 0, st>>>(p, (const float*)g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2,
+                                            eps, weight_decay, bc1, bc2s, grad_scale, scale_dev);
   G4R_LAUNCH_CHECK("adamw_step");
+  return G4R_OK;
+}
+
+extern "C" int g4r_adamw_step(float* p, const void* g, int g_bf16, float* m, float* v, void* p_bf16, long long n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                              float grad_scale, void* stream) {
+  return adamw_launch(p, g, g_bf16, m, v, p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, nullptr, stream);
+}
+
+extern "C" int g4r_adamw_step_ex(float* p, const void* g, int g_bf16, float* m, float* v, void* p_bf16, long long n,
+                                 float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                 float grad_scale, const float* scale_dev, void* stream) {
+  return adamw_launch(p, g, g_bf16, m, v, p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, scale_dev, stream);
+}
+
+extern "C" int g4r_sumsq_slabs(void) { return kSumsqSlabs; }
+
+extern "C" int g4r_sumsq(const void* g, int g_bf16, long long n, float* slab, void* stream) {
+  G4R_REQUIRE(g && slab && n > 0, "sumsq: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_bf16) sumsq_partial<__nv_bfloat16><<<kSumsqSlabs, 256, 0, st>>>((const __nv_bfloat16*)g, n, slab);
+  else sumsq_partial<float><<<kSumsqSlabs, 256, 0, st>>>((const float*)g, n, slab);
+  G4R_LAUNCH_CHECK("sumsq_partial");
+  return G4R_OK;
+}
+
+extern "C" int g4r_grad_clip_coef(const float* slabs, long long n_slabs, float pre_scale, float max_norm, float* out2,
+                                  void* stream) {
+  G4R_REQUIRE(slabs && out2 && n_slabs > 0, "grad_clip_coef: bad arguments");
+  grad_clip_coef<<<1, 256, 0, (cudaStream_t)stream>>>(slabs, n_slabs, pre_scale, max_norm, out2);
+  G4R_LAUNCH_CHECK("grad_clip_coef");
   return G4R_OK;
 }

@@ -92,7 +92,7 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     return out.reshape(*x.shape[:-1], n_out) if out.is_contiguous() else out
 
 
-def matmul_t(a, b, a_mn=False, b_mn=False, out_dtype=torch.bfloat16):
+def matmul_t(a, b, a_mn=False, b_mn=False, out_dtype=torch.bfloat16, out=None):
     """D[M,N] = op(a) @ op(b).T on the tensor cores with the transposes folded into the operand descriptors.
     a: [M,K] (a_mn=False) or stored [K,M] (a_mn=True); b: [N,K] (b_mn=False) or stored [K,N] (b_mn=True).
     Linear backward:  grad_x = matmul_t(grad_y, W, b_mn=True);  grad_W = matmul_t(grad_y, x, a_mn=True, b_mn=True)."""
@@ -105,7 +105,10 @@ def matmul_t(a, b, a_mn=False, b_mn=False, out_dtype=torch.bfloat16):
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
     if K != Kb:
         raise RuntimeError('matmul_t: contraction mismatch %d vs %d' % (K, Kb))
-    out = torch.empty((M, N), dtype=out_dtype, device=dev)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=dev)
+    elif tuple(out.shape) != (M, N) or out.dtype != out_dtype or out.stride(1) != 1:
+        raise RuntimeError('matmul_t: `out` must be [%d,%d] %s with unit inner stride' % (M, N, out_dtype))
     with torch.cuda.device(dev):
         _ps = _prof_begin(dev)
         _L.check(_L.load().g4r_gemm_bf16_t(_L.ptr(a), a.stride(0), int(a_mn), _L.ptr(b), b.stride(0), int(b_mn),

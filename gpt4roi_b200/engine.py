@@ -55,12 +55,18 @@ def _b(t, dev):
 class PrefillEngine:
     """Holds re-laid-out weights on one GPU and runs the fused forward."""
 
-    def __init__(self, cfg, llm_sd, vit_sd, device):
+    def __init__(self, cfg, llm_sd, vit_sd, device, parts=('vit', 'spi', 'llm')):
+        """parts: which weight groups to prepare -- ('spi',) builds an SPI-module-only engine (the model-seam
+        mirrors of MLVLROIQueryModule / MLVLFuseModule / MlvlRoIExtractor run on it)."""
         self.cfg = cfg
         self.dev = torch.device(device)
-        self._prepare_vit(vit_sd)
-        self._prepare_spi(llm_sd)
-        self._prepare_llm(llm_sd)
+        self.parts = tuple(parts)
+        if 'vit' in self.parts:
+            self._prepare_vit(vit_sd)
+        if 'spi' in self.parts:
+            self._prepare_spi(llm_sd)
+        if 'llm' in self.parts:
+            self._prepare_llm(llm_sd)
         self._rope_cache = {}
 
     # ------------------------------------------------------------------ weight preparation
@@ -118,7 +124,8 @@ class PrefillEngine:
         self.pos = [_b(sd[q + 'pos_embedd.%s' % n], dev) for n in
                     ('0.weight', '0.bias', '2.weight', '2.bias', '3.weight', '3.bias', '5.weight', '5.bias')]
         self.up_w, self.up_b = _b(sd[q + 'updims.weight'], dev), _b(sd[q + 'updims.bias'], dev)
-        self.proj_w, self.proj_b = _b(sd['model.mm_projector.weight'], dev), _b(sd['model.mm_projector.bias'], dev)
+        if 'model.mm_projector.weight' in sd:
+            self.proj_w, self.proj_b = _b(sd['model.mm_projector.weight'], dev), _b(sd['model.mm_projector.bias'], dev)
         kb = self.flat_w.shape[1] // 64
         self.flat_splits = next(s for s in (16, 14, 8, 7, 4, 2, 1) if kb % s == 0)
 
@@ -138,7 +145,7 @@ class PrefillEngine:
                 wdown=_b(sd[q + 'mlp.down_proj.weight'], dev)))
             del g, u
         self.norm_w = _b(sd['model.norm.weight'], dev)
-        self.lm_head = _b(sd['lm_head.weight'], dev)
+        self.lm_head = _b(sd['lm_head.weight'], dev) if 'lm_head.weight' in sd else None   # LlamaModel-only seam
         self.vocab_pad = (c.vocab + 63) // 64 * 64
 
     def _rope(self, L):
@@ -179,16 +186,23 @@ class PrefillEngine:
                 taps[i + 1] = x.view(B, T, c.vit_hidden)
         return taps
 
-    def fuse_maps(self, taps):
+    def fuse_maps(self, taps, has_cls=True, pre_upsampled=False):
         """MLVLROIQueryModule upsampling + MLVLFuseModule: returns the last round's raw conv outputs
-        (bf16 NHWC) and the per-(image,channel) GroupNorm scale/shift still to be applied."""
+        (bf16 NHWC) and the per-(image,channel) GroupNorm scale/shift still to be applied.
+        taps: {layer: [B, 1+P, C]} ViT hidden states (CLS first), or with has_cls=False a list / dict of
+        [B, P, C] token maps in level order (what MLVLROIQueryModule.forward receives, layers.py:218-224).
+        pre_upsampled: the level-l entry already has the pyramid size [B, H_l*H_l, C] (MLVLFuseModule.forward's
+        input, layers.py:182): the resampling step degenerates to the identity and only appends the coordinates."""
         c = self.cfg
         C = c.spi_dim
+        if isinstance(taps, (list, tuple)):
+            taps = {layer: t for layer, t in zip(c.level_layers, taps)}
         B = next(iter(taps.values())).shape[0]
         maps = []
         for l, layer in enumerate(c.level_layers):
             H = c.level_sizes[l]
-            up = kernels.upsample_tokens_coords(taps[layer], c.grid, H, self.spi_cpad)
+            up = kernels.upsample_tokens_coords(taps[layer], H if pre_upsampled else c.grid, H, self.spi_cpad,
+                                                has_cls=has_cls)
             m = dense.linear(up.view(-1, self.spi_cpad), self.in_w[l], self.in_b[l]).view(B, H, H, C)
             maps.append(m)
         ss = [None] * c.num_levels
@@ -213,8 +227,10 @@ class PrefillEngine:
         K = boxes.shape[0]
         rois = torch.cat([batch_idx[:, None], boxes * float(c.image_size)], 1).contiguous()  # layers.py:294-302
         scales = [float(torch.tensor(1.0 / s, dtype=torch.float32)) for s in c.strides]
+        # ss=None: the maps are already activated (MlvlRoIExtractor.forward called on its own)
         feats = roi_align_mlvl(maps, rois, c.roi_out, scales, c.roi_sampling, True, out_dtype=BF16,
-                               gn_scale=[s for s, _ in ss], gn_shift=[b for _, b in ss])
+                               gn_scale=None if ss is None else [s for s, _ in ss],
+                               gn_shift=None if ss is None else [b for _, b in ss])
         R = c.roi_out
         pc = dense.conv_nhwc(feats.view(c.num_levels * K, R, R, c.spi_dim), self.pconv_w, self.pconv_b,
                              act='relu', levels=c.num_levels)
@@ -224,7 +240,10 @@ class PrefillEngine:
         t = kernels.add_bias_pos_cast(acc, self.flat_b, pos)
         return dense.linear(t, self.up_w, self.up_b)
 
-    def llama(self, embeds, B, L, last_only=False, seqlens=None, cache=None):
+    def llama(self, embeds, B, L, last_only=False, seqlens=None, cache=None, hidden_taps=None, want='logits'):
+        """hidden_taps: optional dict {n: None}; filled with a copy of the residual stream after decoder layer n
+        (1-based; the parity tests record error growth with depth).  want='hidden' returns the final-norm
+        hidden states [B, L, hidden] instead of logits (LlamaModel.forward's last_hidden_state)."""
         c = self.cfg
         x = embeds.view(B * L, c.hidden)
         cos, sin = self._rope(L)
@@ -243,9 +262,15 @@ class PrefillEngine:
             h = kernels.rmsnorm(x, w['ln_post'], c.rms_eps)
             f = dense.linear(h, w['wgu'], act='swiglu')
             x = dense.linear(f, w['wdown'], residual=x)
+            if hidden_taps is not None and (li + 1) in hidden_taps:
+                hidden_taps[li + 1] = x.view(B, L, c.hidden).clone()
         if last_only:
             x = x.view(B, L, c.hidden)[:, -1].contiguous()
         x = kernels.rmsnorm(x, self.norm_w, c.rms_eps)
+        if want == 'hidden':
+            return x.view(B, -1, c.hidden)
+        if self.lm_head is None:
+            raise RuntimeError('this engine was built without lm_head.weight (LlamaModel seam): use want="hidden"')
         rows = x.shape[0]
         # padded row stride keeps the epilogue's 128-bit stores aligned (vocab 32006 is not a multiple of 8)
         buf = torch.empty((rows, self.vocab_pad), dtype=BF16, device=self.dev)
@@ -270,10 +295,20 @@ class PrefillEngine:
             bidx = torch.zeros((0,), dtype=torch.float32, device=self.dev)
         return dict(K=K, boxes=boxes, bidx=bidx, offs=offs)
 
-    def forward_device(self, input_ids, images, plan, validate=True, last_only=False, seqlens=None, cache=None):
-        """Device-only forward (capturable): input_ids int64 [B,L], images bf16 [B,3,S,S] on the GPU."""
+    def forward_device(self, input_ids, images, plan, validate=True, last_only=False, seqlens=None, cache=None,
+                       hidden_taps=None, want='logits', stage_taps=None):
+        """Device-only forward (capturable): input_ids int64 [B,L], images bf16 [B,3,S,S] on the GPU.
+        images=None: text-only forward (spi_llava.py:47-48 skips the vision branch when no image is given).
+        stage_taps: optional dict filled with 'vit_taps', 'region', 'embeds' (parity tests)."""
         c = self.cfg
         B, L = input_ids.shape
+        if images is None:
+            embeds = splice_region_tokens(input_ids, self.embed, None, None, 0, c.im_patch_token, c.im_start_token,
+                                          c.im_end_token, c.bbox_token, validate=False)
+            if cache is not None:
+                cache.length = L
+            return self.llama(embeds, B, L, last_only=last_only, seqlens=seqlens, cache=cache,
+                              hidden_taps=hidden_taps, want=want)
         taps = self.vit(images)
         feat = kernels.cast_tokens_f32_bf16(taps[c.select_index])  # spi_llava.py:68-73 (+ autocast cast, CLS dropped)
         img_rows = dense.linear(feat, self.proj_w, self.proj_b).view(B, c.num_patches, c.hidden)
@@ -287,11 +322,17 @@ class PrefillEngine:
             region = (rows, plan['offs'])
         embeds = splice_region_tokens(input_ids, self.embed, img_rows, region, c.num_patches, c.im_patch_token,
                                       c.im_start_token, c.im_end_token, c.bbox_token, validate=validate)
+        if stage_taps is not None:
+            stage_taps['vit_taps'] = [taps[l][:, 1:] for l in c.level_layers]
+            stage_taps['region'] = region[0] if (region is not None and plan['K'] > 0) else None
+            stage_taps['embeds'] = embeds
         if cache is not None:
             cache.length = L
-        return self.llama(embeds, B, L, last_only=last_only, seqlens=seqlens, cache=cache)
+        return self.llama(embeds, B, L, last_only=last_only, seqlens=seqlens, cache=cache, hidden_taps=hidden_taps,
+                          want=want)
 
-    def forward(self, input_ids, images, bboxes, validate=True, last_only=False, attention_mask=None):
+    def forward(self, input_ids, images, bboxes, validate=True, last_only=False, attention_mask=None,
+                hidden_taps=None, want='logits', stage_taps=None, cache=None):
         """Public entry: input_ids int64 [B,L]; images [B,3,S,S]; bboxes list (len B) of [K_i,4]
         normalised xyxy or None (host or device tensors).  Returns logits [B,L,V] (bf16) -- [B,1,V]
         with last_only.  attention_mask: None / all-ones, or a RIGHT-padded 0/1 mask [B,L] (the collator's
@@ -305,7 +346,9 @@ class PrefillEngine:
                 raise NotImplementedError('only right-padded attention masks are supported')
             seqlens = lens.to(torch.int32).contiguous()
         return self.forward_device(input_ids.to(self.dev, non_blocking=True),
-                                   images.to(self.dev, BF16, non_blocking=True), plan, validate, last_only, seqlens)
+                                   None if images is None else images.to(self.dev, BF16, non_blocking=True),
+                                   plan, validate, last_only, seqlens, cache=cache, hidden_taps=hidden_taps, want=want,
+                                   stage_taps=stage_taps)
 
 
 class KVCache:

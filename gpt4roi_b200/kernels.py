@@ -101,14 +101,18 @@ def vit_embed(patch, cls, pos, B, P):
     return out
 
 
-def upsample_tokens_coords(hidden, G, Ho, cpad):
-    """hidden: [B, 1+G*G, C] ViT hidden state, bf16 or fp32 (CLS first); returns bf16 NHWC [B,Ho,Ho,cpad]."""
+def upsample_tokens_coords(hidden, G, Ho, cpad, has_cls=True):
+    """hidden: [B, 1+G*G, C] ViT hidden state, bf16 or fp32 (CLS first; has_cls=False: [B, G*G, C]);
+    returns bf16 NHWC [B,Ho,Ho,cpad]."""
     B, T, C = hidden.shape
-    assert T == G * G + 1 and hidden.is_contiguous()
+    skip = 1 if has_cls else 0
+    if T != G * G + skip or not hidden.is_contiguous() or hidden.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError('upsample_tokens_coords: contiguous bf16/fp32 [B,%d,C] tokens required, got %s %s'
+                           % (G * G + skip, tuple(hidden.shape), hidden.dtype))
     out = torch.empty((B, Ho, Ho, cpad), dtype=torch.bfloat16, device=hidden.device)
     import ctypes
     f32 = hidden.dtype == torch.float32
-    tok = ctypes.c_void_p(hidden.data_ptr() + C * (4 if f32 else 2))  # skip CLS
+    tok = ctypes.c_void_p(hidden.data_ptr() + skip * C * (4 if f32 else 2))  # skip CLS
     _call('g4r_upsample_tokens_coords_f32' if f32 else 'g4r_upsample_tokens_coords_bf16', hidden.device, tok, C,
           T * C, _L.ptr(out), B, G, Ho, C, cpad)
     return out
@@ -137,6 +141,15 @@ def gn_finalize(stats, gamma, beta, count, eps=1e-5):
     _call('g4r_gn_finalize', stats.device, _L.ptr(stats), _L.ptr(gamma), _L.ptr(beta), _L.ptr(scale),
           _L.ptr(shift), B, C, groups, slots, float(count), float(eps))
     return scale, shift
+
+
+def affine_relu_nhwc(z, scale, shift):
+    """z bf16 NHWC [B,H,W,C], scale/shift fp32 [B,C] (gn_finalize) -> relu(z*scale+shift) bf16 NHWC."""
+    _bf16(z)
+    B, H, W, C = z.shape
+    out = torch.empty_like(z)
+    _call('g4r_affine_relu_nhwc_bf16', z.device, _L.ptr(z), _L.ptr(scale), _L.ptr(shift), _L.ptr(out), B, H * W, C)
+    return out
 
 
 def pos_embed_mlp(boxes, w0, b0, g2, be2, w3, b3, g5, be5, eps=1e-5):

@@ -79,6 +79,11 @@ SIGNATURES = {
     'g4r_pos_embed_mlp_bwd': (_i, [_vp] * 9 + [_ll, _vp, _vp, _i, _f, _vp]),
     'g4r_relu_bwd_bf16': (_i, [_vp, _vp, _vp, _ll, _vp]),
     'g4r_adamw_step': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    'g4r_adamw_step_ex': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
+    'g4r_sumsq_slabs': (_i, []),
+    'g4r_sumsq': (_i, [_vp, _i, _ll, _vp, _vp]),
+    'g4r_grad_clip_coef': (_i, [_vp, _ll, _f, _f, _vp, _vp]),
+    'g4r_affine_relu_nhwc_bf16': (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
     'g4r_add_bias_pos_cast': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
 }
 

@@ -91,8 +91,10 @@ def splice_backward(plan, d_out, num_patches, n_regions, vocab, want_embed_grad=
     dev = d_out.device
     P, K = int(num_patches), int(n_regions)
     d_out = d_out.contiguous()
-    d_image = torch.empty((B, P, D), dtype=d_out.dtype, device=dev) if P > 0 else None
-    d_region = torch.empty((K, D), dtype=d_out.dtype, device=dev) if K > 0 else None
+    # zero-filled: the kernel writes only rows the plan tags as image / region rows -- a text-only sample
+    # (spi_llava.py:104-111) leaves its d_image rows, a sample whose boxes are unused its d_region rows, untouched
+    d_image = torch.zeros((B, P, D), dtype=d_out.dtype, device=dev) if P > 0 else None
+    d_region = torch.zeros((K, D), dtype=d_out.dtype, device=dev) if K > 0 else None
     with torch.cuda.device(dev):
         _L.check(_L.load().g4r_splice_backward(_L.ptr(plan), _L.ptr(d_out), _L.ptr(d_image), _L.ptr(d_region),
                                                B, L, P, D, _L.stream_ptr(dev)))

@@ -58,16 +58,26 @@ def unfuse_llama_layer(layer, i):
             q + 'post_attention_layernorm.weight': layer['ln_post']}
 
 
-def save_checkpoint(state_dict, out_dir, max_shard_bytes=10 * 1024 ** 3, dtype=None):
+def save_checkpoint(state_dict, out_dir, max_shard_bytes=10 * 1024 ** 3, dtype=None, config=None, rank=None):
     """Write `state_dict` (reference parameter names) the way the reference's trainer does
-    (train.py:88-98 -> Trainer._save -> save_pretrained): `pytorch_model-XXXXX-of-YYYYY.bin` shards plus
-    `pytorch_model.bin.index.json`, loadable by SPILlavaMPTForCausalLM.from_pretrained.  Returns the shard file names."""
+    (train.py:88-98 -> Trainer._save -> save_pretrained): `pytorch_model-XXXXX-of-YYYYY.bin` shards,
+    `pytorch_model.bin.index.json` and -- when `config` (a transformers config or a dict) is given -- `config.json`,
+    so that SPILlavaMPTForCausalLM.from_pretrained(out_dir) loads it.  Only rank 0 writes (`rank` defaults to
+    torch.distributed's rank, or 0); other ranks return [].  Resume needs the fp32 weights: pass dtype=None.
+    Returns the shard file names."""
     import json
     import os
+    if rank is None:
+        import torch.distributed as dist
+        rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+    if rank != 0:
+        return []
     os.makedirs(out_dir, exist_ok=True)
     shards, cur, cur_bytes = [], {}, 0
     for k, v in state_dict.items():
         t = v.detach().to('cpu', dtype if dtype is not None else v.dtype).contiguous()
+        if t.untyped_storage().nbytes() != t.numel() * t.element_size():
+            t = t.clone()                 # a view of a larger (fused) storage: torch.save would write all of it
         nbytes = t.numel() * t.element_size()
         if cur and cur_bytes + nbytes > max_shard_bytes:
             shards.append(cur)
@@ -85,6 +95,12 @@ def save_checkpoint(state_dict, out_dir, max_shard_bytes=10 * 1024 ** 3, dtype=N
             total += t.numel() * t.element_size()
     with open(os.path.join(out_dir, 'pytorch_model.bin.index.json'), 'w') as f:
         json.dump({'metadata': {'total_size': total}, 'weight_map': weight_map}, f, indent=2, sort_keys=True)
+    if config is not None:
+        if hasattr(config, 'save_pretrained'):
+            config.save_pretrained(out_dir)
+        else:
+            with open(os.path.join(out_dir, 'config.json'), 'w') as f:
+                json.dump(dict(config), f, indent=2, sort_keys=True)
     return names
 
 
@@ -100,37 +116,99 @@ def load_checkpoint(ckpt_dir):
     return out
 
 
-class LlamaTrainStack:
-    """LLaMA decoder stack with explicit forward / backward / AdamW on the sm_100a kernels."""
+def lr_lambda(step, total_steps, warmup_steps, kind='cosine'):
+    """Multiplier of the base learning rate at optimizer step `step` (0-based), exactly transformers'
+    get_cosine_schedule_with_warmup / get_linear_schedule_with_warmup / constant (the reference runs
+    `--lr_scheduler_type cosine --warmup_ratio 0.003 [--warmup_steps 3000]`, train_stage1.sh:31-32,
+    train_stage2.sh:47-53; HF: warmup_steps wins over warmup_ratio when > 0)."""
+    import math
+    if kind == 'constant' or total_steps is None:
+        return 1.0
+    if step < warmup_steps:
+        return float(step) / float(max(1, warmup_steps))
+    prog = float(step - warmup_steps) / float(max(1, total_steps - warmup_steps))
+    if kind == 'linear':
+        return max(0.0, 1.0 - prog)
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 
-    def __init__(self, cfg, state_dict, device, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+
+def warmup_steps_for(total_steps, warmup_steps=0, warmup_ratio=0.0):
+    """transformers.TrainingArguments.get_warmup_steps."""
+    import math
+    return warmup_steps if warmup_steps > 0 else math.ceil(total_steps * warmup_ratio)
+
+
+MATRIX_KEYS = ('wqkv', 'wo', 'wgu', 'wdown')      # bf16 gradients: one flat bucket per layer, in this order
+NORM_KEYS = ('ln_in', 'ln_post')                  # fp32 gradients [hidden]: one [n_layers, 2, hidden] buffer
+
+
+class LlamaTrainStack:
+    """LLaMA decoder stack with explicit forward / backward / AdamW on the sm_100a kernels.
+
+    own_optimizer=False: no fp32 masters / moments are allocated -- the bf16 weights are refreshed from an external
+    state dict (`load_weights`, the model-seam path where torch.optim owns the parameters).
+    train_layers / train_head=False (stage 1, ONLY_SPI=1, train.py:685-696): the backward computes only the
+    activation gradients (no weight-gradient GEMMs) and the optimizer skips those tensors."""
+
+    def __init__(self, cfg, state_dict, device, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 own_optimizer=True, train_layers=True, train_head=True):
         """cfg: engine.EngineConfig; state_dict: HF names (model.layers.N..., model.norm.weight, lm_head.weight).
         weight_decay follows llava_trainer.py:59-144: decay on matrices, none on norm weights."""
         self.cfg, self.dev = cfg, torch.device(device)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.train_layers, self.train_head = train_layers, train_head
         self.step_count = 0
         if cfg.head_dim != 128:
             raise ValueError('LlamaTrainStack: head_dim 128 required (fused-RoPE QKV GEMM)')
+        self.own_layers = own_optimizer and train_layers
+        self.own_head = own_optimizer and train_head
         f32 = lambda t: t.detach().to(self.dev, F32).contiguous()
-        self.master = [fuse_llama_layer(state_dict, i, self.dev) for i in range(cfg.n_layers)]   # fp32 masters
-        self.master_top = dict(norm=f32(state_dict['model.norm.weight']), lm_head=f32(state_dict['lm_head.weight']))
-        self.w = [{k: v.to(BF16) for k, v in m.items()} for m in self.master]      # bf16 compute copies
-        self.w_top = {k: v.to(BF16) for k, v in self.master_top.items()}
         zeros = lambda t: torch.zeros_like(t)
-        self.m1 = [{k: zeros(v) for k, v in m.items()} for m in self.master]
-        self.m2 = [{k: zeros(v) for k, v in m.items()} for m in self.master]
-        self.m1_top = {k: zeros(v) for k, v in self.master_top.items()}
-        self.m2_top = {k: zeros(v) for k, v in self.master_top.items()}
+        if self.own_layers:
+            self.master = [fuse_llama_layer(state_dict, i, self.dev) for i in range(cfg.n_layers)]   # fp32 masters
+            self.w = [{k: v.to(BF16) for k, v in m.items()} for m in self.master]      # bf16 compute copies
+            self.m1 = [{k: zeros(v) for k, v in m.items()} for m in self.master]
+            self.m2 = [{k: zeros(v) for k, v in m.items()} for m in self.master]
+        else:
+            self.master = self.m1 = self.m2 = None
+            self.w = [fuse_llama_layer(state_dict, i, self.dev, BF16) for i in range(cfg.n_layers)]
+        if self.own_head:
+            self.master_top = dict(norm=f32(state_dict['model.norm.weight']), lm_head=f32(state_dict['lm_head.weight']))
+            self.w_top = {k: v.to(BF16) for k, v in self.master_top.items()}
+            self.m1_top = {k: zeros(v) for k, v in self.master_top.items()}
+            self.m2_top = {k: zeros(v) for k, v in self.master_top.items()}
+        else:
+            self.master_top = self.m1_top = self.m2_top = None
+            self.w_top = dict(norm=state_dict['model.norm.weight'].detach().to(self.dev, BF16).contiguous(),
+                              lm_head=state_dict['lm_head.weight'].detach().to(self.dev, BF16).contiguous())
         self._rope_cache = {}
         self.saved = None
         self.grads = None
 
+    def load_weights(self, state_dict):
+        """Refresh the bf16 compute weights in place from a reference-named state dict (any float dtype)."""
+        H = self.cfg.hidden
+        for i, w in enumerate(self.w):
+            q = 'model.layers.%d.' % i
+            for j, n in enumerate('qkv'):
+                w['wqkv'][j * H:(j + 1) * H].copy_(state_dict[q + 'self_attn.%s_proj.weight' % n])
+            w['wo'].copy_(state_dict[q + 'self_attn.o_proj.weight'])
+            w['wgu'][0::2].copy_(state_dict[q + 'mlp.gate_proj.weight'])
+            w['wgu'][1::2].copy_(state_dict[q + 'mlp.up_proj.weight'])
+            w['wdown'].copy_(state_dict[q + 'mlp.down_proj.weight'])
+            w['ln_in'].copy_(state_dict[q + 'input_layernorm.weight'])
+            w['ln_post'].copy_(state_dict[q + 'post_attention_layernorm.weight'])
+        self.w_top['norm'].copy_(state_dict['model.norm.weight'])
+        self.w_top['lm_head'].copy_(state_dict['lm_head.weight'])
+
     def state_dict(self):
-        """fp32 master weights under the reference's parameter names (views of the fused tensors)."""
+        """Weights under the reference's parameter names (views of the fused tensors): the fp32 masters where this
+        object owns the optimizer, else the bf16 compute copies."""
         out = {}
-        for i, m in enumerate(self.master):
+        for i, m in enumerate(self.master if self.master is not None else self.w):
             out.update(unfuse_llama_layer(m, i))
-        out['model.norm.weight'], out['lm_head.weight'] = self.master_top['norm'], self.master_top['lm_head']
+        top = self.master_top if self.master_top is not None else self.w_top
+        out['model.norm.weight'], out['lm_head.weight'] = top['norm'], top['lm_head']
         return out
 
     # ------------------------------------------------------------------ helpers
@@ -144,7 +222,7 @@ class LlamaTrainStack:
         return self._rope_cache[L]
 
     # ------------------------------------------------------------------ forward
-    def forward(self, inputs_embeds, targets):
+    def forward(self, inputs_embeds, targets, seqlens=None):
         """inputs_embeds [B, L, hidden] bf16; targets int64 [B, L]: labels shifted left by one
         (targets[:, t] = labels[:, t+1], targets[:, -1] = -100).  Returns the mean loss (0-d fp32 tensor)."""
         c = self.cfg
@@ -174,10 +252,12 @@ class LlamaTrainStack:
         return loss
 
     # ------------------------------------------------------------------ backward
-    def backward(self, loss_scale=1.0, on_layer_grads=None):
-        """Gradients of loss_scale * loss.  Fills self.grads (bf16 matrices, fp32 norm weights) and returns the
-        gradient w.r.t. inputs_embeds [B, L, hidden] (bf16).  on_layer_grads(i, grads_i) is called as soon as
-        decoder layer i's gradients are complete (DDP bucket hook)."""
+    def backward(self, loss_scale=1.0, on_layer_grads=None, on_top_grads=None):
+        """Gradients of loss_scale * loss.  Fills self.grads and returns the gradient w.r.t. inputs_embeds
+        [B, L, hidden] (bf16).  Per decoder layer the four matrix gradients (bf16) are views of ONE flat buffer
+        (`g['flat']`, the DDP bucket: one collective per layer) and the two norm-weight gradients rows of one
+        fp32 [n_layers, 2, hidden] buffer.  on_top_grads(g_top) fires as soon as the lm_head / final-norm
+        gradients exist (start of the backward), on_layer_grads(i, g) when decoder layer i's are complete."""
         c, s = self.cfg, self.saved
         B, L = s['B'], s['L']
         _, _, nsin = self._rope(L)
@@ -185,87 +265,154 @@ class LlamaTrainStack:
         scale = c.head_dim ** -0.5
         _, _, dlogits = train_ops.cross_entropy(s['logits'], s['targets'], grad_scale=loss_scale, want_grad=True)
         g_top = {}
-        g_top['lm_head'] = dense.matmul_t(dlogits, s['hn'], a_mn=True, b_mn=True)           # dW = dY^T X
-        dhn = dense.matmul_t(dlogits, self.w_top['lm_head'], b_mn=True)                      # dX = dY W
+        if self.train_head:
+            g_top['lm_head'] = dense.matmul_t(dlogits, s['hn'], a_mn=True, b_mn=True)           # dW = dY^T X
+        dhn = dense.matmul_t(dlogits, self.w_top['lm_head'], b_mn=True)                          # dX = dY W
         del dlogits
-        dx, g_top['norm'] = train_ops.rmsnorm_bwd(s['x_last'], self.w_top['norm'], dhn, c.rms_eps)
-        grads = [None] * len(self.w)
-        for i in range(len(self.w) - 1, -1, -1):
+        dx, gn = train_ops.rmsnorm_bwd(s['x_last'], self.w_top['norm'], dhn, c.rms_eps)
+        if self.train_head:
+            g_top['norm'] = gn
+            if on_top_grads is not None:
+                on_top_grads(g_top)
+        nl = len(self.w)
+        grads = [None] * nl
+        norm_g = torch.empty((nl, 2, c.hidden), dtype=F32, device=self.dev) if self.train_layers else None
+        tl = self.train_layers
+        for i in range(nl - 1, -1, -1):
             w, a = self.w[i], s['layers'][i]
             g = {}
+            if tl:
+                shapes = [w[k].shape for k in MATRIX_KEYS]
+                flat = torch.empty(sum(sh.numel() for sh in shapes), dtype=BF16, device=self.dev)
+                o = 0
+                for k, sh in zip(MATRIX_KEYS, shapes):
+                    g[k] = flat[o:o + sh.numel()].view(sh)
+                    o += sh.numel()
+                g['flat'] = flat
             # x_out = x_mid + down(f)
-            g['wdown'] = dense.matmul_t(dx, a['f'], a_mn=True, b_mn=True)
+            if tl:
+                dense.matmul_t(dx, a['f'], a_mn=True, b_mn=True, out=g['wdown'])
             df = dense.matmul_t(dx, w['wdown'], b_mn=True)
             dgu = train_ops.swiglu_bwd(a['gu'], df)
-            g['wgu'] = dense.matmul_t(dgu, a['h2'], a_mn=True, b_mn=True)
+            if tl:
+                dense.matmul_t(dgu, a['h2'], a_mn=True, b_mn=True, out=g['wgu'])
             dh2 = dense.matmul_t(dgu, w['wgu'], b_mn=True)
-            dx_mid, g['ln_post'] = train_ops.rmsnorm_bwd(a['x_mid'], w['ln_post'], dh2, c.rms_eps, dres=dx)
+            dx_mid, gln = train_ops.rmsnorm_bwd(a['x_mid'], w['ln_post'], dh2, c.rms_eps, dres=dx)
+            if tl:
+                norm_g[i, 1].copy_(gln)
+                g['ln_post'] = norm_g[i, 1]
             # x_mid = x_in + o_proj(attn)
-            g['wo'] = dense.matmul_t(dx_mid, a['a'], a_mn=True, b_mn=True)
+            if tl:
+                dense.matmul_t(dx_mid, a['a'], a_mn=True, b_mn=True, out=g['wo'])
             da = dense.matmul_t(dx_mid, w['wo'], b_mn=True)
             dqkv = train_ops.attention_bwd(a['qkv'], a['a'], da, a['lse'], B, L, c.n_heads, c.head_dim, True, scale)
             kernels.rope_inplace(dqkv, cos, nsin, L, 2 * c.n_heads, c.head_dim)             # RoPE^T = RoPE(-theta)
-            g['wqkv'] = dense.matmul_t(dqkv, a['h1'], a_mn=True, b_mn=True)
+            if tl:
+                dense.matmul_t(dqkv, a['h1'], a_mn=True, b_mn=True, out=g['wqkv'])
             dh1 = dense.matmul_t(dqkv, w['wqkv'], b_mn=True)
-            dx, g['ln_in'] = train_ops.rmsnorm_bwd(a['x_in'], w['ln_in'], dh1, c.rms_eps, dres=dx_mid)
+            dx, gln = train_ops.rmsnorm_bwd(a['x_in'], w['ln_in'], dh1, c.rms_eps, dres=dx_mid)
+            if tl:
+                norm_g[i, 0].copy_(gln)
+                g['ln_in'] = norm_g[i, 0]
             grads[i] = g
             s['layers'][i] = None                                                            # free activations
-            if on_layer_grads is not None:
+            if tl and on_layer_grads is not None:
                 on_layer_grads(i, g)
-        self.grads = dict(layers=grads, top=g_top)
+        self.grads = dict(layers=grads, top=g_top, norms=norm_g)
         self.saved = None
         return dx.view(B, L, c.hidden)
 
+    def grad_tensors(self):
+        """Contiguous gradient tensors of this stack (for the global norm): layer flats, the norm buffer, top."""
+        out = []
+        if self.train_layers:
+            out += [g['flat'] for g in self.grads['layers']] + [self.grads['norms']]
+        if self.train_head:
+            out += [self.grads['top']['lm_head'], self.grads['top']['norm']]
+        return out
+
+    def grads_state_dict(self):
+        """Gradients under the reference's parameter names (views; model-seam path)."""
+        out = {}
+        if self.train_layers:
+            for i, g in enumerate(self.grads['layers']):
+                out.update(unfuse_llama_layer(g, i))
+        if self.train_head:
+            out['model.norm.weight'], out['lm_head.weight'] = self.grads['top']['norm'], self.grads['top']['lm_head']
+        return out
+
     # ------------------------------------------------------------------ optimizer
-    def optimizer_step(self, grad_scale=1.0):
-        """Fused AdamW on every tensor (fp32 master + moments, refreshes the bf16 compute copy)."""
+    def optimizer_step(self, grad_scale=1.0, lr=None, scale_dev=None):
+        """Fused AdamW on every trained tensor (fp32 master + moments, refreshes the bf16 compute copy)."""
         self.step_count += 1
         t = self.step_count
+        lr = self.lr if lr is None else lr
 
         def upd(master, m1, m2, w16, grad, name):
             wd = 0.0 if name.startswith('ln') or name == 'norm' else self.wd
-            train_ops.adamw_step(master.view(-1), grad.reshape(-1), m1.view(-1), m2.view(-1), w16.view(-1), self.lr,
-                                 self.betas, self.eps, wd, t, grad_scale)
-        for i, g in enumerate(self.grads['layers']):
-            for k in LAYER_KEYS:
-                upd(self.master[i][k], self.m1[i][k], self.m2[i][k], self.w[i][k], g[k], k)
-        for k in ('norm', 'lm_head'):
-            upd(self.master_top[k], self.m1_top[k], self.m2_top[k], self.w_top[k], self.grads['top'][k], k)
+            train_ops.adamw_step(master.view(-1), grad.reshape(-1), m1.view(-1), m2.view(-1), w16.view(-1), lr,
+                                 self.betas, self.eps, wd, t, grad_scale, scale_dev)
+        if self.own_layers:
+            for i, g in enumerate(self.grads['layers']):
+                for k in LAYER_KEYS:
+                    upd(self.master[i][k], self.m1[i][k], self.m2[i][k], self.w[i][k], g[k], k)
+        if self.own_head:
+            for k in ('norm', 'lm_head'):
+                upd(self.master_top[k], self.m1_top[k], self.m2_top[k], self.w_top[k], self.grads['top'][k], k)
         self.grads = None
 
 
 class LayerBucketAllReduce:
-    """DDP gradient all-reduce, one bucket per decoder layer, launched from the backward hook on a side stream so
-    the collective of layer i overlaps the backward of layers < i (NCCL over NVLink; gloo in the CPU tests).
-    Sums in place; the 1/world average is folded into AdamW's grad_scale."""
+    """DDP gradient all-reduce (NCCL over NVLink; gloo in the CPU tests): ONE collective per decoder layer -- the
+    layer's flat bf16 gradient buffer -- launched from the backward hook on a side stream so that the collective of
+    layer i overlaps the backward of layers < i; the lm_head / final-norm gradients go out at the start of the
+    backward, the small fp32 tensors (norm weights, front end) as one flat buffer at the end.
+    Sums in place; the 1/world average is folded into AdamW's grad_scale.
+    reduce_fp32=True all-reduces an fp32 copy of each bucket (the reference's DDP/FSDP reduce fp32 gradients)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, reduce_fp32=False):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.handles = []
+        self.reduce_fp32 = reduce_fp32
+        self.calls = 0
         self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
 
-    def hook(self, i, grads):
-        if not (self.dist.is_available() and self.dist.is_initialized()) or self.dist.get_world_size(self.group) == 1:
-            return
-        tensors = [grads[k] for k in LAYER_KEYS]
-        if self.stream is not None and tensors[0].is_cuda:
-            self.stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.stream):
-                for t in tensors:
-                    self.handles.append(self.dist.all_reduce(t, group=self.group, async_op=True))
-        else:
-            for t in tensors:
-                self.handles.append(self.dist.all_reduce(t, group=self.group, async_op=True))
+    def active(self):
+        return self.dist.is_available() and self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1
+
+    def _issue(self, tensors):
+        for t in tensors:
+            self.calls += 1
+            if self.reduce_fp32 and t.dtype != F32:
+                t32 = t.float()
+                h = self.dist.all_reduce(t32, group=self.group, async_op=True)
+                self.handles.append((h, t, t32))
+            else:
+                self.handles.append((self.dist.all_reduce(t, group=self.group, async_op=True), None, None))
 
     def reduce_now(self, tensors):
-        if self.dist.is_available() and self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1:
-            for t in tensors:
-                self.handles.append(self.dist.all_reduce(t, group=self.group, async_op=True))
+        if not self.active():
+            return
+        tensors = [t for t in tensors if t is not None]
+        if self.stream is not None and tensors and tensors[0].is_cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                self._issue(tensors)
+        else:
+            self._issue(tensors)
+
+    def hook(self, i, grads):
+        self.reduce_now([grads['flat']] if 'flat' in grads else [grads[k] for k in LAYER_KEYS])
+
+    def top_hook(self, g_top):
+        self.reduce_now([g_top.get('lm_head')])
 
     def wait(self):
-        for h in self.handles:
-            h.wait()
+        for h, dst, src in self.handles:
+            h.wait()                       # the current stream waits for the collective
+            if dst is not None:
+                dst.copy_(src)
         self.handles = []
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
@@ -275,9 +422,10 @@ def train_step(stack, inputs_embeds, targets, reducer=None, world_size=1):
     """One optimisation step of the LLaMA stack: forward, backward (+ overlapped gradient all-reduce), AdamW.
     Returns (loss tensor, d_inputs_embeds)."""
     loss = stack.forward(inputs_embeds, targets)
-    d_in = stack.backward(on_layer_grads=reducer.hook if reducer is not None else None)
+    d_in = stack.backward(on_layer_grads=reducer.hook if reducer is not None else None,
+                          on_top_grads=reducer.top_hook if reducer is not None else None)
     if reducer is not None:
-        reducer.reduce_now([stack.grads['top']['lm_head'], stack.grads['top']['norm']])
+        reducer.reduce_now([stack.grads['norms'], stack.grads['top']['norm']])
         reducer.wait()
     stack.optimizer_step(grad_scale=1.0 / world_size)
     return loss, d_in
@@ -334,16 +482,23 @@ class FrontEndTrain:
         self.saved = dict(feat=feat, plan=plan, pc=pc, t=t, K=K, B=B)
         return embeds
 
-    def backward(self, d_embeds):
-        """d_embeds [B,L,hidden] bf16 -> dict of gradients under the reference's parameter names."""
+    def backward(self, d_embeds, want_embed=True, want_proj=True, want_spi=True):
+        """d_embeds [B,L,hidden] bf16 -> dict of gradients under the reference's parameter names.
+        want_*: skip the gradients of frozen groups (stage 1 trains the SPI module only, train.py:685-696)."""
         from .splice import splice_backward
         eng, c, s = self.eng, self.eng.cfg, self.saved
-        d_image, d_region, d_embed = splice_backward(s['plan'], d_embeds, c.num_patches, s['K'], c.vocab)
-        out = {'model.embed_tokens.weight': d_embed}
-        _, gw, gb = train_ops.linear_bwd(s['feat'], eng.proj_w, d_image.view(-1, c.hidden), need_dx=False)
-        out['model.mm_projector.weight'], out['model.mm_projector.bias'] = gw, gb
-        if s['K'] > 0 and not self.head_only:
+        d_image, d_region, d_embed = splice_backward(s['plan'], d_embeds, c.num_patches, s['K'], c.vocab,
+                                                     want_embed_grad=want_embed)
+        out = {}
+        if want_embed:
+            out['model.embed_tokens.weight'] = d_embed
+        if want_proj:
+            _, gw, gb = train_ops.linear_bwd(s['feat'], eng.proj_w, d_image.view(-1, c.hidden), need_dx=False)
+            out['model.mm_projector.weight'], out['model.mm_projector.bias'] = gw, gb
+        if s['K'] > 0 and not self.head_only and want_spi:
             out.update(self.spi.backward(d_region))
+        elif s['K'] > 0 and not self.head_only:
+            pass
         elif s['K'] > 0:
             q = 'model.spi_module.roi_align.'
             dt, out[q + 'updims.weight'], out[q + 'updims.bias'] = train_ops.linear_bwd(s['t'], eng.up_w, d_region)
@@ -370,15 +525,18 @@ class SpiTrain:
         self.eng = engine
         self.saved = None
 
-    def forward(self, taps, plan_b):
+    def forward(self, taps, plan_b, has_cls=True):
+        """taps: {layer: [B,1+P,C]} ViT hidden states, or (has_cls=False) a list of [B,P,C] token maps in level order."""
         from .roi_align import roi_align_mlvl
         eng, c = self.eng, self.eng.cfg
         C, n = c.spi_dim, c.num_levels
+        if isinstance(taps, (list, tuple)):
+            taps = {layer: t for layer, t in zip(c.level_layers, taps)}
         B = next(iter(taps.values())).shape[0]
         ups, maps = [], []
         for l, layer in enumerate(c.level_layers):
             H = c.level_sizes[l]
-            up = kernels.upsample_tokens_coords(taps[layer], c.grid, H, eng.spi_cpad)
+            up = kernels.upsample_tokens_coords(taps[layer], c.grid, H, eng.spi_cpad, has_cls=has_cls)
             ups.append(up)
             maps.append(dense.linear(up.view(-1, eng.spi_cpad), eng.in_w[l], eng.in_b[l]).view(B, H, H, C))
         zs, sts, sss = [maps], [None], [[None] * n]
@@ -472,35 +630,87 @@ class SpiTrain:
         return g
 
 
+FRONT_GROUPS = (('embed', ('model.embed_tokens.weight',)), ('proj', ('model.mm_projector.',)), ('spi', ('model.spi_module.',)))
+ALL_GROUPS = ('embed', 'proj', 'spi', 'llama', 'head')
+
+
+def trainable_from_env(environ=None):
+    """The reference's trainable-set switches (gpt4roi/train/train.py:685-696): ONLY_SPI=1 trains the SPI module
+    only (stage 1, train_stage1.sh:8), PROJ=1 additionally un-freezes mm_projector; otherwise stage 2 trains
+    everything except the CLIP tower.  Returns (groups, spi_decay): llava_trainer.py:68-90 gives the SPI group
+    weight_decay 0.01 on every tensor when ONLY_SPI is set without PROJ, else 0."""
+    import os
+    env = os.environ if environ is None else environ
+    if env.get('ONLY_SPI'):
+        if env.get('PROJ'):
+            return ('spi', 'proj'), 0.0
+        return ('spi',), 0.01
+    return ALL_GROUPS, None
+
+
 class Stage2Trainer:
-    """One optimisation step of GPT4RoI stage 2 (scripts/train_stage2.sh -> gpt4roi/train/train.py:698-712): every
-    parameter except the frozen CLIP tower is trained -- embed_tokens, mm_projector, the SPI module, the 32 LLaMA
-    layers, final norm and lm_head -- with the loss of llava/model/llava.py:238-249, DDP gradient all-reduce and
-    torch.optim.AdamW semantics.  Forward, backward and optimizer run on the sm_100a kernels; no autograd.
+    """One optimisation step of GPT4RoI training (scripts train_stage{1,2}.sh -> gpt4roi/train/train.py:698-712 ->
+    HF Trainer.training_step): forward, backward, DDP gradient all-reduce, global grad-norm clip
+    (max_grad_norm 1.0, the HF default the scripts do not override), warm-up + cosine learning rate
+    (train_stage2.sh:47-53) and torch.optim.AdamW semantics -- all on the sm_100a kernels; no autograd.
+    Stage 2 trains every parameter except the frozen CLIP tower (embed_tokens, mm_projector, the SPI module, the
+    32 LLaMA layers, final norm, lm_head); `trainable` selects the reference's other sets
+    (ONLY_SPI / PROJ, `trainable_from_env`).  Loss: llava/model/llava.py:238-249.
 
         front = FrontEndTrain(PrefillEngine without LLaMA layers)   ViT (frozen) -> projector / SPI -> splice
         stack = LlamaTrainStack                                     decoder stack -> lm_head -> cross entropy
     """
 
     def __init__(self, cfg, state_dict, vit_state_dict, device, lr=2e-5, betas=(0.9, 0.999), eps=1e-8,
-                 weight_decay=0.0, reducer=None, world_size=1):
+                 weight_decay=0.0, reducer=None, world_size=1, trainable=ALL_GROUPS, max_grad_norm=1.0,
+                 schedule=None, spi_decay_all=None, own_optimizer=True):
+        """schedule: None (constant lr) or dict(total_steps=N, warmup_steps=0, warmup_ratio=0.003, kind='cosine').
+        spi_decay_all: weight decay applied to EVERY SPI tensor (the ONLY_SPI group of llava_trainer.py:68-78);
+        None = the default rule (decay `weight_decay` on matrices, none on biases / norm weights)."""
         import copy
         from .engine import PrefillEngine
         self.cfg, self.dev = cfg, torch.device(device)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.reducer, self.world = reducer, world_size
+        self.trainable = tuple(trainable)
+        bad = set(self.trainable) - set(ALL_GROUPS)
+        if bad:
+            raise ValueError('unknown trainable groups %s (choose from %s)' % (sorted(bad), ALL_GROUPS))
+        self.max_grad_norm = max_grad_norm
+        self.schedule = dict(schedule) if schedule else None
+        if self.schedule is not None:
+            self.schedule.setdefault('kind', 'cosine')
+            self.schedule['warmup_steps'] = warmup_steps_for(self.schedule['total_steps'], self.schedule.get('warmup_steps', 0),
+                                                             self.schedule.get('warmup_ratio', 0.0))
+        self.spi_decay_all = spi_decay_all
+        self.own_optimizer = own_optimizer
         fcfg = copy.copy(cfg)
         fcfg.n_layers = 0                                   # the front-end engine holds no decoder layers
         self.eng = PrefillEngine(fcfg, state_dict, vit_state_dict, device)
         self.front = FrontEndTrain(self.eng)
-        self.stack = LlamaTrainStack(cfg, state_dict, device, lr, betas, eps, weight_decay)
-        names = [k for k in state_dict if k.startswith('model.spi_module.') or k.startswith('model.mm_projector.')
-                 or k == 'model.embed_tokens.weight']
-        self.master = {k: state_dict[k].detach().to(self.dev, F32).contiguous() for k in names}
-        self.m1 = {k: torch.zeros_like(v) for k, v in self.master.items()}
-        self.m2 = {k: torch.zeros_like(v) for k, v in self.master.items()}
-        self.w16 = {k: v.to(BF16) for k, v in self.master.items()}
-        self.front_grads = None
+        self.stack = LlamaTrainStack(cfg, state_dict, device, lr, betas, eps, weight_decay, own_optimizer=own_optimizer,
+                                     train_layers='llama' in self.trainable, train_head='head' in self.trainable)
+        front_all = [k for k in state_dict if k.startswith('model.spi_module.') or k.startswith('model.mm_projector.')
+                     or k == 'model.embed_tokens.weight']
+        self.w16 = {k: state_dict[k].detach().to(self.dev, BF16).contiguous() for k in front_all}
+        names = [k for k in front_all if any(grp in self.trainable and k.startswith(pre)
+                                             for grp, pres in FRONT_GROUPS for pre in pres)]
+        self.front_names = names
+        self.front_shapes = {k: tuple(state_dict[k].shape) for k in names}
+        self.front_offsets, o = {}, 0
+        for k in names:
+            self.front_offsets[k] = o
+            o += (state_dict[k].numel() + 3) // 4 * 4          # 16-byte aligned slices of the flat fp32 bucket
+        self.front_numel = o
+        if own_optimizer:
+            self.master = {k: state_dict[k].detach().to(self.dev, F32).contiguous() for k in names}
+            self.m1 = {k: torch.zeros_like(v) for k, v in self.master.items()}
+            self.m2 = {k: torch.zeros_like(v) for k, v in self.master.items()}
+        else:
+            self.master, self.m1, self.m2 = {}, {}, {}
+        self.front_flat = None
+        self.clip = None          # device fp32 [2]: (gradient norm, clip coefficient) of the last step
+        self.last_lr = lr
 
     @staticmethod
     def shift_labels(labels):
@@ -509,75 +719,158 @@ class Stage2Trainer:
         t[:, :-1] = labels[:, 1:]
         return t
 
-    def forward_backward(self, input_ids, images, bboxes, labels):
-        """Returns the loss; gradients are left in self.stack.grads and self.front_grads (already all-reduced)."""
-        embeds = self.front.forward(input_ids, images, bboxes)
-        loss = self.stack.forward(embeds, self.shift_labels(labels.to(self.dev)))
-        d_embeds = self.stack.backward(on_layer_grads=self.reducer.hook if self.reducer is not None else None)
-        self.front_grads = {k: v for k, v in self.front.backward(d_embeds).items() if k in self.master}
-        if self.reducer is not None:
-            top = self.stack.grads['top']
-            # every rank must contribute the same tensors to the collective: a rank whose micro-batch has no boxes
-            # (no SPI gradients) contributes zeros, in the master's key order
-            self.front_grads = {k: (self.front_grads[k].reshape(self.master[k].shape).contiguous() if k in self.front_grads
-                                    else torch.zeros(self.master[k].shape, dtype=F32, device=self.dev)) for k in self.master}
-            self.front_grads = {k: (v if v.dtype == F32 else v.float()) for k, v in self.front_grads.items()}
-            self.reducer.reduce_now([top['lm_head'], top['norm']] + list(self.front_grads.values()))
-            self.reducer.wait()
-        return loss
+    def _front_slice(self, k):
+        o = self.front_offsets[k]
+        n = 1
+        for d in self.front_shapes[k]:
+            n *= d
+        return self.front_flat[o:o + n].view(self.front_shapes[k])
 
-    def optimizer_step(self):
-        scale = 1.0 / self.world
-        self.stack.optimizer_step(grad_scale=scale)
-        t = self.stack.step_count
-        for k, gr in self.front_grads.items():
-            no_decay = k.endswith('.bias') or '.gn.' in k or 'pos_embedd.2.' in k or 'pos_embedd.5.' in k
-            gr = gr.reshape(-1)
-            if gr.dtype not in (BF16, F32):
-                gr = gr.float()
-            train_ops.adamw_step(self.master[k].view(-1), gr, self.m1[k].view(-1), self.m2[k].view(-1),
-                                 self.w16[k].view(-1), self.lr, self.betas, self.eps, 0.0 if no_decay else self.wd, t, scale)
-        self.front_grads = None
-        # refresh the engine's bf16 tensors (its own layouts: padded 1x1 weights, KHWC convs, stacked pconvs ...)
+    def load_weights(self, state_dict):
+        """Model-seam path (own_optimizer=False): refresh every bf16 compute weight from the reference-named
+        parameters that torch.optim just updated."""
+        for k in self.w16:
+            self.w16[k].copy_(state_dict[k])
         self.eng._prepare_spi(self.w16)
         self.eng.embed = self.w16['model.embed_tokens.weight']
+        self.stack.load_weights(state_dict)
+
+    def forward_loss(self, input_ids, images, bboxes, labels):
+        embeds = self.front.forward(input_ids, images, bboxes)
+        return self.stack.forward(embeds, self.shift_labels(labels.to(self.dev)))
+
+    def backward(self, loss_scale=1.0):
+        """Backward of the last forward_loss; gradients are left in self.stack.grads and self.front_flat (already
+        all-reduced over the data-parallel group when a reducer is attached)."""
+        red = self.reducer if (self.reducer is not None and self.reducer.active()) else None
+        d_embeds = self.stack.backward(loss_scale=loss_scale, on_layer_grads=red.hook if red is not None else None,
+                                       on_top_grads=red.top_hook if red is not None else None)
+        tr = self.trainable
+        fg = self.front.backward(d_embeds, want_embed='embed' in tr, want_proj='proj' in tr, want_spi='spi' in tr)
+        # one flat fp32 bucket for every front-end gradient: a rank whose micro-batch has no boxes (no SPI
+        # gradients) contributes zeros, so every rank hands the same buffer to the collective
+        self.front_flat = torch.zeros(max(self.front_numel, 4), dtype=F32, device=self.dev)
+        for k in self.front_names:
+            if k in fg and fg[k] is not None:
+                self._front_slice(k).copy_(fg[k].reshape(self.front_shapes[k]))
+        if red is not None:
+            small = [self.front_flat]
+            if self.stack.train_layers:
+                small.append(self.stack.grads['norms'])
+            if self.stack.train_head:
+                small.append(self.stack.grads['top']['norm'])
+            red.reduce_now(small)
+            red.wait()
+
+    def forward_backward(self, input_ids, images, bboxes, labels):
+        """Returns the loss; see backward()."""
+        loss = self.forward_loss(input_ids, images, bboxes, labels)
+        self.backward()
+        return loss
+
+    def grad_tensors(self):
+        return self.stack.grad_tensors() + ([self.front_flat] if self.front_numel else [])
+
+    def current_lr(self):
+        if self.schedule is None:
+            return self.lr
+        return self.lr * lr_lambda(self.stack.step_count, self.schedule['total_steps'], self.schedule['warmup_steps'],
+                                   self.schedule['kind'])
+
+    def _front_decay(self, k):
+        if k.startswith('model.spi_module.') and self.spi_decay_all is not None:
+            return self.spi_decay_all
+        no_decay = k.endswith('.bias') or '.gn.' in k or 'pos_embedd.2.' in k or 'pos_embedd.5.' in k
+        return 0.0 if no_decay else self.wd
+
+    def optimizer_step(self):
+        """clip_grad_norm_(max_grad_norm) -> AdamW at the scheduled learning rate (HF Trainer order)."""
+        if not self.own_optimizer:
+            raise RuntimeError('this trainer was built with own_optimizer=False (torch.optim owns the parameters)')
+        scale = 1.0 / self.world
+        scale_dev = None
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            self.clip = train_ops.clip_coef(train_ops.grad_sumsq(self.grad_tensors()), self.max_grad_norm, pre_scale=scale)
+            scale_dev = self.clip[1:]
+        lr = self.last_lr = self.current_lr()
+        self.stack.optimizer_step(grad_scale=scale, lr=lr, scale_dev=scale_dev)
+        t = self.stack.step_count
+        for k in self.front_names:
+            train_ops.adamw_step(self.master[k].view(-1), self._front_slice(k).reshape(-1), self.m1[k].view(-1),
+                                 self.m2[k].view(-1), self.w16[k].view(-1), lr, self.betas, self.eps,
+                                 self._front_decay(k), t, scale, scale_dev)
+        self.front_flat = None
+        if self.front_names:
+            # refresh the engine's bf16 tensors (its own layouts: padded 1x1 weights, KHWC convs, stacked pconvs ...)
+            self.eng._prepare_spi(self.w16)
+            self.eng.embed = self.w16['model.embed_tokens.weight']
 
     def step(self, input_ids, images, bboxes, labels):
         loss = self.forward_backward(input_ids, images, bboxes, labels)
         self.optimizer_step()
         return loss
 
+    @property
+    def front_grads(self):
+        """Front-end gradients (fp32 views of the flat bucket) under the reference's parameter names."""
+        return None if self.front_flat is None else {k: self._front_slice(k) for k in self.front_names}
+
+    def grads_state_dict(self):
+        """Every gradient of the last backward under the reference's parameter names (model-seam path)."""
+        out = {k: self._front_slice(k) for k in self.front_names}
+        out.update(self.stack.grads_state_dict())
+        return out
+
     # ------------------------------------------------------------------ checkpoint / resume
     def state_dict(self):
-        """All trained parameters, fp32, reference names and layouts -- what the reference's trainer saves
-        (train.py:88-98); the CLIP tower is not part of the model's state dict (llava.py:47-48)."""
-        out = dict(self.master)
+        """All parameters of the model's state dict under reference names and layouts -- what the reference's
+        trainer saves (train.py:88-98): fp32 masters for the trained tensors, bf16 for frozen ones; the CLIP tower
+        is not part of the model's state dict (llava.py:47-48)."""
+        out = dict(self.w16)
+        out.update(self.master)
         out.update(self.stack.state_dict())
         return out
 
-    def save_pretrained(self, out_dir, dtype=None, max_shard_bytes=10 * 1024 ** 3):
-        return save_checkpoint(self.state_dict(), out_dir, max_shard_bytes, dtype)
+    def save_pretrained(self, out_dir, dtype=None, max_shard_bytes=10 * 1024 ** 3, config=None, rank=None):
+        return save_checkpoint(self.state_dict(), out_dir, max_shard_bytes, dtype, config=config, rank=rank)
 
     def optimizer_state(self):
-        """AdamW step count and moments under reference names (resume: pass the saved weights to __init__, then
-        load_optimizer_state)."""
+        """AdamW step count (= scheduler position) and moments under reference names (resume: pass the saved fp32
+        weights to __init__, then load_optimizer_state)."""
         m1, m2 = dict(self.m1), dict(self.m2)
-        for i in range(len(self.stack.master)):
-            m1.update(unfuse_llama_layer(self.stack.m1[i], i))
-            m2.update(unfuse_llama_layer(self.stack.m2[i], i))
-        for k, name in (('norm', 'model.norm.weight'), ('lm_head', 'lm_head.weight')):
-            m1[name], m2[name] = self.stack.m1_top[k], self.stack.m2_top[k]
-        return dict(step=self.stack.step_count, exp_avg=m1, exp_avg_sq=m2)
+        if self.stack.own_layers:
+            for i in range(len(self.stack.master)):
+                m1.update(unfuse_llama_layer(self.stack.m1[i], i))
+                m2.update(unfuse_llama_layer(self.stack.m2[i], i))
+        if self.stack.own_head:
+            for k, name in (('norm', 'model.norm.weight'), ('lm_head', 'lm_head.weight')):
+                m1[name], m2[name] = self.stack.m1_top[k], self.stack.m2_top[k]
+        return dict(step=self.stack.step_count, exp_avg=m1, exp_avg_sq=m2, schedule=self.schedule, lr=self.lr)
 
     def load_optimizer_state(self, state):
         self.stack.step_count = int(state['step'])
+        if state.get('schedule') is not None:
+            self.schedule = dict(state['schedule'])
         for src, dst_front, dst_layers, dst_top in ((state['exp_avg'], self.m1, self.stack.m1, self.stack.m1_top),
                                                     (state['exp_avg_sq'], self.m2, self.stack.m2, self.stack.m2_top)):
             for k in dst_front:
                 dst_front[k].copy_(src[k])
-            for i in range(len(dst_layers)):
-                fused = fuse_llama_layer(src, i, self.dev)
-                for k in LAYER_KEYS:
-                    dst_layers[i][k].copy_(fused[k])
-            dst_top['norm'].copy_(src['model.norm.weight'])
-            dst_top['lm_head'].copy_(src['lm_head.weight'])
+            if self.stack.own_layers:
+                for i in range(len(dst_layers)):
+                    fused = fuse_llama_layer(src, i, self.dev)
+                    for k in LAYER_KEYS:
+                        dst_layers[i][k].copy_(fused[k])
+            if self.stack.own_head:
+                dst_top['norm'].copy_(src['model.norm.weight'])
+                dst_top['lm_head'].copy_(src['lm_head.weight'])
+
+    def save_optimizer(self, path):
+        """optimizer.pt + scheduler position in one file (HF Trainer writes optimizer.pt / scheduler.pt beside the
+        weights; train_stage2.sh:21 excludes them when bootstrapping stage 2 from stage 1)."""
+        st = self.optimizer_state()
+        st['exp_avg'] = {k: v.detach().cpu().clone() for k, v in st['exp_avg'].items()}
+        st['exp_avg_sq'] = {k: v.detach().cpu().clone() for k, v in st['exp_avg_sq'].items()}
+        torch.save(st, path)
+
+    def load_optimizer(self, path):
+        self.load_optimizer_state(torch.load(path, map_location='cpu'))

@@ -217,13 +217,36 @@ def attention_bwd(qkv, out, dout, lse, B, L, n_heads, head_dim, causal, scale):
     return dqkv
 
 
-def adamw_step(p32, grad, m, v, p16, lr, betas, eps, weight_decay, step, grad_scale=1.0):
-    """In-place torch.optim.AdamW update of the fp32 master `p32` (+ bf16 copy `p16`, optional)."""
+def grad_sumsq(tensors, slabs=None):
+    """Per-CTA partial sums of squares of every gradient tensor (bf16 / fp32, contiguous) into one fp32 slab
+    buffer [len(tensors), g4r_sumsq_slabs()]; feeds clip_coef.  Fixed summation order: reproducible."""
+    n = _L.load().g4r_sumsq_slabs()
+    dev = tensors[0].device
+    if slabs is None:
+        slabs = torch.empty((len(tensors), n), dtype=torch.float32, device=dev)
+    for i, t in enumerate(tensors):
+        if t.dtype not in (BF16, torch.float32) or not t.is_contiguous():
+            raise TypeError('grad_sumsq: contiguous bf16/fp32 tensors required')
+        _call('g4r_sumsq', dev, _L.ptr(t), int(t.dtype == BF16), t.numel(), _L.ptr(slabs[i]))
+    return slabs
+
+
+def clip_coef(slabs, max_norm, pre_scale=1.0):
+    """-> device fp32 [2] = (total gradient norm * pre_scale, min(1, max_norm / (norm + 1e-6))):
+    torch.nn.utils.clip_grad_norm_ semantics (what HF Trainer applies with max_grad_norm=1.0), no host sync."""
+    out = torch.empty(2, dtype=torch.float32, device=slabs.device)
+    _call('g4r_grad_clip_coef', slabs.device, _L.ptr(slabs), slabs.numel(), float(pre_scale), float(max_norm), _L.ptr(out))
+    return out
+
+
+def adamw_step(p32, grad, m, v, p16, lr, betas, eps, weight_decay, step, grad_scale=1.0, scale_dev=None):
+    """In-place torch.optim.AdamW update of the fp32 master `p32` (+ bf16 copy `p16`, optional).
+    scale_dev: optional device float multiplied into grad_scale (clip_coef(...)[1:])."""
     n = p32.numel()
     if not (p32.is_contiguous() and grad.is_contiguous() and m.is_contiguous() and v.is_contiguous()):
         raise RuntimeError('adamw_step: contiguous tensors required')
     if grad.dtype not in (BF16, torch.float32) or grad.numel() != n:
         raise TypeError('adamw_step: grad must be bf16 or fp32 with the parameter\'s size')
-    _call('g4r_adamw_step', p32.device, _L.ptr(p32), _L.ptr(grad), int(grad.dtype == BF16), _L.ptr(m), _L.ptr(v),
+    _call('g4r_adamw_step_ex', p32.device, _L.ptr(p32), _L.ptr(grad), int(grad.dtype == BF16), _L.ptr(m), _L.ptr(v),
           _L.ptr(p16), n, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
-          float(grad_scale))
+          float(grad_scale), _L.ptr(scale_dev))

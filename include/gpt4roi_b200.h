@@ -403,12 +403,34 @@ int g4r_pos_embed_mlp_bwd(const float* boxes, const void* w0, const void* b0, co
 /* ReLU backward from the saved output: out = y > 0 ? dy : 0 (bf16, n elements, n % 8 == 0). */
 int g4r_relu_bwd_bf16(const void* dy, const void* y, void* out, long long n, void* stream);
 
+/* Apply a pending GroupNorm affine + ReLU to an NHWC bf16 map: out = relu(z * scale[b,c] + shift[b,c]) with the
+ * fp32 [B,C] scale / shift of g4r_gn_finalize.  The activated map is what MLVLFuseModule.forward returns
+ * (gpt4roi/models/layers.py:182-195; mmcv ConvModule conv -> GN -> ReLU, conv_module.py:196-208); inside the fused
+ * engine the affine stays folded into the consumer's taps, so only the module-level seam calls this. */
+int g4r_affine_relu_nhwc_bf16(const void* z, const float* scale, const float* shift, void* out, int B,
+                              long long pix_per_img, int C, void* stream);
+
 /* torch.optim.AdamW step (HF Trainer optim="adamw_torch"; param groups llava_trainer.py:59-144): fp32 master
  * weights p and moments m, v; gradient bf16 (g_bf16=1) or fp32, multiplied by grad_scale (1/world, clip factor);
  * p_bf16 (optional) receives the bf16 copy used by the next forward.  step counts from 1. */
 int g4r_adamw_step(float* p, const void* g, int g_bf16, float* m, float* v, void* p_bf16, long long n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                    void* stream);
+/* Same, with the gradient scale additionally multiplied by the device float *scale_dev (NULL = 1): the clip
+ * coefficient of g4r_grad_clip_coef, so that clipping costs no host synchronisation. */
+int g4r_adamw_step_ex(float* p, const void* g, int g_bf16, float* m, float* v, void* p_bf16, long long n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                      const float* scale_dev, void* stream);
+
+/* Global gradient-norm clip (HF Trainer max_grad_norm=1.0 -> torch.nn.utils.clip_grad_norm_, called between
+ * backward and optimizer.step() by transformers Trainer.training_step; reference gpt4roi/train/train.py:698-712).
+ * g4r_sumsq writes g4r_sumsq_slabs() per-CTA partial sums of squares of one gradient tensor (bf16 or fp32) to
+ * slab; g4r_grad_clip_coef adds n_slabs partials in a fixed order and writes out2[0] = sqrt(sum) * pre_scale
+ * (pre_scale = 1/world for summed, not averaged, DDP gradients) and out2[1] = min(1, max_norm / (out2[0] + 1e-6)). */
+int g4r_sumsq_slabs(void);
+int g4r_sumsq(const void* g, int g_bf16, long long n, float* slab, void* stream);
+int g4r_grad_clip_coef(const float* slabs, long long n_slabs, float pre_scale, float max_norm, float* out2,
+                       void* stream);
 
 #ifdef __cplusplus
 }
