@@ -96,38 +96,42 @@ class PrefillEngine:
                 w2=_b(sd[q + 'mlp.fc2.weight'], dev), b2=_b(sd[q + 'mlp.fc2.bias'], dev)))
 
     def _prepare_spi(self, sd):
+        """SPI-module weights in engine layout.  The two halves are independent (a stand-alone MLVLFuseModule or
+        MlvlRoIExtractor mirror owns only one of them): whatever keys are present are prepared."""
         c, dev = self.cfg, self.dev
         p = 'model.spi_module.'
         C = c.spi_dim
         self.spi_cpad = (C + 2 + 63) // 64 * 64  # 1026 -> 1088
-        self.in_w, self.in_b = [], []
-        for l in range(c.num_levels):
-            w = sd[p + 'mlvl_fuse.input_conv.%d.weight' % l].reshape(C, C + 2)
-            wp = torch.zeros(C, self.spi_cpad, dtype=BF16, device=dev)
-            wp[:, :C + 2] = w.to(dev, BF16)
-            self.in_w.append(wp)
-            self.in_b.append(_b(sd[p + 'mlvl_fuse.input_conv.%d.bias' % l], dev))
-        self.fuse = []
-        for r in range(5):
-            q = p + 'mlvl_fuse.fuse_convs.%d.' % r
-            w = sd[q + 'conv.weight'].to(dev, BF16).permute(0, 2, 3, 1).contiguous()  # [Cout,kh,kw,Cin]
-            self.fuse.append(dict(w=w, gamma=_b(sd[q + 'gn.weight'], dev), beta=_b(sd[q + 'gn.bias'], dev)))
+        if p + 'mlvl_fuse.input_conv.0.weight' in sd:
+            self.in_w, self.in_b = [], []
+            for l in range(c.num_levels):
+                w = sd[p + 'mlvl_fuse.input_conv.%d.weight' % l].reshape(C, C + 2)
+                wp = torch.zeros(C, self.spi_cpad, dtype=BF16, device=dev)
+                wp[:, :C + 2] = w.to(dev, BF16)
+                self.in_w.append(wp)
+                self.in_b.append(_b(sd[p + 'mlvl_fuse.input_conv.%d.bias' % l], dev))
+            self.fuse = []
+            for r in range(5):
+                q = p + 'mlvl_fuse.fuse_convs.%d.' % r
+                w = sd[q + 'conv.weight'].to(dev, BF16).permute(0, 2, 3, 1).contiguous()  # [Cout,kh,kw,Cin]
+                self.fuse.append(dict(w=w, gamma=_b(sd[q + 'gn.weight'], dev), beta=_b(sd[q + 'gn.bias'], dev)))
         q = p + 'roi_align.'
-        pw = torch.stack([sd[q + 'pconvs.%d.weight' % l].to(dev, BF16).permute(0, 2, 3, 1)
-                          for l in range(c.num_levels)], 1).contiguous()  # [Cout, L, kh, kw, Cin]
-        self.pconv_w = pw
-        self.pconv_b = sum(sd[q + 'pconvs.%d.bias' % l].to(dev, torch.float32) for l in range(c.num_levels)).contiguous()
-        R = c.roi_out
-        fw = sd[q + 'flatten_linear.weight']  # [1024, C*R*R] in (c, ph, pw) order (layers.py:326)
-        self.flat_w = fw.to(dev, BF16).reshape(-1, C, R, R).permute(0, 2, 3, 1).reshape(fw.shape[0], -1).contiguous()
-        self.flat_b = _b(sd[q + 'flatten_linear.bias'], dev)
-        self.pos = [_b(sd[q + 'pos_embedd.%s' % n], dev) for n in
-                    ('0.weight', '0.bias', '2.weight', '2.bias', '3.weight', '3.bias', '5.weight', '5.bias')]
-        self.up_w, self.up_b = _b(sd[q + 'updims.weight'], dev), _b(sd[q + 'updims.bias'], dev)
+        if q + 'flatten_linear.weight' in sd:
+            pw = torch.stack([sd[q + 'pconvs.%d.weight' % l].to(dev, BF16).permute(0, 2, 3, 1)
+                              for l in range(c.num_levels)], 1).contiguous()  # [Cout, L, kh, kw, Cin]
+            self.pconv_w = pw
+            self.pconv_b = sum(sd[q + 'pconvs.%d.bias' % l].to(dev, torch.float32) for l in range(c.num_levels)).contiguous()
+            R = c.roi_out
+            fw = sd[q + 'flatten_linear.weight']  # [1024, C*R*R] in (c, ph, pw) order (layers.py:326)
+            self.flat_w = fw.to(dev, BF16).reshape(-1, C, R, R).permute(0, 2, 3, 1).reshape(fw.shape[0], -1).contiguous()
+            self.flat_b = _b(sd[q + 'flatten_linear.bias'], dev)
+            self.pos = [_b(sd[q + 'pos_embedd.%s' % n], dev) for n in
+                        ('0.weight', '0.bias', '2.weight', '2.bias', '3.weight', '3.bias', '5.weight', '5.bias')]
+            self.up_w, self.up_b = _b(sd[q + 'updims.weight'], dev), _b(sd[q + 'updims.bias'], dev)
+            kb = self.flat_w.shape[1] // 64
+            self.flat_splits = next(s for s in (16, 14, 8, 7, 4, 2, 1) if kb % s == 0)
         if 'model.mm_projector.weight' in sd:
             self.proj_w, self.proj_b = _b(sd['model.mm_projector.weight'], dev), _b(sd['model.mm_projector.bias'], dev)
-        kb = self.flat_w.shape[1] // 64
-        self.flat_splits = next(s for s in (16, 14, 8, 7, 4, 2, 1) if kb % s == 0)
 
     def _prepare_llm(self, sd):
         c, dev = self.cfg, self.dev

@@ -80,29 +80,6 @@ def _spi_engine(module, prefix, sd_extra, grid, device):
     return cache['eng']
 
 
-def _zero_spi_sd(device, which):
-    """Zero stand-ins for the half of the SPI state dict a stand-alone sub-module does not own."""
-    z = lambda *s: torch.zeros(*s, device=device, dtype=BF16)
-    sd = {}
-    if which == 'roi_align':
-        q = SPI_PREFIX + 'roi_align.'
-        for l in range(4):
-            sd[q + 'pconvs.%d.weight' % l], sd[q + 'pconvs.%d.bias' % l] = z(1024, 1024, 3, 3), z(1024)
-        for n, s in (('0.weight', (256, 4)), ('0.bias', (256,)), ('2.weight', (256,)), ('2.bias', (256,)),
-                     ('3.weight', (1024, 256)), ('3.bias', (1024,)), ('5.weight', (1024,)), ('5.bias', (1024,))):
-            sd[q + 'pos_embedd.' + n] = z(*s)
-        sd[q + 'updims.weight'], sd[q + 'updims.bias'] = z(8, 1024), z(8)
-        sd[q + 'flatten_linear.weight'], sd[q + 'flatten_linear.bias'] = z(8, 1024 * 14 * 14), z(8)
-    else:
-        q = SPI_PREFIX + 'mlvl_fuse.'
-        for l in range(4):
-            sd[q + 'input_conv.%d.weight' % l], sd[q + 'input_conv.%d.bias' % l] = z(1024, 1026, 1, 1), z(1024)
-        for r in range(5):
-            sd[q + 'fuse_convs.%d.conv.weight' % r] = z(1024, 1024, 3, 3)
-            sd[q + 'fuse_convs.%d.gn.weight' % r], sd[q + 'fuse_convs.%d.gn.bias' % r] = z(1024), z(1024)
-    return sd
-
-
 def _to_tokens(feats):
     """list of [B,P,C] token maps or [B,C,G,G] NCHW maps (layers.py:219-224) -> (list of contiguous [B,P,C], G)."""
     out = []
@@ -145,7 +122,7 @@ class MLVLFuseModule(nn.Module):
             raise NotImplementedError('the sm_100a SPI kernels are built for the GPT4RoI configuration (4 levels, 5 rounds, 1024 ch)')
         dev = inputs[0].device
         G = inputs[-1].shape[-1]
-        eng = _spi_engine(self, 'mlvl_fuse.', _zero_spi_sd(dev, 'roi_align'), G, dev)
+        eng = _spi_engine(self, 'mlvl_fuse.', {}, G, dev)
         if [m.shape[-1] for m in inputs] != eng.cfg.level_sizes:
             raise ValueError('expected pyramid sizes %s, got %s' % (eng.cfg.level_sizes, [m.shape[-1] for m in inputs]))
         maps, ss = eng.fuse_maps(_to_tokens(inputs)[0], has_cls=False, pre_upsampled=True)
@@ -184,7 +161,7 @@ class MlvlRoIExtractor(nn.Module):
         image side = 14 x the coarsest map side here (SURVEY.md 8(c), 336-px lift).  Inference only."""
         dev = feats[0].device
         G = feats[-1].shape[-1]
-        eng = _spi_engine(self, 'roi_align.', _zero_spi_sd(dev, 'mlvl_fuse'), G, dev)
+        eng = _spi_engine(self, 'roi_align.', {}, G, dev)
         maps = [f.permute(0, 2, 3, 1).to(BF16).contiguous() for f in feats]
         plan = eng.plan_boxes(rois)
         if plan is None or plan['K'] == 0:
@@ -384,7 +361,7 @@ def _seqlens(eng, attention_mask, L):
 
 @torch.no_grad()
 def _run_engine(eng, input_ids, images, bboxes, attention_mask, past_key_values, inputs_embeds, use_cache, want,
-                training=False, max_cache=None):
+                training=False, max_cache=None, last_only=False):
     """Inference dispatch shared by both model classes: prefill (ids or embeds, with or without the vision
     branch) or one decode step on our cache.  Mirrors spi_llava.py:44-48: the vision branch runs when images are
     given and (the input is longer than one token or the module is in training mode)."""
@@ -419,16 +396,15 @@ def _run_engine(eng, input_ids, images, bboxes, attention_mask, past_key_values,
         x = inputs_embeds.to(eng.dev, BF16).contiguous()
         if kv is not None:
             kv.length = L
-        out = eng.llama(x, B, L, seqlens=_seqlens(eng, attention_mask, L), cache=kv, want=want)
+        out = eng.llama(x, B, L, seqlens=_seqlens(eng, attention_mask, L), cache=kv, want=want, last_only=last_only)
         return out, new_cache
     B, L = input_ids.shape
     run_vision = images is not None and (L != 1 or training)
     if type(images) is list:
         raise NotImplementedError('list-of-images input is undefined in the reference SPI branch (spi_llava.py:52-64)')
+    mask = attention_mask if _seqlens(eng, attention_mask, L) is not None else None
     out = eng.forward(input_ids, images if run_vision else None, bboxes if run_vision else None,
-                      attention_mask=None, want=want, cache=kv) if _seqlens(eng, attention_mask, L) is None else \
-        eng.forward(input_ids, images if run_vision else None, bboxes if run_vision else None,
-                    attention_mask=attention_mask, want=want, cache=kv)
+                      attention_mask=mask, want=want, cache=kv, last_only=last_only)
     return out, new_cache
 
 
@@ -548,7 +524,9 @@ class SPILlavaMPTForCausalLM(LlamaForCausalLM, _EngineHost):
                 inputs_embeds: Optional[torch.FloatTensor] = None, labels: Optional[torch.LongTensor] = None,
                 use_cache: Optional[bool] = None, output_attentions: Optional[bool] = None,
                 output_hidden_states: Optional[bool] = None, images: Optional[torch.FloatTensor] = None,
-                return_dict: Optional[bool] = None, img_metas=None, bboxes=None, **kwargs):
+                return_dict: Optional[bool] = None, img_metas=None, bboxes=None, logits_to_keep: int = 0, **kwargs):
+        """logits_to_keep=1 (HF's convention; our prepare_inputs_for_generation sets it): the prefill computes the
+        final norm + lm_head for the last position only and returns logits [B,1,V]."""
         if output_attentions or output_hidden_states:
             raise NotImplementedError('attention maps / per-layer hidden states are not materialised by the fused engine')
         return_dict = return_dict if return_dict is not None else getattr(self.config, 'use_return_dict', True)
@@ -572,7 +550,8 @@ class SPILlavaMPTForCausalLM(LlamaForCausalLM, _EngineHost):
             raise NotImplementedError('a differentiable forward needs `labels` (the loss is part of the fused training node)')
         eng = self._get_engine(dev)
         logits, cache = _run_engine(eng, input_ids, images, bboxes, attention_mask, past_key_values, inputs_embeds,
-                                    use_cache, want='logits', training=self.training)
+                                    use_cache, want='logits', training=self.training,
+                                    last_only=(logits_to_keep == 1 and labels is None))
         loss = None
         if labels is not None:  # llava.py:238-249
             shift_logits = logits[..., :-1, :].float().reshape(-1, self.config.vocab_size)
@@ -594,7 +573,8 @@ class SPILlavaMPTForCausalLM(LlamaForCausalLM, _EngineHost):
         else:
             model_inputs = {'input_ids': input_ids}
         model_inputs.update({'past_key_values': past_key_values, 'use_cache': kwargs.get('use_cache'),
-                             'attention_mask': attention_mask, 'images': kwargs.get('images', None)})
+                             'attention_mask': attention_mask, 'images': kwargs.get('images', None),
+                             'logits_to_keep': 1})
         if 'bboxes' in kwargs:
             model_inputs['bboxes'] = kwargs['bboxes']
         return model_inputs

@@ -57,7 +57,7 @@ def build_llm(cfg, sd, device, dtype=torch.float32):
 
 @torch.no_grad()
 def forward(cfg, sd, vit_sd, input_ids, images, bboxes, device, autocast_bf16=False, vit=None, llm=None,
-            return_intermediates=False):
+            return_intermediates=False, hidden_layers=()):
     """Returns logits [B,L,V] (fp32 tensor).  Weights: fp32 copies of the given state dicts, or bf16
     copies when autocast_bf16 (the reference's deployment mode: bf16 weights + autocast)."""
     wdt = torch.bfloat16 if autocast_bf16 else torch.float32
@@ -103,7 +103,13 @@ def forward(cfg, sd, vit_sd, input_ids, images, bboxes, device, autocast_bf16=Fa
             new.append(cur)
         embeds = torch.stack(new, 0)
         inter['embeds'] = embeds.float()
-        logits = llm(inputs_embeds=embeds, use_cache=False).logits
+        if hidden_layers:
+            # hidden_states[n] = residual stream after decoder layer n (n < n_layers; the last entry is post-norm)
+            res = llm(inputs_embeds=embeds, use_cache=False, output_hidden_states=True)
+            inter['hidden'] = {n: res.hidden_states[n].float() for n in hidden_layers}
+            logits = res.logits
+        else:
+            logits = llm(inputs_embeds=embeds, use_cache=False).logits
     if return_intermediates:
         return logits.float(), inter
     return logits.float()

@@ -92,3 +92,10 @@ def load_layers(image_size=224):
     mod = types.ModuleType('gpt4roi_models_layers_%d' % image_size)
     exec(compile(src, 'layers_lifted_%d.py' % image_size, 'exec'), mod.__dict__)
     return mod
+
+
+def build_roi_query_module(image_size=224):
+    """The reference's own MLVLROIQueryModule(embed_dims=1024, out_dims=4096, num_levels=4) (gpt4roi/models/
+    layers.py:198-236) on CPU -- used by bench.py's CPU arm in this container to time the reference's code path."""
+    layers = load_layers(image_size)
+    return layers.MLVLROIQueryModule(embed_dims=1024, out_dims=4096, num_levels=4)

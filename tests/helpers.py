@@ -51,3 +51,17 @@ def make_rois(rng, n_img, k_per_img, size, adversarial=False):
 PYRAMID = {224: (128, 64, 32, 16), 336: (192, 96, 48, 24)}
 STRIDES = (14 / 8, 14 / 4, 14 / 2, 14)
 SCALES = tuple(float(np.float32(1.0 / s)) for s in STRIDES)
+
+
+def golden_stream_mismatch():
+    """The golden fixtures hold the reference's OUTPUTS; their inputs and weights (hundreds of MB) are regenerated
+    from seeded CPU generators and verified by checksum.  A different RNG stream (another torch build) would make
+    every pin to the reference disappear silently if the tests merely skipped -- so this FAILS unless
+    G4R_ALLOW_GOLDEN_SKIP=1 is set (then it skips, loudly)."""
+    import pytest
+    import torch
+    msg = ('seeded CPU RNG stream differs from the one the golden fixtures were generated with (torch %s); regenerate them '
+           'with tests/golden/make_golden.py where /root/reference exists' % torch.__version__)
+    if os.environ.get('G4R_ALLOW_GOLDEN_SKIP') == '1':
+        pytest.skip(msg)
+    pytest.fail(msg)

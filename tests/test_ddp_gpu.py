@@ -1,0 +1,105 @@
+"""2-rank NCCL test of the training step's only collective (the DDP gradient all-reduce):
+a DDP step on a batch split over two GPUs must equal the single-GPU step on the concatenated batch -- same loss,
+same (averaged) gradients, same clip norm, same weights after AdamW within bf16 tolerance.
+
+Needs >= 2 GPUs (skipped otherwise; run with `gpurun --gpus 2 -- python -m pytest tests/test_ddp_gpu.py -m gpu`).
+The CPU/gloo counterpart of the reducer plumbing is tests/test_dist_cpu.py."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _inputs(cfg):
+    from tests.test_engine_gpu import make_inputs
+    ids, images, boxes = make_inputs(cfg, 4, [2, 2, 2, 2], 24, seed=77)
+    labels = ids.clone()
+    labels[:, :cfg.num_patches + 8] = -100          # every sample keeps the same number of supervised positions, so
+    labels[ids == cfg.bbox_token] = -100            # mean-of-rank-means == mean over the concatenated batch
+    return ids, images, boxes, labels
+
+
+def _weights(cfg, dev):
+    from gpt4roi_b200.engine import random_state_dicts
+    sd, vit_sd = random_state_dicts(cfg, dev, seed=91)
+    return {k: v.to(BF).float() for k, v in sd.items()}, vit_sd
+
+
+def _worker(rank, world, port, out_dir, reduce_fp32):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank), NCCL_DEBUG='WARN')
+    import torch.distributed as dist
+    from gpt4roi_b200.engine import EngineConfig
+    from gpt4roi_b200.train import LayerBucketAllReduce, Stage2Trainer
+    torch.cuda.set_device(rank)
+    dev = 'cuda:%d' % rank
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(dev))
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=2)
+    sd, vit_sd = _weights(cfg, dev)
+    ids, images, boxes, labels = _inputs(cfg)
+    lo, hi = rank * 2, rank * 2 + 2
+    red = LayerBucketAllReduce(reduce_fp32=reduce_fp32)
+    tr = Stage2Trainer(cfg, sd, vit_sd, dev, lr=1e-3, reducer=red, world_size=world, max_grad_norm=1.0)
+    loss = tr.forward_backward(ids[lo:hi], images[lo:hi], boxes[lo:hi], labels[lo:hi])
+    grads = {k: (v.detach().float() / world).cpu() for k, v in tr.grads_state_dict().items()}
+    tr.optimizer_step()
+    norm = tr.clip[0].item()
+    loss2 = tr.forward_backward(ids[lo:hi], images[lo:hi], boxes[lo:hi], labels[lo:hi])
+    tr.optimizer_step()
+    weights = {k: v.detach().float().cpu() for k, v in tr.state_dict().items()}
+    torch.save(dict(loss=loss.item(), loss2=loss2.item(), grads=grads, norm=norm, weights=weights, calls=red.calls),
+               os.path.join(out_dir, 'rank%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('reduce_fp32', [False, True])
+def test_ddp_two_ranks_equal_single_rank_on_the_concatenated_batch(reduce_fp32):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from gpt4roi_b200.engine import EngineConfig
+    from gpt4roi_b200.train import Stage2Trainer
+    from tests.test_dist_cpu import _free_port
+    from tests.test_engine_gpu import rel
+    out_dir = tempfile.mkdtemp()
+    mp.spawn(_worker, args=(2, _free_port(), out_dir, reduce_fp32), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(out_dir, 'rank0.pt'))
+    r1 = torch.load(os.path.join(out_dir, 'rank1.pt'))
+    # both ranks end with identical weights (they applied the same all-reduced gradients)
+    for k in r0['weights']:
+        assert torch.equal(r0['weights'][k], r1['weights'][k]), k
+    assert r0['norm'] == r1['norm']
+    # one collective per decoder layer + lm_head + one flat bucket for the small tensors: 2 + 1 + 3 per step
+    assert r0['calls'] == 2 * (2 + 1 + 3), r0['calls']
+    # single-rank reference on the whole batch
+    dev = 'cuda:0'
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=2)
+    sd, vit_sd = _weights(cfg, dev)
+    ids, images, boxes, labels = _inputs(cfg)
+    tr = Stage2Trainer(cfg, sd, vit_sd, dev, lr=1e-3, max_grad_norm=1.0)
+    w0 = {k: v.detach().float().cpu().clone() for k, v in tr.state_dict().items()}
+    loss = tr.forward_backward(ids, images, boxes, labels)
+    want = {k: v.detach().float().cpu() for k, v in tr.grads_state_dict().items()}
+    tr.optimizer_step()
+    norm = tr.clip[0].item()
+    tr.forward_backward(ids, images, boxes, labels)
+    tr.optimizer_step()
+    w2 = {k: v.detach().float().cpu() for k, v in tr.state_dict().items()}
+    mean_loss = 0.5 * (r0['loss'] + r1['loss'])
+    assert abs(mean_loss - loss.item()) < 2e-3 * abs(loss.item()), (mean_loss, loss.item())
+    assert abs(r0['norm'] - norm) < 2e-2 * norm, (r0['norm'], norm)
+    worst = max((rel(r0['grads'][k].reshape(want[k].shape), want[k]), k) for k in want)
+    print('DDP(2) vs single rank: worst gradient rel-L2 %.2e (%s); grad norm %.4f vs %.4f' % (worst + (r0['norm'], norm)))
+    # bf16 per-rank gradients summed over 2 ranks vs one bf16 gradient of the 4-sample batch: independent roundings
+    assert worst[0] < 3e-2, worst
+    # weights after two AdamW steps: compare the UPDATES (w2 - w0); Adam's m/sqrt(v) flips sign on near-zero gradients,
+    # so the bar is on the bulk: rel-L2 of the update per tensor, largest tensors
+    for k in ('lm_head.weight', 'model.layers.1.mlp.down_proj.weight', 'model.spi_module.roi_align.updims.weight',
+              'model.mm_projector.weight'):
+        du_ddp, du_one = r0['weights'][k] - w0[k], w2[k] - w0[k]
+        assert rel(du_ddp, du_one) < 0.25, (k, rel(du_ddp, du_one))

@@ -87,7 +87,13 @@ def _reducer_worker(rank, world, port, q):
         red.hook(i, g)                                # async all-reduce of the layer's bucket
     top = [torch.full((4,), float(100 + rank))]
     red.reduce_now(top)
+    # the trainer's layout: the four matrix gradients of a layer are views of ONE flat buffer -> one collective
+    flat = torch.arange(8, dtype=torch.float32) + rank
+    red.hook(0, {'flat': flat, 'wqkv': flat[:4].view(2, 2)})
+    red.top_hook({'lm_head': top[0]})                 # lm_head goes out again here: 2 * (100 + 101)
     red.wait()
+    assert red.calls == 2 * 6 + 1 + 1 + 1, red.calls
+    assert torch.equal(flat, 2 * torch.arange(8, dtype=torch.float32) + 1)
     out = {i: {k: float(v[0, 0]) for k, v in g.items()} for i, g in layers}
     q.put((rank, out, float(top[0][0])))
     dist.destroy_process_group()
@@ -111,4 +117,4 @@ def test_layer_bucket_allreduce_sums_over_ranks():
         for i in (0, 1):
             for j, k in enumerate(LAYER_KEYS):
                 assert out[i][k] == 2 * (10 * i + j) + 1            # (v + 0) + (v + 1)
-        assert top == 201.0
+        assert top == 402.0

@@ -1,0 +1,292 @@
+"""GPU tests of the MODEL SEAM: the reference-named classes of gpt4roi_b200.spi_llava are
+instantiated, loaded through `load_state_dict` with reference-named weights, and driven exactly the way the
+reference's callers drive them -- HF Trainer (`model(**inputs)` -> `loss.backward()` -> `optimizer.step()`,
+gpt4roi/train/train.py:698-712), the demo (`gpt4roi/app.py:74-104,278-300`: tokens set on the vision config,
+`model.model.tokenizer`, boxes bound with functools.partial, `generate`), and the SPI sub-modules
+(`gpt4roi/models/layers.py:182-195,218-236,280-335`).  Checked against the oracle (oracle/model_oracle.py,
+oracle/spi_oracle.py, pinned to the reference's own outputs by the golden fixtures) with stated tolerances."""
+from functools import partial
+
+import pytest
+import torch
+
+from gpt4roi_b200.engine import EngineConfig, PrefillEngine, random_state_dicts
+from gpt4roi_b200.spi_llava import (KeywordsStoppingCriteria, LlavaConfig, MLVLROIQueryModule,
+                                    SPILlavaMPTForCausalLM)
+from oracle import model_oracle, spi_oracle
+from tests.test_engine_gpu import make_inputs, rel
+from tests.test_spi_oracle_cpu import golden_case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+BF = torch.bfloat16
+
+
+class _Tok:
+    """Stand-in for the slow LLaMA tokenizer (no tokenizer files offline): only the calls the model makes."""
+
+    def __init__(self, cfg):
+        self.ids = {'<bbox>': cfg.bbox_token, '<im_patch>': cfg.im_patch_token, '<im_start>': cfg.im_start_token,
+                    '<im_end>': cfg.im_end_token}
+
+    def convert_tokens_to_ids(self, toks):
+        return [self.ids[t] for t in toks]
+
+    def __call__(self, s):
+        return type('Enc', (), {'input_ids': [2]})()
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        return [' '.join(str(int(i)) for i in row) for row in ids]
+
+
+def build_seam_model(cfg, sd, vit_sd, dtype=torch.float32, app_style=False):
+    """SPILlavaMPTForCausalLM(config) + load_state_dict(reference-named weights) + the CLIP tower in a python list
+    (llava.py:47-48).  app_style: token ids exactly as gpt4roi/app.py:100-104,283 sets them (no bbox_token on the
+    vision config, tokenizer on model.model)."""
+    lc = LlavaConfig(hidden_size=cfg.hidden, intermediate_size=cfg.mlp, num_hidden_layers=cfg.n_layers,
+                     num_attention_heads=cfg.n_heads, num_key_value_heads=cfg.n_heads, vocab_size=cfg.vocab,
+                     rms_norm_eps=cfg.rms_eps, max_position_embeddings=4096, tie_word_embeddings=False,
+                     mm_vision_select_layer=cfg.select_layer, use_mm_proj=True, mm_hidden_size=cfg.vit_hidden)
+    with torch.device(DEV):
+        model = SPILlavaMPTForCausalLM(lc)
+    missing, unexpected = model.load_state_dict({k: v.to(DEV, dtype) for k, v in sd.items()}, strict=False)
+    assert not unexpected and all('rotary' in k or 'inv_freq' in k for k in missing), (missing, unexpected)
+    model = model.to(dtype)
+    vt = model_oracle.build_vit(cfg, vit_sd, DEV, dtype)
+    model.model.vision_tower = [vt]
+    vc = vt.config
+    vc.im_patch_token, vc.im_start_token, vc.im_end_token = cfg.im_patch_token, cfg.im_start_token, cfg.im_end_token
+    vc.use_im_start_end = True
+    if app_style:
+        model.model.tokenizer = _Tok(cfg)
+    else:
+        vc.bbox_token = cfg.bbox_token
+    return model
+
+
+def test_causal_lm_forward_labels_matches_oracle():
+    """forward(input_ids, attention_mask, labels, images, bboxes) -> CausalLMOutputWithPast: logits vs the fp32
+    oracle (same bar as the engine tests: at least as close as 1.5x the reference's own bf16-autocast run, or
+    2e-2), loss vs the oracle's cross entropy (3e-3 rel)."""
+    cfg = EngineConfig(image_size=224, vit_layers=24, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=31)
+    ids, images, boxes = make_inputs(cfg, 2, [2, 1], 24, seed=3)
+    labels = ids.clone()
+    labels[:, :cfg.num_patches + 6] = -100
+    model = build_seam_model(cfg, sd, vit_sd).eval()
+    with torch.no_grad():
+        out = model(input_ids=ids.to(DEV), attention_mask=torch.ones_like(ids).to(DEV), labels=labels.to(DEV),
+                    images=images.to(DEV), img_metas=[None, None], bboxes=[b.to(DEV) for b in boxes])
+    ref32 = model_oracle.forward(cfg, sd, vit_sd, ids, images.to(BF).float(), boxes, DEV)
+    ref16 = model_oracle.forward(cfg, sd, vit_sd, ids, images.to(BF), boxes, DEV, autocast_bf16=True)
+    e, e16 = rel(out.logits, ref32), rel(ref16, ref32)
+    print('seam forward: logits rel-L2 vs fp32 oracle %.3e (reference under bf16 autocast %.3e)' % (e, e16))
+    assert e < max(1.5 * e16, 2e-2)
+    want = torch.nn.functional.cross_entropy(ref32[:, :-1].reshape(-1, cfg.vocab), labels[:, 1:].reshape(-1).to(DEV))
+    assert abs(out.loss.item() - want.item()) < 3e-3 * want.item()
+    assert out.past_key_values is None
+    # the inner LlamaModel mirror returns the final-norm hidden states; lm_head on them reproduces the logits
+    h = model.model(input_ids=ids.to(DEV), images=images.to(DEV), bboxes=boxes).last_hidden_state
+    lg = torch.nn.functional.linear(h.float(), sd['lm_head.weight'].float())
+    assert rel(lg, out.logits) < 1e-2
+    # weights changed in place -> the engine is rebuilt (parameter version counters), not silently stale
+    with torch.no_grad():
+        model.lm_head.weight.mul_(0.5)
+        out2 = model(input_ids=ids.to(DEV), images=images.to(DEV), bboxes=boxes)
+    assert rel(out2.logits, 0.5 * out.logits.float()) < 1e-2
+
+
+def test_demo_style_setup_and_generate_loops():
+    """gpt4roi/app.py path: tokens on the vision config WITHOUT bbox_token, tokenizer on model.model, boxes bound
+    through functools.partial, fp16 inputs; engine loop and HF GenerationMixin loop return the same greedy tokens,
+    and every generated token is the oracle's arg-max (or within its near-tie margin) under teacher forcing."""
+    cfg = EngineConfig(image_size=224, vit_layers=24, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=37)
+    ids, images, boxes = make_inputs(cfg, 1, [2], 24, seed=5)
+    model = build_seam_model(cfg, sd, vit_sd, dtype=torch.float16, app_style=True).eval()
+    n_new = 6
+    stop = KeywordsStoppingCriteria(['###'], _Tok(cfg), ids)
+    model.orig_forward = model.forward
+    model.forward = partial(model.orig_forward, img_metas=[None], bboxes=[boxes[0].to(DEV).half()])
+    with torch.inference_mode():
+        out_a = model.generate(ids.to(DEV), images=images.half().to(DEV), do_sample=False, max_new_tokens=n_new,
+                               stopping_criteria=[stop])
+        out_b = model.generate(ids.to(DEV), images=images.half().to(DEV), do_sample=False, max_new_tokens=n_new,
+                               use_hf_loop=True, pad_token_id=0)
+    model.forward = model.orig_forward
+    L0 = ids.shape[1]
+    assert out_a.shape == (1, L0 + n_new) and torch.equal(out_a[:, :L0].cpu(), ids)
+    assert torch.equal(out_a, out_b), (out_a[:, L0:], out_b[:, L0:])
+    # teacher-forced oracle check (fp32 transformers with the same fp16-representable weights)
+    ref = model_oracle.forward(cfg, {k: v.half().float() for k, v in sd.items()},
+                               {k: v.half().float() for k, v in vit_sd.items()}, out_a[:, :-1].cpu(),
+                               images.half().float(), boxes, DEV)
+    for t in range(n_new):
+        row = ref[0, L0 - 1 + t]
+        tok = int(out_a[0, L0 + t])
+        margin = (row.max() - row[tok]).item()
+        assert margin <= 3e-2 * row.std().item(), (t, tok, int(row.argmax()), margin)
+
+
+def test_mlvl_roi_query_module_forward_matches_reference_golden():
+    """MLVLROIQueryModule.forward(mlvl_feats, bboxes) (layers.py:218-236) on the module's own parameters vs the
+    reference module's own output (golden, 224 and 336); the two sub-modules called one after the other
+    (MLVLFuseModule.forward -> MlvlRoIExtractor.forward, as layers.py:234-236 does) agree with the fused call."""
+    for size in (224, 336):
+        cfg, sd, toks, boxes, want = golden_case(size)
+        with torch.device(DEV):
+            mod = MLVLROIQueryModule(embed_dims=1024, out_dims=4096, num_levels=4)
+        mod.load_state_dict({k[len('model.spi_module.'):]: v.to(DEV) for k, v in sd.items()
+                             if k.startswith('model.spi_module.')})
+        with torch.no_grad():
+            got = mod([t.to(DEV) for t in toks], [b.to(DEV) for b in boxes])
+        assert [g.shape[0] for g in got] == [b.shape[0] for b in boxes]
+        e = rel(torch.cat(got).cpu(), torch.from_numpy(want))
+        print('MLVLROIQueryModule.forward vs reference golden (%d): rel-L2 %.3e' % (size, e))
+        assert e < 2e-2
+        # NCHW entry (layers.py:219-224 accepts [B,C,G,G] too) and the sub-modules on their own
+        G = size // 14
+        nchw = [t.to(DEV).reshape(t.shape[0], G, G, -1).permute(0, 3, 1, 2).contiguous() for t in toks]
+        with torch.no_grad():
+            got2 = mod(nchw, [b.to(DEV) for b in boxes])
+            ups = [torch.nn.functional.interpolate(f, size=(s, s), mode='bilinear', align_corners=True)
+                   for f, s in zip(nchw, cfg.level_sizes)]
+            fused = mod.mlvl_fuse(ups)
+            got3 = mod.roi_align(fused, [b.to(DEV) for b in boxes])
+        assert rel(torch.cat(got2), torch.cat(got)) < 1e-6
+        assert [tuple(f.shape) for f in fused] == [(toks[0].shape[0], 1024, s, s) for s in cfg.level_sizes]
+        _, inter = spi_oracle.roi_query_forward({k: v.to(DEV) for k, v in sd.items()}, [t.to(DEV) for t in toks],
+                                                [b.to(DEV) for b in boxes], size, return_intermediates=True)
+        for l in range(4):
+            assert rel(fused[l], inter["fused"][l]) < 3e-2, l
+        assert rel(torch.cat(got3), torch.cat(got)) < 1e-2
+
+
+def _train_batch(cfg, seed=6):
+    ids, images, boxes = make_inputs(cfg, 2, [2, 1], 24, seed=seed)
+    labels = ids.clone()
+    labels[:, :cfg.num_patches + 8] = -100
+    labels[ids == cfg.bbox_token] = -100
+    return ids, images, boxes, labels
+
+
+def test_training_through_the_seam_like_hf_trainer():
+    """HF Trainer's inner loop on the seam: model.train(); loss = model(**inputs).loss; loss.backward();
+    clip_grad_norm_; AdamW.step().  Gradients in `.grad` equal Stage2Trainer's explicit backward (same kernels;
+    that trainer is pinned to the reference's own autograd golden in tests/test_train_gpu.py), the parameters move,
+    the next forward sees them (version-keyed refresh) and the loss drops."""
+    from gpt4roi_b200.train import Stage2Trainer
+    cfg = EngineConfig(image_size=224, vit_layers=24, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=41)
+    sd = {k: v.to(BF).float() for k, v in sd.items()}
+    ids, images, boxes, labels = _train_batch(cfg)
+    model = build_seam_model(cfg, sd, vit_sd).train()
+    inputs = dict(input_ids=ids.to(DEV), attention_mask=torch.ones_like(ids).to(DEV), labels=labels.to(DEV),
+                  images=images.to(DEV), img_metas=[None, None], bboxes=[b.to(DEV) for b in boxes])
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.0)
+    out = model(**inputs)
+    out.loss.backward()
+    ref = Stage2Trainer(cfg, sd, vit_sd, DEV, lr=1e-3)
+    want_loss = ref.forward_backward(ids, images, boxes, labels)
+    assert abs(out.loss.item() - want_loss.item()) < 1e-5 * abs(want_loss.item())
+    want = ref.grads_state_dict()
+    named = dict(model.named_parameters())
+    assert set(want) == {n for n, p in named.items() if p.requires_grad}
+    worst = max((rel(named[n].grad, want[n].reshape(named[n].shape)), n) for n in want)
+    print('seam .grad vs Stage2Trainer: worst rel-L2 %.2e (%s)' % worst)
+    assert worst[0] < 1e-4, worst
+    total = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    assert torch.isfinite(total)
+    before = model.model.spi_module.roi_align.updims.weight.detach().clone()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    assert not torch.equal(before, model.model.spi_module.roi_align.updims.weight)
+    loss2 = model(**inputs).loss
+    assert loss2.item() < out.loss.item(), (out.loss.item(), loss2.item())
+    # eval-mode inference after training picks up the updated weights as well
+    model.eval()
+    with torch.no_grad():
+        lg = model(input_ids=ids.to(DEV), images=images.to(DEV), bboxes=boxes, labels=labels.to(DEV))
+    assert abs(lg.loss.item() - loss2.item()) < 2e-2 * abs(loss2.item())
+
+
+def test_stage1_only_spi_through_the_seam():
+    """ONLY_SPI=1 (train_stage1.sh:8, train.py:685-691): requires_grad only on spi_module parameters -> only they
+    receive gradients, equal to the full stage-2 backward's SPI gradients; PROJ=1 adds mm_projector."""
+    cfg = EngineConfig(image_size=224, vit_layers=24, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=43)
+    sd = {k: v.to(BF).float() for k, v in sd.items()}
+    ids, images, boxes, labels = _train_batch(cfg, seed=8)
+    model = build_seam_model(cfg, sd, vit_sd).train()
+    inputs = dict(input_ids=ids.to(DEV), labels=labels.to(DEV), images=images.to(DEV), bboxes=boxes)
+    model(**inputs).loss.backward()
+    full = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    for n, p in model.named_parameters():
+        p.requires_grad = 'spi_module' in n or 'mm_projector' in n
+    loss = model(**inputs).loss
+    loss.backward()
+    for n, p in model.named_parameters():
+        if 'spi_module' in n or 'mm_projector' in n:
+            assert rel(p.grad, full[n]) < 1e-4, n
+        else:
+            assert p.grad is None, n
+
+
+def test_text_only_sample_in_a_training_batch():
+    """A non-multimodal sample inside a multimodal batch (spi_llava.py:104-111): with its labels ignored, every
+    gradient must equal the gradients of the batch without it (its d_image / d_region rows are zero, not
+    uninitialised memory)."""
+    from gpt4roi_b200.train import Stage2Trainer
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=1)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=47)
+    sd = {k: v.to(BF).float() for k, v in sd.items()}
+    ids, images, boxes = make_inputs(cfg, 2, [2, 0], 20, seed=12)
+    g = torch.Generator().manual_seed(5)
+    ids[1] = torch.randint(3, 31000, (ids.shape[1],), generator=g)       # plain text: no <im_patch>, no <bbox>
+    labels = ids.clone()
+    labels[0, :cfg.num_patches + 6] = -100
+    labels[0][ids[0] == cfg.bbox_token] = -100
+    labels[1] = -100
+    tr = Stage2Trainer(cfg, sd, vit_sd, DEV)
+    # poison the allocator's free blocks so that uninitialised reads cannot look like zeros by luck
+    junk = torch.full((64, 1024, 1024), float('nan'), device=DEV)
+    del junk
+    loss2 = tr.forward_backward(ids, images, boxes, labels)
+    got = {k: v.clone().float() for k, v in tr.grads_state_dict().items()}
+    loss1 = tr.forward_backward(ids[:1], images[:1], boxes[:1], labels[:1])
+    want = tr.grads_state_dict()
+    assert abs(loss1.item() - loss2.item()) < 1e-5 * abs(loss1.item())
+    for k in want:
+        assert torch.isfinite(got[k]).all(), k
+        assert rel(got[k], want[k]) < 2e-3, (k, rel(got[k], want[k]))
+
+
+def test_grad_clip_and_schedule_in_stage2_trainer():
+    """clip_grad_norm_(1.0) + warm-up/cosine LR inside Stage2Trainer.optimizer_step equal torch's own
+    clip_grad_norm_ + AdamW + get_cosine_schedule_with_warmup applied to the same gradients."""
+    from transformers import get_cosine_schedule_with_warmup
+    from gpt4roi_b200.train import Stage2Trainer
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=1)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=53)
+    sd = {k: v.to(BF).float() for k, v in sd.items()}
+    ids, images, boxes, labels = _train_batch(cfg, seed=14)
+    sched = dict(total_steps=10, warmup_steps=2, kind='cosine')
+    tr = Stage2Trainer(cfg, sd, vit_sd, DEV, lr=1e-3, max_grad_norm=1.0, schedule=sched)
+    params = {k: torch.nn.Parameter(v.detach().clone().to(DEV)) for k, v in tr.state_dict().items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-3, weight_decay=0.0)
+    sch = get_cosine_schedule_with_warmup(opt, 2, 10)
+    for step in range(3):
+        tr.forward_backward(ids, images, boxes, labels)
+        grads = {k: v.detach().clone().float() for k, v in tr.grads_state_dict().items()}
+        for k, p in params.items():
+            p.grad = grads[k].reshape(p.shape).clone()
+        norm = torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        assert abs(tr.current_lr() - opt.param_groups[0]['lr']) < 1e-12
+        tr.optimizer_step()
+        assert abs(tr.clip[0].item() - norm.item()) < 2e-3 * norm.item()
+        opt.step()
+        sch.step()
+        got = tr.state_dict()
+        worst = max((params[k].detach() - got[k].reshape(params[k].shape).float()).abs().max().item() for k in params)
+        assert worst < 2e-5, (step, worst)

@@ -9,6 +9,8 @@ import contextlib
 import pytest
 import torch
 
+from tests.helpers import golden_stream_mismatch
+
 from gpt4roi_b200.engine import EngineConfig, random_state_dicts
 from gpt4roi_b200.train import LAYER_KEYS, LlamaTrainStack, train_step
 from oracle import model_oracle
@@ -343,7 +345,7 @@ def test_stage2_step_matches_reference_autograd_golden():
     vit_sd = {k: v.to(BF).float() for k, v in vit_sd.items()}
     if int(ids.sum()) != int(gold['ids_checksum'][0]) or \
             not np.allclose(float(sd['lm_head.weight'].double().sum()), gold['w_checksum'][0], rtol=1e-9):
-        pytest.skip('seeded CPU RNG stream differs from the one the golden was generated with')
+        golden_stream_mismatch()
     tr = Stage2Trainer(cfg, sd, vit_sd, DEV)
     loss = tr.forward_backward(ids, images, boxes, labels).item()
     want_loss = float(gold['loss'][0])
