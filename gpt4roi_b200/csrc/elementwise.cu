@@ -111,7 +111,8 @@ norm_rows_bf16(const TI* __restrict__ x, long long ldx, const __nv_bfloat16* __r
     unpack8(wv[vi], wf);
     if (RMS) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) o[j] = wf[j] * bf16_round(v[i][j] * rstd);
+      for (int j = 0; j < 8; j++)   // LlamaRMSNorm: weight * (x * rstd).to(input_dtype) -- no rounding for an fp32 stream
+        o[j] = wf[j] * (sizeof(TI) == 4 ? v[i][j] * rstd : bf16_round(v[i][j] * rstd));
     } else {
       float bf[8];
       unpack8(bv[vi], bf);
@@ -230,14 +231,14 @@ static int launch_norm(const void* x, long long ldx, const void* w, const void* 
   return G4R_OK;
 }
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, bool RMS = false>
 static int launch_ln_ex(const void* x, long long ldx, const void* w, const void* b, void* out, long long ldo,
                         int M, int D, float eps, cudaStream_t st) {
   const int per_lane = (D / 8 + 31) / 32;
   const dim3 grid((M + 7) / 8);
 #define G4R_LN_CASE(PL)                                                                                   \
-  norm_rows_bf16<false, PL, TI, TO><<<grid, 256, 0, st>>>((const TI*)x, ldx, (const __nv_bfloat16*)w,      \
-                                                          (const __nv_bfloat16*)b, (TO*)out, ldo, M, D, eps)
+  norm_rows_bf16<RMS, PL, TI, TO><<<grid, 256, 0, st>>>((const TI*)x, ldx, (const __nv_bfloat16*)w,        \
+                                                        (const __nv_bfloat16*)b, (TO*)out, ldo, M, D, eps)
   if (per_lane <= 1) G4R_LN_CASE(1);
   else if (per_lane <= 2) G4R_LN_CASE(2);
   else if (per_lane <= 4) G4R_LN_CASE(4);
@@ -858,6 +859,15 @@ extern "C" int g4r_layernorm_ex(const void* x, long long ldx, int x_f32, const v
                             : launch_ln_ex<float, __nv_bfloat16>(x, ldx, w, b, out, ldo, M, D, eps, st);
   return out_f32 ? launch_ln_ex<__nv_bfloat16, float>(x, ldx, w, b, out, ldo, M, D, eps, st)
                  : launch_ln_ex<__nv_bfloat16, __nv_bfloat16>(x, ldx, w, b, out, ldo, M, D, eps, st);
+}
+
+extern "C" int g4r_rmsnorm_ex(const void* x, long long ldx, int x_f32, const void* w, void* out, long long ldo, int M,
+                              int D, float eps, void* stream) {
+  G4R_REQUIRE(x && w && out && M > 0 && D > 0 && D % 8 == 0 && D <= 8192 && ldx % 8 == 0 && ldo % 8 == 0,
+              "rmsnorm_ex: bad arguments (D=%d)", D);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x_f32) return launch_norm<true>(x, ldx, w, nullptr, out, ldo, M, D, eps, st);
+  return launch_ln_ex<float, __nv_bfloat16, true>(x, ldx, w, nullptr, out, ldo, M, D, eps, st);
 }
 
 extern "C" int g4r_cast_f32_bf16(const void* x, long long ld, long long bst, void* out, int B, int rows_per_batch,

@@ -31,8 +31,18 @@ class EngineConfig:
                  vit_mlp=4096, vit_eps=1e-5, select_layer=-2, num_levels=4,
                  hidden=4096, n_heads=32, n_layers=32, mlp=11008, vocab=32006, rms_eps=1e-6,
                  rope_theta=10000.0, roi_out=14, roi_sampling=2, spi_dim=1024, gn_groups=64,
-                 im_patch_token=32001, bbox_token=32002, im_start_token=32004, im_end_token=32005):
+                 im_patch_token=32001, bbox_token=32002, im_start_token=32004, im_end_token=32005,
+                 llama_stream=None):
+        """llama_stream: dtype of the LLaMA residual stream in the prefill -- 'fp32' (default; what the reference has
+        whenever its parameters are fp32 under autocast, i.e. in training, and strictly more accurate) or 'bf16'
+        (what a model cast to bf16 has).  Env G4R_LLAMA_STREAM overrides the default."""
+        import os
+        if llama_stream is None:
+            llama_stream = os.environ.get('G4R_LLAMA_STREAM', 'fp32')
+        if llama_stream not in ('fp32', 'bf16'):
+            raise ValueError('llama_stream must be fp32 or bf16')
         self.__dict__.update(locals())
+        del self.__dict__['os']
         del self.__dict__['self']
         self.grid = image_size // patch_size
         self.num_patches = self.grid ** 2
@@ -252,6 +262,9 @@ class PrefillEngine:
         x = embeds.view(B * L, c.hidden)
         cos, sin = self._rope(L)
         scale = c.head_dim ** -0.5
+        # fp32 residual stream: the first o_proj epilogue widens it (bf16 residual in, fp32 out); every branch output
+        # is rounded to bf16 before the fp32 add, as a bf16 nn.Linear output added to an fp32 stream under autocast
+        f32 = dict(out_dtype=torch.float32, round_branch=True) if c.llama_stream == 'fp32' else {}
         for li, w in enumerate(self.layers):
             h = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
             if c.head_dim == 128 and (2 * c.hidden) % 256 == 0:
@@ -262,10 +275,10 @@ class PrefillEngine:
             if cache is not None:  # keep post-RoPE K and V for the decode loop
                 kernels.kv_append(qkv, cache.k[li], cache.v[li], B, L, 0)
             a = kernels.attention(qkv, B, L, c.n_heads, c.head_dim, True, scale, seqlens=seqlens)
-            x = dense.linear(a, w['wo'], residual=x)
+            x = dense.linear(a, w['wo'], residual=x, **f32)
             h = kernels.rmsnorm(x, w['ln_post'], c.rms_eps)
             f = dense.linear(h, w['wgu'], act='swiglu')
-            x = dense.linear(f, w['wdown'], residual=x)
+            x = dense.linear(f, w['wdown'], residual=x, **f32)
             if hidden_taps is not None and (li + 1) in hidden_taps:
                 hidden_taps[li + 1] = x.view(B, L, c.hidden).clone()
         if last_only:

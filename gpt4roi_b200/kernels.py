@@ -47,12 +47,15 @@ def cast_tokens_f32_bf16(hidden, skip_first=1):
 
 
 def rmsnorm(x, weight, eps=1e-6, out=None):
-    _bf16(x, weight)
+    """x bf16 or fp32 rows (an fp32 residual stream); bf16 output."""
+    _bf16(weight)
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError('rmsnorm: bf16 or fp32 rows required, got %s' % x.dtype)
     D = x.shape[-1]
     x2 = x.reshape(-1, D)
-    out = torch.empty_like(x2) if out is None else out
-    _call('g4r_rmsnorm_bf16', x.device, _L.ptr(x2), x2.stride(0), _L.ptr(weight), _L.ptr(out), out.stride(0),
-          x2.shape[0], D, float(eps))
+    out = torch.empty(x2.shape, dtype=torch.bfloat16, device=x.device) if out is None else out
+    _call('g4r_rmsnorm_ex', x.device, _L.ptr(x2), x2.stride(0), int(x.dtype == torch.float32), _L.ptr(weight),
+          _L.ptr(out), out.stride(0), x2.shape[0], D, float(eps))
     return out.view(x.shape) if out.is_contiguous() and out.numel() == x.numel() else out
 
 

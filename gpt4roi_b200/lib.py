@@ -49,6 +49,7 @@ SIGNATURES = {
     'g4r_layernorm_ex': (_i, [_vp, _ll, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
     'g4r_cast_f32_bf16': (_i, [_vp, _ll, _ll, _vp, _i, _i, _i, _vp]),
     'g4r_rmsnorm_bf16': (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _vp]),
+    'g4r_rmsnorm_ex': (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _i, _f, _vp]),
     'g4r_rope_inplace_bf16': (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp]),
     'g4r_patchify_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'g4r_vit_embed_bf16': (_i, [_vp] * 4 + [_i] * 3 + [_vp]),

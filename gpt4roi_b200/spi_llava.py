@@ -74,7 +74,7 @@ def _spi_engine(module, prefix, sd_extra, grid, device):
     if cache.get('key') != key:
         sd = {SPI_PREFIX + prefix + k: v for k, v in module.state_dict().items()}
         sd.update(sd_extra)
-        cfg = EngineConfig(image_size=int(grid) * 14, n_layers=0, vit_layers=0)
+        cfg = EngineConfig(image_size=int(grid) * 14, n_layers=0)
         cache['eng'] = PrefillEngine(cfg, sd, None, device, parts=('spi',))
         cache['key'] = key
     return cache['eng']

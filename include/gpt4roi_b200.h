@@ -272,6 +272,12 @@ int g4r_cast_f32_bf16(const void* x, long long ld, long long bst, void* out,
 /* LlamaRMSNorm: w * bf16(x * rsqrt(mean(x^2)+eps))  (transformers modeling_llama.py:53-67). */
 int g4r_rmsnorm_bf16(const void* x, long long ldx, const void* w,
                      void* out, long long ldo, int M, int D, float eps, void* stream);
+/* Same for an fp32 (x_f32=1) or bf16 residual stream; bf16 output rows (the operand of the next GEMM).  With an
+ * fp32 stream the normalised value is not rounded before the weight multiply, exactly LlamaRMSNorm on an fp32
+ * input (modeling_llama.py:53-67: `self.weight * hidden_states.to(input_dtype)`) -- the reference's residual stream
+ * is fp32 whenever its parameters are (training under autocast), bf16 when the model was cast to bf16. */
+int g4r_rmsnorm_ex(const void* x, long long ldx, int x_f32, const void* w, void* out, long long ldo, int M, int D,
+                   float eps, void* stream);
 /* apply_rotary_pos_emb in place on the first n_heads_qk heads of each packed row
  * (modeling_llama.py:138-168); cos/sin bf16 [L, head_dim]; position = row % L. */
 int g4r_rope_inplace_bf16(void* qkv, long long ld, const void* cos_t, const void* sin_t,

@@ -192,9 +192,13 @@ def test_training_through_the_seam_like_hf_trainer():
     want = ref.grads_state_dict()
     named = dict(model.named_parameters())
     assert set(want) == {n for n, p in named.items() if p.requires_grad}
-    worst = max((rel(named[n].grad, want[n].reshape(named[n].shape)), n) for n in want)
+    # everything behind the LLaMA stack is bitwise repeatable; the SPI gradients pass through the fp32 atomics of
+    # the RoIAlign backward (as in the reference kernel), whose summation order flips bf16 roundings downstream
+    errs = {n: rel(named[n].grad, want[n].reshape(named[n].shape)) for n in want}
+    worst = max((e, n) for n, e in errs.items())
     print('seam .grad vs Stage2Trainer: worst rel-L2 %.2e (%s)' % worst)
-    assert worst[0] < 1e-4, worst
+    for n, e in errs.items():
+        assert e < (2e-2 if 'spi_module' in n else 1e-5), (n, e)
     total = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
     assert torch.isfinite(total)
     before = model.model.spi_module.roi_align.updims.weight.detach().clone()
@@ -228,7 +232,7 @@ def test_stage1_only_spi_through_the_seam():
     loss.backward()
     for n, p in model.named_parameters():
         if 'spi_module' in n or 'mm_projector' in n:
-            assert rel(p.grad, full[n]) < 1e-4, n
+            assert rel(p.grad, full[n]) < (2e-2 if 'spi_module' in n else 1e-5), n
         else:
             assert p.grad is None, n
 
@@ -259,7 +263,7 @@ def test_text_only_sample_in_a_training_batch():
     assert abs(loss1.item() - loss2.item()) < 1e-5 * abs(loss1.item())
     for k in want:
         assert torch.isfinite(got[k]).all(), k
-        assert rel(got[k], want[k]) < 2e-3, (k, rel(got[k], want[k]))
+        assert rel(got[k], want[k]) < (2e-2 if 'spi_module' in k else 1e-4), (k, rel(got[k], want[k]))
 
 
 def test_grad_clip_and_schedule_in_stage2_trainer():
