@@ -279,8 +279,7 @@ def cpu_reference_sample(repeats=3):
 
 def roialign_microbench(dev, pk, how, n_maps=256, rois_per_map=100):
     """BASELINE configs[4] at its full size: 256 images x 4-level 224-pyramid (128,64,32,16) x 1024 ch NHWC fp32,
-    100 RoIs per image (K = 25 600), 7x7, sampling 2, ONE fused launch; runs before the 7B engine is built (43 GB of
-    operands).  achieved = algorithmic bytes (whole maps read once + output written once + rois) / CUDA-event time.
+    100 RoIs per image (K = 25 600), 7x7, sampling 2, ONE fused launch (43 GB of operands).  achieved = algorithmic bytes (whole maps read once + output written once + rois) / CUDA-event time.
     14x14 (the SPI module's own setting) and bf16 are reported beside it."""
     import numpy as np
     import torch
@@ -335,7 +334,7 @@ def roialign_microbench(dev, pk, how, n_maps=256, rois_per_map=100):
         pass
     del flush
     torch.cuda.empty_cache()
-    return dict(bound='hbm', kernel='roi_align_fwd_nhwc_mlvl', achieved=ach, peak=pk['hbm_gbs'], unit='GB/s',
+    return dict(bound='hbm', kernel='roi_align_fwd_nhwc_mlvl_dedup', achieved=ach, peak=pk['hbm_gbs'], unit='GB/s',
                 frac=ach / pk['hbm_gbs'], peak_kind=how, ms=ms, algorithmic_GB=alg / 1e9,
                 config='%d maps x %d RoIs, 7x7, 4 levels x 1024 ch (128,64,32,16), fp32 NHWC, L2 flushed between launches'
                        % (n_maps, rois_per_map),
@@ -497,15 +496,6 @@ def run_ours(args):
     dist_utils.init('nccl', dev)   # NCCL only for the barrier + max-over-ranks time (no data-path collective in the prefill)
     pk, how = peaks()
 
-    # ---- second half of the BASELINE metric first (43 GB of operands, freed before the 7B engine is built) ----
-    roi = None
-    if rank == 0 and not args.no_roialign and not args.ncu:
-        try:
-            roi = roialign_microbench(dev, pk, how)
-        except Exception as e:
-            roi = dict(skipped=str(e)[:200])
-        torch.cuda.empty_cache()
-
     cfg = EngineConfig(image_size=WORKLOAD['image_size'], n_layers=args.layers, vit_layers=24)
     B, K, T = WORKLOAD['batch_per_gpu'], WORKLOAD['rois_per_image'], WORKLOAD['text_tokens']
     sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
@@ -618,6 +608,16 @@ def run_ours(args):
                 launches=len(prof), flops_per_launch_avg=gemm_flops / max(len(prof), 1),
                 avg_launch_ms=gemm_ms / max(len(prof), 1), share_of_step=gemm_ms / ms_step,
                 note='events around each launch in one eager instrumented step after the timed region')
+
+    # ---- second half of the BASELINE metric (43 GB of operands beside the 14.6 GB engine; after the headline so
+    #      that its 0.6 s of sustained HBM traffic does not pre-heat the headline's power-capped clocks) ----
+    roi = None
+    if rank == 0 and not args.no_roialign:
+        try:
+            roi = roialign_microbench(dev, pk, how)
+        except Exception as e:
+            roi = dict(skipped=str(e)[:200])
+        torch.cuda.empty_cache()
 
     # ---- configs[2]'s shape: 16 RoIs per image, 8 images per GPU (batch 64 across 8 GPUs) ----------------------
     cfg2 = None

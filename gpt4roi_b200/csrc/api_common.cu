@@ -29,7 +29,24 @@ int num_sms() {
   return cached[dev];
 }
 
+// SMs the persistent (one CTA per SM) GEMM kernels may occupy: all of them minus the reserve set through
+// g4r_set_sm_reserve().  A collective running beside the backward (NCCL's CTAs are long-lived too) needs SMs of its
+// own: if the GEMM grid covers every SM, its statically scheduled CTAs queue behind the collective's CTAs and the two
+// serialise instead of overlapping.
+static int g_sm_reserve = 0;
+int sm_budget() {
+  int n = num_sms() - g_sm_reserve;
+  return n < 2 ? 2 : n;
+}
+void set_sm_reserve_impl(int n) { g_sm_reserve = n < 0 ? 0 : n; }
+
 }  // namespace g4r
+
+extern "C" int g4r_set_sm_reserve(int n_sms) {
+  const int prev = g4r::g_sm_reserve;
+  g4r::set_sm_reserve_impl(n_sms);
+  return prev;
+}
 
 extern "C" const char* g4r_last_error(void) { return g4r::g_err; }
 extern "C" int g4r_version(void) { return 1000; }

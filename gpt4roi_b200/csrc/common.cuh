@@ -46,6 +46,7 @@ inline size_t dtype_size(int dt) {
 }
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+int sm_budget();  // num_sms() minus the reserve of g4r_set_sm_reserve (grid size of the persistent GEMM kernels)
 
 // ---- element conversion -----------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);

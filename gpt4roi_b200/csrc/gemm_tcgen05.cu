@@ -707,7 +707,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_set = true;
   }
   const int total = p.num_m_tiles * p.num_n_tiles * p.k_splits;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = total < sm_budget() ? total : sm_budget();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
   G4R_LAUNCH_CHECK("gemm_bf16_tcgen05");
   return G4R_OK;
@@ -723,7 +723,7 @@ static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const G
     attr_set = true;
   }
   const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles * p.k_splits;
-  const int max_clusters = num_sms() / 2;
+  const int max_clusters = sm_budget() / 2;
   const int clusters = pairs < max_clusters ? pairs : max_clusters;
   kern<<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);  // __cluster_dims__(2,1,1)
   G4R_LAUNCH_CHECK("gemm_bf16_tcgen05_2sm");

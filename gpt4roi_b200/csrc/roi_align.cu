@@ -569,6 +569,185 @@ roi_align_fwd_nhwc_mlvl(const __grid_constant__ MlvlParams p) {
 }
 
 // ------------------------------------------------------------------------------------
+// Tap-deduplicating forward for the fixed 2x2 sampling grid (RoIAlign(14, sampling_ratio=2) of the SPI module,
+// gpt4roi/models/layers.py:205-212, and the 7x7 BASELINE microbench).
+//
+// The table kernel above is bound by the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 76 %, DRAM 34 %):
+// every bin issues 16 16-byte tap loads per 16-byte store.  On the coarse levels the two samples of a bin axis are
+// less than a pixel apart, so their (lo, hi) tap pairs overlap: per axis the four taps (lo0, hi0, lo1, hi1) are
+//     P2: lo1 == lo0              -> 2 distinct columns      (taps map to slots 0,1,0,1)
+//     P3: lo1 == hi0 == lo0 + 1   -> 3 distinct columns      (slots 0,1,1,2)
+//     P4: anything else (>= 2 px apart, clamped at the border, out of range) -> 4 loads (slots 0,1,2,3)
+// The pattern of a bin row / bin column is the same for every channel and every lane of the CTA, so it is classified
+// once per (RoI, level) into shared memory and each bin branches -- uniformly -- into one of 3 x 3 straight-line
+// variants that issue NSY x NSX unconditional loads (4 ... 16) and then the UNCHANGED arithmetic: every sample still
+// computes w1*v1 + w2*v2 + w3*v3 + w4*v4 in the reference's association (roi_align_cuda_kernel.cuh:63-66) with the
+// same weights, the duplicated taps simply read the same register.  Bit-identical to the table kernel.
+// ------------------------------------------------------------------------------------
+// slot of tap t in (lo0, hi0, lo1, hi1) for NS distinct rows / columns
+template <int NS>
+__host__ __device__ constexpr int tap_slot(int t) {
+  return NS == 2 ? (t & 1) : (NS == 3 ? (t == 0 ? 0 : (t == 3 ? 2 : 1)) : t);
+}
+
+__device__ __forceinline__ int tap_pattern(const AxisEntry<float>& a, const AxisEntry<float>& b) {
+  if (!a.valid || !b.valid) return 4;
+  if (a.hi != a.lo + 1 || b.hi != b.lo + 1) return 4;   // clamped at the far border
+  if (b.lo == a.lo) return 2;
+  if (b.lo == a.hi) return 3;
+  return 4;
+}
+
+template <typename Tin, typename Tout, bool AFFINE, int NSY, int NSX>
+__device__ __forceinline__ void dedup_bin(const char* __restrict__ mpb, const PackedAxis& ey0, const PackedAxis& ey1,
+                                          const PackedAxis& ex0, const PackedAxis& ex1, const float* __restrict__ sa,
+                                          const float* __restrict__ sb, f32x2 one2, Tout* __restrict__ outp) {
+  constexpr int VEC = 16 / (int)sizeof(Tin);
+  // distinct row / column offsets of this bin
+  unsigned yo[NSY], xo[NSX];
+  yo[0] = (unsigned)ey0.off_lo; yo[1] = (unsigned)ey0.off_hi;
+  if constexpr (NSY == 3) yo[2] = (unsigned)ey1.off_hi;
+  if constexpr (NSY == 4) { yo[2] = (unsigned)ey1.off_lo; yo[3] = (unsigned)ey1.off_hi; }
+  xo[0] = (unsigned)ex0.off_lo; xo[1] = (unsigned)ex0.off_hi;
+  if constexpr (NSX == 3) xo[2] = (unsigned)ex1.off_hi;
+  if constexpr (NSX == 4) { xo[2] = (unsigned)ex1.off_lo; xo[3] = (unsigned)ex1.off_hi; }
+  uint4 R[NSY][NSX];   // raw 16-byte taps; widened (and, AFFINE, normalised + ReLU'd) where they are used
+#pragma unroll
+  for (int sy = 0; sy < NSY; sy++) {
+    const char* row = mpb + (size_t)yo[sy] * sizeof(Tin);
+#pragma unroll
+    for (int sx = 0; sx < NSX; sx++) {
+      const void* q = row + (size_t)xo[sx] * 16;
+      asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(R[sy][sx].x), "=r"(R[sy][sx].y), "=r"(R[sy][sx].z), "=r"(R[sy][sx].w) : "l"(q));
+    }
+  }
+  float ga[VEC], gb[VEC];
+  if constexpr (AFFINE) {
+#pragma unroll
+    for (int i = 0; i < VEC; i++) { ga[i] = sa[i]; gb[i] = sb[i]; }
+  }
+  auto tap = [&](const uint4& raw, float (&v)[VEC]) {
+    const Tin* e = reinterpret_cast<const Tin*>(&raw);
+#pragma unroll
+    for (int i = 0; i < VEC; i++) v[i] = to_f32<Tin>(e[i]);
+    if constexpr (AFFINE) {   // fused GroupNorm affine + ReLU (same op on the same value as the table kernel)
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        float a, b;
+        unpack2(fma2(pack2(v[i], v[i + 1]), pack2(ga[i], ga[i + 1]), pack2(gb[i], gb[i + 1])), a, b);
+        v[i] = fmaxf(a, 0.f);
+        v[i + 1] = fmaxf(b, 0.f);
+      }
+    }
+  };
+  f32x2 acc2[VEC / 2];
+#pragma unroll
+  for (int i = 0; i < VEC / 2; i++) acc2[i] = 0ull;
+#pragma unroll
+  for (int iy = 0; iy < 2; iy++) {
+    const PackedAxis& ey = iy ? ey1 : ey0;
+#pragma unroll
+    for (int ix = 0; ix < 2; ix++) {
+      const PackedAxis& ex = ix ? ex1 : ex0;
+      const float w1 = ey.h * ex.h, w2 = ey.h * ex.l, w3 = ey.l * ex.h, w4 = ey.l * ex.l;
+      const f32x2 W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3), W4 = pack2(w4, w4);
+      float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+      tap(R[tap_slot<NSY>(2 * iy)][tap_slot<NSX>(2 * ix)], v1);
+      tap(R[tap_slot<NSY>(2 * iy)][tap_slot<NSX>(2 * ix + 1)], v2);
+      tap(R[tap_slot<NSY>(2 * iy + 1)][tap_slot<NSX>(2 * ix)], v3);
+      tap(R[tap_slot<NSY>(2 * iy + 1)][tap_slot<NSX>(2 * ix + 1)], v4);
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        f32x2 t = mul2(W1, pack2(v1[i], v1[i + 1]));
+        t = add2_unfused(t, mul2(W2, pack2(v2[i], v2[i + 1])), one2);
+        t = add2_unfused(t, mul2(W3, pack2(v3[i], v3[i + 1])), one2);
+        t = add2_unfused(t, mul2(W4, pack2(v4[i], v4[i + 1])), one2);
+        acc2[i / 2] = add2_unfused(acc2[i / 2], t, one2);
+      }
+    }
+  }
+  float o[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; i += 2) unpack2(acc2[i / 2], o[i], o[i + 1]);
+#pragma unroll
+  for (int i = 0; i < VEC; i++) o[i] = o[i] * 0.25f;   // / 4 exactly (count = 2 x 2)
+  store_vec<Tout, VEC>(outp, o);
+}
+
+template <typename Tin, typename Tout, bool AFFINE>
+__global__ void __launch_bounds__(kThreads, (sizeof(Tin) == 4 ? (AFFINE ? 3 : 4) : 2))
+roi_align_fwd_nhwc_mlvl_dedup(const __grid_constant__ MlvlParams p) {
+  constexpr int VEC = 16 / (int)sizeof(Tin);
+  constexpr int G = 2;
+  __shared__ PackedAxis ytab[kTab];
+  __shared__ PackedAxis xtab[kTab];
+  __shared__ unsigned char ypat[kTab / 2];
+  __shared__ unsigned char xpat[kTab / 2];
+
+  const int lvl = blockIdx.y;
+  const int rpc = p.rows_per_cta_lvl[lvl];
+  const int row_groups = (p.PH + rpc - 1) / rpc;
+  const int k = blockIdx.x / row_groups;
+  if (k >= p.K) return;
+  const int ph0 = (blockIdx.x % row_groups) * rpc;
+  const int nrows = min(rpc, p.PH - ph0);
+  const int H = p.H[lvl], W = p.W[lvl], C = p.C, PW = p.PW;
+  const float* r = p.rois + (size_t)k * 5;
+  const RoiGeom<float> g = roi_geom<float>(r[0], r[1], r[2], r[3], r[4], p.scale[lvl], p.PH, PW, G, p.aligned != 0, true);
+  const int lanes = C / VEC;
+  const Tin* map = reinterpret_cast<const Tin*>(p.maps[lvl]) + (size_t)g.batch * H * W * C;
+  Tout* out = reinterpret_cast<Tout*>(p.out) + (((size_t)lvl * p.K + k) * p.PH + ph0) * (size_t)PW * C;
+  const f32x2 one2 = pack2(p.one, p.one);
+
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+    const AxisEntry<float> a = axis_entry<float>(g.start_h, g.bin_h, ph0 + i, 0, G, H);
+    const AxisEntry<float> b = axis_entry<float>(g.start_h, g.bin_h, ph0 + i, 1, G, H);
+    ytab[2 * i] = pack_axis(a, W * C);
+    ytab[2 * i + 1] = pack_axis(b, W * C);
+    ypat[i] = (unsigned char)tap_pattern(a, b);
+  }
+  for (int i = threadIdx.x; i < PW; i += blockDim.x) {
+    const AxisEntry<float> a = axis_entry<float>(g.start_w, g.bin_w, i, 0, G, W);
+    const AxisEntry<float> b = axis_entry<float>(g.start_w, g.bin_w, i, 1, G, W);
+    xtab[2 * i] = pack_axis(a, C * (int)sizeof(Tin) / 16);   // 16-byte units
+    xtab[2 * i + 1] = pack_axis(b, C * (int)sizeof(Tin) / 16);
+    xpat[i] = (unsigned char)tap_pattern(a, b);
+  }
+  __syncthreads();
+
+  const int ngrp = blockDim.x >= lanes ? blockDim.x / lanes : 1;
+  const int grp = blockDim.x >= lanes ? threadIdx.x / lanes : 0;
+  for (int lane = threadIdx.x % lanes; lane < lanes; lane += (blockDim.x >= lanes ? lanes : blockDim.x)) {
+    const int coff = lane * VEC;
+    const char* mpb = reinterpret_cast<const char*>(map + coff);
+    const float* sa = nullptr;
+    const float* sb = nullptr;
+    if constexpr (AFFINE) {
+      sa = p.gn_scale[lvl] + (size_t)g.batch * C + coff;
+      sb = p.gn_shift[lvl] + (size_t)g.batch * C + coff;
+    }
+    for (int prow = 0; prow < nrows; prow++) {
+      const PackedAxis ey0 = ytab[2 * prow], ey1 = ytab[2 * prow + 1];
+      const int py = ypat[prow];
+      for (int pw = grp; pw < PW; pw += ngrp) {
+        const PackedAxis ex0 = xtab[2 * pw], ex1 = xtab[2 * pw + 1];
+        Tout* outp = out + ((size_t)prow * PW + pw) * C + coff;
+        const int px = xpat[pw];
+#define G4R_DEDUP_CASE(NY, NX) dedup_bin<Tin, Tout, AFFINE, NY, NX>(mpb, ey0, ey1, ex0, ex1, sa, sb, one2, outp)
+        if (py == 2) {
+          if (px == 2) G4R_DEDUP_CASE(2, 2); else if (px == 3) G4R_DEDUP_CASE(2, 3); else G4R_DEDUP_CASE(2, 4);
+        } else if (py == 3) {
+          if (px == 2) G4R_DEDUP_CASE(3, 2); else if (px == 3) G4R_DEDUP_CASE(3, 3); else G4R_DEDUP_CASE(3, 4);
+        } else {
+          if (px == 2) G4R_DEDUP_CASE(4, 2); else if (px == 3) G4R_DEDUP_CASE(4, 3); else G4R_DEDUP_CASE(4, 4);
+        }
+#undef G4R_DEDUP_CASE
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // "Row walk" forward for the fixed 2x2 sampling grid (the SPI module's RoIAlign(14, sampling_ratio=2),
 // gpt4roi/models/layers.py:205-212, and the 7x7 microbench).
 //
@@ -858,6 +1037,17 @@ static int launch_fwd_mlvl(MlvlParams& p, bool affine, cudaStream_t st) {
     walk_env = e ? atoi(e) : 0;
   }
   const int lanes = p.C / VEC;
+  static int dedup_env = -1;
+  if (dedup_env < 0) {
+    const char* e = getenv("G4R_ROI_DEDUP");
+    dedup_env = e ? atoi(e) : 1;
+  }
+  if (g2 && dedup_env == 1 && walk_env != 1 && !nv2 && (kThreads % lanes == 0 || lanes % kThreads == 0)) {
+    if (affine) roi_align_fwd_nhwc_mlvl_dedup<Tin, Tout, true><<<grid, kThreads, 0, st>>>(p);
+    else roi_align_fwd_nhwc_mlvl_dedup<Tin, Tout, false><<<grid, kThreads, 0, st>>>(p);
+    G4R_LAUNCH_CHECK("roi_align_fwd_nhwc_mlvl_dedup");
+    return G4R_OK;
+  }
   if (g2 && walk_env == 1 && !nv2 && (kThreads % lanes == 0 || lanes % kThreads == 0)) {
     if (affine) roi_align_fwd_nhwc_mlvl_walk<Tin, Tout, true><<<grid, kThreads, 0, st>>>(p);
     else roi_align_fwd_nhwc_mlvl_walk<Tin, Tout, false><<<grid, kThreads, 0, st>>>(p);
@@ -880,6 +1070,109 @@ static int launch_fwd_mlvl(MlvlParams& p, bool affine, cudaStream_t st) {
     else roi_align_fwd_nhwc_mlvl<Tin, Tout, 0, false, 1><<<grid, kThreads, 0, st>>>(p);
   }
   G4R_LAUNCH_CHECK("roi_align_fwd_nhwc_mlvl");
+  return G4R_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// NCHW drop-in, large-work fast path: [N,C,H,W] -> NHWC transpose (tiled through shared memory), the NHWC
+// multi-level kernel above on one level (coalesced 16-byte channel vectors, tap dedup), and the [K,PH,PW,C] ->
+// [K,C,PH,PW] transpose back.  Three streaming passes instead of the plane gather of the reference layout
+// (roi_align_cuda_kernel.cuh:17-108: one thread per output scalar, 16 scattered 4-byte loads each): the same
+// arithmetic in the same order, so the results stay bit-identical to the direct NCHW kernel.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_batched(const T* __restrict__ in, T* __restrict__ out, int R, int S) {
+  // per batch b = blockIdx.z: in [R][S] -> out [S][R].  Tile = 32 rows x 32 16-byte vectors: global reads are
+  // 16-byte vectors along S (4 in flight per thread), global writes 4-byte-per-lane runs along R (coalesced);
+  // the row pitch of the shared tile keeps the vector stores conflict-free and the transposed reads 4-way.
+  constexpr int VEC = 16 / (int)sizeof(T);
+  constexpr int TS = 32 * VEC;
+  __shared__ __align__(16) T tile[32][TS + VEC];
+  const size_t base = (size_t)blockIdx.z * R * S;
+  const int s0 = blockIdx.x * TS, r0 = blockIdx.y * 32;
+  const bool vec_ok = (S % VEC == 0) && ((reinterpret_cast<uintptr_t>(in + base) & 15) == 0);
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const int idx = threadIdx.x + it * 256;
+    const int row = idx >> 5, vc = idx & 31;
+    const int r = r0 + row, sidx = s0 + vc * VEC;
+    if (r < R && sidx < S) {
+      if (vec_ok) {
+        *reinterpret_cast<uint4*>(&tile[row][vc * VEC]) = *reinterpret_cast<const uint4*>(in + base + (size_t)r * S + sidx);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; i++)
+          if (sidx + i < S) tile[row][vc * VEC + i] = in[base + (size_t)r * S + sidx + i];
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = r0 + lane;
+  for (int sl = warp; sl < TS; sl += 8) {
+    const int sidx = s0 + sl;
+    if (sidx < S && r < R) out[base + (size_t)sidx * R + r] = tile[lane][sl];
+  }
+}
+
+template <typename T>
+__global__ void widen_rois(const T* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = to_f32<T>(in[i]);
+}
+
+static bool nchw_fast_ok(int N, int C, int H, int W, int K, int PH, int PW, int sampling_ratio, int pool_mode, int dtype) {
+  if (pool_mode != G4R_POOL_AVG) return false;
+  if (dtype != G4R_F32 && dtype != G4R_F16 && dtype != G4R_BF16) return false;
+  const int vec = 16 / (int)dtype_size(dtype);
+  if (C < 64 || C % vec != 0) return false;
+  if (H > 65535 || W > 65535) return false;
+  const int g = sampling_ratio > 0 ? sampling_ratio : 2;
+  // worth three streaming passes only when the tap work outweighs touching every map element twice
+  return (double)K * PH * PW * 4.0 * g * g >= 2.0 * (double)N * H * W;
+}
+
+static size_t nchw_fast_bytes(int N, int C, int H, int W, int K, int PH, int PW, int dtype) {
+  const size_t es = dtype_size(dtype);
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  return al((size_t)N * C * H * W * es) + al((size_t)K * C * PH * PW * es) + al((size_t)K * 5 * 4);
+}
+
+template <typename T>
+static int nchw_fast_run(const void* input, const void* rois, void* output, int N, int C, int H, int W, int K, int PH,
+                         int PW, float scale, int sr, int aligned, int dtype, void* ws, cudaStream_t st) {
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t es = sizeof(T);
+  char* w0 = (char*)ws;
+  T* in_t = (T*)w0;
+  T* out_t = (T*)(w0 + al((size_t)N * C * H * W * es));
+  float* rois32 = (float*)(w0 + al((size_t)N * C * H * W * es) + al((size_t)K * C * PH * PW * es));
+  const int HW = H * W;
+  G4R_REQUIRE(N <= 65535 && K <= 65535 * 64, "nchw fast path: batch too large");
+  transpose_batched<T><<<dim3((HW + 32 * (16 / (int)sizeof(T)) - 1) / (32 * (16 / (int)sizeof(T))), (C + 31) / 32, N), 256, 0, st>>>((const T*)input, in_t, C, HW);
+  G4R_LAUNCH_CHECK("transpose_batched(in)");
+  const float* rp = (const float*)rois;
+  if (dtype != G4R_F32) {
+    widen_rois<T><<<(K * 5 + 255) / 256, 256, 0, st>>>((const T*)rois, rois32, K * 5);
+    G4R_LAUNCH_CHECK("widen_rois");
+    rp = rois32;
+  }
+  MlvlParams p{};
+  p.maps[0] = in_t; p.H[0] = H; p.W[0] = W; p.scale[0] = scale;
+  p.rois = rp; p.out = out_t;
+  p.N = N; p.C = C; p.K = K; p.PH = PH; p.PW = PW; p.sampling_ratio = sr; p.aligned = aligned; p.n_levels = 1;
+  p.one = 1.0f;
+  int rc = launch_fwd_mlvl<T, T>(p, false, st);
+  if (rc) return rc;
+  // out_t [K][PH*PW][C] -> output [K][C][PH*PW]; K can exceed gridDim.z: chunk it
+  const int P = PH * PW;
+  for (int k0 = 0; k0 < K; k0 += 65535) {
+    const int kb = K - k0 < 65535 ? K - k0 : 65535;
+    transpose_batched<T><<<dim3((C + 32 * (16 / (int)sizeof(T)) - 1) / (32 * (16 / (int)sizeof(T))), (P + 31) / 32, kb), 256, 0, st>>>(out_t + (size_t)k0 * P * C,
+                                                                               (T*)output + (size_t)k0 * P * C, P, C);
+    G4R_LAUNCH_CHECK("transpose_batched(out)");
+  }
   return G4R_OK;
 }
 
@@ -1008,6 +1301,32 @@ extern "C" int g4r_roi_align_forward(const void* input, const void* rois, void* 
     case G4R_F64: return launch_fwd_nchw<double>(input, rois, output, argmax_y, argmax_x, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
     case G4R_F16: return launch_fwd_nchw<__half>(input, rois, output, argmax_y, argmax_x, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
     default: return launch_fwd_nchw<__nv_bfloat16>(input, rois, output, argmax_y, argmax_x, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, pool_mode, aligned, st);
+  }
+}
+
+extern "C" size_t g4r_roi_align_forward_workspace(int N, int C, int H, int W, int K, int PH, int PW,
+                                                  int sampling_ratio, int pool_mode, int dtype, int layout) {
+  if (layout != G4R_NCHW || K <= 0) return 0;
+  if (!nchw_fast_ok(N, C, H, W, K, PH, PW, sampling_ratio, pool_mode, dtype)) return 0;
+  return nchw_fast_bytes(N, C, H, W, K, PH, PW, dtype);
+}
+
+extern "C" int g4r_roi_align_forward_ws(const void* input, const void* rois, void* output, void* argmax_y,
+                                        void* argmax_x, int N, int C, int H, int W, int K, int PH, int PW,
+                                        float spatial_scale, int sampling_ratio, int pool_mode, int aligned,
+                                        int dtype, int layout, void* workspace, size_t workspace_bytes, void* stream) {
+  const size_t need = g4r_roi_align_forward_workspace(N, C, H, W, K, PH, PW, sampling_ratio, pool_mode, dtype, layout);
+  if (need == 0 || workspace == nullptr || workspace_bytes < need)
+    return g4r_roi_align_forward(input, rois, output, argmax_y, argmax_x, N, C, H, W, K, PH, PW, spatial_scale,
+                                 sampling_ratio, pool_mode, aligned, dtype, layout, stream);
+  int rc = check_common(input, rois, output, N, C, H, W, K, PH, PW, pool_mode, dtype, layout);
+  if (rc) return rc;
+  G4R_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case G4R_F32: return nchw_fast_run<float>(input, rois, output, N, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, aligned, dtype, workspace, st);
+    case G4R_F16: return nchw_fast_run<__half>(input, rois, output, N, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, aligned, dtype, workspace, st);
+    default: return nchw_fast_run<__nv_bfloat16>(input, rois, output, N, C, H, W, K, PH, PW, spatial_scale, sampling_ratio, aligned, dtype, workspace, st);
   }
 }
 

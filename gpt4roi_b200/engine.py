@@ -33,12 +33,13 @@ class EngineConfig:
                  rope_theta=10000.0, roi_out=14, roi_sampling=2, spi_dim=1024, gn_groups=64,
                  im_patch_token=32001, bbox_token=32002, im_start_token=32004, im_end_token=32005,
                  llama_stream=None):
-        """llama_stream: dtype of the LLaMA residual stream in the prefill -- 'fp32' (default; what the reference has
-        whenever its parameters are fp32 under autocast, i.e. in training, and strictly more accurate) or 'bf16'
-        (what a model cast to bf16 has).  Env G4R_LLAMA_STREAM overrides the default."""
+        """llama_stream: dtype of the LLaMA residual stream in the prefill -- 'bf16' (default: what the reference has
+        when the model was cast to bf16, the BASELINE "7B bf16 prefill" mode) or 'fp32' (what the reference has
+        whenever its parameters are fp32 under autocast; 25 % closer to the fp32 anchor at 32 layers, 2.4 % slower:
+        tests/test_parity_7b_gpu.py, profiles/r2_bench_stream_ab.json).  Env G4R_LLAMA_STREAM overrides the default."""
         import os
         if llama_stream is None:
-            llama_stream = os.environ.get('G4R_LLAMA_STREAM', 'fp32')
+            llama_stream = os.environ.get('G4R_LLAMA_STREAM', 'bf16')
         if llama_stream not in ('fp32', 'bf16'):
             raise ValueError('llama_stream must be fp32 or bf16')
         self.__dict__.update(locals())

@@ -31,7 +31,10 @@ SIGNATURES = {
     'g4r_last_error': (_c.c_char_p, []),
     'g4r_version': (_i, []),
     'g4r_built_arch': (_i, []),
+    'g4r_set_sm_reserve': (_i, [_i]),
     'g4r_roi_align_forward': (_i, [_vp] * 5 + [_i] * 7 + [_f] + [_i] * 5 + [_vp]),
+    'g4r_roi_align_forward_workspace': (_c.c_size_t, [_i] * 11),
+    'g4r_roi_align_forward_ws': (_i, [_vp] * 5 + [_i] * 7 + [_f] + [_i] * 5 + [_vp, _c.c_size_t, _vp]),
     'g4r_roi_align_backward': (_i, [_vp] * 5 + [_i] * 7 + [_f] + [_i] * 5 + [_vp]),
     'g4r_roi_align_mlvl_forward': (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 9 + [_vp] * 3),
     'g4r_roi_align_mlvl_backward': (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 8 + [_vp]),
@@ -118,6 +121,11 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def set_sm_reserve(n):
+    """Keep n SMs free of the persistent GEMM kernels (room for an overlapped collective); returns the previous value."""
+    return int(load().g4r_set_sm_reserve(int(n)))
 
 
 def check(rc, launches=1):

@@ -42,14 +42,20 @@ def roi_align_forward(input, rois, output, argmax_y, argmax_x, aligned_height, a
     pool_mode = int(pool_mode)
     if pool_mode == _L.POOL_MAX and (argmax_y.shape != output.shape or argmax_x.shape != output.shape):
         raise RuntimeError('max pooling needs argmax_y/argmax_x shaped like output')
+    lib = _L.load()
+    code = _L.dtype_code(input)
+    # scratch for the transpose -> NHWC kernel -> transpose path (0 when the direct NCHW kernel is the better fit)
+    need = int(lib.g4r_roi_align_forward_workspace(n, c, h, w, k, int(aligned_height), int(aligned_width),
+                                                   int(sampling_ratio), pool_mode, code, _L.NCHW))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None
     with torch.cuda.device(dev):
-        _L.check(_L.load().g4r_roi_align_forward(
+        _L.check(lib.g4r_roi_align_forward_ws(
             _L.ptr(input), _L.ptr(rois), _L.ptr(output),
             _L.ptr(argmax_y) if pool_mode == _L.POOL_MAX else None,
             _L.ptr(argmax_x) if pool_mode == _L.POOL_MAX else None,
             n, c, h, w, k, int(aligned_height), int(aligned_width), float(spatial_scale),
-            int(sampling_ratio), pool_mode, int(bool(aligned)), _L.dtype_code(input), _L.NCHW,
-            _L.stream_ptr(dev)))
+            int(sampling_ratio), pool_mode, int(bool(aligned)), code, _L.NCHW,
+            _L.ptr(ws), need, _L.stream_ptr(dev)), launches=3 if need else 1)
 
 
 def roi_align_backward(grad_output, rois, argmax_y, argmax_x, grad_input, aligned_height,

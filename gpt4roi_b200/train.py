@@ -663,7 +663,7 @@ class Stage2Trainer:
 
     def __init__(self, cfg, state_dict, vit_state_dict, device, lr=2e-5, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, reducer=None, world_size=1, trainable=ALL_GROUPS, max_grad_norm=1.0,
-                 schedule=None, spi_decay_all=None, own_optimizer=True):
+                 schedule=None, spi_decay_all=None, own_optimizer=True, sm_reserve=None):
         """schedule: None (constant lr) or dict(total_steps=N, warmup_steps=0, warmup_ratio=0.003, kind='cosine').
         spi_decay_all: weight decay applied to EVERY SPI tensor (the ONLY_SPI group of llava_trainer.py:68-78);
         None = the default rule (decay `weight_decay` on matrices, none on biases / norm weights)."""
@@ -684,6 +684,10 @@ class Stage2Trainer:
                                                              self.schedule.get('warmup_ratio', 0.0))
         self.spi_decay_all = spi_decay_all
         self.own_optimizer = own_optimizer
+        # SMs kept free of the persistent GEMM kernels while a gradient collective runs beside the backward
+        # (lib.set_sm_reserve); pair it with NCCL_MAX_CTAS=<same> set before the process group is created
+        import os
+        self.sm_reserve = int(os.environ.get('G4R_DDP_SM_RESERVE', '8')) if sm_reserve is None else int(sm_reserve)
         fcfg = copy.copy(cfg)
         fcfg.n_layers = 0                                   # the front-end engine holds no decoder layers
         self.eng = PrefillEngine(fcfg, state_dict, vit_state_dict, device)
@@ -743,6 +747,9 @@ class Stage2Trainer:
         """Backward of the last forward_loss; gradients are left in self.stack.grads and self.front_flat (already
         all-reduced over the data-parallel group when a reducer is attached)."""
         red = self.reducer if (self.reducer is not None and self.reducer.active()) else None
+        from . import lib as _lib
+        if red is not None and self.sm_reserve > 0:
+            _lib.set_sm_reserve(self.sm_reserve)
         d_embeds = self.stack.backward(loss_scale=loss_scale, on_layer_grads=red.hook if red is not None else None,
                                        on_top_grads=red.top_hook if red is not None else None)
         tr = self.trainable
@@ -761,6 +768,8 @@ class Stage2Trainer:
                 small.append(self.stack.grads['top']['norm'])
             red.reduce_now(small)
             red.wait()
+            if self.sm_reserve > 0:
+                _lib.set_sm_reserve(0)
 
     def forward_backward(self, input_ids, images, bboxes, labels):
         """Returns the loss; see backward()."""

@@ -40,6 +40,10 @@ const char* g4r_last_error(void);
 /* Library/ABI version (major*1000+minor) and the SM arch it was built for. */
 int g4r_version(void);
 int g4r_built_arch(void); /* 100 for sm_100a */
+/* Keep n_sms SMs free of the persistent (one CTA per SM) tcgen05 GEMM kernels -- room for the CTAs of a collective
+ * that runs beside the backward (the DDP gradient all-reduce of gpt4roi/train/train.py:698-712).  Returns the
+ * previous reserve.  Process-wide; 0 (default) = the GEMMs use every SM. */
+int g4r_set_sm_reserve(int n_sms);
 
 /* ---- RoIAlign: operator seam -------------------------------------------- */
 /*
@@ -64,6 +68,21 @@ int g4r_roi_align_forward(const void* input, const void* rois, void* output,
                           float spatial_scale, int sampling_ratio,
                           int pool_mode, int aligned,
                           int dtype, int layout, void* stream);
+
+/*
+ * Same operator with a caller-provided scratch buffer: for the NCHW drop-in layout with enough RoIs
+ * (g4r_roi_align_forward_workspace() > 0: avg pooling, fp32/fp16/bf16, C a multiple of the 16-byte vector and
+ * >= 64, tap work >= twice the map size) the call runs as NCHW->NHWC transpose, the coalesced NHWC kernel, and
+ * the transpose back -- three streaming passes instead of the reference layout's plane gather
+ * (roi_align_cuda_kernel.cuh:17-108), bit-identical results.  With workspace == NULL, too small, or a
+ * configuration the fast path does not cover, it is exactly g4r_roi_align_forward.  workspace: 256-byte aligned.
+ */
+size_t g4r_roi_align_forward_workspace(int N, int C, int H, int W, int K, int PH, int PW, int sampling_ratio,
+                                       int pool_mode, int dtype, int layout);
+int g4r_roi_align_forward_ws(const void* input, const void* rois, void* output, void* argmax_y, void* argmax_x,
+                             int N, int C, int H, int W, int K, int PH, int PW, float spatial_scale,
+                             int sampling_ratio, int pool_mode, int aligned, int dtype, int layout,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Replaces mmcv._ext.roi_align_backward

@@ -10,9 +10,9 @@ the model seam (`gpt4roi_b200.spi_llava.SPILlavaMPTForCausalLM.forward`, weights
 Error is recorded per stage and with depth (ViT taps, region tokens, spliced embeddings, residual stream after decoder
 layers 8 / 16 / 24 / 31, logits) as rel-L2 = ||a-b|| / ||b|| and max-rel = max|a-b| / max|b|.
 
-Two engine modes are measured: the default fp32 LLaMA residual stream (EngineConfig.llama_stream='fp32': what the
-reference has in training -- fp32 parameters under autocast -- and strictly more accurate) and the bf16 stream (what a
-model cast to bf16 has; the reference's bf16-autocast run below is this mode).
+Two engine modes are measured: the default bf16 LLaMA residual stream (what a model cast to bf16 has; the reference's
+bf16-autocast run below is this mode) and EngineConfig.llama_stream='fp32' (what the reference has in training -- fp32
+parameters under autocast; more accurate, 2.4 % slower).
 
 Stated tolerance (what bf16 GEMM operands can hold at 32 layers; north_star's "1e-3" is an fp32-vs-fp32 figure that the
 reference's own bf16 mode misses by 36x at this depth: 3.6e-2):
@@ -58,7 +58,7 @@ def test_full_7b_forward_through_the_seam_vs_fp32_and_bf16_oracles():
     images = images.to(BF)
     depth = (8, 16, 24, 31)
 
-    # ---- the product, through the model seam (default mode: fp32 residual stream) -------------------------
+    # ---- the product, through the model seam (default mode: bf16 residual stream) -------------------------
     from gpt4roi_b200.engine import PrefillEngine
     model = build_seam_model(cfg, sd, vit_sd, dtype=BF).eval()
     with torch.no_grad():
@@ -67,7 +67,7 @@ def test_full_7b_forward_through_the_seam_vs_fp32_and_bf16_oracles():
     logits = out.logits.float()
     assert logits.shape == (B, T + cfg.num_patches + 2, cfg.vocab) and torch.isfinite(logits).all()
     eng = model._get_engine(torch.device(DEV))
-    assert eng.cfg.llama_stream == 'fp32'
+    assert eng.cfg.llama_stream == 'bf16'
 
     def run(engine):
         stage, htaps = {}, {n: None for n in depth}
@@ -83,7 +83,7 @@ def test_full_7b_forward_through_the_seam_vs_fp32_and_bf16_oracles():
     assert torch.equal(got['logits'], logits)                        # same engine, no atomics: bitwise repeatable
     del model, eng, out
     torch.cuda.empty_cache()
-    cfg16 = EngineConfig(image_size=336, vit_layers=24, n_layers=32, llama_stream='bf16')
+    cfg16 = EngineConfig(image_size=336, vit_layers=24, n_layers=32, llama_stream='fp32')
     eng16 = PrefillEngine(cfg16, sd, vit_sd, DEV)
     got16 = run(eng16)
     del eng16
@@ -104,7 +104,7 @@ def test_full_7b_forward_through_the_seam_vs_fp32_and_bf16_oracles():
                                         return_intermediates=True, hidden_layers=depth))
     order = ['vit%d' % l for l in cfg.level_layers] + ['region', 'embeds'] + ['h%d' % n for n in depth] + ['logits']
     agree16 = (r16['logits'].argmax(-1) == r32['logits'].argmax(-1)).float().mean().item()
-    for name, g, slack, lim in (('fp32 stream (default)', got, 1.0, (3e-2, 4e-2)), ('bf16 stream', got16, 1.25, (4e-2, 5e-2))):
+    for name, g, slack, lim in (('bf16 stream (default)', got, 1.25, (4e-2, 5e-2)), ('fp32 stream', got16, 1.0, (3e-2, 4e-2))):
         print('\n[%s]\nstage      | engine vs fp32      | bf16-ref vs fp32    | engine vs bf16-ref   (rel-L2 / max-rel)' % name)
         rows = {}
         for k in order:

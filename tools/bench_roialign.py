@@ -46,7 +46,7 @@ def main():
     ap.add_argument('--rois', type=int, default=100)
     ap.add_argument('--size', type=int, default=224)
     ap.add_argument('--iters', type=int, default=5)
-    ap.add_argument('--variants', default='all')
+    ap.add_argument('--variants', default='all', help="'all', 'nhwc' (skip the NCHW comparisons) or 'headline' (fp32 7x7 only)")
     a = ap.parse_args()
     dev = 'cuda:0'
     C = 1024
@@ -68,9 +68,11 @@ def main():
         print(json.dumps(r), flush=True)
 
     for dt, dname, esz in ((torch.float32, 'fp32', 4), (torch.bfloat16, 'bf16', 2)):
+        if a.variants == 'headline' and dname != 'fp32':
+            continue
         maps = [torch.randn(a.maps, h, h, C, device=dev, dtype=dt) for h in hs]
         in_b = a.maps * px * C * esz
-        for ph in (7, 14):
+        for ph in ((7,) if a.variants == 'headline' else (7, 14)):
             out_b = 4 * K * ph * ph * C * esz
             free = torch.cuda.mem_get_info()[0]
             if out_b > free * 0.9:
@@ -83,6 +85,8 @@ def main():
         del maps
         torch.cuda.empty_cache()
 
+    if a.variants in ('nhwc', 'headline'):
+        return
     # NCHW fp32 comparisons: drop-in kernel, reference CUDA kernel (sm_100a build), torchvision
     nm = min(a.maps, 64)  # NCHW copies; keep memory bounded
     sub = rois[rois[:, 0] < nm].contiguous()
@@ -105,6 +109,13 @@ def main():
         for l in range(4):
             g.roi_align_forward(mapsn[l], sub, outs[l], e0, e0, 7, 7, SCALES[l], 2, 1, True)
     scale_report('b200_nchw_dropin_fp32_p7', time_fn(ours, a.iters, flush))
+
+    def ours_direct():   # the plane-gather kernel the fast path replaces (no workspace)
+        from gpt4roi_b200 import lib as L
+        for l in range(4):
+            L.check(L.load().g4r_roi_align_forward(L.ptr(mapsn[l]), L.ptr(sub), L.ptr(outs[l]), None, None, nm, C, hs[l], hs[l],
+                                                   Ks, 7, 7, SCALES[l], 2, 1, 1, L.F32, L.NCHW, L.stream_ptr(torch.device(dev))))
+    scale_report('b200_nchw_direct_kernel_fp32_p7', time_fn(ours_direct, a.iters, flush))
     try:
         from oracle import build_ref
         ref = build_ref.load_cuda()

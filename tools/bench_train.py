@@ -95,7 +95,7 @@ def full_step(a, world, rank, dev, reducer):
     from gpt4roi_b200.train import Stage2Trainer
     cfg = EngineConfig(image_size=336, n_layers=a.layers)
     sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
-    tr = Stage2Trainer(cfg, sd, vit_sd, dev, lr=2e-5, reducer=reducer, world_size=world)
+    tr = Stage2Trainer(cfg, sd, vit_sd, dev, lr=2e-5, reducer=reducer, world_size=world)   # G4R_DDP_SM_RESERVE / NCCL_MAX_CTAS from the env
     del sd, vit_sd
     torch.cuda.empty_cache()
     ids, images, boxes = synthetic_inputs(cfg, a.batch, 8, 128, seed=100 + rank)   # a different micro-batch per rank
@@ -131,6 +131,7 @@ def full_step(a, world, rank, dev, reducer):
                                           % (ids.shape[1], a.batch), layers=a.layers, trained_params=n_params, global_batch=world * a.batch),
                               tokens_per_sec=world * a.batch * ids.shape[1] / (ms / 1e3), gpu_launches_per_step=(L.LAUNCHES - l0) // a.steps,
                               peak_mem_GB=torch.cuda.max_memory_allocated() / 1e9, losses=[round(v, 4) for v in losses],
+                              sm_reserve=tr.sm_reserve, nccl_max_ctas=os.environ.get('NCCL_MAX_CTAS'),
                               data='synthetic images / boxes / tokens, random-init weights')), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
