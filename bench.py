@@ -414,7 +414,8 @@ def decode_extra(eng, cfg, dev, pk, n_new=48):
 
 def train_extra(dev, world, rank, steps=4, warmup=2, batch=4, stage1=True):
     """BASELINE configs[3]: stage-2 training step (ViT frozen), bf16, per-GPU batch 4 (global 32 at 8 GPUs), DDP with
-    the NCCL gradient all-reduce overlapped with the backward; plus the ONLY_SPI stage-1 variant."""
+    the NCCL gradient all-reduce overlapped with the backward; the same step with the sharded optimizer (reduce-scatter
+    / AdamW on slices / all-gather: what train_stage2.sh's FSDP does); and the ONLY_SPI stage-1 variant."""
     import torch
     import torch.distributed as dist
     from gpt4roi_b200 import lib
@@ -446,6 +447,8 @@ def train_extra(dev, world, rank, steps=4, warmup=2, batch=4, stage1=True):
         return ms, float(loss.item())
 
     variants = [('stage2', dict(trainable=('embed', 'proj', 'spi', 'llama', 'head')))]
+    if world > 1:   # FSDP-equivalent of train_stage2.sh:51-52: reduce-scatter + AdamW on 1/world slices + all-gather
+        variants.append(('stage2_sharded_optimizer', dict(trainable=('embed', 'proj', 'spi', 'llama', 'head'), shard_optimizer=True)))
     if stage1:
         variants.append(('stage1_only_spi', dict(trainable=('spi',), spi_decay_all=0.01)))
     for name, kw in variants:
@@ -465,7 +468,7 @@ def train_extra(dev, world, rank, steps=4, warmup=2, batch=4, stage1=True):
                    g4r_launches_per_step=launches, peak_mem_GB=torch.cuda.max_memory_allocated(dev) / 1e9,
                    losses=[round(v, 4) for v in losses + [loss]],
                    grad_norm=float(tr.clip[0].item()) if tr.clip is not None else None)
-        if world > 1:
+        if world > 1 and not kw.get('shard_optimizer'):
             tr.reducer = None                                         # same step without the collectives
             ms_local, _ = timed(tr, max(2, steps // 2))
             rec['ms_per_step_no_allreduce'] = ms_local

@@ -142,8 +142,31 @@ MATRIX_KEYS = ('wqkv', 'wo', 'wgu', 'wdown')      # bf16 gradients: one flat buc
 NORM_KEYS = ('ln_in', 'ln_post')                  # fp32 gradients [hidden]: one [n_layers, 2, hidden] buffer
 
 
+def layer_views(flat, cfg):
+    """The four matrices of one decoder layer (engine layout: wqkv | wo | wgu | wdown) as views of one flat buffer."""
+    H, F = cfg.hidden, cfg.mlp
+    shapes = dict(wqkv=(3 * H, H), wo=(H, H), wgu=(2 * F, H), wdown=(H, F))
+    out, o = {}, 0
+    for k in MATRIX_KEYS:
+        n = shapes[k][0] * shapes[k][1]
+        out[k] = flat[o:o + n].view(shapes[k])
+        o += n
+    return out
+
+
+def layer_numel(cfg):
+    H, F = cfg.hidden, cfg.mlp
+    return 3 * H * H + H * H + 2 * F * H + H * F
+
+
 class LlamaTrainStack:
     """LLaMA decoder stack with explicit forward / backward / AdamW on the sm_100a kernels.
+
+    Storage: per decoder layer ONE flat bf16 weight buffer (the four matrices are views of it) and, where this object
+    owns the optimizer, flat fp32 master / moment buffers -- the whole vector, or this rank's 1/world slice of it
+    (`shard=True`, the FSDP-equivalent of train_stage2.sh:51-52: gradients are reduce-scattered, AdamW runs on the
+    slice, the updated bf16 slice is all-gathered back into the flat weight buffer).  lm_head is one more such
+    buffer; norm weights (fp32 gradients, 4096 floats each) stay replicated.
 
     own_optimizer=False: no fp32 masters / moments are allocated -- the bf16 weights are refreshed from an external
     state dict (`load_weights`, the model-seam path where torch.optim owns the parameters).
@@ -151,7 +174,7 @@ class LlamaTrainStack:
     activation gradients (no weight-gradient GEMMs) and the optimizer skips those tensors."""
 
     def __init__(self, cfg, state_dict, device, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 own_optimizer=True, train_layers=True, train_head=True):
+                 own_optimizer=True, train_layers=True, train_head=True, shard=False, world=1, rank=0):
         """cfg: engine.EngineConfig; state_dict: HF names (model.layers.N..., model.norm.weight, lm_head.weight).
         weight_decay follows llava_trainer.py:59-144: decay on matrices, none on norm weights."""
         self.cfg, self.dev = cfg, torch.device(device)
@@ -162,25 +185,49 @@ class LlamaTrainStack:
             raise ValueError('LlamaTrainStack: head_dim 128 required (fused-RoPE QKV GEMM)')
         self.own_layers = own_optimizer and train_layers
         self.own_head = own_optimizer and train_head
-        f32 = lambda t: t.detach().to(self.dev, F32).contiguous()
-        zeros = lambda t: torch.zeros_like(t)
-        if self.own_layers:
-            self.master = [fuse_llama_layer(state_dict, i, self.dev) for i in range(cfg.n_layers)]   # fp32 masters
-            self.w = [{k: v.to(BF16) for k, v in m.items()} for m in self.master]      # bf16 compute copies
-            self.m1 = [{k: zeros(v) for k, v in m.items()} for m in self.master]
-            self.m2 = [{k: zeros(v) for k, v in m.items()} for m in self.master]
-        else:
-            self.master = self.m1 = self.m2 = None
-            self.w = [fuse_llama_layer(state_dict, i, self.dev, BF16) for i in range(cfg.n_layers)]
+        self.shard = bool(shard) and world > 1
+        self.world, self.rank = (world, rank) if self.shard else (1, 0)
+        n = layer_numel(cfg)
+        nh = cfg.vocab * cfg.hidden
+        if n % (self.world * 8) or nh % (self.world * 8):
+            raise ValueError('sharded optimizer: the flat layer size must divide by 8 x world')
+        self.slice = slice(self.rank * (n // self.world), (self.rank + 1) * (n // self.world))
+        self.slice_head = slice(self.rank * (nh // self.world), (self.rank + 1) * (nh // self.world))
+        self.wflat, self.w = [], []
+        self.mflat, self.m1flat, self.m2flat = [], [], []
+        self.master_ln, self.m1_ln, self.m2_ln = [], [], []
+        for i in range(cfg.n_layers):
+            fused = fuse_llama_layer(state_dict, i, self.dev, F32 if self.own_layers else BF16)
+            flat = torch.empty(n, dtype=BF16, device=self.dev)
+            views = layer_views(flat, cfg)
+            for k in MATRIX_KEYS:
+                views[k].copy_(fused[k])
+            views['ln_in'], views['ln_post'] = fused['ln_in'].to(BF16), fused['ln_post'].to(BF16)
+            self.wflat.append(flat)
+            self.w.append(views)
+            if self.own_layers:
+                full = torch.cat([fused[k].reshape(-1) for k in MATRIX_KEYS]) if self.world == 1 else None
+                if full is None:   # only this rank's slice is kept in fp32
+                    full = torch.cat([fused[k].reshape(-1) for k in MATRIX_KEYS])[self.slice].clone()
+                self.mflat.append(full)
+                self.m1flat.append(torch.zeros_like(full))
+                self.m2flat.append(torch.zeros_like(full))
+                ln = dict(ln_in=fused['ln_in'].float().clone(), ln_post=fused['ln_post'].float().clone())
+                self.master_ln.append(ln)
+                self.m1_ln.append({k: torch.zeros_like(v) for k, v in ln.items()})
+                self.m2_ln.append({k: torch.zeros_like(v) for k, v in ln.items()})
+            del fused
+        head = state_dict['lm_head.weight'].detach().to(self.dev)
+        self.w_top = dict(norm=state_dict['model.norm.weight'].detach().to(self.dev, BF16).contiguous(),
+                          lm_head=head.to(BF16).contiguous())
         if self.own_head:
-            self.master_top = dict(norm=f32(state_dict['model.norm.weight']), lm_head=f32(state_dict['lm_head.weight']))
-            self.w_top = {k: v.to(BF16) for k, v in self.master_top.items()}
-            self.m1_top = {k: zeros(v) for k, v in self.master_top.items()}
-            self.m2_top = {k: zeros(v) for k, v in self.master_top.items()}
-        else:
-            self.master_top = self.m1_top = self.m2_top = None
-            self.w_top = dict(norm=state_dict['model.norm.weight'].detach().to(self.dev, BF16).contiguous(),
-                              lm_head=state_dict['lm_head.weight'].detach().to(self.dev, BF16).contiguous())
+            hf = head.to(F32).reshape(-1)
+            self.mflat_head = hf[self.slice_head].clone() if self.world > 1 else hf.clone()
+            self.m1_head, self.m2_head = torch.zeros_like(self.mflat_head), torch.zeros_like(self.mflat_head)
+            self.master_norm = state_dict['model.norm.weight'].detach().to(self.dev, F32).contiguous().clone()
+            self.m1_norm, self.m2_norm = torch.zeros_like(self.master_norm), torch.zeros_like(self.master_norm)
+        del head
+        self.pending = {}          # layer index (or 'head') -> all-gather work handle of its refreshed bf16 weights
         self._rope_cache = {}
         self.saved = None
         self.grads = None
@@ -201,15 +248,69 @@ class LlamaTrainStack:
         self.w_top['norm'].copy_(state_dict['model.norm.weight'])
         self.w_top['lm_head'].copy_(state_dict['lm_head.weight'])
 
-    def state_dict(self):
-        """Weights under the reference's parameter names (views of the fused tensors): the fp32 masters where this
-        object owns the optimizer, else the bf16 compute copies."""
-        out = {}
-        for i, m in enumerate(self.master if self.master is not None else self.w):
-            out.update(unfuse_llama_layer(m, i))
-        top = self.master_top if self.master_top is not None else self.w_top
-        out['model.norm.weight'], out['lm_head.weight'] = top['norm'], top['lm_head']
+    def _full(self, shard_t, group=None):
+        """fp32 slice -> the whole vector (all-gather over the data-parallel group when sharded)."""
+        if self.world == 1:
+            return shard_t
+        import torch.distributed as dist
+        out = torch.empty(shard_t.numel() * self.world, dtype=shard_t.dtype, device=shard_t.device)
+        dist.all_gather_into_tensor(out, shard_t.contiguous(), group=group)
         return out
+
+    def _named(self, flats, lns, head, norm):
+        out = {}
+        for i in range(len(self.w)):
+            d = dict(layer_views(self._full(flats[i]), self.cfg))
+            d['ln_in'], d['ln_post'] = lns[i]['ln_in'], lns[i]['ln_post']
+            out.update(unfuse_llama_layer(d, i))
+        if head is not None:
+            out['lm_head.weight'] = self._full(head).view(self.cfg.vocab, self.cfg.hidden)
+            out['model.norm.weight'] = norm
+        return out
+
+    def state_dict(self):
+        """Weights under the reference's parameter names: the fp32 masters where this object owns the optimizer
+        (gathered from the ranks' slices when sharded -- a collective call: every rank must make it), else the bf16
+        compute copies."""
+        if self.own_layers:
+            out = self._named(self.mflat, self.master_ln, None, None)
+        else:
+            out = {}
+            for i, w in enumerate(self.w):
+                out.update(unfuse_llama_layer(w, i))
+        if self.own_head:
+            out['lm_head.weight'] = self._full(self.mflat_head).view(self.cfg.vocab, self.cfg.hidden)
+            out['model.norm.weight'] = self.master_norm
+        else:
+            out['model.norm.weight'], out['lm_head.weight'] = self.w_top['norm'], self.w_top['lm_head']
+        return out
+
+    def moments(self):
+        """(exp_avg, exp_avg_sq) under reference names for the tensors this object optimises (collective if sharded)."""
+        m1, m2 = {}, {}
+        if self.own_layers:
+            m1.update(self._named(self.m1flat, self.m1_ln, None, None))
+            m2.update(self._named(self.m2flat, self.m2_ln, None, None))
+        if self.own_head:
+            for d, h, nrm in ((m1, self.m1_head, self.m1_norm), (m2, self.m2_head, self.m2_norm)):
+                d['lm_head.weight'] = self._full(h).view(self.cfg.vocab, self.cfg.hidden)
+                d['model.norm.weight'] = nrm
+        return m1, m2
+
+    def load_moments(self, exp_avg, exp_avg_sq):
+        for src, flats, lns, head, nrm in ((exp_avg, self.m1flat, self.m1_ln, 'm1_head', 'm1_norm'),
+                                           (exp_avg_sq, self.m2flat, self.m2_ln, 'm2_head', 'm2_norm')):
+            if self.own_layers:
+                for i in range(len(self.w)):
+                    fused = fuse_llama_layer(src, i, self.dev)
+                    full = torch.cat([fused[k].reshape(-1) for k in MATRIX_KEYS])
+                    flats[i].copy_(full[self.slice] if self.world > 1 else full)
+                    lns[i]['ln_in'].copy_(fused['ln_in'])
+                    lns[i]['ln_post'].copy_(fused['ln_post'])
+            if self.own_head:
+                hf = src['lm_head.weight'].to(self.dev, F32).reshape(-1)
+                getattr(self, head).copy_(hf[self.slice_head] if self.world > 1 else hf)
+                getattr(self, nrm).copy_(src['model.norm.weight'])
 
     # ------------------------------------------------------------------ helpers
     def _rope(self, L):
@@ -220,6 +321,13 @@ class LlamaTrainStack:
             cos, sin = emb.cos().to(self.dev, BF16).contiguous(), emb.sin().to(self.dev, BF16).contiguous()
             self._rope_cache[L] = (cos, sin, (-sin).contiguous())
         return self._rope_cache[L]
+
+    def _wait_weights(self, key):
+        """Sharded optimizer: the all-gather that refreshes this layer's bf16 weights was launched by the last
+        optimizer step on the side stream; the forward waits for it only here, right before the first use."""
+        h = self.pending.pop(key, None)
+        if h is not None:
+            h.wait()
 
     # ------------------------------------------------------------------ forward
     def forward(self, inputs_embeds, targets, seqlens=None):
@@ -232,7 +340,8 @@ class LlamaTrainStack:
         scale = c.head_dim ** -0.5
         x = inputs_embeds.reshape(M, Hd).contiguous()
         saved = []
-        for w in self.w:
+        for li, w in enumerate(self.w):
+            self._wait_weights(li)
             h1 = kernels.rmsnorm(x, w['ln_in'], c.rms_eps)
             qkv = dense.qkv_rope(h1, w['wqkv'], cos, sin, L, 2 * c.hidden)
             a, lse = train_ops.attention_fwd_lse(qkv, B, L, c.n_heads, c.head_dim, True, scale)
@@ -243,6 +352,7 @@ class LlamaTrainStack:
             x_out = dense.linear(f, w['wdown'], residual=x_mid)
             saved.append(dict(x_in=x, h1=h1, qkv=qkv, a=a, lse=lse, x_mid=x_mid, h2=h2, gu=gu, f=f))
             x = x_out
+        self._wait_weights('head')
         hn = kernels.rmsnorm(x, self.w_top['norm'], c.rms_eps)
         vpad = (c.vocab + 63) // 64 * 64                       # 16-byte-aligned logits rows
         logits = torch.empty((M, vpad), dtype=BF16, device=self.dev)[:, :c.vocab]
@@ -267,6 +377,7 @@ class LlamaTrainStack:
         g_top = {}
         if self.train_head:
             g_top['lm_head'] = dense.matmul_t(dlogits, s['hn'], a_mn=True, b_mn=True)           # dW = dY^T X
+            g_top['flat'] = g_top['lm_head'].view(-1)
         dhn = dense.matmul_t(dlogits, self.w_top['lm_head'], b_mn=True)                          # dX = dY W
         del dlogits
         dx, gn = train_ops.rmsnorm_bwd(s['x_last'], self.w_top['norm'], dhn, c.rms_eps)
@@ -323,16 +434,20 @@ class LlamaTrainStack:
         return dx.view(B, L, c.hidden)
 
     def grad_tensors(self):
-        """Contiguous gradient tensors of this stack (for the global norm): layer flats, the norm buffer, top."""
-        out = []
+        """(sharded, replicated) contiguous gradient tensors of this stack for the global norm.  Sharded mode: the
+        reduce-scattered slices (each rank holds a different 1/world of the summed gradient); replicated tensors are
+        identical on every rank after their all-reduce."""
+        sharded, repl = [], []
         if self.train_layers:
-            out += [g['flat'] for g in self.grads['layers']] + [self.grads['norms']]
+            (sharded if self.shard else repl).extend(g['rs'] if self.shard else g['flat'] for g in self.grads['layers'])
+            repl.append(self.grads['norms'])
         if self.train_head:
-            out += [self.grads['top']['lm_head'], self.grads['top']['norm']]
-        return out
+            (sharded if self.shard else repl).append(self.grads['top']['rs'] if self.shard else self.grads['top']['flat'])
+            repl.append(self.grads['top']['norm'])
+        return sharded, repl
 
     def grads_state_dict(self):
-        """Gradients under the reference's parameter names (views; model-seam path)."""
+        """Gradients under the reference's parameter names (views; model-seam path, unsharded)."""
         out = {}
         if self.train_layers:
             for i, g in enumerate(self.grads['layers']):
@@ -342,23 +457,33 @@ class LlamaTrainStack:
         return out
 
     # ------------------------------------------------------------------ optimizer
-    def optimizer_step(self, grad_scale=1.0, lr=None, scale_dev=None):
-        """Fused AdamW on every trained tensor (fp32 master + moments, refreshes the bf16 compute copy)."""
+    def optimizer_step(self, grad_scale=1.0, lr=None, scale_dev=None, reducer=None):
+        """Fused AdamW on every trained tensor: ONE launch per decoder layer over the flat fp32 master / moments (or
+        this rank's slice of them), writing the refreshed bf16 weights straight into the flat weight buffer; sharded
+        mode then all-gathers each layer's bf16 slice (async on the reducer's stream; the next forward waits per layer)."""
         self.step_count += 1
         t = self.step_count
         lr = self.lr if lr is None else lr
 
-        def upd(master, m1, m2, w16, grad, name):
-            wd = 0.0 if name.startswith('ln') or name == 'norm' else self.wd
-            train_ops.adamw_step(master.view(-1), grad.reshape(-1), m1.view(-1), m2.view(-1), w16.view(-1), lr,
-                                 self.betas, self.eps, wd, t, grad_scale, scale_dev)
+        def upd(master, m1, m2, w16, grad, decay):
+            train_ops.adamw_step(master.view(-1), grad.reshape(-1), m1.view(-1), m2.view(-1), w16.reshape(-1), lr,
+                                 self.betas, self.eps, self.wd if decay else 0.0, t, grad_scale, scale_dev)
         if self.own_layers:
             for i, g in enumerate(self.grads['layers']):
-                for k in LAYER_KEYS:
-                    upd(self.master[i][k], self.m1[i][k], self.m2[i][k], self.w[i][k], g[k], k)
+                w16 = self.wflat[i][self.slice] if self.shard else self.wflat[i]
+                upd(self.mflat[i], self.m1flat[i], self.m2flat[i], w16, g['rs'] if self.shard else g['flat'], True)
+                if self.shard:
+                    self.pending[i] = reducer.all_gather(self.wflat[i], w16)
+                for k in NORM_KEYS:
+                    upd(self.master_ln[i][k], self.m1_ln[i][k], self.m2_ln[i][k], self.w[i][k], g[k], False)
         if self.own_head:
-            for k in ('norm', 'lm_head'):
-                upd(self.master_top[k], self.m1_top[k], self.m2_top[k], self.w_top[k], self.grads['top'][k], k)
+            hflat = self.w_top['lm_head'].view(-1)
+            w16 = hflat[self.slice_head] if self.shard else hflat
+            upd(self.mflat_head, self.m1_head, self.m2_head, w16,
+                self.grads['top']['rs'] if self.shard else self.grads['top']['flat'], True)
+            if self.shard:
+                self.pending['head'] = reducer.all_gather(hflat, w16)
+            upd(self.master_norm, self.m1_norm, self.m2_norm, self.w_top['norm'], self.grads['top']['norm'], False)
         self.grads = None
 
 
@@ -370,11 +495,14 @@ class LayerBucketAllReduce:
     Sums in place; the 1/world average is folded into AdamW's grad_scale.
     reduce_fp32=True all-reduces an fp32 copy of each bucket (the reference's DDP/FSDP reduce fp32 gradients)."""
 
-    def __init__(self, group=None, reduce_fp32=False):
+    def __init__(self, group=None, reduce_fp32=False, shard_grads=False):
+        """shard_grads=True: the per-layer buckets are reduce-scattered instead of all-reduced (each rank receives
+        1/world of the summed gradient) -- used with the sharded optimizer of LlamaTrainStack(shard=True)."""
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.handles = []
         self.reduce_fp32 = reduce_fp32
+        self.shard_grads = shard_grads
         self.calls = 0
         self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
 
@@ -403,10 +531,42 @@ class LayerBucketAllReduce:
             self._issue(tensors)
 
     def hook(self, i, grads):
+        if self.shard_grads and 'flat' in grads:
+            grads['rs'] = self.reduce_scatter(grads['flat'])
+            return
         self.reduce_now([grads['flat']] if 'flat' in grads else [grads[k] for k in LAYER_KEYS])
 
     def top_hook(self, g_top):
+        if self.shard_grads and 'flat' in g_top:
+            g_top['rs'] = self.reduce_scatter(g_top['flat'])
+            return
         self.reduce_now([g_top.get('lm_head')])
+
+    def reduce_scatter(self, flat):
+        """Sum `flat` over the ranks, this rank keeping slice [rank*n/world, (rank+1)*n/world) (bf16 in, bf16 out):
+        the gradient half of the FSDP-equivalent step.  Async on the side stream; returns the output slice tensor
+        (valid after wait())."""
+        world = self.dist.get_world_size(self.group)
+        out = torch.empty(flat.numel() // world, dtype=flat.dtype, device=flat.device)
+        self.calls += 1
+        if self.stream is not None and flat.is_cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                h = self.dist.reduce_scatter_tensor(out, flat, group=self.group, async_op=True)
+        else:
+            h = self.dist.reduce_scatter_tensor(out, flat, group=self.group, async_op=True)
+        self.handles.append((h, None, None))
+        return out
+
+    def all_gather(self, full, mine):
+        """In-place all-gather of every rank's slice into `full` (`mine` is this rank's slice OF `full`): the weight
+        half of the FSDP-equivalent step.  Async on the side stream; returns the work handle (wait() before use)."""
+        self.calls += 1
+        if self.stream is not None and full.is_cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                return self.dist.all_gather_into_tensor(full, mine, group=self.group, async_op=True)
+        return self.dist.all_gather_into_tensor(full, mine, group=self.group, async_op=True)
 
     def wait(self):
         for h, dst, src in self.handles:
@@ -663,15 +823,27 @@ class Stage2Trainer:
 
     def __init__(self, cfg, state_dict, vit_state_dict, device, lr=2e-5, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, reducer=None, world_size=1, trainable=ALL_GROUPS, max_grad_norm=1.0,
-                 schedule=None, spi_decay_all=None, own_optimizer=True, sm_reserve=None):
+                 schedule=None, spi_decay_all=None, own_optimizer=True, sm_reserve=None, shard_optimizer=False):
         """schedule: None (constant lr) or dict(total_steps=N, warmup_steps=0, warmup_ratio=0.003, kind='cosine').
         spi_decay_all: weight decay applied to EVERY SPI tensor (the ONLY_SPI group of llava_trainer.py:68-78);
-        None = the default rule (decay `weight_decay` on matrices, none on biases / norm weights)."""
+        None = the default rule (decay `weight_decay` on matrices, none on biases / norm weights).
+        shard_optimizer: FSDP-equivalent of train_stage2.sh:51-52 (`--fsdp "full_shard auto_wrap"` over
+        LlamaDecoderLayer): per decoder layer (and lm_head) the gradient bucket is reduce-scattered, each rank keeps
+        fp32 masters + AdamW moments for its 1/world slice only, and the refreshed bf16 slice is all-gathered into
+        the flat weight buffer, overlapped with the next forward.  The bf16 compute weights stay replicated (14 GB)."""
         import copy
         from .engine import PrefillEngine
         self.cfg, self.dev = cfg, torch.device(device)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.reducer, self.world = reducer, world_size
+        self.shard = bool(shard_optimizer) and world_size > 1 and own_optimizer
+        self.rank = 0
+        if self.shard:
+            import torch.distributed as dist
+            if reducer is None or not reducer.active():
+                raise ValueError('shard_optimizer=True needs an initialised process group and a reducer')
+            self.rank = dist.get_rank(reducer.group)
+            reducer.shard_grads = True
         self.trainable = tuple(trainable)
         bad = set(self.trainable) - set(ALL_GROUPS)
         if bad:
@@ -687,13 +859,16 @@ class Stage2Trainer:
         # SMs kept free of the persistent GEMM kernels while a gradient collective runs beside the backward
         # (lib.set_sm_reserve); pair it with NCCL_MAX_CTAS=<same> set before the process group is created
         import os
-        self.sm_reserve = int(os.environ.get('G4R_DDP_SM_RESERVE', '8')) if sm_reserve is None else int(sm_reserve)
+        # measured on 2 x B200 (profiles/r2_ddp_sm_reserve_sweep_2gpu.jsonl): reserving SMs does not shorten the step
+        # (260.3 ms with 0, 268 with 8, 263 with 16), so the default is 0
+        self.sm_reserve = int(os.environ.get('G4R_DDP_SM_RESERVE', '0')) if sm_reserve is None else int(sm_reserve)
         fcfg = copy.copy(cfg)
         fcfg.n_layers = 0                                   # the front-end engine holds no decoder layers
         self.eng = PrefillEngine(fcfg, state_dict, vit_state_dict, device)
         self.front = FrontEndTrain(self.eng)
         self.stack = LlamaTrainStack(cfg, state_dict, device, lr, betas, eps, weight_decay, own_optimizer=own_optimizer,
-                                     train_layers='llama' in self.trainable, train_head='head' in self.trainable)
+                                     train_layers='llama' in self.trainable, train_head='head' in self.trainable,
+                                     shard=self.shard, world=world_size, rank=self.rank)
         front_all = [k for k in state_dict if k.startswith('model.spi_module.') or k.startswith('model.mm_projector.')
                      or k == 'model.embed_tokens.weight']
         self.w16 = {k: state_dict[k].detach().to(self.dev, BF16).contiguous() for k in front_all}
@@ -777,8 +952,19 @@ class Stage2Trainer:
         self.backward()
         return loss
 
-    def grad_tensors(self):
-        return self.stack.grad_tensors() + ([self.front_flat] if self.front_numel else [])
+    def _clip_coef(self, scale):
+        """Global gradient norm over every trained tensor (torch clip_grad_norm_ semantics) -> device (norm, coef).
+        Sharded mode: each rank sums the squares of its reduce-scattered slices, rank 0 adds the replicated tensors,
+        one 4-byte all-reduce joins them."""
+        sharded, repl = self.stack.grad_tensors()
+        if self.front_numel:
+            repl = repl + [self.front_flat]
+        if self.shard:
+            mine = sharded + (repl if self.rank == 0 else [])
+            tot = train_ops.grad_sumsq(mine).sum().reshape(1) if mine else torch.zeros(1, dtype=F32, device=self.dev)
+            self.reducer.dist.all_reduce(tot, group=self.reducer.group)
+            return train_ops.clip_coef(tot, self.max_grad_norm, pre_scale=scale)
+        return train_ops.clip_coef(train_ops.grad_sumsq(sharded + repl), self.max_grad_norm, pre_scale=scale)
 
     def current_lr(self):
         if self.schedule is None:
@@ -799,10 +985,10 @@ class Stage2Trainer:
         scale = 1.0 / self.world
         scale_dev = None
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
-            self.clip = train_ops.clip_coef(train_ops.grad_sumsq(self.grad_tensors()), self.max_grad_norm, pre_scale=scale)
+            self.clip = self._clip_coef(scale)
             scale_dev = self.clip[1:]
         lr = self.last_lr = self.current_lr()
-        self.stack.optimizer_step(grad_scale=scale, lr=lr, scale_dev=scale_dev)
+        self.stack.optimizer_step(grad_scale=scale, lr=lr, scale_dev=scale_dev, reducer=self.reducer)
         t = self.stack.step_count
         for k in self.front_names:
             train_ops.adamw_step(self.master[k].view(-1), self._front_slice(k).reshape(-1), self.m1[k].view(-1),
@@ -826,6 +1012,8 @@ class Stage2Trainer:
 
     def grads_state_dict(self):
         """Every gradient of the last backward under the reference's parameter names (model-seam path)."""
+        if self.shard:
+            raise RuntimeError('sharded optimizer: full gradients are never materialised (each rank holds 1/world slices)')
         out = {k: self._front_slice(k) for k in self.front_names}
         out.update(self.stack.grads_state_dict())
         return out
@@ -845,33 +1033,21 @@ class Stage2Trainer:
 
     def optimizer_state(self):
         """AdamW step count (= scheduler position) and moments under reference names (resume: pass the saved fp32
-        weights to __init__, then load_optimizer_state)."""
+        weights to __init__, then load_optimizer_state).  Sharded mode: a collective call (slices are gathered)."""
         m1, m2 = dict(self.m1), dict(self.m2)
-        if self.stack.own_layers:
-            for i in range(len(self.stack.master)):
-                m1.update(unfuse_llama_layer(self.stack.m1[i], i))
-                m2.update(unfuse_llama_layer(self.stack.m2[i], i))
-        if self.stack.own_head:
-            for k, name in (('norm', 'model.norm.weight'), ('lm_head', 'lm_head.weight')):
-                m1[name], m2[name] = self.stack.m1_top[k], self.stack.m2_top[k]
+        s1, s2 = self.stack.moments()
+        m1.update(s1)
+        m2.update(s2)
         return dict(step=self.stack.step_count, exp_avg=m1, exp_avg_sq=m2, schedule=self.schedule, lr=self.lr)
 
     def load_optimizer_state(self, state):
         self.stack.step_count = int(state['step'])
         if state.get('schedule') is not None:
             self.schedule = dict(state['schedule'])
-        for src, dst_front, dst_layers, dst_top in ((state['exp_avg'], self.m1, self.stack.m1, self.stack.m1_top),
-                                                    (state['exp_avg_sq'], self.m2, self.stack.m2, self.stack.m2_top)):
-            for k in dst_front:
-                dst_front[k].copy_(src[k])
-            if self.stack.own_layers:
-                for i in range(len(dst_layers)):
-                    fused = fuse_llama_layer(src, i, self.dev)
-                    for k in LAYER_KEYS:
-                        dst_layers[i][k].copy_(fused[k])
-            if self.stack.own_head:
-                dst_top['norm'].copy_(src['model.norm.weight'])
-                dst_top['lm_head'].copy_(src['lm_head.weight'])
+        for src, dst in ((state['exp_avg'], self.m1), (state['exp_avg_sq'], self.m2)):
+            for k in dst:
+                dst[k].copy_(src[k])
+        self.stack.load_moments(state['exp_avg'], state['exp_avg_sq'])
 
     def save_optimizer(self, path):
         """optimizer.pt + scheduler position in one file (HF Trainer writes optimizer.pt / scheduler.pt beside the

@@ -73,7 +73,7 @@ def main():
         ms = t.item()
     losses.append(loss.item())
     if rank == 0:
-        n_params = sum(v.numel() for m in stack.master for v in m.values()) + sum(v.numel() for v in stack.master_top.values())
+        n_params = sum(f.numel() + 2 * cfg.hidden for f in stack.wflat) + stack.w_top['lm_head'].numel() + cfg.hidden
         tokens = a.batch * a.seq
         # 6 flop / parameter / token (fwd 2 + bwd 4) + causal attention (fwd 2*2*L*hid/2, bwd 2.5x incl. recompute)
         attn = a.layers * a.batch * (4.0 * a.seq * a.seq * cfg.hidden / 2) * 3.5
@@ -95,7 +95,8 @@ def full_step(a, world, rank, dev, reducer):
     from gpt4roi_b200.train import Stage2Trainer
     cfg = EngineConfig(image_size=336, n_layers=a.layers)
     sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
-    tr = Stage2Trainer(cfg, sd, vit_sd, dev, lr=2e-5, reducer=reducer, world_size=world)   # G4R_DDP_SM_RESERVE / NCCL_MAX_CTAS from the env
+    tr = Stage2Trainer(cfg, sd, vit_sd, dev, lr=2e-5, reducer=reducer, world_size=world,
+                       shard_optimizer=os.environ.get('G4R_SHARD') == '1')   # G4R_DDP_SM_RESERVE / NCCL_MAX_CTAS / G4R_SHARD from the env
     del sd, vit_sd
     torch.cuda.empty_cache()
     ids, images, boxes = synthetic_inputs(cfg, a.batch, 8, 128, seed=100 + rank)   # a different micro-batch per rank
@@ -123,7 +124,7 @@ def full_step(a, world, rank, dev, reducer):
         ms = t.item()
     losses.append(loss.item())
     if rank == 0:
-        n_params = sum(v.numel() for m in tr.stack.master for v in m.values()) + sum(v.numel() for v in tr.stack.master_top.values()) \
+        n_params = sum(f.numel() + 2 * cfg.hidden for f in tr.stack.wflat) + tr.stack.w_top['lm_head'].numel() + cfg.hidden \
             + sum(v.numel() for v in tr.master.values())
         print(json.dumps(dict(metric='train_step_stage2_samples_per_sec', value=world * a.batch / (ms / 1e3), unit='samples/s',
                               n_gpus=world, ms_per_step=ms, steps=a.steps, warmup=a.warmup,
@@ -131,7 +132,7 @@ def full_step(a, world, rank, dev, reducer):
                                           % (ids.shape[1], a.batch), layers=a.layers, trained_params=n_params, global_batch=world * a.batch),
                               tokens_per_sec=world * a.batch * ids.shape[1] / (ms / 1e3), gpu_launches_per_step=(L.LAUNCHES - l0) // a.steps,
                               peak_mem_GB=torch.cuda.max_memory_allocated() / 1e9, losses=[round(v, 4) for v in losses],
-                              sm_reserve=tr.sm_reserve, nccl_max_ctas=os.environ.get('NCCL_MAX_CTAS'),
+                              sm_reserve=tr.sm_reserve, nccl_max_ctas=os.environ.get('NCCL_MAX_CTAS'), sharded=tr.shard,
                               data='synthetic images / boxes / tokens, random-init weights')), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
