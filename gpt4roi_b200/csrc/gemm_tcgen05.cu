@@ -730,15 +730,16 @@ static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const G
   return G4R_OK;
 }
 
-// 2-CTA tiles when there is enough work to keep all SM pairs busy.  Measured on B200 (profiles/):
-// equal to the 1-CTA kernel for the convs (tile counts are exact multiples) and ~3 % slower for the
-// LLaMA GEMMs, whose M = B*L = 5648 rows leave a 94 %-empty last 256-row pair.  Default: conv only;
-// G4R_GEMM_2SM=1 forces it for plain GEMMs too, =0 disables it everywhere.
+// 2-CTA tiles (cta_group::2, UMMA_M = 256) whenever there is enough work to keep all SM pairs busy.  Measured on
+// B200, round 2 (profiles/r2_gemm_2sm_ab.md): the 2-CTA kernel beats the 1-CTA kernel on every LLaMA shape
+// (qkv 1416 vs 1317, o 1322 vs 1253, gate/up 1470 vs 1415, down 1413 vs 1305 TFLOP/s under ncu) although
+// M = B*L = 5648 rows leave a 94 %-empty last 256-row pair, and runs the convs at 1.58 PFLOP/s; whole step 106.0 vs
+// 107.4 ms.  G4R_GEMM_2SM=0 disables it everywhere, =2 restores the round-1 policy (convs only).
 static bool use_2sm(int N, int m_tiles, int k_splits, bool conv) {
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("G4R_GEMM_2SM");
-    env = !e ? 2 : (e[0] == '0' ? 0 : 1);
+    env = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
   }
   if (env == 0 || (env == 2 && !conv) || N <= 128 || m_tiles < 2) return false;
   const long pairs = (long)((m_tiles + 1) / 2) * ((N + 255) / 256) * k_splits;

@@ -359,6 +359,23 @@ def _seqlens(eng, attention_mask, L):
     return lens.to(torch.int32).contiguous()
 
 
+def _stack_images(images):
+    """`images` as a python list of [3,S,S] tensors (the LLaVA base's variable-length branch, spi_llava.py:52-64 /
+    train.py:440-464 `image_aspect_ratio`): the reference pushes each through the CLIP tower on its own and then leaves
+    `mlvl_spi_features` undefined, so region tokens cannot be used with it there.  CLIP's fixed position embedding
+    makes every admissible image S x S anyway, so the list is one batch: it is stacked and takes the fused path
+    (region features included).  Mixed sizes have no defined result in the reference and raise here."""
+    if type(images) is not list:
+        return images
+    if len(images) == 0:
+        return None
+    shapes = {tuple(im.shape[-3:]) for im in images}
+    if len(shapes) != 1:
+        raise NotImplementedError('images of different sizes in one batch: the CLIP tower has one position-embedding '
+                                  'grid (got %s)' % sorted(shapes))
+    return torch.stack([im.reshape(im.shape[-3:]) for im in images], 0)
+
+
 @torch.no_grad()
 def _run_engine(eng, input_ids, images, bboxes, attention_mask, past_key_values, inputs_embeds, use_cache, want,
                 training=False, max_cache=None, last_only=False):
@@ -400,8 +417,7 @@ def _run_engine(eng, input_ids, images, bboxes, attention_mask, past_key_values,
         return out, new_cache
     B, L = input_ids.shape
     run_vision = images is not None and (L != 1 or training)
-    if type(images) is list:
-        raise NotImplementedError('list-of-images input is undefined in the reference SPI branch (spi_llava.py:52-64)')
+    images = _stack_images(images)
     mask = attention_mask if _seqlens(eng, attention_mask, L) is not None else None
     out = eng.forward(input_ids, images if run_vision else None, bboxes if run_vision else None,
                       attention_mask=mask, want=want, cache=kv, last_only=last_only)
@@ -536,8 +552,9 @@ class SPILlavaMPTForCausalLM(LlamaForCausalLM, _EngineHost):
         if train_path:
             if inputs_embeds is not None or past_key_values is not None:
                 raise NotImplementedError('the training forward takes input_ids (HF Trainer passes the collator keys, data_modules.py:41-54)')
-            if images is None or type(images) is list:
-                raise NotImplementedError('training batches carry one image tensor per sample (data_modules.py:46-52)')
+            images = _stack_images(images)
+            if images is None:
+                raise NotImplementedError('training batches carry one image per sample (data_modules.py:46-52)')
             runner = self._get_runner(dev)
             loss = _TrainStepFn.apply(runner, input_ids, images, bboxes, labels, tuple(n for n, _ in named),
                                       *[p for _, p in named])

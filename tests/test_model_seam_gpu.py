@@ -89,6 +89,12 @@ def test_causal_lm_forward_labels_matches_oracle():
     h = model.model(input_ids=ids.to(DEV), images=images.to(DEV), bboxes=boxes).last_hidden_state
     lg = torch.nn.functional.linear(h.float(), sd['lm_head.weight'].float())
     assert rel(lg, out.logits) < 1e-2
+    # `images` as a python list of [3,S,S] tensors: one batch, region tokens included
+    with torch.no_grad():
+        out_l = model(input_ids=ids.to(DEV), images=[im.to(DEV) for im in images], bboxes=boxes)
+    assert torch.equal(out_l.logits, out.logits)
+    with pytest.raises(NotImplementedError):
+        model(input_ids=ids.to(DEV), images=[images[0].to(DEV), images[1][:, :112, :112].to(DEV)], bboxes=boxes)
     # weights changed in place -> the engine is rebuilt (parameter version counters), not silently stale
     with torch.no_grad():
         model.lm_head.weight.mul_(0.5)

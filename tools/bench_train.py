@@ -27,6 +27,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=2)
     ap.add_argument('--full', action='store_true', help='whole stage-2 step (BASELINE config 4): CLIP (frozen) + SPI + projector + '
                     'embeddings + LLaMA, 336 px, 8 RoIs/img, 128 text tokens; default is the LLaMA stack only')
+    ap.add_argument('--ncu', action='store_true', help='one steady-state step inside a cudaProfiler window (run under '
+                    'ncu --profile-from-start off)')
     a = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -107,6 +109,13 @@ def full_step(a, world, rank, dev, reducer):
     losses = []
     for _ in range(a.warmup):
         losses.append(tr.step(ids, images, boxes, labels).item())
+    if a.ncu:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        tr.step(ids, images, boxes, labels)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
