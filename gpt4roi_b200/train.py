@@ -591,6 +591,26 @@ def train_step(stack, inputs_embeds, targets, reducer=None, world_size=1):
     return loss, d_in
 
 
+def apply_delta(base_state_dict, delta_state_dict):
+    """scripts/apply_delta.py:15-43 on state dicts: GPT4RoI's released weights are a DELTA over LLaMA-7B.
+    target[name] = delta[name] + base[name]; `mm_projector.*` / `spi_module.*` exist only in the delta and are kept;
+    `embed_tokens` / `lm_head` have 6 more rows than the base (the added special tokens): the base is added to the
+    leading block.  Any other name missing from the base raises NameError, like the script.  Modifies and returns delta."""
+    for name, param in delta_state_dict.items():
+        if name not in base_state_dict:
+            if name in ('model.mm_projector.weight', 'model.mm_projector.bias') or 'spi_module' in name:
+                continue
+            raise NameError(name)
+        bparam = base_state_dict[name].to(device=param.device, dtype=param.dtype)
+        if param.shape == bparam.shape:
+            param += bparam
+        else:
+            assert name in ('model.embed_tokens.weight', 'lm_head.weight'), \
+                '%s dimension mismatch: %s vs %s' % (name, tuple(param.shape), tuple(bparam.shape))
+            param[:bparam.shape[0], :bparam.shape[1]] += bparam
+    return delta_state_dict
+
+
 class FrontEndTrain:
     """Training-mode front end: the region-token forward up to `inputs_embeds` with the tensors its backward needs,
     and the backward of everything in front of the LLaMA stack that stage 2 trains: splice

@@ -428,6 +428,18 @@ int g4r_pos_embed_mlp_bwd(const float* boxes, const void* w0, const void* b0, co
 /* ReLU backward from the saved output: out = y > 0 ? dy : 0 (bf16, n elements, n % 8 == 0). */
 int g4r_relu_bwd_bf16(const void* dy, const void* y, void* out, long long n, void* stream);
 
+/* ---- input pipeline ------------------------------------------------------------------------
+ * Image side of gpt4roi/datasets/coco_det.py:60-71 for a whole batch in one launch: Resize(S,S) [cv2 INTER_LINEAR on
+ * uint8, integer-exact] -> RandomShift [zero-filled, per-image (shift_x, shift_y); NULL = none] -> horizontal
+ * RandomFlip [per-image flag; NULL = none] -> Normalize(mean, std, to_rgb) [mmcv.imnormalize_ arithmetic] -> CHW.
+ * src_packed: decoded uint8 HWC 3-channel images back to back (device); offsets[b] = byte offset of image b;
+ * src_hw[b] = (h, w); out [B,3,S,S] fp32 (bit-identical to the reference pipeline) or bf16.  mean3 / std3: HOST float[3].
+ * Replaces mmdet/datasets/pipelines/transforms.py:209-243 (Resize), :505-562 (RandomShift), :422-470 (RandomFlip),
+ * Normalize / Pad / DefaultFormatBundle, which the reference runs per sample on CPU dataloader workers. */
+int g4r_preprocess_images(const void* src_packed, const long long* offsets, const int* src_hw, const int* shift_xy,
+                          const int* flip, void* out, int B, int S, const float* mean3, const float* std3, int to_rgb,
+                          int out_dtype, void* stream);
+
 /* Apply a pending GroupNorm affine + ReLU to an NHWC bf16 map: out = relu(z * scale[b,c] + shift[b,c]) with the
  * fp32 [B,C] scale / shift of g4r_gn_finalize.  The activated map is what MLVLFuseModule.forward returns
  * (gpt4roi/models/layers.py:182-195; mmcv ConvModule conv -> GN -> ReLU, conv_module.py:196-208); inside the fused

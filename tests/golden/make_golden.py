@@ -360,3 +360,72 @@ def train_step_golden():
 
 if __name__ == '__main__' and '--train' in sys.argv:
     train_step_golden()
+
+
+# ---------------------------------------------------------------------------------------------
+# Input pipeline: the reference's OWN transform classes (mmdet/datasets/pipelines/transforms.py,
+# loading.py; mmcv.imresize / imnormalize underneath), in the order coco_det.py:60-71 lists them, on synthetic uint8
+# BGR images with controlled augmentation decisions.  Stored: source images, source boxes, the decisions, the
+# pipeline's image tensor and boxes -> tests/golden/input_pipeline_ref.npz.
+# ---------------------------------------------------------------------------------------------
+INPUT_CASES = [  # (name, src_h, src_w, S, n_boxes, shift (x, y) or None, flip)
+    ('down_plain', 120, 90, 56, 3, None, False),
+    ('down_shift_flip', 97, 131, 56, 4, (7, -5), True),
+    ('up_shift', 37, 53, 56, 2, (-32, 11), False),
+    ('square_flip', 64, 64, 112, 3, None, True),
+    ('shift_kills_all_boxes', 80, 100, 56, 1, (32, 32), False),   # RandomShift must then leave image AND boxes alone
+    ('wide', 33, 200, 112, 5, (3, 32), True),
+]
+
+
+def input_pipeline_golden():
+    import importlib
+    import random
+    import ref_shims
+    ref_shims.install()
+    T = importlib.import_module('mmdet.datasets.pipelines.transforms')
+    Ld = importlib.import_module('mmdet.datasets.pipelines.loading')
+    rng = np.random.default_rng(7)
+    mean = [0.48145466 * 255, 0.4578275 * 255, 0.40821073 * 255]
+    std = [0.26862954 * 255, 0.26130258 * 255, 0.27577711 * 255]
+    store = {'names': np.array([c[0] for c in INPUT_CASES])}
+    for name, h, w, S, nb, shift, flip in INPUT_CASES:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        p = np.sort(rng.uniform(0, 1, (nb, 2, 2)), axis=1)
+        boxes = (np.concatenate([p[:, 0, :], p[:, 1, :]], 1) * np.array([w, h, w, h])).astype(np.float32)
+        if name == 'shift_kills_all_boxes':
+            boxes = np.array([[w * 0.9, h * 0.9, w * 0.99, h * 0.99]], np.float32)
+        res = dict(img=img.copy(), img_shape=img.shape, ori_shape=img.shape, img_fields=['img'], bbox_fields=['gt_bboxes'],
+                   gt_bboxes=boxes.copy(), gt_labels=np.arange(nb))
+        res = T.Resize(img_scale=(S, S), keep_ratio=False)(res)
+        if shift is not None:      # RandomShift with its draws forced to the chosen shift (transforms.py uses
+            draws = iter([shift[0], shift[1]])   # `from numpy import random`: random.random(), random.randint(-32, 32) x then y)
+            class _Forced:
+                random = staticmethod(lambda: 0.0)
+                randint = staticmethod(lambda a, b: next(draws))
+            orig = T.random
+            T.random = _Forced
+            try:
+                res = T.RandomShift(shift_ratio=0.5, max_shift_px=32)(res)
+            finally:
+                T.random = orig
+        out = Ld.FilterAnnotations(min_gt_bbox_wh=(2.0, 2.0))(res)
+        kept_any = out is not None
+        if kept_any:
+            res = out
+        res = T.RandomFlip(flip_ratio=1.0 if flip else 0.0)(res)
+        res = T.Normalize(mean=mean, std=std, to_rgb=True)(res)
+        res = T.Pad(size_divisor=S)(res)
+        chw = np.ascontiguousarray(res['img'].transpose(2, 0, 1))       # DefaultFormatBundle: HWC -> CHW
+        store[name + '.src'] = img
+        store[name + '.src_boxes'] = boxes
+        store[name + '.params'] = np.array([S, 0 if shift is None else shift[0], 0 if shift is None else shift[1], int(flip),
+                                            int(kept_any)], np.int32)
+        store[name + '.image'] = chw.astype(np.float32)
+        store[name + '.boxes'] = (res['gt_bboxes'] / chw.shape[1]).astype(np.float32) if kept_any else np.zeros((0, 4), np.float32)
+    np.savez_compressed(os.path.join(HERE, 'input_pipeline_ref.npz'), **store)
+    print('wrote input_pipeline_ref.npz (%d cases)' % len(INPUT_CASES))
+
+
+if __name__ == '__main__' and '--input' in sys.argv:
+    input_pipeline_golden()

@@ -194,3 +194,40 @@ def test_llama_train_stack_state_dict_round_trip_on_cpu():
     out = stack.state_dict()
     assert set(out) == set(sd) and all(torch.equal(out[k], sd[k]) for k in sd)
     assert stack.w[0]['wqkv'].dtype == torch.bfloat16 and stack.w[0]['wqkv'].shape == (768, 256)
+
+
+def test_apply_delta_follows_the_reference_script():
+    """scripts/apply_delta.py:21-40: equal shapes add, embed / lm_head add into the leading block, projector / SPI tensors
+    pass through, anything else missing from the base raises NameError."""
+    import pytest
+    import torch
+    from gpt4roi_b200.train import apply_delta
+    base = {'model.layers.0.self_attn.q_proj.weight': torch.ones(4, 4), 'model.embed_tokens.weight': torch.ones(10, 4),
+            'lm_head.weight': torch.full((10, 4), 2.0)}
+    delta = {'model.layers.0.self_attn.q_proj.weight': torch.full((4, 4), 0.5), 'model.embed_tokens.weight': torch.zeros(16, 4),
+             'lm_head.weight': torch.zeros(16, 4), 'model.mm_projector.weight': torch.full((4, 2), 3.0),
+             'model.spi_module.roi_align.updims.bias': torch.full((4,), 7.0)}
+    out = apply_delta(base, delta)
+    assert torch.equal(out['model.layers.0.self_attn.q_proj.weight'], torch.full((4, 4), 1.5))
+    assert torch.equal(out['model.embed_tokens.weight'][:10], torch.ones(10, 4)) and out['model.embed_tokens.weight'][10:].abs().sum() == 0
+    assert torch.equal(out['lm_head.weight'][:10], torch.full((10, 4), 2.0))
+    assert torch.equal(out['model.mm_projector.weight'], torch.full((4, 2), 3.0))
+    assert torch.equal(out['model.spi_module.roi_align.updims.bias'], torch.full((4,), 7.0))
+    with pytest.raises(NameError):
+        apply_delta(base, {'model.layers.9.foo': torch.zeros(1)})
+
+
+def test_save_checkpoint_writes_config_and_is_rank0_only(tmp_path):
+    import json
+    import torch
+    from gpt4roi_b200 import train
+    sd = {'a.weight': torch.arange(6.0).view(2, 3)}
+    fused = torch.arange(12.0)
+    sd['view'] = fused[:4]                                    # a view of a larger storage must not drag all of it along
+    assert train.save_checkpoint(sd, str(tmp_path / 'r1'), rank=1) == []
+    assert not (tmp_path / 'r1').exists()
+    names = train.save_checkpoint(sd, str(tmp_path / 'r0'), config=dict(model_type='llava', hidden_size=4096), rank=0)
+    assert json.load(open(tmp_path / 'r0' / 'config.json'))['model_type'] == 'llava'
+    back = train.load_checkpoint(str(tmp_path / 'r0'))
+    assert torch.equal(back['view'], fused[:4]) and back['view'].untyped_storage().nbytes() == 16
+    assert (tmp_path / 'r0' / names[0]).stat().st_size < 4000

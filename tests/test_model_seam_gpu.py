@@ -300,3 +300,35 @@ def test_grad_clip_and_schedule_in_stage2_trainer():
         got = tr.state_dict()
         worst = max((params[k].detach() - got[k].reshape(params[k].shape).float()).abs().max().item() for k in params)
         assert worst < 2e-5, (step, worst)
+
+
+def test_checkpoint_round_trip_on_the_gpu(tmp_path):
+    """save_pretrained (sharded HF layout + config.json, train.py:88-98) -> load_checkpoint -> a fresh trainer and a fresh
+    seam model reproduce the trained model's loss; the optimizer state file resumes the AdamW trajectory bit for bit."""
+    from gpt4roi_b200.train import Stage2Trainer, load_checkpoint
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=1)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=61)
+    sd = {k: v.to(BF).float() for k, v in sd.items()}
+    ids, images, boxes, labels = _train_batch(cfg, seed=16)
+    tr = Stage2Trainer(cfg, sd, vit_sd, DEV, lr=1e-3, schedule=dict(total_steps=20, warmup_steps=1))
+    for _ in range(2):
+        tr.step(ids, images, boxes, labels)
+    tr.save_pretrained(str(tmp_path / 'ckpt'), config=dict(model_type='llava', hidden_size=cfg.hidden), max_shard_bytes=200 * 2 ** 20)
+    tr.save_optimizer(str(tmp_path / 'ckpt' / 'optimizer.pt'))
+    assert (tmp_path / 'ckpt' / 'config.json').exists() and len(list((tmp_path / 'ckpt').glob('pytorch_model-*.bin'))) > 1
+    want = tr.step(ids, images, boxes, labels).item()                      # third step of the original run
+    back = load_checkpoint(str(tmp_path / 'ckpt'))
+    assert set(back) == set(sd) and all(v.dtype == torch.float32 for v in back.values())
+    tr2 = Stage2Trainer(cfg, back, vit_sd, DEV, lr=1e-3, schedule=dict(total_steps=20, warmup_steps=1))
+    tr2.load_optimizer(str(tmp_path / 'ckpt' / 'optimizer.pt'))
+    assert tr2.stack.step_count == 2
+    got = tr2.step(ids, images, boxes, labels).item()
+    assert abs(got - want) < 2e-3 * abs(want), (got, want)                  # SPI atomics: last-bit differences only
+    after = tr2.state_dict()
+    ref = tr.state_dict()
+    for k in ('lm_head.weight', 'model.layers.0.mlp.down_proj.weight', 'model.embed_tokens.weight'):
+        assert rel(after[k], ref[k]) < 1e-4, k
+    model = build_seam_model(cfg, back, vit_sd).eval()                      # the same files through the model seam
+    with torch.no_grad():
+        out = model(input_ids=ids.to(DEV), images=images.to(DEV), bboxes=boxes, labels=labels.to(DEV))
+    assert abs(out.loss.item() - want) < 2e-2 * abs(want)
