@@ -32,6 +32,7 @@ struct FaParams {
   int L, H;
   float scale;
   const int* seqlens;
+  float* lse;   // optional [B, H, L]: natural-log sum-exp of the scaled scores (training forward; attention_bwd reads it)
 };
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -81,7 +82,9 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // heaviest query blocks first (causal: block i attends to i+1 key blocks): the long CTAs start early and the
+  // short ones fill the tail of the last wave (LPT order)
+  const int qb = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * kFaBM;
   const int row_base = b * p.L;
   const int Lk = p.seqlens ? min(max(p.seqlens[b], 1), p.L) : p.L;
@@ -277,6 +280,8 @@ fa_fwd_tcgen05(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     ptx::mbar_wait(pv_done, (nblk - 1) & 1);
     ptx::tcgen05_after_thread_sync();
     const float inv = 1.f / l_run;
+    if (p.lse != nullptr && qrow < p.L)   // p = 2^((s - m_used) c) = e^(scale (s - m_used))  =>  lse = scale m_used + ln l
+      p.lse[((long long)b * p.H + h) * p.L + qrow] = (m_used == -INFINITY ? 0.f : m_used) * p.scale + logf(l_run);
     __nv_bfloat16* orow = p.out + (long long)b * p.bso + (long long)qrow * p.ldo + (long long)h * D;
 #pragma unroll 1
     for (int cc = 0; cc < D / 32; cc++) {
@@ -360,9 +365,9 @@ using namespace g4r;
 
 // Same contract as g4r_attention_bf16 (attention.cu), with the restriction that q/k/v are contiguous in
 // the batch dimension (bs == L*ld: the packed [B*L, width] QKV buffer), which the TMA descriptors need.
-extern "C" int g4r_attention_tc_bf16(const void* q, const void* k, const void* v, void* out, long long ld,
-                                     long long bs, long long ldo, long long bso, int B, int H, int L,
-                                     int head_dim, int causal, float scale, const int* seqlens, void* stream) {
+static int attention_tc_impl(const void* q, const void* k, const void* v, void* out, long long ld,
+                             long long bs, long long ldo, long long bso, int B, int H, int L,
+                             int head_dim, int causal, float scale, const int* seqlens, float* lse, void* stream) {
   G4R_REQUIRE(q && k && v && out && B > 0 && H > 0 && L > 0, "attention_tc: bad arguments");
   G4R_REQUIRE(head_dim == 64 || head_dim == 128, "attention_tc: head_dim %d (64 or 128)", head_dim);
   G4R_REQUIRE(bs == (long long)L * ld, "attention_tc: q/k/v must be one packed [B*L, width] buffer (bs == L*ld)");
@@ -379,10 +384,24 @@ extern "C" int g4r_attention_tc_bf16(const void* q, const void* k, const void* v
   if ((rc = make_tmap_rows(&tq, q, cols, rows, ld, 128))) return rc;
   if ((rc = make_tmap_rows(&tk, k, cols, rows, ld, bn))) return rc;
   if ((rc = make_tmap_rows(&tv, v, cols, rows, ld, bn))) return rc;
-  FaParams p{(__nv_bfloat16*)out, ldo, bso, L, H, scale, seqlens};
+  FaParams p{(__nv_bfloat16*)out, ldo, bso, L, H, scale, seqlens, lse};
   cudaStream_t st = (cudaStream_t)stream;
 #define G4R_FA(DD, BB) (causal ? launch_fa<DD, BB, true>(tq, tk, tv, p, B, st) : launch_fa<DD, BB, false>(tq, tk, tv, p, B, st))
   if (head_dim == 64) return bn == 128 ? G4R_FA(64, 128) : G4R_FA(64, 64);
   return bn == 128 ? G4R_FA(128, 128) : G4R_FA(128, 64);
 #undef G4R_FA
+}
+
+extern "C" int g4r_attention_tc_bf16(const void* q, const void* k, const void* v, void* out, long long ld,
+                                     long long bs, long long ldo, long long bso, int B, int H, int L,
+                                     int head_dim, int causal, float scale, const int* seqlens, void* stream) {
+  return attention_tc_impl(q, k, v, out, ld, bs, ldo, bso, B, H, L, head_dim, causal, scale, seqlens, nullptr, stream);
+}
+
+// Training forward on the tcgen05 kernel: additionally writes lse[B, H, L] (fp32, natural log) for g4r_attention_bwd_bf16.
+extern "C" int g4r_attention_tc_lse_bf16(const void* q, const void* k, const void* v, void* out, long long ld,
+                                         long long bs, long long ldo, long long bso, int B, int H, int L,
+                                         int head_dim, int causal, float scale, float* lse, void* stream) {
+  G4R_REQUIRE(lse, "attention_tc_lse: lse is NULL");
+  return attention_tc_impl(q, k, v, out, ld, bs, ldo, bso, B, H, L, head_dim, causal, scale, nullptr, lse, stream);
 }

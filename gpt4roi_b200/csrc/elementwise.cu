@@ -59,7 +59,7 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // ------------------------------------------------------------------------------------------
 // PER_LANE = ceil(D/8/32) vectors per lane, compile-time so the row stays in registers.
 template <bool RMS, int PER_LANE, typename TI = __nv_bfloat16, typename TO = __nv_bfloat16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (sizeof(TI) == 2 && PER_LANE >= 16 ? 2 : 1))
 norm_rows_bf16(const TI* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
                const __nv_bfloat16* __restrict__ b, TO* __restrict__ out, long long ldo, int M,
                int D, float eps) {
@@ -68,19 +68,31 @@ norm_rows_bf16(const TI* __restrict__ x, long long ldx, const __nv_bfloat16* __r
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   const TI* xr = x + (long long)row * ldx;
-  float v[PER_LANE][8];
+  // The row lives in registers between the statistics pass and the output pass.  16-bit rows are kept PACKED (one
+  // uint4 per 8 elements, widened on use): half the registers of a widened copy, so two to three CTAs fit per SM at
+  // D = 4096 instead of one -- the kernel is latency-bound, not ALU-bound (round 1: 3.0 TB/s).
+  constexpr bool PACKED = sizeof(TI) == 2;
+  uint4 raw[PACKED ? PER_LANE : 1];
+  float v[PACKED ? 1 : PER_LANE][8];
   float sum = 0.f, sumsq = 0.f;
 #pragma unroll
   for (int i = 0; i < PER_LANE; i++) {
     const int vi = lane + (i << 5);
+    float t[8];
     if (vi < nvec) {
-      load8<TI>(xr + vi * 8, v[i]);
+      if constexpr (PACKED) { raw[i] = *reinterpret_cast<const uint4*>(xr + vi * 8); unpack8(raw[i], t); }
+      else load8<TI>(xr + vi * 8, t);
     } else {
+      if constexpr (PACKED) raw[i] = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int j = 0; j < 8; j++) v[i][j] = 0.f;
+      for (int j = 0; j < 8; j++) t[j] = 0.f;
+    }
+    if constexpr (!PACKED) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[i][j] = t[j];
     }
 #pragma unroll
-    for (int j = 0; j < 8; j++) { sum += v[i][j]; sumsq += v[i][j] * v[i][j]; }
+    for (int j = 0; j < 8; j++) { sum += t[j]; sumsq += t[j] * t[j]; }
   }
   sum = warp_sum(sum);
   sumsq = warp_sum(sumsq);
@@ -93,8 +105,10 @@ norm_rows_bf16(const TI* __restrict__ x, long long ldx, const __nv_bfloat16* __r
 #pragma unroll
     for (int i = 0; i < PER_LANE; i++) {
       if (lane + (i << 5) < nvec) {
+        float t[8];
+        if constexpr (PACKED) unpack8(raw[i], t);
 #pragma unroll
-        for (int j = 0; j < 8; j++) { const float d = v[i][j] - mean; var += d * d; }
+        for (int j = 0; j < 8; j++) { const float d = (PACKED ? t[j] : v[i][j]) - mean; var += d * d; }
       }
     }
     var = warp_sum(var);
@@ -107,17 +121,22 @@ norm_rows_bf16(const TI* __restrict__ x, long long ldx, const __nv_bfloat16* __r
   for (int i = 0; i < PER_LANE; i++) {
     const int vi = lane + (i << 5);
     if (vi >= nvec) continue;
-    float wf[8], o[8];
+    float wf[8], o[8], t[8];
     unpack8(wv[vi], wf);
+    if constexpr (PACKED) unpack8(raw[i], t);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) t[j] = v[i][j];
+    }
     if (RMS) {
 #pragma unroll
       for (int j = 0; j < 8; j++)   // LlamaRMSNorm: weight * (x * rstd).to(input_dtype) -- no rounding for an fp32 stream
-        o[j] = wf[j] * (sizeof(TI) == 4 ? v[i][j] * rstd : bf16_round(v[i][j] * rstd));
+        o[j] = wf[j] * (sizeof(TI) == 4 ? t[j] * rstd : bf16_round(t[j] * rstd));
     } else {
       float bf[8];
       unpack8(bv[vi], bf);
 #pragma unroll
-      for (int j = 0; j < 8; j++) o[j] = (v[i][j] - mean) * rstd * wf[j] + bf[j];
+      for (int j = 0; j < 8; j++) o[j] = (t[j] - mean) * rstd * wf[j] + bf[j];
     }
     store8<TO>(orow + vi * 8, o);
   }

@@ -39,6 +39,10 @@ struct SkinnyParams {
   const __nv_bfloat16* rope_cos; const __nv_bfloat16* rope_sin;
   int rope_cols, rope_L, rope_pos0;
   const int* rope_pos_dev;
+  // decode-step fusions (all optional):
+  const __nv_bfloat16* norm_w; float norm_eps;   // RMSNorm of the activation rows before the product (K = hidden)
+  __nv_bfloat16* kcache; __nv_bfloat16* vcache;  // [M, cache_lmax, cache_hd]: k / v columns are also written at `pos`
+  int cache_lmax, cache_hd;
 };
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* ptr) {
@@ -60,7 +64,22 @@ __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__floa
 // MT: 16-row weight tiles per CTA (1 or 2); MB: 8-row activation blocks (1: M<=8, 2: M<=16);
 // ROPE: the two tiles are 64 rows apart (dims d and d+64 of one 128-dim head) so the rotation has
 // both partners in the CTA.
-template <int MT, int MB, int WARPS, bool ROPE>
+// RMSNorm folded into the activation fragment (LlamaRMSNorm, modeling_llama.py:53-67, with the rounding points of
+// norm_rows_bf16: bf16(x * rstd), times the bf16 weight, rounded to bf16): 8 packed bf16 -> 8 packed bf16.
+__device__ __forceinline__ uint4 norm8(const uint4& x, const uint4& w, float rstd) {
+  const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&x);
+  const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&w);
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float2 xf = __bfloat1622float2(xh[j]), wf = __bfloat1622float2(wh[j]);
+    oh[j] = __floats2bfloat162_rn(wf.x * bf16r(xf.x * rstd), wf.y * bf16r(xf.y * rstd));
+  }
+  return o;
+}
+
+template <int MT, int MB, int WARPS, bool ROPE, bool NORM = false>
 __global__ void __launch_bounds__(WARPS * 32)
 gemm_skinny_bf16(const SkinnyParams p) {
   constexpr int KB = 128;        // k per warp iteration: 4 sub-blocks of 32 (one 16-byte load per row each)
@@ -68,6 +87,7 @@ gemm_skinny_bf16(const SkinnyParams p) {
   constexpr int MC = MB * 8;
   __shared__ float red[WARPS][NT][MC + 1];
   __shared__ float ctot[NT][MC];   // this CTA's k-slice total, read by cluster rank 0
+  __shared__ float s_rstd[MC];
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int KS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -102,6 +122,29 @@ gemm_skinny_bf16(const SkinnyParams p) {
     xrow[i] = p.A + (long long)(xok[i] ? m : 0) * p.lda + 8 * t;
   }
 
+  if constexpr (NORM) {
+    // rstd of every activation row, recomputed by each CTA (M <= 16 rows of K bf16 from L2): warp w takes rows w, w+WARPS, ..
+    for (int m = warp; m < MC; m += WARPS) {
+      float ss = 0.f;
+      if (m < p.M) {
+        const __nv_bfloat16* xr = p.A + (long long)m * p.lda;
+        for (int k = lane * 8; k < p.K; k += 256) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + k));
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; j++) { const float2 f = __bfloat1622float2(h2[j]); ss += f.x * f.x + f.y * f.y; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) s_rstd[m] = rsqrtf(ss / p.K + p.norm_eps);
+    }
+    __syncthreads();
+  }
+  float rstd[MB];
+#pragma unroll
+  for (int i = 0; i < MB; i++) rstd[i] = NORM ? s_rstd[i * 8 + g] : 1.f;
+
 #pragma unroll 1
   for (int k0 = (rank * WARPS + warp) * KB; k0 < p.K; k0 += KS * WARPS * KB) {
     uint4 a[4][MT][2], b[4][MB];
@@ -117,6 +160,13 @@ gemm_skinny_bf16(const SkinnyParams p) {
 #pragma unroll
       for (int i = 0; i < MB; i++)
         b[s][i] = (kok && xok[i]) ? __ldg(reinterpret_cast<const uint4*>(xrow[i] + kk)) : make_uint4(0, 0, 0, 0);
+      if constexpr (NORM) {
+        if (kok) {
+          const uint4 w8 = __ldg(reinterpret_cast<const uint4*>(p.norm_w + kk + 8 * t));
+#pragma unroll
+          for (int i = 0; i < MB; i++) b[s][i] = norm8(b[s][i], w8, rstd[i]);
+        }
+      }
     }
 #pragma unroll
     for (int s = 0; s < 4; s++)
@@ -173,11 +223,24 @@ gemm_skinny_bf16(const SkinnyParams p) {
         const float x1 = bf16r(v1), x2 = bf16r(v2);
         const float a1 = bf16r(x1 * __bfloat162float(ct[d])), b1 = bf16r(-x2 * __bfloat162float(st[d]));
         const float a2 = bf16r(x2 * __bfloat162float(ct[d + 64])), b2 = bf16r(x1 * __bfloat162float(st[d + 64]));
-        o[n1] = __float2bfloat16_rn(a1 + b1);
-        o[n2] = __float2bfloat16_rn(a2 + b2);
+        const __nv_bfloat16 r1 = __float2bfloat16_rn(a1 + b1), r2 = __float2bfloat16_rn(a2 + b2);
+        o[n1] = r1;
+        o[n2] = r2;
+        if (p.kcache != nullptr && n1 >= p.cache_hd) {   // a key column: also the cache row of sample m at this position
+          __nv_bfloat16* kc = p.kcache + ((long long)m * p.cache_lmax + pos) * p.cache_hd - p.cache_hd;
+          kc[n1] = r1;
+          kc[n2] = r2;
+        }
       } else {
-        o[n1] = __float2bfloat16_rn(v1);
-        o[n2] = __float2bfloat16_rn(v2);
+        const __nv_bfloat16 r1 = __float2bfloat16_rn(v1), r2 = __float2bfloat16_rn(v2);
+        o[n1] = r1;
+        o[n2] = r2;
+        if (p.vcache != nullptr && n1 >= 2 * p.cache_hd) {
+          const int pos = (p.rope_pos_dev ? *p.rope_pos_dev : p.rope_pos0) + m % p.rope_L;
+          __nv_bfloat16* vc = p.vcache + ((long long)m * p.cache_lmax + pos) * p.cache_hd - 2 * p.cache_hd;
+          vc[n1] = r1;
+          vc[n2] = r2;
+        }
       }
     }
     cluster.sync();
@@ -218,7 +281,7 @@ static int skinny_target_ctas() {
   return v;
 }
 
-template <int MT, int MB, int WARPS, bool ROPE>
+template <int MT, int MB, int WARPS, bool ROPE, bool NORM = false>
 static int launch_skinny(const SkinnyParams& p, unsigned tiles, cudaStream_t st) {
   // cluster split-K factor: enough CTAs for several waves, every warp keeps >= 1 k-block of 128
   int ks = 1;
@@ -233,7 +296,7 @@ static int launch_skinny(const SkinnyParams& p, unsigned tiles, cudaStream_t st)
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ks; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  G4R_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_bf16<MT, MB, WARPS, ROPE>, p));
+  G4R_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_bf16<MT, MB, WARPS, ROPE, NORM>, p));
   return G4R_OK;
 }
 
@@ -267,4 +330,55 @@ int gemm_skinny_dispatch(const void* A, long long lda, const void* B, long long 
   return M <= 8 ? launch_skinny<1, 1, 16, false>(p, grid, st) : launch_skinny<1, 2, 16, false>(p, grid, st);
 }
 
+// Decode-step fused entry (M <= 16): [RMSNorm ->] GEMM [-> RoPE + KV-cache write | SwiGLU | residual].
+int gemm_skinny_fused(const SkinnyParams& p0, cudaStream_t st) {
+  SkinnyParams p = p0;
+  if (p.M > 16 || p.K % 32 != 0) return -1;
+  p.rope_L = p.rope_L > 0 ? p.rope_L : 1;
+  const bool norm = p.norm_w != nullptr;
+  if (norm && p.K % 256 != 0) return -1;
+  if (p.rope_cos != nullptr) {
+    if (p.N % 128 != 0) return -1;
+    const unsigned grid = (unsigned)(p.N / 128) * 4;
+    if (norm) return p.M <= 8 ? launch_skinny<2, 1, 4, true, true>(p, grid, st) : launch_skinny<2, 2, 4, true, true>(p, grid, st);
+    return p.M <= 8 ? launch_skinny<2, 1, 4, true>(p, grid, st) : launch_skinny<2, 2, 4, true>(p, grid, st);
+  }
+  if (p.act == SK_ACT_SWIGLU && (p.N % 2 != 0)) return -1;
+  const bool wide = (p.N + 31) / 32 >= 2 * num_sms();
+  if (wide) {
+    const unsigned grid = (unsigned)((p.N + 31) / 32);
+    if (norm) return p.M <= 8 ? launch_skinny<2, 1, 4, false, true>(p, grid, st) : launch_skinny<2, 2, 4, false, true>(p, grid, st);
+    return p.M <= 8 ? launch_skinny<2, 1, 4, false>(p, grid, st) : launch_skinny<2, 2, 4, false>(p, grid, st);
+  }
+  const unsigned grid = (unsigned)((p.N + 15) / 16);
+  if (norm) return p.M <= 8 ? launch_skinny<1, 1, 16, false, true>(p, grid, st) : launch_skinny<1, 2, 16, false, true>(p, grid, st);
+  return p.M <= 8 ? launch_skinny<1, 1, 16, false>(p, grid, st) : launch_skinny<1, 2, 16, false>(p, grid, st);
+}
+
 }  // namespace g4r
+
+using namespace g4r;
+
+extern "C" int g4r_decode_gemm_bf16(const void* x, long long ldx, const void* W, long long ldw, void* out, long long ldo,
+                                    int M, int N, int K, const void* norm_w, float norm_eps, int act, const void* residual,
+                                    long long ldr, const void* rope_cos, const void* rope_sin, int rope_cols, int pos0,
+                                    const int* pos_dev, void* kcache, void* vcache, int cache_lmax, int cache_hd,
+                                    void* stream) {
+  G4R_REQUIRE(x && W && out && M > 0 && M <= 16 && N > 0 && K > 0, "decode_gemm: M must be 1..16 (got %d)", M);
+  G4R_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && K % 32 == 0, "decode_gemm: K %% 32 == 0 and 16-byte-aligned rows required");
+  G4R_REQUIRE(act == SK_ACT_NONE || act == SK_ACT_SWIGLU, "decode_gemm: act must be none or swiglu");
+  G4R_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "decode_gemm: both RoPE tables or none");
+  G4R_REQUIRE(!(kcache || vcache) || (rope_cos && kcache && vcache && cache_lmax > 0 && cache_hd > 0 && N == 3 * cache_hd),
+              "decode_gemm: the KV-cache write needs the fused q|k|v projection with RoPE (N == 3 * cache_hd)");
+  SkinnyParams p{};
+  p.A = (const __nv_bfloat16*)x; p.lda = ldx; p.W = (const __nv_bfloat16*)W; p.ldb = ldw;
+  p.D = (__nv_bfloat16*)out; p.ldd = ldo; p.M = M; p.N = N; p.K = K;
+  p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act;
+  p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin;
+  p.rope_cols = rope_cols; p.rope_L = 1; p.rope_pos0 = pos0; p.rope_pos_dev = pos_dev;
+  p.norm_w = (const __nv_bfloat16*)norm_w; p.norm_eps = norm_eps;
+  p.kcache = (__nv_bfloat16*)kcache; p.vcache = (__nv_bfloat16*)vcache; p.cache_lmax = cache_lmax; p.cache_hd = cache_hd;
+  const int rc = gemm_skinny_fused(p, (cudaStream_t)stream);
+  if (rc == -1) { set_error("decode_gemm: shape not supported (M=%d N=%d K=%d)", M, N, K); return G4R_EUNSUPPORTED; }
+  return rc;
+}

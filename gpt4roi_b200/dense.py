@@ -177,3 +177,34 @@ def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None, leve
             ACT[act], _L.ptr(gn_stats), groups, _L.stream_ptr(dev)))
         _prof_end(dev, _ps, 'conv', 2.0 * n * h * w * cout * kh * kw * cin * levels)
     return out
+
+
+def decode_gemm(x, weight, norm_w=None, norm_eps=1e-6, act=None, residual=None, rope=None, kv=None):
+    """Decode-step GEMM (M = batch <= 16): out = [RoPE | SwiGLU | + residual](RMSNorm(x) @ weight.T), the norm, the
+    rotary embedding and the KV-cache append folded into one weight-streaming launch (g4r_decode_gemm_bf16).
+    rope = (cos, sin, rope_cols, pos0, pos_dev); kv = (kcache [B,Lmax,HD], vcache) -- needs rope on the fused q|k|v weight."""
+    M, K = x.shape
+    N = weight.shape[0]
+    dev = _L.require_cuda_same_device([('x', x), ('weight', weight), ('norm_w', norm_w), ('residual', residual)])
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError('decode_gemm: bf16 operands required')
+    n_out = N // 2 if act == 'swiglu' else N
+    out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
+    cos = sin = pos_dev = None
+    rope_cols = pos0 = 0
+    if rope is not None:
+        cos, sin, rope_cols, pos0, pos_dev = rope
+    kc = vc = None
+    lmax = hd = 0
+    if kv is not None:
+        kc, vc = kv
+        lmax, hd = kc.shape[1], kc.shape[2]
+    with torch.cuda.device(dev):
+        _ps = _prof_begin(dev)
+        _L.check(_L.load().g4r_decode_gemm_bf16(
+            _L.ptr(x), x.stride(0), _L.ptr(weight), weight.stride(0), _L.ptr(out), out.stride(0), M, N, K,
+            _L.ptr(norm_w), float(norm_eps), ACT[act], _L.ptr(residual), residual.stride(0) if residual is not None else 0,
+            _L.ptr(cos), _L.ptr(sin), int(rope_cols), int(pos0), _L.ptr(pos_dev), _L.ptr(kc), _L.ptr(vc), int(lmax), int(hd),
+            _L.stream_ptr(dev)))
+        _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
+    return out

@@ -216,6 +216,19 @@ int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* B, long lon
                            void* stream);
 
 /* ---- decode loop (KV cache) -------------------------------------------------- */
+/* Decode-step GEMM (M = batch <= 16 new tokens, one per sample; the LLaMA stack behind generate(), llava.py:263-283,
+ * spi_llava.py:47-48), weight-streaming, with the neighbouring memory-bound steps folded in:
+ *   out = [RoPE | SwiGLU | + residual]( RMSNorm_{norm_w, eps}(x) . W^T )
+ * norm_w (optional, bf16 [K]): LlamaRMSNorm of the activation rows (modeling_llama.py:53-67, same rounding points as
+ * g4r_rmsnorm_bf16) recomputed per CTA; rope_cos/sin (optional): rotate columns [0, rope_cols) at position pos0 / *pos_dev;
+ * kcache / vcache (optional, with RoPE on the fused q|k|v projection, N == 3 * cache_hd): the rotated key and the value
+ * columns of sample m are also written to cache[m, pos, :] -- replaces g4r_rmsnorm_bf16 + g4r_gemm_qkv_rope_bf16 +
+ * g4r_kv_append_bf16 (3 launches) and g4r_rmsnorm_bf16 + g4r_gemm_bf16_ex(swiglu) (2 launches) of the unfused step. */
+int g4r_decode_gemm_bf16(const void* x, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M,
+                         int N, int K, const void* norm_w, float norm_eps, int act, const void* residual, long long ldr,
+                         const void* rope_cos, const void* rope_sin, int rope_cols, int pos0, const int* pos_dev,
+                         void* kcache, void* vcache, int cache_lmax, int cache_hd, void* stream);
+
 /* Append the k and v parts of packed rows [B*Ln, (q|k|v) of width HD each] to the caches
  * [B, Lmax, HD] at positions pos0..pos0+Ln-1 (prefill: pos0=0, Ln=L; decode: Ln=1).  */
 int g4r_kv_append_bf16(const void* qkv, long long ld, void* kcache, void* vcache,
@@ -365,6 +378,11 @@ int g4r_swiglu_bwd_bf16(const void* gu, long long ldg, const void* df, long long
 int g4r_attention_fwd_lse_bf16(const void* q, const void* k, const void* v, void* out, long long ld,
                                long long bs, long long ldo, long long bso, int B, int H, int L,
                                int head_dim, int causal, float scale, float* lse, void* stream);
+/* Same contract on the tcgen05 / TMEM attention kernel (q, k, v must be one packed [B*L, width] buffer, bs == L*ld):
+ * the training forward's default since round 2. */
+int g4r_attention_tc_lse_bf16(const void* q, const void* k, const void* v, void* out, long long ld, long long bs,
+                              long long ldo, long long bso, int B, int H, int L, int head_dim, int causal, float scale,
+                              float* lse, void* stream);
 int g4r_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* out, const void* dout,
                            const float* lse, float* delta, void* dq, void* dk, void* dv, long long ld,
                            long long bs, long long ldo, long long bso, long long ldg, long long bsg, int B,

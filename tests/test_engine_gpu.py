@@ -264,3 +264,29 @@ def test_graphed_decode_is_bitwise_equal_to_eager_decode():
     st.step(toks[0])
     with pytest.raises(RuntimeError):
         st.step(toks[1])
+
+
+def test_fused_decode_step_matches_the_unfused_sequence():
+    """g4r_decode_gemm_bf16 (RMSNorm + q|k|v + RoPE + KV append in one launch; RMSNorm + gate/up + SwiGLU in one) vs the
+    8-launch sequence it replaces: same rounding points -> logits within 2e-3 rel-L2 (the norm's row sum is accumulated in
+    a different order), KV cache rows equal to the same tolerance; batch 1, 8 and 16 (both activation-block variants)."""
+    import gpt4roi_b200.engine as E
+    from gpt4roi_b200.engine import KVCache
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=2)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=23)
+    eng = PrefillEngine(cfg, sd, vit_sd, DEV)
+    for B in (1, 8, 16):
+        ids, images, boxes = make_inputs(cfg, B, [1] * B, 12, seed=30 + B)
+        images = images.to(DEV, torch.bfloat16)
+        plan = eng.plan_boxes(boxes)
+        toks = torch.randint(3, 32000, (3, B, 1), generator=torch.Generator().manual_seed(B)).to(DEV)
+        res = {}
+        for fused in (True, False):
+            E._DECODE_FUSED = fused
+            cache = KVCache(cfg, B, ids.shape[1] + 4, DEV)
+            eng.forward_device(ids.to(DEV), images, plan, last_only=True, cache=cache)
+            outs = [eng.decode_step(toks[t], cache).float().clone() for t in range(3)]
+            res[fused] = (torch.stack(outs), cache.k[1][:, :cache.length].float().clone(), cache.v[1][:, :cache.length].float().clone())
+        E._DECODE_FUSED = True
+        for a, b in zip(res[True], res[False]):
+            assert rel(a, b) < 2e-3, (B, rel(a, b))
