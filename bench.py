@@ -617,6 +617,8 @@ def run_ours(args):
     roi = None
     if rank == 0 and not args.no_roialign:
         try:
+            torch.cuda.synchronize(dev)
+            time.sleep(3.0)    # let the power-capped SM clock recover: the kernel is L1 / issue bound, i.e. SM-clock bound
             roi = roialign_microbench(dev, pk, how)
         except Exception as e:
             roi = dict(skipped=str(e)[:200])
