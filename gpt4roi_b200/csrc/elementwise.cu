@@ -466,24 +466,29 @@ fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restri
   const int ppb = blockDim.x / nvec;  // pixels per block (launcher guarantees blockDim % nvec == 0)
   const long long npix = (long long)B * H * H;
   const int v = threadIdx.x % nvec;
+  // the channel slice -- and with it the source map and its GroupNorm scale / shift vectors -- is fixed per thread;
+  // the scale / shift (64 bytes per thread, 4x the 16-byte payload of an own-channel pixel) are reloaded only when
+  // the grid-stride loop crosses into another image
+  const int c = v * 8;
+  // out channels [0,C/2) <- own; [C/2,3C/4) <- top[:, 3C/4 + j]; [3C/4,C) <- down[:, C/2 + j]
+  const bool is_own = c < 2 * q, from_top = c < 3 * q;
+  const FuseSrc& s = is_own ? own : (from_top ? top : down);
+  const int sc0 = is_own ? c : (from_top ? c + q : c - q);
+  const bool affine = s.sc != nullptr;
+  float aa[8], dd[8];
+  int cur_b = -1;
   for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / nvec; pix < npix;
        pix += (long long)gridDim.x * ppb) {
     const int x = (int)(pix % H);
     const int y = (int)((pix / H) % H);
     const int b = (int)(pix / ((long long)H * H));
-    const int c = v * 8;
-    // out channels [0,C/2) <- own; [C/2,3C/4) <- top[:, 3C/4 + j]; [3C/4,C) <- down[:, C/2 + j]
-    const bool is_own = c < 2 * q, from_top = c < 3 * q;
-    const FuseSrc& s = is_own ? own : (from_top ? top : down);
-    const int sc0 = is_own ? c : (from_top ? c + q : c - q);
-    const bool affine = s.sc != nullptr;
-    float aa[8], dd[8];
-    if (affine) {
+    if (affine && b != cur_b) {
       const float4* a = reinterpret_cast<const float4*>(s.sc + (long long)b * C + sc0);
       const float4* d = reinterpret_cast<const float4*>(s.sh + (long long)b * C + sc0);
       const float4 a0 = a[0], a1 = a[1], d0 = d[0], d1 = d[1];
       aa[0] = a0.x; aa[1] = a0.y; aa[2] = a0.z; aa[3] = a0.w; aa[4] = a1.x; aa[5] = a1.y; aa[6] = a1.z; aa[7] = a1.w;
       dd[0] = d0.x; dd[1] = d0.y; dd[2] = d0.z; dd[3] = d0.w; dd[4] = d1.x; dd[5] = d1.y; dd[6] = d1.z; dd[7] = d1.w;
+      cur_b = b;
     }
     const __nv_bfloat16* base = s.p + (long long)b * s.H * s.H * C + sc0;
     float o[8];

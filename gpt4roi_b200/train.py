@@ -591,6 +591,31 @@ def train_step(stack, inputs_embeds, targets, reducer=None, world_size=1):
     return loss, d_in
 
 
+def bootstrap_stage2(stage1_dir, stage2_dir):
+    """train_stage2.sh:10-24: when the stage-2 work dir has no checkpoint yet, create `checkpoint-0` in it and soft-link
+    every stage-1 file EXCEPT the optimizer / scheduler / trainer state (`scheduler.pt`, `training_args.bin`,
+    `optimizer.pt`, `trainer_state.json`, and this package's optimizer file), so that stage 2 starts from the stage-1
+    weights with a fresh optimizer.  Returns the checkpoint directory to load (the newest `checkpoint-*` when one exists:
+    "WORKDIR is not empty, resume training")."""
+    import os
+    existing = sorted((d for d in os.listdir(stage2_dir) if os.path.isdir(os.path.join(stage2_dir, d))),
+                      key=lambda d: (int(d.split('-')[-1]) if d.split('-')[-1].isdigit() else -1)) if os.path.isdir(stage2_dir) else []
+    if existing:
+        return os.path.join(stage2_dir, existing[-1])
+    if not os.path.isdir(stage1_dir):
+        raise FileNotFoundError('Stage1 work directory %s does not exist.' % stage1_dir)
+    ck = os.path.join(stage2_dir, 'checkpoint-0')
+    os.makedirs(ck, exist_ok=True)
+    skip = {'scheduler.pt', 'training_args.bin', 'optimizer.pt', 'trainer_state.json', 'g4r_optimizer.pt'}
+    for name in sorted(os.listdir(stage1_dir)):
+        src = os.path.join(stage1_dir, name)
+        if os.path.isfile(src) and name not in skip:
+            dst = os.path.join(ck, name)
+            if not os.path.lexists(dst):
+                os.symlink(os.path.abspath(src), dst)
+    return ck
+
+
 def apply_delta(base_state_dict, delta_state_dict):
     """scripts/apply_delta.py:15-43 on state dicts: GPT4RoI's released weights are a DELTA over LLaMA-7B.
     target[name] = delta[name] + base[name]; `mm_projector.*` / `spi_module.*` exist only in the delta and are kept;

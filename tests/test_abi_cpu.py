@@ -231,3 +231,24 @@ def test_save_checkpoint_writes_config_and_is_rank0_only(tmp_path):
     back = train.load_checkpoint(str(tmp_path / 'r0'))
     assert torch.equal(back['view'], fused[:4]) and back['view'].untyped_storage().nbytes() == 16
     assert (tmp_path / 'r0' / names[0]).stat().st_size < 4000
+
+
+def test_stage1_to_stage2_bootstrap_follows_the_script(tmp_path):
+    """train_stage2.sh:10-24: checkpoint-0 with links to the stage-1 files minus optimizer / scheduler / trainer state;
+    a non-empty stage-2 dir resumes from its newest checkpoint instead."""
+    import torch
+    from gpt4roi_b200 import train
+    s1, s2 = tmp_path / 'stage1', tmp_path / 'stage2'
+    sd = {'a.weight': torch.arange(4.0)}
+    train.save_checkpoint(sd, str(s1), config=dict(model_type='llava'), rank=0)
+    for junk in ('optimizer.pt', 'scheduler.pt', 'trainer_state.json', 'training_args.bin'):
+        (s1 / junk).write_bytes(b'x')
+    s2.mkdir()
+    ck = train.bootstrap_stage2(str(s1), str(s2))
+    assert ck.endswith('checkpoint-0')
+    names = sorted(p.name for p in (s2 / 'checkpoint-0').iterdir())
+    assert 'config.json' in names and 'pytorch_model.bin.index.json' in names and not ({'optimizer.pt', 'scheduler.pt'} & set(names))
+    assert all((s2 / 'checkpoint-0' / n).is_symlink() for n in names)
+    assert torch.equal(train.load_checkpoint(ck)['a.weight'], sd['a.weight'])
+    (s2 / 'checkpoint-3000').mkdir()
+    assert train.bootstrap_stage2(str(s1), str(s2)).endswith('checkpoint-3000')
