@@ -81,4 +81,17 @@ __device__ __forceinline__ void store16(T* p, const float (&v)[16 / sizeof(T)]) 
   *reinterpret_cast<uint4*>(p) = raw;
 }
 
+// i / d and i % d for a grid-stride element index: 32-bit unsigned arithmetic whenever the index fits (always, for the
+// tensors of this path) -- a 64-bit div/mod pair by a run-time divisor costs more instructions than the element's math.
+__device__ __forceinline__ void divmod_idx(long long i, int d, long long& q, int& r) {
+  if (i >= 0 && i <= 0xffffffffLL) {
+    const unsigned ii = (unsigned)i, qq = ii / (unsigned)d;
+    q = qq;
+    r = (int)(ii - qq * (unsigned)d);
+  } else {
+    q = i / d;
+    r = (int)(i - q * d);
+  }
+}
+
 }  // namespace g4r

@@ -406,10 +406,12 @@ upsample_tokens_coords_bf16(const TT* __restrict__ tok, long long ldt, long long
   const long long total = (long long)B * Ho * Ho * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nvec);
-    const int xo = (int)((i / nvec) % Ho);
-    const int yo = (int)((i / ((long long)nvec * Ho)) % Ho);
-    const int b = (int)(i / ((long long)nvec * Ho * Ho));
+    long long q1, q2, bq;
+    int v, xo, yo;
+    divmod_idx(i, nvec, q1, v);
+    divmod_idx(q1, Ho, q2, xo);
+    divmod_idx(q2, Ho, bq, yo);
+    const int b = (int)bq;
     float o[8];
     if (v * 8 < C) {
       const Lerp ly = lerp_ac(yo, G, Ho), lx = lerp_ac(xo, G, Ho);
@@ -477,11 +479,27 @@ fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restri
   const bool affine = s.sc != nullptr;
   float aa[8], dd[8];
   int cur_b = -1;
-  for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / nvec; pix < npix;
-       pix += (long long)gridDim.x * ppb) {
-    const int x = (int)(pix % H);
-    const int y = (int)((pix / H) % H);
-    const int b = (int)(pix / ((long long)H * H));
+  // (b, y, x) advance incrementally with the grid stride: no 64-bit div / mod per pixel (three of them cost more
+  // instructions than the pixel's arithmetic); the align_corners scale is loop-invariant
+  const long long pix0 = (long long)blockIdx.x * ppb + threadIdx.x / nvec;
+  const long long step = (long long)gridDim.x * ppb;
+  const int HH = H * H;
+  int b = (int)(pix0 / HH), y = (int)((pix0 % HH) / H), x = (int)(pix0 % H);
+  const int sb = (int)(step / HH), sy = (int)((step % HH) / H), sx = (int)(step % H);
+  const float lscale = (H > 1 && s.H != H) ? (float)(s.H - 1) / (float)(H - 1) : 0.f;
+  auto lerp = [&](int dst) {
+    const float src = lscale * dst;
+    Lerp r;
+    r.i0 = (int)src;
+    if (r.i0 > s.H - 1) r.i0 = s.H - 1;
+    r.i1 = r.i0 + (r.i0 < s.H - 1 ? 1 : 0);
+    r.l1 = src - r.i0;
+    r.l0 = 1.f - r.l1;
+    return r;
+  };
+  for (long long pix = pix0; pix < npix; pix += step, x += sx, y += sy, b += sb) {
+    if (x >= H) { x -= H; y++; }
+    if (y >= H) { y -= H; b++; }
     if (affine && b != cur_b) {
       const float4* a = reinterpret_cast<const float4*>(s.sc + (long long)b * C + sc0);
       const float4* d = reinterpret_cast<const float4*>(s.sh + (long long)b * C + sc0);
@@ -495,7 +513,7 @@ fuse_gather_bf16(FuseSrc own, FuseSrc top, FuseSrc down, __nv_bfloat16* __restri
     if (s.H == H) {  // own channels, or a same-size "resize" (identity)
       act8(*reinterpret_cast<const uint4*>(base + ((long long)y * H + x) * C), affine, aa, dd, o);
     } else {
-      const Lerp ly = lerp_ac(y, s.H, H), lx = lerp_ac(x, s.H, H);
+      const Lerp ly = lerp(y), lx = lerp(x);
       const uint4 r00 = *reinterpret_cast<const uint4*>(base + ((long long)ly.i0 * s.H + lx.i0) * C);
       const uint4 r01 = *reinterpret_cast<const uint4*>(base + ((long long)ly.i0 * s.H + lx.i1) * C);
       const uint4 r10 = *reinterpret_cast<const uint4*>(base + ((long long)ly.i1 * s.H + lx.i0) * C);
@@ -563,7 +581,11 @@ fuse_gather_bwd(FuseGrad own, FuseGrad dn0, FuseGrad dn1, FuseGrad tp0, FuseGrad
   const long long npix = (long long)B * H * H;
   const int v = threadIdx.x % nvec;
   for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / nvec; pix < npix; pix += (long long)gridDim.x * ppb) {
-    const int x = (int)(pix % H), y = (int)((pix / H) % H), b = (int)(pix / ((long long)H * H));
+    long long rowq, bq;
+    int x, y;
+    divmod_idx(pix, H, rowq, x);
+    divmod_idx(rowq, H, bq, y);
+    const int b = (int)bq;
     const int c = v * 8;
     float acc[8];
 #pragma unroll

@@ -260,8 +260,9 @@ swiglu_fwd(const __nv_bfloat16* __restrict__ gu, long long ldg, __nv_bfloat16* _
   const int nv = F >> 2;  // 4 outputs (= 8 interleaved inputs, 16 bytes) per thread-step
   const long long total = M * nv;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const long long r = i / nv;
-    const int c = (int)(i % nv);
+    long long r;
+    int c;
+    divmod_idx(i, nv, r, c);
     float v[8];
     unpack8f(*reinterpret_cast<const uint4*>(gu + r * ldg + c * 8), v);
     __nv_bfloat162 o[2];
@@ -280,8 +281,9 @@ swiglu_bwd(const __nv_bfloat16* __restrict__ gu, long long ldg, const __nv_bfloa
   const int nv = F >> 2;
   const long long total = M * nv;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const long long r = i / nv;
-    const int c = (int)(i % nv);
+    long long r;
+    int c;
+    divmod_idx(i, nv, r, c);
     float v[8], o[8];
     unpack8f(*reinterpret_cast<const uint4*>(gu + r * ldg + c * 8), v);
     const uint2 draw = *reinterpret_cast<const uint2*>(df + r * ldf + c * 4);
@@ -400,12 +402,16 @@ pad_nhwc_rows(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ o
   const long long rows = 2LL * guard + (long long)n * (H + 2) * (W + 2);
   const long long total = rows * nvec;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int v = (int)(i % nvec);
-    const long long r = i / nvec - guard;
+    long long r0;
+    int v;
+    divmod_idx(i, nvec, r0, v);
+    const long long r = r0 - guard;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (r >= 0 && r < (long long)n * (H + 2) * (W + 2)) {
-      const int xp = (int)(r % (W + 2)), yp = (int)((r / (W + 2)) % (H + 2));
-      const long long b = r / ((long long)(W + 2) * (H + 2));
+      long long ry, b;
+      int xp, yp;
+      divmod_idx(r, W + 2, ry, xp);
+      divmod_idx(ry, H + 2, b, yp);
       if (xp >= 1 && xp <= W && yp >= 1 && yp <= H)
         val = *reinterpret_cast<const uint4*>(x + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)C) + v * 8);
     }
@@ -540,8 +546,11 @@ gn_bwd_apply(const __nv_bfloat16* __restrict__ z, const TA* __restrict__ dA, con
   const long long total = (long long)B * HW * nvec;
   const float inv_n = 1.f / ((float)HW * cpg);
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int v = (int)(i % nvec);
-    const int b = (int)(i / ((long long)nvec * HW));
+    long long pixel, bq;
+    int v, hw_r;
+    divmod_idx(i, nvec, pixel, v);
+    divmod_idx(pixel, HW, bq, hw_r);
+    const int b = (int)bq;
     const int c0 = v * 8, g = c0 / cpg;
     const float mean = mean_rstd[((long long)b * groups + g) * 2], rstd = mean_rstd[((long long)b * groups + g) * 2 + 1];
     const float m1 = gs[((long long)b * groups + g) * 2] * inv_n, m2 = gs[((long long)b * groups + g) * 2 + 1] * inv_n;
