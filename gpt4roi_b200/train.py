@@ -228,6 +228,11 @@ class LlamaTrainStack:
             self.m1_norm, self.m2_norm = torch.zeros_like(self.master_norm), torch.zeros_like(self.master_norm)
         del head
         self.pending = {}          # layer index (or 'head') -> all-gather work handle of its refreshed bf16 weights
+        # AdamW runs on a side stream, one launch per layer in FORWARD order, each followed by an event: the next step's
+        # forward waits per layer (layer 0's update is ready long before layer 31's), so the optimizer's HBM-bound 197 GB
+        # of traffic hides behind the compute-bound GEMMs of the next forward instead of standing between two steps
+        self.opt_stream = torch.cuda.Stream(device=self.dev) if (self.dev.type == 'cuda' and own_optimizer) else None
+        self.opt_events = {}
         self._rope_cache = {}
         self.saved = None
         self.grads = None
@@ -272,6 +277,7 @@ class LlamaTrainStack:
         """Weights under the reference's parameter names: the fp32 masters where this object owns the optimizer
         (gathered from the ranks' slices when sharded -- a collective call: every rank must make it), else the bf16
         compute copies."""
+        self.sync_optimizer()
         if self.own_layers:
             out = self._named(self.mflat, self.master_ln, None, None)
         else:
@@ -287,6 +293,7 @@ class LlamaTrainStack:
 
     def moments(self):
         """(exp_avg, exp_avg_sq) under reference names for the tensors this object optimises (collective if sharded)."""
+        self.sync_optimizer()
         m1, m2 = {}, {}
         if self.own_layers:
             m1.update(self._named(self.m1flat, self.m1_ln, None, None))
@@ -328,6 +335,15 @@ class LlamaTrainStack:
         h = self.pending.pop(key, None)
         if h is not None:
             h.wait()
+        ev = self.opt_events.pop(key, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.dev).wait_event(ev)
+
+    def sync_optimizer(self):
+        """Make the current stream wait for every optimizer update still in flight on the side stream."""
+        if self.opt_stream is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.opt_stream)
+        self.opt_events.clear()
 
     # ------------------------------------------------------------------ forward
     def forward(self, inputs_embeds, targets, seqlens=None):
@@ -468,22 +484,46 @@ class LlamaTrainStack:
         def upd(master, m1, m2, w16, grad, decay):
             train_ops.adamw_step(master.view(-1), grad.reshape(-1), m1.view(-1), m2.view(-1), w16.reshape(-1), lr,
                                  self.betas, self.eps, self.wd if decay else 0.0, t, grad_scale, scale_dev)
-        if self.own_layers:
-            for i, g in enumerate(self.grads['layers']):
-                w16 = self.wflat[i][self.slice] if self.shard else self.wflat[i]
-                upd(self.mflat[i], self.m1flat[i], self.m2flat[i], w16, g['rs'] if self.shard else g['flat'], True)
+        side = self.opt_stream if (self.opt_stream is not None and not self.shard) else None
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(self.dev))     # gradients, clip coefficient
+            ctx = torch.cuda.stream(side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            if self.own_layers:
+                if side is not None:
+                    self.grads['norms'].record_stream(side)
+                for i, g in enumerate(self.grads['layers']):
+                    w16 = self.wflat[i][self.slice] if self.shard else self.wflat[i]
+                    gflat = g['rs'] if self.shard else g['flat']
+                    upd(self.mflat[i], self.m1flat[i], self.m2flat[i], w16, gflat, True)
+                    if self.shard:
+                        self.pending[i] = reducer.all_gather(self.wflat[i], w16)
+                    for k in NORM_KEYS:
+                        upd(self.master_ln[i][k], self.m1_ln[i][k], self.m2_ln[i][k], self.w[i][k], g[k], False)
+                    if side is not None:
+                        gflat.record_stream(side)       # the allocator may reuse the buffer only after this update ran
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        self.opt_events[i] = ev
+            if self.own_head:
+                hflat = self.w_top['lm_head'].view(-1)
+                w16 = hflat[self.slice_head] if self.shard else hflat
+                gtop = self.grads['top']['rs'] if self.shard else self.grads['top']['flat']
+                upd(self.mflat_head, self.m1_head, self.m2_head, w16, gtop, True)
                 if self.shard:
-                    self.pending[i] = reducer.all_gather(self.wflat[i], w16)
-                for k in NORM_KEYS:
-                    upd(self.master_ln[i][k], self.m1_ln[i][k], self.m2_ln[i][k], self.w[i][k], g[k], False)
-        if self.own_head:
-            hflat = self.w_top['lm_head'].view(-1)
-            w16 = hflat[self.slice_head] if self.shard else hflat
-            upd(self.mflat_head, self.m1_head, self.m2_head, w16,
-                self.grads['top']['rs'] if self.shard else self.grads['top']['flat'], True)
-            if self.shard:
-                self.pending['head'] = reducer.all_gather(hflat, w16)
-            upd(self.master_norm, self.m1_norm, self.m2_norm, self.w_top['norm'], self.grads['top']['norm'], False)
+                    self.pending['head'] = reducer.all_gather(hflat, w16)
+                upd(self.master_norm, self.m1_norm, self.m2_norm, self.w_top['norm'], self.grads['top']['norm'], False)
+                if side is not None:
+                    gtop.record_stream(side)
+                    self.grads['top']['norm'].record_stream(side)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    self.opt_events['head'] = ev
+        if side is not None and scale_dev is not None:
+            scale_dev.record_stream(side)
         self.grads = None
 
 

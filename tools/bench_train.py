@@ -124,6 +124,7 @@ def full_step(a, world, rank, dev, reducer):
     e0.record()
     for _ in range(a.steps):
         loss = tr.step(ids, images, boxes, labels)
+    tr.stack.sync_optimizer()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
