@@ -233,6 +233,21 @@ class LlamaTrainStack:
         # of traffic hides behind the compute-bound GEMMs of the next forward instead of standing between two steps
         self.opt_stream = torch.cuda.Stream(device=self.dev) if (self.dev.type == 'cuda' and own_optimizer) else None
         self.opt_events = {}
+        if self.opt_stream is not None:
+            # these buffers are written by kernels queued on the side stream: tell the caching allocator, so that freeing
+            # this object (end of a test, `del trainer` in bench.py) cannot hand their memory to a main-stream allocation
+            # while the last update is still in flight
+            persistent = list(self.wflat) + list(self.mflat) + list(self.m1flat) + list(self.m2flat)
+            for d in list(self.master_ln) + list(self.m1_ln) + list(self.m2_ln):
+                persistent += list(d.values())
+            for w in self.w:
+                persistent += [w['ln_in'], w['ln_post']]
+            persistent += [self.w_top['norm'], self.w_top['lm_head']]
+            if self.own_head:
+                persistent += [self.mflat_head, self.m1_head, self.m2_head, self.master_norm, self.m1_norm, self.m2_norm]
+            for t_ in persistent:
+                if t_.is_cuda:
+                    t_.record_stream(self.opt_stream)
         self._rope_cache = {}
         self.saved = None
         self.grads = None

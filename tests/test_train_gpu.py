@@ -135,6 +135,8 @@ def test_frontend_backward_matches_autograd():
         else:
             rows.append(emb[code])
     ref = torch.stack(rows).view(B, L, Hd)
+    for name, t_ in (('embeds', embeds), ('feat', saved['feat']), ('pc', saved['pc']), ('pos', pos), ('img', img), ('region', region)):
+        assert torch.isfinite(t_.float()).all(), 'non-finite values in %s' % name
     assert rel(embeds, ref) < 6e-3
     (ref * d.float()).sum().backward()
     q = 'model.spi_module.roi_align.'
