@@ -332,3 +332,45 @@ def test_checkpoint_round_trip_on_the_gpu(tmp_path):
     with torch.no_grad():
         out = model(input_ids=ids.to(DEV), images=images.to(DEV), bboxes=boxes, labels=labels.to(DEV))
     assert abs(out.loss.item() - want) < 2e-2 * abs(want)
+
+
+def test_hf_trainer_drives_the_seam_model(tmp_path):
+    """The reference's training entry point itself (gpt4roi/train/train.py:698-712: `LLaVATrainer(model=..., args=...,
+    **data_module).train()`, an HF `Trainer`): transformers' own Trainer -- its dataloader, `model(**inputs)`, autocast,
+    `accelerator.backward`, `clip_grad_norm_`, AdamW and cosine scheduler -- runs three optimisation steps over the seam
+    model with the collator's keys (data_modules.py:41-54: input_ids, labels, attention_mask, images, bboxes, img_metas);
+    the loss falls and the SPI / LLaMA parameters move."""
+    from transformers import Trainer, TrainingArguments
+    cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=1)
+    sd, vit_sd = random_state_dicts(cfg, DEV, seed=71)
+    sd = {k: v.to(BF).float() for k, v in sd.items()}
+    model = build_seam_model(cfg, sd, vit_sd)
+    ids, images, boxes, labels = _train_batch(cfg, seed=18)
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 6
+
+        def __getitem__(self, i):
+            j = i % 2
+            return dict(input_ids=ids[j], labels=labels[j], image=images[j], bboxes=boxes[j])
+
+    def collate(instances):   # gpt4roi/datasets/data_modules.py:22-56
+        return dict(input_ids=torch.stack([x['input_ids'] for x in instances]), labels=torch.stack([x['labels'] for x in instances]),
+                    attention_mask=torch.ones(len(instances), ids.shape[1], dtype=torch.long),
+                    images=torch.stack([x['image'] for x in instances]), bboxes=[x['bboxes'] for x in instances],
+                    img_metas=[None] * len(instances))
+    args = TrainingArguments(output_dir=str(tmp_path), per_device_train_batch_size=2, max_steps=3, learning_rate=1e-3,
+                             weight_decay=0.0, warmup_ratio=0.0, lr_scheduler_type='cosine', logging_steps=1, report_to=[],
+                             save_strategy='no', bf16=True, remove_unused_columns=False, dataloader_num_workers=0,
+                             max_grad_norm=1.0, seed=0, disable_tqdm=True)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()
+              if n in ('model.spi_module.roi_align.updims.weight', 'model.layers.0.mlp.down_proj.weight', 'lm_head.weight')}
+    trainer = Trainer(model=model, args=args, train_dataset=DS(), data_collator=collate)
+    out = trainer.train()
+    losses = [h['loss'] for h in trainer.state.log_history if 'loss' in h]
+    print('HF Trainer over the seam model: losses %s, train_loss %.4f' % (losses, out.training_loss))
+    assert len(losses) == 3 and losses[-1] < losses[0], losses
+    after = dict(model.named_parameters())
+    for n, b in before.items():
+        assert not torch.equal(after[n].detach(), b), n

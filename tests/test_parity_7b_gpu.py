@@ -48,6 +48,9 @@ def maxrel(a, b):
 
 def test_full_7b_forward_through_the_seam_vs_fp32_and_bf16_oracles():
     from tests.test_model_seam_gpu import build_seam_model
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()          # blocks cached by earlier tests of the same process do not count as used
     free = torch.cuda.mem_get_info()[0]
     if free < 110e9:
         pytest.skip('needs ~100 GB of free HBM (fp32 7B oracle + bf16 oracle + engine); %.0f GB free' % (free / 1e9))
