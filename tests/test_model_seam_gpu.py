@@ -340,7 +340,8 @@ def test_hf_trainer_drives_the_seam_model(tmp_path):
     `accelerator.backward`, `clip_grad_norm_`, AdamW and cosine scheduler -- runs three optimisation steps over the seam
     model with the collator's keys (data_modules.py:41-54: input_ids, labels, attention_mask, images, bboxes, img_metas);
     the loss falls and the SPI / LLaMA parameters move."""
-    from transformers import Trainer, TrainingArguments
+    pytest.importorskip('accelerate')   # transformers.Trainer needs it; absent from this image (the test above runs the
+    from transformers import Trainer, TrainingArguments   # Trainer's inner loop by hand instead)
     cfg = EngineConfig(image_size=224, vit_layers=12, n_layers=1)
     sd, vit_sd = random_state_dicts(cfg, DEV, seed=71)
     sd = {k: v.to(BF).float() for k, v in sd.items()}
