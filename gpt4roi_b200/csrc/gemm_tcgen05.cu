@@ -587,12 +587,31 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const int im = img < p.lvl_img_stride ? img + lvl * p.lvl_img_stride : p.lvl_img_stride * p.levels;
             ptx::tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], cc * kBlockK, x0 + dx,
                                  y0 + dy, im);
+          } else if (p.a_mn) {
+            // MN-major A (backward GEMMs): two [64 k][64 m] boxes, one 128-byte swizzle atom of m each
+#pragma unroll
+            for (int a = 0; a < kBlockM / 64; a++)
+              ptx::tma_load_2d_2sm(smem_a + stage * Cfg::kABytes + a * (kBlockK * 128), &tmap_a, &full[stage],
+                                   m_blk * kBlockM + a * 64, kg * kBlockK);
           } else {
             ptx::tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full[stage], kg * kBlockK,
                                  m_blk * kBlockM);
           }
-          ptx::tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full[stage], kg * kBlockK,
-                               n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2));
+          const int nb0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);    // this CTA's half of the B tile
+          if (!CONV && p.b_mn == 2) {
+            const int tap = nb0 / p.dw_cin, c0 = nb0 % p.dw_cin;
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 2 / 64; a++)
+              ptx::tma_load_4d_2sm(smem_b + stage * Cfg::kBBytes + a * (kBlockK * 128), &tmap_b, &full[stage],
+                                   c0 + a * 64, tap % 3, kg * kBlockK, tap / 3);
+          } else if (!CONV && p.b_mn) {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 2 / 64; a++)
+              ptx::tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes + a * (kBlockK * 128), &tmap_b, &full[stage],
+                                   nb0 + a * 64, kg * kBlockK);
+          } else {
+            ptx::tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full[stage], kg * kBlockK, nb0);
+          }
           if (leader) {
             ptx::mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)(p.a_rows * kBlockK * 2 + Cfg::kBBytes));
           } else {
@@ -604,7 +623,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   } else if (warp == 1 && leader) {
     // ============================ MMA issuer (leader CTA only) ============================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBlockM, BLOCK_N);
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBlockM, BLOCK_N) | (p.a_mn ? 1u << 15 : 0u) | (p.b_mn ? 1u << 16 : 0u);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -618,11 +637,13 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         ptx::mbar_wait(&full[stage], phase);
         ptx::tcgen05_after_thread_sync();
         if (lane == 0) {
-          const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint32_t sa = ptx::smem_u32(smem_a + stage * Cfg::kABytes), sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
+          const uint64_t da = p.a_mn ? ptx::make_smem_desc_mn_sw128(sa, kBlockK * 128) : ptx::make_smem_desc_sw128(sa);
+          const uint64_t db = p.b_mn ? ptx::make_smem_desc_mn_sw128(sb, kBlockK * 128) : ptx::make_smem_desc_sw128(sb);
+          const uint64_t ia = p.a_mn ? 128 : 2, ib = p.b_mn ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; k++)
-            ptx::umma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            ptx::umma_f16_ss_2sm(tmem_d, da + ia * k, db + ib * k, idesc, (kb | k) != 0);
           ptx::umma_commit_2sm(&empty[stage], 3);
           if (kb == p.num_k_blocks - 1) ptx::umma_commit_2sm(&tmem_full[acc], 3);
         }
@@ -837,7 +858,11 @@ extern "C" int g4r_gemm_bf16_t(const void* A, long long lda, int a_mn, const voi
   p.D = D; p.ldd = ldd; p.out_f32 = out_f32;
   p.a_rows = kBlockM;
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
-  const int bn = pick_block_n(N, p.num_m_tiles, 1);
+  // 2-CTA tiles for the backward GEMMs too (G4R_GEMM_T_2SM=0: 1-CTA kernel); MN-major boxes are 64 x 64 either way
+  static int t2 = -1;
+  if (t2 < 0) { const char* e = getenv("G4R_GEMM_T_2SM"); t2 = (e && e[0] == '0') ? 0 : 1; }
+  const bool two = t2 && N % 256 == 0 && use_2sm(N, p.num_m_tiles, 1, false);
+  const int bn = two ? 256 : pick_block_n(N, p.num_m_tiles, 1);
   p.num_n_tiles = (N + bn - 1) / bn;
   CUtensorMap ta, tb;
   {
@@ -850,11 +875,12 @@ extern "C" int g4r_gemm_bf16_t(const void* A, long long lda, int a_mn, const voi
   {
     cuuint64_t dims[2] = {(cuuint64_t)(b_mn ? N : K), (cuuint64_t)(b_mn ? K : N)};
     cuuint64_t str[1] = {(cuuint64_t)ldb * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(b_mn ? kBlockK : bn)};
+    cuuint32_t box[2] = {64, (cuuint32_t)(b_mn ? kBlockK : (two ? bn / 2 : bn))};
     int rc = make_tmap(&tb, B, 2, dims, str, box);
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (two) return launch_gemm_2sm<false>(ta, tb, p, st);
   return bn == 256 ? launch_gemm<256, false>(ta, tb, p, st) : launch_gemm<128, false>(ta, tb, p, st);
 }
 
@@ -898,6 +924,9 @@ extern "C" int g4r_conv3x3_dw_bf16(const void* dz_pad, const void* x_pad_origin,
     int rc = make_tmap(&tb, x_pad_origin, 4, dims, str, box);
     if (rc) return rc;
   }
+  static int t2 = -1;
+  if (t2 < 0) { const char* e = getenv("G4R_GEMM_T_2SM"); t2 = (e && e[0] == '0') ? 0 : 1; }
+  if (t2 && use_2sm(p.N, p.num_m_tiles, 1, false)) return launch_gemm_2sm<false>(ta, tb, p, (cudaStream_t)stream);
   return launch_gemm<256, false>(ta, tb, p, (cudaStream_t)stream);
 }
 
