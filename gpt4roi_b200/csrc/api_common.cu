@@ -40,7 +40,27 @@ int sm_budget() {
 }
 void set_sm_reserve_impl(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 
+// Programmatic dependent launch is opt-in per call sequence (g4r_set_pdl): a kernel launched this way reads its
+// weights BEFORE the predecessor kernel's writes are guaranteed visible, which is only sound when no kernel of the
+// sequence writes them -- true for the decode step, not for arbitrary callers (a cast or an optimizer kernel may
+// directly precede a small GEMM).
+static int g_pdl_on = 0;
+int pdl_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("G4R_PDL");
+    v = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
+  }
+  return g_pdl_on ? v : 0;
+}
+
 }  // namespace g4r
+
+extern "C" int g4r_set_pdl(int on) {
+  const int prev = g4r::g_pdl_on;
+  g4r::g_pdl_on = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int g4r_set_sm_reserve(int n_sms) {
   const int prev = g4r::g_sm_reserve;

@@ -48,6 +48,50 @@ inline size_t dtype_size(int dt) {
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 int sm_budget();  // num_sms() minus the reserve of g4r_set_sm_reserve (grid size of the persistent GEMM kernels)
 
+// ---- programmatic dependent launch (the decode step's kernel chain) -----------------------------------------
+// The decode step behind generate() is ~230 short, HBM-bound kernels in one CUDA graph; what separates it from the
+// weight-streaming floor is each kernel's ramp-up and tail.  Kernels launched through launch_pdl() may start while
+// their predecessor in the stream is still running: they fetch what does not depend on it (their first weight
+// block) and then execute pdl_wait(), which returns once the predecessor grid has completed and its writes are
+// visible.  Everything read BEFORE pdl_wait() must be constant for the step (weights); everything the predecessor
+// produced is read after it, through ordinary (coherent) loads.  Every kernel launched this way must execute
+// pdl_wait() before it exits, so completion stays transitive along the chain.
+//   pdl_mode(): 0 unless the caller has switched the chain on with g4r_set_pdl(1) (the decode step does; nothing else
+//   may -- see api_common.cu); then env G4R_PDL -- 0 off (plain stream order), 1 (default) dependents released once
+//   this kernel's own inputs are ready (one kernel of look-ahead), 2 dependents released at kernel start.
+int pdl_mode();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// prologue of a PDL-aware kernel, after the loads that do not depend on the predecessor have been issued
+__device__ __forceinline__ void pdl_sync(int mode) {
+  if (mode == 2) pdl_release();
+  pdl_wait();
+  if (mode != 2) pdl_release();
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     dim3 cluster, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeClusterDimension;
+  attr[n].val.clusterDim.x = cluster.x; attr[n].val.clusterDim.y = cluster.y; attr[n].val.clusterDim.z = cluster.z;
+  n++;
+  if (pdl_mode() != 0) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- element conversion -----------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -146,14 +146,22 @@ norm_rows_bf16(const TI* __restrict__ x, long long ldx, const __nv_bfloat16* __r
 // PER_LANE dependent rounds of a single warp.  Same rounding points as norm_rows_bf16.
 template <bool RMS, int PER>
 __global__ void __launch_bounds__(256)
-norm_row_cta_bf16(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
-                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, long long ldo, int D,
-                  float eps) {
+norm_row_cta_bf16(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* out, long long ldo, int D,
+                  float eps, int pdl) {
   __shared__ float red[8];
   __shared__ float stat;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nvec = D >> 3;
   const __nv_bfloat16* xr = x + (long long)blockIdx.x * ldx;
+  // programmatic dependent launch (common.cuh): the norm weights are constant -- fetch them, then wait for the
+  // kernel that produces x.  x carries no __restrict__ so its loads stay on the coherent path.
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  const uint4* bv = reinterpret_cast<const uint4*>(b);
+  uint4 wraw[PER];
+#pragma unroll
+  for (int i = 0; i < PER; i++) wraw[i] = tid + i * 256 < nvec ? __ldg(wv + tid + i * 256) : make_uint4(0, 0, 0, 0);
+  pdl_sync(pdl);
   float v[PER][8];
   float sum = 0.f, sumsq = 0.f;
 #pragma unroll
@@ -198,14 +206,12 @@ norm_row_cta_bf16(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv
     rstd = rsqrtf(block_sum(var) / D + eps);
   }
   __nv_bfloat16* orow = out + (long long)blockIdx.x * ldo;
-  const uint4* wv = reinterpret_cast<const uint4*>(w);
-  const uint4* bv = reinterpret_cast<const uint4*>(b);
 #pragma unroll
   for (int i = 0; i < PER; i++) {
     const int vi = tid + i * 256;
     if (vi >= nvec) continue;
     float wf[8], o[8];
-    unpack8(wv[vi], wf);
+    unpack8(wraw[i], wf);
     if (RMS) {
 #pragma unroll
       for (int j = 0; j < 8; j++) o[j] = wf[j] * bf16_round(v[i][j] * rstd);
@@ -225,8 +231,9 @@ static int launch_norm(const void* x, long long ldx, const void* w, const void* 
   if (M <= 64 && D <= 8192) {
     const int per = (D / 8 + 255) / 256;
 #define G4R_NORM_ROW_CASE(PR)                                                                              \
-  norm_row_cta_bf16<RMS, PR><<<M, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,      \
-                                               (const __nv_bfloat16*)b, (__nv_bfloat16*)out, ldo, D, eps)
+  G4R_CUDA(launch_pdl(norm_row_cta_bf16<RMS, PR>, dim3(M), dim3(256), 0, st, dim3(1, 1, 1),                \
+                      (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b,     \
+                      (__nv_bfloat16*)out, ldo, D, eps, pdl_mode()))
     if (per <= 1) G4R_NORM_ROW_CASE(1);
     else if (per <= 2) G4R_NORM_ROW_CASE(2);
     else G4R_NORM_ROW_CASE(4);

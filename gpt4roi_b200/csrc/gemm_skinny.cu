@@ -43,12 +43,22 @@ struct SkinnyParams {
   const __nv_bfloat16* norm_w; float norm_eps;   // RMSNorm of the activation rows before the product (K = hidden)
   __nv_bfloat16* kcache; __nv_bfloat16* vcache;  // [M, cache_lmax, cache_hd]: k / v columns are also written at `pos`
   int cache_lmax, cache_hd;
+  int pdl;   // pdl_mode() of the launch (common.cuh)
 };
 
+// weights: constant for the lifetime of the step, read exactly once.  volatile: the first block is issued BEFORE
+// pdl_wait() and must stay there.
 __device__ __forceinline__ uint4 ldg_stream16(const void* ptr) {
   uint4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+// activations: written by the predecessor kernel, read after pdl_wait() on the coherent path (no .nc).  volatile asm:
+// keeps its order relative to griddepcontrol.wait (also volatile) and stays an unconditional, straight-line load.
+__device__ __forceinline__ uint4 ldg_act16(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
   return v;
 }
 
@@ -122,6 +132,30 @@ gemm_skinny_bf16(const SkinnyParams p) {
     xrow[i] = p.A + (long long)(xok[i] ? m : 0) * p.lda + 8 * t;
   }
 
+  // The first weight block of every warp does not depend on the predecessor kernel: issue it, then wait for the
+  // predecessor (programmatic dependent launch, common.cuh) -- its tail and this kernel's ramp-up overlap.
+  const int kstep = KS * WARPS * KB;
+  int k0 = (rank * WARPS + warp) * KB;
+  uint4 a[4][MT][2];
+  auto load_w = [&](int kb) {
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      // K % 32 == 0: a sub-block is whole or absent.  Loads are unconditional (absent blocks / rows re-read element 0
+      // and are zeroed or never stored), so the block is straight-line code the scheduler can issue back to back.
+      const bool kok = kb + 32 * s < p.K;
+      const int kk = kok ? kb + 32 * s : 0;
+#pragma unroll
+      for (int j = 0; j < MT; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint4 v = ldg_stream16(wrow[j][h] + kk);
+          a[s][j][h] = kok ? v : make_uint4(0, 0, 0, 0);
+        }
+    }
+  };
+  if (k0 < p.K) load_w(k0);
+  pdl_sync(p.pdl);
+
   if constexpr (NORM) {
     // rstd of every activation row, recomputed by each CTA (M <= 16 rows of K bf16 from L2): warp w takes rows w, w+WARPS, ..
     for (int m = warp; m < MC; m += WARPS) {
@@ -129,7 +163,7 @@ gemm_skinny_bf16(const SkinnyParams p) {
       if (m < p.M) {
         const __nv_bfloat16* xr = p.A + (long long)m * p.lda;
         for (int k = lane * 8; k < p.K; k += 256) {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + k));
+          const uint4 raw = ldg_act16(xr + k);
           const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
           for (int j = 0; j < 4; j++) { const float2 f = __bfloat1622float2(h2[j]); ss += f.x * f.x + f.y * f.y; }
@@ -145,29 +179,29 @@ gemm_skinny_bf16(const SkinnyParams p) {
 #pragma unroll
   for (int i = 0; i < MB; i++) rstd[i] = NORM ? s_rstd[i * 8 + g] : 1.f;
 
-#pragma unroll 1
-  for (int k0 = (rank * WARPS + warp) * KB; k0 < p.K; k0 += KS * WARPS * KB) {
-    uint4 a[4][MT][2], b[4][MB];
+  // activation fragments of a k-block; like the weights they are fetched one block ahead, so that all loads of a block
+  // are issued back to back (left inside the loop body, ptxas strings them out between the dependent HMMAs)
+  uint4 b[4][MB];
+  auto load_x = [&](int kb) {
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-      const int kk = k0 + 32 * s;
-      const bool kok = kk < p.K;   // K % 32 == 0: a sub-block is whole or absent
+      const bool kok = kb + 32 * s < p.K;
+      const int kk = kok ? kb + 32 * s : 0;
 #pragma unroll
-      for (int j = 0; j < MT; j++)
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-          a[s][j][h] = (kok && wok[j][h]) ? ldg_stream16(wrow[j][h] + kk) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int i = 0; i < MB; i++)
-        b[s][i] = (kok && xok[i]) ? __ldg(reinterpret_cast<const uint4*>(xrow[i] + kk)) : make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < MB; i++) {
+        const uint4 v = ldg_act16(xrow[i] + kk);   // rows >= M alias row 0; their outputs are never stored
+        b[s][i] = kok ? v : make_uint4(0, 0, 0, 0);
+      }
       if constexpr (NORM) {
-        if (kok) {
-          const uint4 w8 = __ldg(reinterpret_cast<const uint4*>(p.norm_w + kk + 8 * t));
+        const uint4 w8 = __ldg(reinterpret_cast<const uint4*>(p.norm_w + kk + 8 * t));
 #pragma unroll
-          for (int i = 0; i < MB; i++) b[s][i] = norm8(b[s][i], w8, rstd[i]);
-        }
+        for (int i = 0; i < MB; i++) b[s][i] = norm8(b[s][i], w8, rstd[i]);
       }
     }
+  };
+  if (k0 < p.K) load_x(k0);
+#pragma unroll 1
+  for (; k0 < p.K; k0 += kstep) {
 #pragma unroll
     for (int s = 0; s < 4; s++)
 #pragma unroll
@@ -177,6 +211,10 @@ gemm_skinny_bf16(const SkinnyParams p) {
           mma_16816(acc[j][i], a[s][j][0].x, a[s][j][1].x, a[s][j][0].y, a[s][j][1].y, b[s][i].x, b[s][i].y);
           mma_16816(acc[j][i], a[s][j][0].z, a[s][j][1].z, a[s][j][0].w, a[s][j][1].w, b[s][i].z, b[s][i].w);
         }
+    if (k0 + kstep < p.K) {   // next block: in flight across the loop edge
+      load_w(k0 + kstep);
+      load_x(k0 + kstep);
+    }
   }
 
   // accumulator fragment: c0,c1 = (weight row g, activation rows 2t, 2t+1); c2,c3 = (weight row g+8, ...)
@@ -286,17 +324,10 @@ static int launch_skinny(const SkinnyParams& p, unsigned tiles, cudaStream_t st)
   // cluster split-K factor: enough CTAs for several waves, every warp keeps >= 1 k-block of 128
   int ks = 1;
   while (ks < 8 && (int)tiles * ks < skinny_target_ctas() && p.K >= 2 * ks * WARPS * 128) ks *= 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tiles, ks, 1);
-  cfg.blockDim = dim3(WARPS * 32);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ks; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  G4R_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_bf16<MT, MB, WARPS, ROPE, NORM>, p));
+  SkinnyParams q = p;
+  q.pdl = pdl_mode();
+  G4R_CUDA(launch_pdl(gemm_skinny_bf16<MT, MB, WARPS, ROPE, NORM>, dim3(tiles, ks, 1), dim3(WARPS * 32), 0, st,
+                      dim3(1, ks, 1), q));
   return G4R_OK;
 }
 

@@ -387,11 +387,22 @@ def _decode_step(self, token_ids, cache, pos_dev=None):
     is skipped exactly as the reference does for input_ids.shape[1] == 1 (spi_llava.py:47-48).
     pos_dev: optional device int32 holding the current length (CUDA-graph replay: the kernels read the
     position from memory instead of from a launch argument)."""
+    from . import lib
+    if cache.length + 1 > cache.max_len:
+        raise RuntimeError('KV cache is full (%d)' % cache.max_len)
+    # every kernel of the step only READS weights: let each one start in its predecessor's tail and fetch its first
+    # weight block before it waits for the predecessor (programmatic dependent launch, csrc/common.cuh)
+    prev = lib.set_pdl(True)
+    try:
+        return _decode_step_chain(self, token_ids, cache, pos_dev)
+    finally:
+        lib.set_pdl(prev)
+
+
+def _decode_step_chain(self, token_ids, cache, pos_dev):
     c = self.cfg
     B = token_ids.shape[0]
     pos = cache.length
-    if pos + 1 > cache.max_len:
-        raise RuntimeError('KV cache is full (%d)' % cache.max_len)
     kv_len = cache.max_len if pos_dev is not None else pos + 1   # sizes the score buffer when device-driven
     x = splice_region_tokens(token_ids, self.embed, None, None, 0, c.im_patch_token, c.im_start_token,
                              c.im_end_token, c.bbox_token, validate=False).view(B, c.hidden)

@@ -32,6 +32,7 @@ SIGNATURES = {
     'g4r_version': (_i, []),
     'g4r_built_arch': (_i, []),
     'g4r_set_sm_reserve': (_i, [_i]),
+    'g4r_set_pdl': (_i, [_i]),
     'g4r_roi_align_forward': (_i, [_vp] * 5 + [_i] * 7 + [_f] + [_i] * 5 + [_vp]),
     'g4r_roi_align_forward_workspace': (_c.c_size_t, [_i] * 11),
     'g4r_roi_align_forward_ws': (_i, [_vp] * 5 + [_i] * 7 + [_f] + [_i] * 5 + [_vp, _c.c_size_t, _vp]),
@@ -130,6 +131,12 @@ def load():
 def set_sm_reserve(n):
     """Keep n SMs free of the persistent GEMM kernels (room for an overlapped collective); returns the previous value."""
     return int(load().g4r_set_sm_reserve(int(n)))
+
+
+def set_pdl(on):
+    """Programmatic dependent launch for the decode step's kernel chain (include/gpt4roi_b200.h: g4r_set_pdl); returns
+    the previous setting."""
+    return int(load().g4r_set_pdl(int(bool(on))))
 
 
 def check(rc, launches=1):

@@ -44,6 +44,13 @@ int g4r_built_arch(void); /* 100 for sm_100a */
  * that runs beside the backward (the DDP gradient all-reduce of gpt4roi/train/train.py:698-712).  Returns the
  * previous reserve.  Process-wide; 0 (default) = the GEMMs use every SM. */
 int g4r_set_sm_reserve(int n_sms);
+/* Programmatic dependent launch for the kernels of the decode step behind generate() (llava/model/llava.py:263-283;
+ * gpt4roi/app.py:293-300): while on != 0, the small-M GEMM, RMSNorm and single-query attention kernels are launched so
+ * that each may start during its predecessor's tail, fetch its first WEIGHT block, and only then wait for the
+ * predecessor.  Sound only for a launch sequence in which no kernel writes weights (the decode step); callers switch
+ * it on around such a sequence and off again.  Returns the previous setting.  Process-wide; default off.
+ * Env G4R_PDL=0 makes it a no-op, =2 releases dependents at kernel start instead of after the kernel's own wait. */
+int g4r_set_pdl(int on);
 
 /* ---- RoIAlign: operator seam -------------------------------------------- */
 /*

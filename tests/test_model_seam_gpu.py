@@ -326,8 +326,11 @@ def test_checkpoint_round_trip_on_the_gpu(tmp_path):
     assert abs(got - want) < 2e-3 * abs(want), (got, want)                  # SPI atomics: last-bit differences only
     after = tr2.state_dict()
     ref = tr.state_dict()
+    # The two third steps differ in the order of the RoIAlign-backward atomics, i.e. in the last bf16 bits of every
+    # gradient; AdamW's normalised update (lr 1e-3 on weights of ~2e-2) turns that into ~5e-5..1.5e-4 rel-L2 on the
+    # weights (measured 1.3e-4 on down_proj).  A resume that lost the moments or the step count is off by > 1e-2.
     for k in ('lm_head.weight', 'model.layers.0.mlp.down_proj.weight', 'model.embed_tokens.weight'):
-        assert rel(after[k], ref[k]) < 1e-4, k
+        assert rel(after[k], ref[k]) < 5e-4, k
     model = build_seam_model(cfg, back, vit_sd).eval()                      # the same files through the model seam
     with torch.no_grad():
         out = model(input_ids=ids.to(DEV), images=images.to(DEV), bboxes=boxes, labels=labels.to(DEV))
