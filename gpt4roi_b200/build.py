@@ -21,6 +21,9 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relax
 EXTRA = {
     'roi_align.cu': ['-fmad=false'],
 }
+# The inference kernels are built twice: bf16 as written, and an fp16 twin (-DG4R_ACT_HALF, csrc/act_type.cuh) for the
+# demo's dtype (gpt4roi/app.py:74-98: model.half()).  Both land in the one shared library.
+FP16_TWINS = ('gemm_tcgen05.cu', 'attention_tcgen05.cu', 'attention.cu', 'elementwise.cu', 'gemm_skinny.cu', 'decode.cu')
 
 
 def nvcc():
@@ -49,11 +52,14 @@ def build(force=False, verbose=False):
     jobs = []
     objs = []
     for src in sources():
-        o = os.path.join(OBJ, src[:-3] + '.o')
-        objs.append(o)
-        if force or _stale(o, [os.path.join(CSRC, src)] + hdrs):
-            cmd = [nvcc()] + ARCH + COMMON + EXTRA.get(src, []) + ['-c', os.path.join(CSRC, src), '-o', o]
-            jobs.append((src, cmd))
+        for tag, defs in (('', []), ('_f16', ['-DG4R_ACT_HALF'])):
+            if tag and src not in FP16_TWINS:
+                continue
+            o = os.path.join(OBJ, src[:-3] + tag + '.o')
+            objs.append(o)
+            if force or _stale(o, [os.path.join(CSRC, src)] + hdrs):
+                cmd = [nvcc()] + ARCH + COMMON + EXTRA.get(src, []) + defs + ['-c', os.path.join(CSRC, src), '-o', o]
+                jobs.append((src[:-3] + tag + '.cu', cmd))
 
     def run(job):
         src, cmd = job
@@ -67,7 +73,7 @@ def build(force=False, verbose=False):
             print('[nvcc] %s ok' % src)
         return src
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs) or 1)) as ex:
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(12, len(jobs) or 1)) as ex:
         list(ex.map(run, jobs))
     if jobs or force or _stale(LIB, objs):
         cmd = [nvcc()] + ARCH + ['-shared', '-o', LIB] + objs + ['-lcudart_static', '-ldl', '-lrt', '-lpthread']

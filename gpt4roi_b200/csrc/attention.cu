@@ -11,8 +11,9 @@
 // reference rounds them to bf16 twice -- after the matmul and after *scale -- which only adds
 // noise); P is cast to bf16 before the PV product like the reference, the output is rounded once.
 #include "common.cuh"
+#include "act_type.cuh"   // bf16 as written; fp16 twin with -DG4R_ACT_HALF
 
-namespace g4r {
+namespace G4R_NS {
 
 constexpr int kBM = 64;   // query rows per CTA (4 warps x 16)
 constexpr int kBN = 64;   // keys per iteration
@@ -37,7 +38,7 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t&
 }
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." G4R_ACT_PTX "." G4R_ACT_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -243,7 +244,7 @@ static int launch_attn(const void* q, const void* k, const void* v, void* o, lon
 
 }  // namespace g4r
 
-using namespace g4r;
+using namespace G4R_NS;
 
 static int attention_impl(const void* q, const void* k, const void* v, void* out, long long ld, long long bs,
                           long long ldo, long long bso, int B, int H, int L, int head_dim, int causal, float scale,
@@ -256,12 +257,14 @@ extern "C" int g4r_attention_bf16(const void* q, const void* k, const void* v, v
 }
 
 // Training forward: same kernel, additionally writes lse[B, H, L] (fp32) for g4r_attention_bwd_bf16.
+#if G4R_BF16_ONLY   // training-step only: no fp16 twin
 extern "C" int g4r_attention_fwd_lse_bf16(const void* q, const void* k, const void* v, void* out, long long ld,
                                           long long bs, long long ldo, long long bso, int B, int H, int L,
                                           int head_dim, int causal, float scale, float* lse, void* stream) {
   G4R_REQUIRE(lse, "attention_fwd_lse: lse is NULL");
   return attention_impl(q, k, v, out, ld, bs, ldo, bso, B, H, L, head_dim, causal, scale, nullptr, lse, stream);
 }
+#endif
 
 static int attention_impl(const void* q, const void* k, const void* v, void* out, long long ld, long long bs,
                           long long ldo, long long bso, int B, int H, int L, int head_dim, int causal, float scale,

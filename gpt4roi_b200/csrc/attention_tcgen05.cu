@@ -19,8 +19,9 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "act_type.cuh"   // bf16 as written; fp16 twin with -DG4R_ACT_HALF
 
-namespace g4r {
+namespace G4R_NS {
 
 constexpr int kFaBM = 128;
 constexpr int kFaThreads = 256;
@@ -361,7 +362,7 @@ static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
 
 }  // namespace g4r
 
-using namespace g4r;
+using namespace G4R_NS;
 
 // Same contract as g4r_attention_bf16 (attention.cu), with the restriction that q/k/v are contiguous in
 // the batch dimension (bs == L*ld: the packed [B*L, width] QKV buffer), which the TMA descriptors need.
@@ -399,9 +400,11 @@ extern "C" int g4r_attention_tc_bf16(const void* q, const void* k, const void* v
 }
 
 // Training forward on the tcgen05 kernel: additionally writes lse[B, H, L] (fp32, natural log) for g4r_attention_bwd_bf16.
+#if G4R_BF16_ONLY   // training-step only: no fp16 twin
 extern "C" int g4r_attention_tc_lse_bf16(const void* q, const void* k, const void* v, void* out, long long ld,
                                          long long bs, long long ldo, long long bso, int B, int H, int L,
                                          int head_dim, int causal, float scale, float* lse, void* stream) {
   G4R_REQUIRE(lse, "attention_tc_lse: lse is NULL");
   return attention_tc_impl(q, k, v, out, ld, bs, ldo, bso, B, H, L, head_dim, causal, scale, nullptr, lse, stream);
 }
+#endif

@@ -5,8 +5,9 @@
 // Both kernels are HBM-bound: the step streams the whole KV cache of the batch once.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include "act_type.cuh"   // bf16 as written; fp16 twin with -DG4R_ACT_HALF
 
-namespace g4r {
+namespace G4R_NS {
 
 // rows [B*Ln, 3*HD] packed (q|k|v) -> caches [B, Lmax, HD] at positions pos0 .. pos0+Ln-1
 __global__ void __launch_bounds__(256)
@@ -184,7 +185,7 @@ decode_attention_bf16(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16
 
 }  // namespace g4r
 
-using namespace g4r;
+using namespace G4R_NS;
 
 extern "C" int g4r_kv_append_bf16(const void* qkv, long long ld, void* kcache, void* vcache, int B, int Ln,
                                   int pos0, const int* pos_dev, int Lmax, int HD, void* stream) {

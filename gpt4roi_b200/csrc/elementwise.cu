@@ -6,8 +6,9 @@
 // reference produces under bf16 autocast (the only mode in which the SPI module runs, see
 // DESIGN.md "numerics").
 #include "common.cuh"
+#include "act_type.cuh"   // bf16 as written; fp16 twin with -DG4R_ACT_HALF
 
-namespace g4r {
+namespace G4R_NS {
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -837,7 +838,7 @@ static inline int grid_for(long long total, int threads) {
 
 }  // namespace g4r
 
-using namespace g4r;
+using namespace G4R_NS;
 
 extern "C" int g4r_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* out,
                                   long long ldo, int M, int D, float eps, void* stream) {
@@ -954,6 +955,7 @@ extern "C" int g4r_fuse_gather_bf16(const void* own, const float* own_sc, const 
   return G4R_OK;
 }
 
+#if G4R_BF16_ONLY   // training-step only: no fp16 twin
 extern "C" int g4r_fuse_gather_bwd(const void* d_own, int H, const void* dn0, int Hdn0, const void* dn1, int Hdn1,
                                    const void* tp0, int Htp0, const void* tp1, int Htp1, float* out, int B, int C,
                                    void* stream) {
@@ -972,6 +974,7 @@ extern "C" int g4r_fuse_gather_bwd(const void* d_own, int H, const void* dn0, in
   G4R_LAUNCH_CHECK("fuse_gather_bwd");
   return G4R_OK;
 }
+#endif
 
 extern "C" int g4r_gn_finalize(const float* stats, const void* gamma, const void* beta, float* scale,
                                float* shift, int B, int C, int groups, int slots, float count, float eps,
@@ -994,8 +997,10 @@ extern "C" int g4r_pos_embed_mlp(const float* boxes, const void* w0, const void*
   return G4R_OK;
 }
 
+#if G4R_BF16_ONLY   // training-step only: no fp16 twin
 extern "C" int g4r_pos_embed_mlp_grad_size(void) { return kPosSlab; }
 
+#if G4R_BF16_ONLY   // training-step only: no fp16 twin
 extern "C" int g4r_pos_embed_mlp_bwd(const float* boxes, const void* w0, const void* b0, const void* g2, const void* be2,
                                      const void* w3, const void* b3, const void* g5, const void* dout, long long ldd,
                                      float* grads, float* slabs, int K, float eps, void* stream) {
@@ -1009,6 +1014,8 @@ extern "C" int g4r_pos_embed_mlp_bwd(const float* boxes, const void* w0, const v
   G4R_LAUNCH_CHECK("pos_slab_reduce");
   return G4R_OK;
 }
+#endif
+#endif
 
 // out = relu(z * scale[b, c] + shift[b, c]) on an NHWC bf16 map: applies a pending GroupNorm affine + ReLU
 // (mmcv ConvModule's norm + activation, conv_module.py:196-208) where a caller needs the activated map itself

@@ -23,8 +23,9 @@
 // Deterministic: partial sums of the warps and of the cluster ranks are added in fixed order.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include "act_type.cuh"   // bf16 as written; fp16 twin with -DG4R_ACT_HALF
 
-namespace g4r {
+namespace G4R_NS {
 
 enum { SK_ACT_NONE = 0, SK_ACT_RELU = 1, SK_ACT_QUICK_GELU = 2, SK_ACT_SWIGLU = 3 };
 
@@ -64,7 +65,7 @@ __device__ __forceinline__ uint4 ldg_act16(const void* ptr) {
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                           uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32." G4R_ACT_PTX "." G4R_ACT_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -388,7 +389,7 @@ int gemm_skinny_fused(const SkinnyParams& p0, cudaStream_t st) {
 
 }  // namespace g4r
 
-using namespace g4r;
+using namespace G4R_NS;
 
 extern "C" int g4r_decode_gemm_bf16(const void* x, long long ldx, const void* W, long long ldw, void* out, long long ldo,
                                     int M, int N, int K, const void* norm_w, float norm_eps, int act, const void* residual,

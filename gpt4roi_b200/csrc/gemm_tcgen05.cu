@@ -25,8 +25,9 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "act_type.cuh"   // bf16 as written; fp16 twin with -DG4R_ACT_HALF
 
-namespace g4r {
+namespace G4R_NS {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom
@@ -777,7 +778,7 @@ static int pick_block_n(int N, int m_tiles, int k_splits) {
 
 }  // namespace g4r
 
-using namespace g4r;
+using namespace G4R_NS;
 
 extern "C" int g4r_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* D,
                              long long ldd, int M, int N, int K, const void* bias, int bias_f32,
@@ -801,7 +802,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
                      const void* rope_cos, const void* rope_sin, int rope_cols, int rope_L, void* stream,
                      int rope_pos0 = 0, const int* rope_pos_dev = nullptr);
 
-namespace g4r {
+namespace G4R_NS {
 // gemm_skinny.cu: M <= 16 weight-streaming path; returns -1 when the shape does not qualify
 int gemm_skinny_dispatch(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
                          int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr, int act,
@@ -843,6 +844,7 @@ extern "C" int g4r_gemm_qkv_rope_bf16(const void* A, long long lda, const void* 
 //   dW[N_out, K_in]  = dY^T . X                  -> A = dY (a_mn 1), B = X  (b_mn 1, contraction M tokens)
 // The transposes happen in the tensor-core operand descriptors (UMMA major bits), never in memory.
 // Replaces the autograd of F.linear inside the stage-2 training step (gpt4roi/train/train.py:698-712).
+#if G4R_BF16_ONLY   // training-step only: no fp16 twin
 extern "C" int g4r_gemm_bf16_t(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D,
                                long long ldd, int M, int N, int K, int out_f32, void* stream) {
   G4R_REQUIRE(A && B && D, "null operand");
@@ -883,6 +885,7 @@ extern "C" int g4r_gemm_bf16_t(const void* A, long long lda, int a_mn, const voi
   if (two) return launch_gemm_2sm<false>(ta, tb, p, st);
   return bn == 256 ? launch_gemm<256, false>(ta, tb, p, st) : launch_gemm<128, false>(ta, tb, p, st);
 }
+#endif
 
 // Weight gradient of a 3x3 / stride 1 / pad 1 convolution (NHWC, bf16) as ONE tensor-core GEMM on the
 // zero-padded layout:  dW[co, ky, kx, ci] = sum_rows dz_pad[row, co] * x_pad[row + (ky-1)*(W+2) + (kx-1), ci]
@@ -892,6 +895,7 @@ extern "C" int g4r_gemm_bf16_t(const void* A, long long lda, int a_mn, const voi
 // x_pad_origin points at the row of x_pad that tap (0,0) pairs with row 0, i.e. (W+2)+1 rows before the first
 // real row; the caller keeps >= (W+2)+1 zero guard rows on both ends.  dW is fp32 [Cout, 9*Cin]; accumulate != 0
 // adds to it (the four pyramid levels of a fuse round share one weight, gpt4roi/models/layers.py:152-180).
+#if G4R_BF16_ONLY   // training-step only: no fp16 twin
 extern "C" int g4r_conv3x3_dw_bf16(const void* dz_pad, const void* x_pad_origin, float* dW, long long rows, int Wp,
                                    int Cin, int Cout, int accumulate, void* stream) {
   G4R_REQUIRE(dz_pad && x_pad_origin && dW && rows > 0 && Wp > 2, "conv3x3_dw: bad arguments");
@@ -929,6 +933,7 @@ extern "C" int g4r_conv3x3_dw_bf16(const void* dz_pad, const void* x_pad_origin,
   if (t2 && use_2sm(p.N, p.num_m_tiles, 1, false)) return launch_gemm_2sm<false>(ta, tb, p, (cudaStream_t)stream);
   return launch_gemm<256, false>(ta, tb, p, (cudaStream_t)stream);
 }
+#endif
 
 static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M,
                      int N, int K, const void* bias, int bias_f32, const void* residual, long long ldr,
@@ -996,11 +1001,13 @@ static void conv_tiling(int H, int W, int* bw_out, int* bh_out) {
   *bh_out = bh;
 }
 
+#if G4R_BF16_ONLY   // independent of the activation type: built once
 extern "C" int g4r_conv_gn_slots(int H, int W) {
   int bw, bh;
   conv_tiling(H, W, &bw, &bh);
   return ((W + bw - 1) / bw) * ((H + bh - 1) / bh) * 4;
 }
+#endif
 
 extern "C" int g4r_conv_nhwc_bf16(const void* X, const void* Wt, void* Y, int n_img, int H, int W, int Cin,
                                   int Cout, int ksize, int levels, const void* bias, int bias_f32, int act,

@@ -159,6 +159,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// The same with A = B = fp16 (a_format = b_format = 0): the fp16 twin of the inference kernels (act_type.cuh).
+__host__ __device__ constexpr uint32_t make_idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 
 
 // ======================= 2-CTA (cta_group::2) variants =================================

@@ -1,7 +1,8 @@
 """Dense contractions (nn.Linear / nn.Conv2d replacements) on the tcgen05 kernels.
 
 Thin torch-tensor front-ends of `g4r_gemm_bf16` / `g4r_conv_nhwc_bf16`
-(csrc/gemm_tcgen05.cu).  bf16 operands, fp32 accumulation; no library GEMM is called.
+(csrc/gemm_tcgen05.cu).  bf16 operands (or fp16 throughout: the `_f16` twins, for the demo's dtype), fp32
+accumulation; no library GEMM is called.
 """
 import torch
 
@@ -30,7 +31,15 @@ def _prof_end(dev, start, kind, flops):
     PROFILE.append((kind, flops, start, e))
 
 
-def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16,
+def _act16(name, *ts):
+    """The one 16-bit storage type (bf16, or fp16 for the demo's dtype) of the given operands."""
+    dt = ts[0].dtype
+    if dt not in (torch.bfloat16, torch.float16) or any(t.dtype != dt for t in ts):
+        raise TypeError('%s: bf16 (or all-fp16) operands required, got %s' % (name, ' / '.join(str(t.dtype) for t in ts)))
+    return dt
+
+
+def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=None,
            k_splits=1, round_branch=False):
     """y = act(x @ weight.T + bias) (+ residual).  x [..., K] bf16, weight [N, K] bf16.
 
@@ -45,8 +54,10 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     M, N = x2.shape[0], weight.shape[0]
     named = [('x', x2), ('weight', weight), ('bias', bias), ('residual', residual)]
     dev = _L.require_cuda_same_device(named)
-    if x2.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
-        raise TypeError('linear: bf16 operands required, got %s / %s' % (x2.dtype, weight.dtype))
+    a16 = _act16('linear', x2, weight)
+    out_dtype = a16 if out_dtype is None else out_dtype
+    if out_dtype not in (a16, torch.float32):
+        raise TypeError('linear: out_dtype must be %s or fp32' % a16)
     if x2.stride(-1) != 1 or weight.stride(-1) != 1:
         raise RuntimeError('linear: operands must be K-major (unit stride on the last dim)')
     if weight.shape[1] != K:
@@ -59,7 +70,7 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
         slabs = torch.empty((k_splits, M, n_out), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _ps = _prof_begin(dev)
-            _L.check(_L.load().g4r_gemm_bf16(
+            _L.check(getattr(_L.load(), _L.sym('g4r_gemm_bf16', a16))(
                 _L.ptr(x2), x2.stride(0), _L.ptr(weight), weight.stride(0), _L.ptr(slabs), n_out,
                 M, N, K, None, 0, None, 0, 0, 1, int(k_splits), _L.stream_ptr(dev)))
             _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
@@ -72,18 +83,18 @@ def linear(x, weight, bias=None, act=None, residual=None, out=None, out_dtype=to
     out2 = out.reshape(-1, n_out) if out.is_contiguous() else out
     res2 = None
     if residual is not None:
-        if residual.dtype not in (torch.bfloat16, torch.float32):
-            raise TypeError('linear: residual must be bf16 or fp32')
+        if residual.dtype not in (a16, torch.float32):
+            raise TypeError('linear: residual must be %s or fp32' % a16)
         res2 = residual.reshape(-1, n_out) if residual.is_contiguous() else residual
     bias_f32 = 0
     if bias is not None:
         if bias.dtype == torch.float32:
             bias_f32 = 1
-        elif bias.dtype != torch.bfloat16:
-            raise TypeError('linear: bias must be bf16 or fp32')
+        elif bias.dtype != a16:
+            raise TypeError('linear: bias must be %s or fp32' % a16)
     with torch.cuda.device(dev):
         _ps = _prof_begin(dev)
-        _L.check(_L.load().g4r_gemm_bf16_ex(
+        _L.check(getattr(_L.load(), _L.sym('g4r_gemm_bf16_ex', a16))(
             _L.ptr(x2), x2.stride(0), _L.ptr(weight), weight.stride(0), _L.ptr(out2), out2.stride(0),
             M, N, K, _L.ptr(bias), bias_f32, _L.ptr(res2), res2.stride(0) if res2 is not None else 0,
             int(res2 is not None and res2.dtype == torch.float32), int(bool(round_branch)),
@@ -124,10 +135,11 @@ def qkv_rope(x, wqkv, cos, sin, L, rope_cols, pos0=0, pos_dev=None):
     M, K = x.shape
     N = wqkv.shape[0]
     dev = _L.require_cuda_same_device([('x', x), ('wqkv', wqkv), ('cos', cos), ('sin', sin)])
-    out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    a16 = _act16('qkv_rope', x, wqkv, cos, sin)
+    out = torch.empty((M, N), dtype=a16, device=dev)
     with torch.cuda.device(dev):
         _ps = _prof_begin(dev)
-        _L.check(_L.load().g4r_gemm_qkv_rope_bf16(
+        _L.check(getattr(_L.load(), _L.sym('g4r_gemm_qkv_rope_bf16', a16))(
             _L.ptr(x), x.stride(0), _L.ptr(wqkv), wqkv.stride(0), _L.ptr(out), N, M, N, K, _L.ptr(cos), _L.ptr(sin),
             int(rope_cols), int(L), int(pos0), _L.ptr(pos_dev), _L.stream_ptr(dev)))
         _prof_end(dev, _ps, 'gemm', 2.0 * M * N * K)
@@ -158,10 +170,9 @@ def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None, leve
         cout, kh, kw, cin2 = weight_khwc.shape
     if kh != kw or kh not in (1, 3) or cin2 != cin:
         raise RuntimeError('conv_nhwc: weight must be [Cout,k,k,Cin] with k in (1,3)')
-    if x.dtype != torch.bfloat16 or weight_khwc.dtype != torch.bfloat16:
-        raise TypeError('conv_nhwc: bf16 operands required')
+    a16 = _act16('conv_nhwc', x, weight_khwc)
     if out is None:
-        out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((n, h, w, cout), dtype=a16, device=dev)
     bias_f32 = int(bias is not None and bias.dtype == torch.float32)
     groups = 0
     if gn_stats is not None:
@@ -172,7 +183,7 @@ def conv_nhwc(x, weight_khwc, bias=None, act=None, gn_stats=None, out=None, leve
         groups = gn_stats.shape[2]
     with torch.cuda.device(dev):
         _ps = _prof_begin(dev)
-        _L.check(_L.load().g4r_conv_nhwc_bf16(
+        _L.check(getattr(_L.load(), _L.sym('g4r_conv_nhwc_bf16', a16))(
             _L.ptr(x), _L.ptr(weight_khwc), _L.ptr(out), n, h, w, cin, cout, kh, int(levels), _L.ptr(bias), bias_f32,
             ACT[act], _L.ptr(gn_stats), groups, _L.stream_ptr(dev)))
         _prof_end(dev, _ps, 'conv', 2.0 * n * h * w * cout * kh * kw * cin * levels)
@@ -186,10 +197,9 @@ def decode_gemm(x, weight, norm_w=None, norm_eps=1e-6, act=None, residual=None, 
     M, K = x.shape
     N = weight.shape[0]
     dev = _L.require_cuda_same_device([('x', x), ('weight', weight), ('norm_w', norm_w), ('residual', residual)])
-    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
-        raise TypeError('decode_gemm: bf16 operands required')
+    a16 = _act16('decode_gemm', x, weight)
     n_out = N // 2 if act == 'swiglu' else N
-    out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
+    out = torch.empty((M, n_out), dtype=a16, device=dev)
     cos = sin = pos_dev = None
     rope_cols = pos0 = 0
     if rope is not None:
@@ -201,7 +211,7 @@ def decode_gemm(x, weight, norm_w=None, norm_eps=1e-6, act=None, residual=None, 
         lmax, hd = kc.shape[1], kc.shape[2]
     with torch.cuda.device(dev):
         _ps = _prof_begin(dev)
-        _L.check(_L.load().g4r_decode_gemm_bf16(
+        _L.check(getattr(_L.load(), _L.sym('g4r_decode_gemm_bf16', a16))(
             _L.ptr(x), x.stride(0), _L.ptr(weight), weight.stride(0), _L.ptr(out), out.stride(0), M, N, K,
             _L.ptr(norm_w), float(norm_eps), ACT[act], _L.ptr(residual), residual.stride(0) if residual is not None else 0,
             _L.ptr(cos), _L.ptr(sin), int(rope_cols), int(pos0), _L.ptr(pos_dev), _L.ptr(kc), _L.ptr(vc), int(lmax), int(hd),

@@ -32,8 +32,11 @@ class EngineConfig:
                  hidden=4096, n_heads=32, n_layers=32, mlp=11008, vocab=32006, rms_eps=1e-6,
                  rope_theta=10000.0, roi_out=14, roi_sampling=2, spi_dim=1024, gn_groups=64,
                  im_patch_token=32001, bbox_token=32002, im_start_token=32004, im_end_token=32005,
-                 llama_stream=None):
-        """llama_stream: dtype of the LLaMA residual stream in the prefill -- 'bf16' (default: what the reference has
+                 llama_stream=None, dtype='bf16'):
+        """dtype: the 16-bit storage type of weights and activations -- 'bf16' (training scripts, BASELINE "7B bf16
+        prefill") or 'fp16' (the demo: gpt4roi/app.py:74-98,271 builds the model with .half()); fp16 runs the `_f16`
+        twins of every kernel (csrc/act_type.cuh), same fp32 accumulation and rounding points.
+        llama_stream: dtype of the LLaMA residual stream in the prefill -- 'bf16' (default: what the reference has
         when the model was cast to bf16, the BASELINE "7B bf16 prefill" mode) or 'fp32' (what the reference has
         whenever its parameters are fp32 under autocast; 25 % closer to the fp32 anchor at 32 layers, 2.4 % slower:
         tests/test_parity_7b_gpu.py, profiles/r2_bench_stream_ab.json).  Env G4R_LLAMA_STREAM overrides the default."""
@@ -41,10 +44,15 @@ class EngineConfig:
         if llama_stream is None:
             llama_stream = os.environ.get('G4R_LLAMA_STREAM', 'bf16')
         if llama_stream not in ('fp32', 'bf16'):
-            raise ValueError('llama_stream must be fp32 or bf16')
+            raise ValueError('llama_stream must be fp32 or bf16 (bf16 = the 16-bit storage type)')
+        if dtype in (torch.bfloat16, torch.float16):
+            dtype = 'bf16' if dtype == torch.bfloat16 else 'fp16'
+        if dtype not in ('bf16', 'fp16'):
+            raise ValueError("dtype must be 'bf16' or 'fp16'")
         self.__dict__.update(locals())
         del self.__dict__['os']
         del self.__dict__['self']
+        self.torch_dtype = torch.bfloat16 if dtype == 'bf16' else torch.float16
         self.grid = image_size // patch_size
         self.num_patches = self.grid ** 2
         self.head_dim = hidden // n_heads
@@ -59,8 +67,8 @@ class EngineConfig:
         self.level_layers = lv
 
 
-def _b(t, dev):
-    return t.detach().to(device=dev, dtype=BF16).contiguous()
+def _b(t, dev, dt=BF16):
+    return t.detach().to(device=dev, dtype=dt).contiguous()
 
 
 class PrefillEngine:
@@ -71,6 +79,7 @@ class PrefillEngine:
         mirrors of MLVLROIQueryModule / MLVLFuseModule / MlvlRoIExtractor run on it)."""
         self.cfg = cfg
         self.dev = torch.device(device)
+        self.dt = cfg.torch_dtype          # bf16, or fp16 for the demo's dtype
         self.parts = tuple(parts)
         if 'vit' in self.parts:
             self._prepare_vit(vit_sd)
@@ -87,24 +96,24 @@ class PrefillEngine:
         kreal = 3 * c.patch_size ** 2
         self.vit_kpad = (kreal + 7) // 8 * 8
         w = sd[p + 'embeddings.patch_embedding.weight'].reshape(c.vit_hidden, kreal)
-        wp = torch.zeros(c.vit_hidden, self.vit_kpad, dtype=BF16, device=dev)
-        wp[:, :kreal] = w.to(dev, BF16)
+        wp = torch.zeros(c.vit_hidden, self.vit_kpad, dtype=self.dt, device=dev)
+        wp[:, :kreal] = w.to(dev, self.dt)
         self.vit_patch_w = wp
-        self.vit_cls = _b(sd[p + 'embeddings.class_embedding'], dev)
-        self.vit_pos = _b(sd[p + 'embeddings.position_embedding.weight'], dev)
-        self.vit_pre_ln = (_b(sd[p + 'pre_layrnorm.weight'], dev), _b(sd[p + 'pre_layrnorm.bias'], dev))
+        self.vit_cls = _b(sd[p + 'embeddings.class_embedding'], dev, self.dt)
+        self.vit_pos = _b(sd[p + 'embeddings.position_embedding.weight'], dev, self.dt)
+        self.vit_pre_ln = (_b(sd[p + 'pre_layrnorm.weight'], dev, self.dt), _b(sd[p + 'pre_layrnorm.bias'], dev, self.dt))
         self.vit_layers = []
         for i in range(c.select_index):  # layers beyond the selected hidden state are dead work
             q = p + 'encoder.layers.%d.' % i
             wqkv = torch.cat([sd[q + 'self_attn.%s_proj.weight' % n] for n in 'qkv'], 0)
             bqkv = torch.cat([sd[q + 'self_attn.%s_proj.bias' % n] for n in 'qkv'], 0)
             self.vit_layers.append(dict(
-                ln1=(_b(sd[q + 'layer_norm1.weight'], dev), _b(sd[q + 'layer_norm1.bias'], dev)),
-                wqkv=_b(wqkv, dev), bqkv=_b(bqkv, dev),
-                wo=_b(sd[q + 'self_attn.out_proj.weight'], dev), bo=_b(sd[q + 'self_attn.out_proj.bias'], dev),
-                ln2=(_b(sd[q + 'layer_norm2.weight'], dev), _b(sd[q + 'layer_norm2.bias'], dev)),
-                w1=_b(sd[q + 'mlp.fc1.weight'], dev), b1=_b(sd[q + 'mlp.fc1.bias'], dev),
-                w2=_b(sd[q + 'mlp.fc2.weight'], dev), b2=_b(sd[q + 'mlp.fc2.bias'], dev)))
+                ln1=(_b(sd[q + 'layer_norm1.weight'], dev, self.dt), _b(sd[q + 'layer_norm1.bias'], dev, self.dt)),
+                wqkv=_b(wqkv, dev, self.dt), bqkv=_b(bqkv, dev, self.dt),
+                wo=_b(sd[q + 'self_attn.out_proj.weight'], dev, self.dt), bo=_b(sd[q + 'self_attn.out_proj.bias'], dev, self.dt),
+                ln2=(_b(sd[q + 'layer_norm2.weight'], dev, self.dt), _b(sd[q + 'layer_norm2.bias'], dev, self.dt)),
+                w1=_b(sd[q + 'mlp.fc1.weight'], dev, self.dt), b1=_b(sd[q + 'mlp.fc1.bias'], dev, self.dt),
+                w2=_b(sd[q + 'mlp.fc2.weight'], dev, self.dt), b2=_b(sd[q + 'mlp.fc2.bias'], dev, self.dt)))
 
     def _prepare_spi(self, sd):
         """SPI-module weights in engine layout.  The two halves are independent (a stand-alone MLVLFuseModule or
@@ -117,50 +126,50 @@ class PrefillEngine:
             self.in_w, self.in_b = [], []
             for l in range(c.num_levels):
                 w = sd[p + 'mlvl_fuse.input_conv.%d.weight' % l].reshape(C, C + 2)
-                wp = torch.zeros(C, self.spi_cpad, dtype=BF16, device=dev)
-                wp[:, :C + 2] = w.to(dev, BF16)
+                wp = torch.zeros(C, self.spi_cpad, dtype=self.dt, device=dev)
+                wp[:, :C + 2] = w.to(dev, self.dt)
                 self.in_w.append(wp)
-                self.in_b.append(_b(sd[p + 'mlvl_fuse.input_conv.%d.bias' % l], dev))
+                self.in_b.append(_b(sd[p + 'mlvl_fuse.input_conv.%d.bias' % l], dev, self.dt))
             self.fuse = []
             for r in range(5):
                 q = p + 'mlvl_fuse.fuse_convs.%d.' % r
-                w = sd[q + 'conv.weight'].to(dev, BF16).permute(0, 2, 3, 1).contiguous()  # [Cout,kh,kw,Cin]
-                self.fuse.append(dict(w=w, gamma=_b(sd[q + 'gn.weight'], dev), beta=_b(sd[q + 'gn.bias'], dev)))
+                w = sd[q + 'conv.weight'].to(dev, self.dt).permute(0, 2, 3, 1).contiguous()  # [Cout,kh,kw,Cin]
+                self.fuse.append(dict(w=w, gamma=_b(sd[q + 'gn.weight'], dev, self.dt), beta=_b(sd[q + 'gn.bias'], dev, self.dt)))
         q = p + 'roi_align.'
         if q + 'flatten_linear.weight' in sd:
-            pw = torch.stack([sd[q + 'pconvs.%d.weight' % l].to(dev, BF16).permute(0, 2, 3, 1)
+            pw = torch.stack([sd[q + 'pconvs.%d.weight' % l].to(dev, self.dt).permute(0, 2, 3, 1)
                               for l in range(c.num_levels)], 1).contiguous()  # [Cout, L, kh, kw, Cin]
             self.pconv_w = pw
             self.pconv_b = sum(sd[q + 'pconvs.%d.bias' % l].to(dev, torch.float32) for l in range(c.num_levels)).contiguous()
             R = c.roi_out
             fw = sd[q + 'flatten_linear.weight']  # [1024, C*R*R] in (c, ph, pw) order (layers.py:326)
-            self.flat_w = fw.to(dev, BF16).reshape(-1, C, R, R).permute(0, 2, 3, 1).reshape(fw.shape[0], -1).contiguous()
-            self.flat_b = _b(sd[q + 'flatten_linear.bias'], dev)
-            self.pos = [_b(sd[q + 'pos_embedd.%s' % n], dev) for n in
+            self.flat_w = fw.to(dev, self.dt).reshape(-1, C, R, R).permute(0, 2, 3, 1).reshape(fw.shape[0], -1).contiguous()
+            self.flat_b = _b(sd[q + 'flatten_linear.bias'], dev, self.dt)
+            self.pos = [_b(sd[q + 'pos_embedd.%s' % n], dev, self.dt) for n in
                         ('0.weight', '0.bias', '2.weight', '2.bias', '3.weight', '3.bias', '5.weight', '5.bias')]
-            self.up_w, self.up_b = _b(sd[q + 'updims.weight'], dev), _b(sd[q + 'updims.bias'], dev)
+            self.up_w, self.up_b = _b(sd[q + 'updims.weight'], dev, self.dt), _b(sd[q + 'updims.bias'], dev, self.dt)
             kb = self.flat_w.shape[1] // 64
             self.flat_splits = next(s for s in (16, 14, 8, 7, 4, 2, 1) if kb % s == 0)
         if 'model.mm_projector.weight' in sd:
-            self.proj_w, self.proj_b = _b(sd['model.mm_projector.weight'], dev), _b(sd['model.mm_projector.bias'], dev)
+            self.proj_w, self.proj_b = _b(sd['model.mm_projector.weight'], dev, self.dt), _b(sd['model.mm_projector.bias'], dev, self.dt)
 
     def _prepare_llm(self, sd):
         c, dev = self.cfg, self.dev
-        self.embed = _b(sd['model.embed_tokens.weight'], dev)
+        self.embed = _b(sd['model.embed_tokens.weight'], dev, self.dt)
         self.layers = []
         for i in range(c.n_layers):
             q = 'model.layers.%d.' % i
-            wqkv = torch.cat([sd[q + 'self_attn.%s_proj.weight' % n].to(dev, BF16) for n in 'qkv'], 0).contiguous()
-            g, u = sd[q + 'mlp.gate_proj.weight'].to(dev, BF16), sd[q + 'mlp.up_proj.weight'].to(dev, BF16)
+            wqkv = torch.cat([sd[q + 'self_attn.%s_proj.weight' % n].to(dev, self.dt) for n in 'qkv'], 0).contiguous()
+            g, u = sd[q + 'mlp.gate_proj.weight'].to(dev, self.dt), sd[q + 'mlp.up_proj.weight'].to(dev, self.dt)
             wgu = torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]).contiguous()  # rows: g0,u0,g1,u1,...
             self.layers.append(dict(
-                ln_in=_b(sd[q + 'input_layernorm.weight'], dev), wqkv=wqkv,
-                wo=_b(sd[q + 'self_attn.o_proj.weight'], dev),
-                ln_post=_b(sd[q + 'post_attention_layernorm.weight'], dev), wgu=wgu,
-                wdown=_b(sd[q + 'mlp.down_proj.weight'], dev)))
+                ln_in=_b(sd[q + 'input_layernorm.weight'], dev, self.dt), wqkv=wqkv,
+                wo=_b(sd[q + 'self_attn.o_proj.weight'], dev, self.dt),
+                ln_post=_b(sd[q + 'post_attention_layernorm.weight'], dev, self.dt), wgu=wgu,
+                wdown=_b(sd[q + 'mlp.down_proj.weight'], dev, self.dt)))
             del g, u
-        self.norm_w = _b(sd['model.norm.weight'], dev)
-        self.lm_head = _b(sd['lm_head.weight'], dev) if 'lm_head.weight' in sd else None   # LlamaModel-only seam
+        self.norm_w = _b(sd['model.norm.weight'], dev, self.dt)
+        self.lm_head = _b(sd['lm_head.weight'], dev, self.dt) if 'lm_head.weight' in sd else None   # LlamaModel-only seam
         self.vocab_pad = (c.vocab + 63) // 64 * 64
 
     def _rope(self, L):
@@ -170,7 +179,7 @@ class PrefillEngine:
             inv = 1.0 / (c.rope_theta ** (torch.arange(0, c.head_dim, 2, dtype=torch.int64).float() / c.head_dim))
             freqs = torch.arange(L, dtype=torch.float32)[:, None] * inv[None, :]
             emb = torch.cat((freqs, freqs), -1)
-            self._rope_cache[L] = (emb.cos().to(self.dev, BF16).contiguous(), emb.sin().to(self.dev, BF16).contiguous())
+            self._rope_cache[L] = (emb.cos().to(self.dev, self.dt).contiguous(), emb.sin().to(self.dev, self.dt).contiguous())
         return self._rope_cache[L]
 
     # ------------------------------------------------------------------ stages
@@ -217,7 +226,7 @@ class PrefillEngine:
         for l, layer in enumerate(c.level_layers):
             H = c.level_sizes[l]
             up = kernels.upsample_tokens_coords(taps[layer], H if pre_upsampled else c.grid, H, self.spi_cpad,
-                                                has_cls=has_cls)
+                                                has_cls=has_cls, dtype=self.dt)
             m = dense.linear(up.view(-1, self.spi_cpad), self.in_w[l], self.in_b[l]).view(B, H, H, C)
             maps.append(m)
         ss = [None] * c.num_levels
@@ -243,7 +252,7 @@ class PrefillEngine:
         rois = torch.cat([batch_idx[:, None], boxes * float(c.image_size)], 1).contiguous()  # layers.py:294-302
         scales = [float(torch.tensor(1.0 / s, dtype=torch.float32)) for s in c.strides]
         # ss=None: the maps are already activated (MlvlRoIExtractor.forward called on its own)
-        feats = roi_align_mlvl(maps, rois, c.roi_out, scales, c.roi_sampling, True, out_dtype=BF16,
+        feats = roi_align_mlvl(maps, rois, c.roi_out, scales, c.roi_sampling, True, out_dtype=self.dt,
                                gn_scale=None if ss is None else [s for s, _ in ss],
                                gn_shift=None if ss is None else [b for _, b in ss])
         R = c.roi_out
@@ -291,7 +300,7 @@ class PrefillEngine:
             raise RuntimeError('this engine was built without lm_head.weight (LlamaModel seam): use want="hidden"')
         rows = x.shape[0]
         # padded row stride keeps the epilogue's 128-bit stores aligned (vocab 32006 is not a multiple of 8)
-        buf = torch.empty((rows, self.vocab_pad), dtype=BF16, device=self.dev)
+        buf = torch.empty((rows, self.vocab_pad), dtype=self.dt, device=self.dev)
         dense.linear(x, self.lm_head, out=buf[:, :c.vocab])
         return buf.view(B, rows // B, self.vocab_pad)[:, :, :c.vocab]
 
@@ -328,7 +337,7 @@ class PrefillEngine:
             return self.llama(embeds, B, L, last_only=last_only, seqlens=seqlens, cache=cache,
                               hidden_taps=hidden_taps, want=want)
         taps = self.vit(images)
-        feat = kernels.cast_tokens_f32_bf16(taps[c.select_index])  # spi_llava.py:68-73 (+ autocast cast, CLS dropped)
+        feat = kernels.cast_tokens_f32_bf16(taps[c.select_index], dtype=self.dt)  # spi_llava.py:68-73 (+ autocast cast, CLS dropped)
         img_rows = dense.linear(feat, self.proj_w, self.proj_b).view(B, c.num_patches, c.hidden)
         region = None
         if plan is not None:
@@ -336,7 +345,7 @@ class PrefillEngine:
                 maps, ss = self.fuse_maps(taps)
                 rows = self.region_tokens(maps, ss, plan['boxes'], plan['bidx'])
             else:
-                rows = torch.zeros((1, c.hidden), dtype=BF16, device=self.dev)
+                rows = torch.zeros((1, c.hidden), dtype=self.dt, device=self.dev)
             region = (rows, plan['offs'])
         embeds = splice_region_tokens(input_ids, self.embed, img_rows, region, c.num_patches, c.im_patch_token,
                                       c.im_start_token, c.im_end_token, c.bbox_token, validate=validate)
@@ -363,8 +372,8 @@ class PrefillEngine:
             if not bool((m == (torch.arange(m.shape[1], device=self.dev)[None] < lens[:, None])).all()):
                 raise NotImplementedError('only right-padded attention masks are supported')
             seqlens = lens.to(torch.int32).contiguous()
-        return self.forward_device(input_ids.to(self.dev, non_blocking=True),
-                                   None if images is None else images.to(self.dev, BF16, non_blocking=True),
+        return self.forward_device(input_ids.to(self.dev, non_blocking=True).contiguous(),
+                                   None if images is None else images.to(self.dev, self.dt, non_blocking=True).contiguous(),
                                    plan, validate, last_only, seqlens, cache=cache, hidden_taps=hidden_taps, want=want,
                                    stage_taps=stage_taps)
 
@@ -373,12 +382,13 @@ _DECODE_FUSED = int(__import__('os').environ.get('G4R_DECODE_FUSED', '1'))
 
 
 class KVCache:
-    """Per-layer K/V cache [B, Lmax, n_heads*head_dim] (bf16, post-RoPE keys) for the decode loop."""
+    """Per-layer K/V cache [B, Lmax, n_heads*head_dim] (the engine's 16-bit type, post-RoPE keys) for the decode loop."""
 
     def __init__(self, cfg, B, max_len, device):
         hd = cfg.n_heads * cfg.head_dim
-        self.k = [torch.empty((B, max_len, hd), dtype=BF16, device=device) for _ in range(cfg.n_layers)]
-        self.v = [torch.empty((B, max_len, hd), dtype=BF16, device=device) for _ in range(cfg.n_layers)]
+        dt = cfg.torch_dtype
+        self.k = [torch.empty((B, max_len, hd), dtype=dt, device=device) for _ in range(cfg.n_layers)]
+        self.v = [torch.empty((B, max_len, hd), dtype=dt, device=device) for _ in range(cfg.n_layers)]
         self.B, self.max_len, self.length = B, max_len, 0
 
 
@@ -442,7 +452,7 @@ def _decode_step_chain(self, token_ids, cache, pos_dev):
         x = dense.linear(f, w['wdown'], residual=x)
     cache.length = pos + 1
     x = kernels.rmsnorm(x, self.norm_w, c.rms_eps)
-    buf = torch.empty((B, self.vocab_pad), dtype=BF16, device=self.dev)
+    buf = torch.empty((B, self.vocab_pad), dtype=self.dt, device=self.dev)
     dense.linear(x, self.lm_head, out=buf[:, :c.vocab])
     return buf[:, None, :c.vocab]
 
@@ -457,7 +467,7 @@ def _generate(self, input_ids, images, bboxes, max_new_tokens=32, do_sample=Fals
     cache = KVCache(self.cfg, B, L + max_new_tokens, self.dev)
     plan = self.plan_boxes(bboxes)
     ids = input_ids.to(self.dev)
-    logits = self.forward_device(ids, images.to(self.dev, BF16), plan, validate=True, last_only=True, cache=cache)
+    logits = self.forward_device(ids, images.to(self.dev, self.dt), plan, validate=True, last_only=True, cache=cache)
     out = ids
     stepper = None
     if use_graph and max_new_tokens > 4 and self.cfg.head_dim == 128:
@@ -524,7 +534,7 @@ class GraphedPrefill:
         self.eng = engine
         dev = engine.dev
         self.ids = input_ids.to(dev).clone()
-        self.images = images.to(dev, BF16).clone()
+        self.images = images.to(dev, engine.dt).clone()
         self.plan = engine.plan_boxes(bboxes)
         self.counts = None if bboxes is None else [0 if b is None else int(b.shape[0]) for b in bboxes]
         side = torch.cuda.Stream(device=dev)

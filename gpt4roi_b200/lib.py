@@ -96,6 +96,45 @@ SIGNATURES = {
     'g4r_add_bias_pos_cast': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
 }
 
+# fp16 twins of the inference entry points (include/gpt4roi_b200.h, last section; csrc/act_type.cuh): same signatures.
+F16_TWINS = {
+    'g4r_gemm_bf16': 'g4r_gemm_f16',
+    'g4r_gemm_bf16_ex': 'g4r_gemm_f16_ex',
+    'g4r_gemm_qkv_rope_bf16': 'g4r_gemm_qkv_rope_f16',
+    'g4r_conv_nhwc_bf16': 'g4r_conv_nhwc_f16',
+    'g4r_attention_tc_bf16': 'g4r_attention_tc_f16',
+    'g4r_attention_bf16': 'g4r_attention_f16',
+    'g4r_layernorm_bf16': 'g4r_layernorm_f16',
+    'g4r_rmsnorm_bf16': 'g4r_rmsnorm_f16',
+    'g4r_rope_inplace_bf16': 'g4r_rope_inplace_f16',
+    'g4r_patchify_bf16': 'g4r_patchify_f16',
+    'g4r_vit_embed_bf16': 'g4r_vit_embed_f16',
+    'g4r_upsample_tokens_coords_bf16': 'g4r_upsample_tokens_coords_f16',
+    'g4r_upsample_tokens_coords_f32': 'g4r_upsample_tokens_coords_f32_f16',
+    'g4r_layernorm_ex': 'g4r_layernorm_ex_f16',
+    'g4r_rmsnorm_ex': 'g4r_rmsnorm_ex_f16',
+    'g4r_cast_f32_bf16': 'g4r_cast_f32_f16',
+    'g4r_fuse_gather_bf16': 'g4r_fuse_gather_f16',
+    'g4r_gn_finalize': 'g4r_gn_finalize_f16',
+    'g4r_pos_embed_mlp': 'g4r_pos_embed_mlp_f16',
+    'g4r_affine_relu_nhwc_bf16': 'g4r_affine_relu_nhwc_f16',
+    'g4r_add_bias_pos_cast': 'g4r_add_bias_pos_cast_f16',
+    'g4r_decode_gemm_bf16': 'g4r_decode_gemm_f16',
+    'g4r_kv_append_bf16': 'g4r_kv_append_f16',
+    'g4r_decode_attention_bf16': 'g4r_decode_attention_f16',
+}
+SIGNATURES.update({twin: SIGNATURES[name] for name, twin in F16_TWINS.items()})
+
+
+def sym(name, dtype):
+    """Entry-point name for 16-bit tensors of `dtype`: the bf16 name itself, or its fp16 twin."""
+    if dtype == torch.float16:
+        return F16_TWINS[name]
+    if dtype != torch.bfloat16:
+        raise TypeError('%s: bf16 or fp16 tensors required, got %s' % (name, dtype))
+    return name
+
+
 _lib = None
 LAUNCHES = 0  # kernels launched through the C ABI (bench.py reports it as gpu_launches)
 

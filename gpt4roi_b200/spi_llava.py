@@ -49,8 +49,16 @@ class LlavaConfig(LlamaConfig):
 
 
 def _param_version(module):
-    """Changes whenever a parameter is updated in place (optimizer step, load_state_dict, .data.copy_) or replaced."""
-    return tuple((id(p), p._version) for p in module.parameters())
+    """Changes whenever a parameter is updated in place (optimizer step, load_state_dict, .data.copy_), replaced, or
+    cast (`.half()` / `.bfloat16()` swap `.data` without bumping the version counter)."""
+    return tuple((id(p), p._version, p.dtype) for p in module.parameters())
+
+
+def _engine_dtype(module):
+    """fp16 parameters (the demo: gpt4roi/app.py:74-98 `.half()`) -> the fp16 kernels; anything else -> bf16 (the
+    training scripts' --bf16, and fp32 masters under autocast)."""
+    p = next(module.parameters(), None)
+    return 'fp16' if p is not None and p.dtype == torch.float16 else 'bf16'
 
 
 # =========================================================================================
@@ -74,20 +82,21 @@ def _spi_engine(module, prefix, sd_extra, grid, device):
     if cache.get('key') != key:
         sd = {SPI_PREFIX + prefix + k: v for k, v in module.state_dict().items()}
         sd.update(sd_extra)
-        cfg = EngineConfig(image_size=int(grid) * 14, n_layers=0)
+        cfg = EngineConfig(image_size=int(grid) * 14, n_layers=0, dtype=_engine_dtype(module))
         cache['eng'] = PrefillEngine(cfg, sd, None, device, parts=('spi',))
         cache['key'] = key
     return cache['eng']
 
 
-def _to_tokens(feats):
-    """list of [B,P,C] token maps or [B,C,G,G] NCHW maps (layers.py:219-224) -> (list of contiguous [B,P,C], G)."""
+def _to_tokens(feats, dt=BF16):
+    """list of [B,P,C] token maps or [B,C,G,G] NCHW maps (layers.py:219-224) -> (list of contiguous [B,P,C], G);
+    dt: the engine's 16-bit type (fp32 maps pass through: the resampling kernel reads them directly)."""
     out = []
     for f in feats:
         if f.dim() == 4:
             f = f.permute(0, 2, 3, 1).reshape(f.shape[0], -1, f.shape[1])
-        if f.dtype not in (torch.float32, BF16):
-            f = f.to(BF16)
+        if f.dtype not in (torch.float32, dt):
+            f = f.to(dt)
         out.append(f.contiguous())
     G = int(round(out[0].shape[1] ** 0.5))
     if G * G != out[0].shape[1]:
@@ -125,7 +134,7 @@ class MLVLFuseModule(nn.Module):
         eng = _spi_engine(self, 'mlvl_fuse.', {}, G, dev)
         if [m.shape[-1] for m in inputs] != eng.cfg.level_sizes:
             raise ValueError('expected pyramid sizes %s, got %s' % (eng.cfg.level_sizes, [m.shape[-1] for m in inputs]))
-        maps, ss = eng.fuse_maps(_to_tokens(inputs)[0], has_cls=False, pre_upsampled=True)
+        maps, ss = eng.fuse_maps(_to_tokens(inputs, eng.dt)[0], has_cls=False, pre_upsampled=True)
         outs = [kernels.affine_relu_nhwc(m, s[0], s[1]) for m, s in zip(maps, ss)]
         return [o.permute(0, 3, 1, 2).to(inputs[0].dtype) for o in outs]
 
@@ -162,7 +171,7 @@ class MlvlRoIExtractor(nn.Module):
         dev = feats[0].device
         G = feats[-1].shape[-1]
         eng = _spi_engine(self, 'roi_align.', {}, G, dev)
-        maps = [f.permute(0, 2, 3, 1).to(BF16).contiguous() for f in feats]
+        maps = [f.permute(0, 2, 3, 1).to(eng.dt).contiguous() for f in feats]
         plan = eng.plan_boxes(rois)
         if plan is None or plan['K'] == 0:
             return [feats[0].new_zeros((0, self.updims.out_features)) for _ in rois]
@@ -205,15 +214,19 @@ class MLVLROIQueryModule(nn.Module):
         up-sampling + coordinate channels, 1x1 input convs, 5 fuse rounds, multi-level RoIAlign, pconvs,
         flatten_linear, box position MLP, updims.  With grad enabled the SPI parameters receive gradients
         (explicit backward on the same kernels)."""
-        tokens, G = _to_tokens(list(mlvl_feats))
+        dt = torch.float16 if _engine_dtype(self) == 'fp16' else BF16
+        tokens, G = _to_tokens(list(mlvl_feats), dt)
         dev = tokens[0].device
         eng = _spi_engine(self, '', {}, G, dev)
         plan = eng.plan_boxes(bboxes)
         out_dims = self.roi_align.updims.out_features
         if plan is None or plan['K'] == 0:
-            return [tokens[0].new_zeros((0, out_dims), dtype=BF16) for _ in bboxes]
+            return [tokens[0].new_zeros((0, out_dims), dtype=dt) for _ in bboxes]
         named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
         if torch.is_grad_enabled() and named:
+            if dt != BF16:
+                raise NotImplementedError('fp16 parameters with grad enabled: the training kernels are bf16 (the reference '
+                                          'trains with --bf16 True); call under torch.no_grad() or cast the module')
             if any(t.requires_grad for t in tokens):
                 raise NotImplementedError('gradients w.r.t. the CLIP features are not provided (the tower is frozen)')
             rows = _SpiQueryFn.apply(self, eng, tokens, plan, tuple(n for n, _ in named), *[p for _, p in named])
@@ -284,7 +297,7 @@ class _EngineHost:
                             hidden=config.hidden_size, n_heads=config.num_attention_heads,
                             n_layers=config.num_hidden_layers, mlp=config.intermediate_size,
                             vocab=config.vocab_size, rms_eps=config.rms_norm_eps,
-                            rope_theta=_rope_theta(config), **self._token_ids(vc))
+                            rope_theta=_rope_theta(config), dtype=_engine_dtype(self), **self._token_ids(vc))
 
 
 def _rope_theta(config):
@@ -410,7 +423,7 @@ def _run_engine(eng, input_ids, images, bboxes, attention_mask, past_key_values,
     kv = new_cache.kv if new_cache is not None else None
     if inputs_embeds is not None:
         B, L = inputs_embeds.shape[:2]
-        x = inputs_embeds.to(eng.dev, BF16).contiguous()
+        x = inputs_embeds.to(eng.dev, eng.dt).contiguous()
         if kv is not None:
             kv.length = L
         out = eng.llama(x, B, L, seqlens=_seqlens(eng, attention_mask, L), cache=kv, want=want, last_only=last_only)

@@ -933,6 +933,9 @@ class Stage2Trainer:
         the flat weight buffer, overlapped with the next forward.  The bf16 compute weights stay replicated (14 GB)."""
         import copy
         from .engine import PrefillEngine
+        if getattr(cfg, 'dtype', 'bf16') != 'bf16':
+            raise NotImplementedError('the training step is bf16 only (train_stage*.sh --bf16 True); the fp16 kernels are '
+                                      'the inference twins for the demo')
         self.cfg, self.dev = cfg, torch.device(device)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.reducer, self.world = reducer, world_size

@@ -494,6 +494,88 @@ int g4r_sumsq(const void* g, int g_bf16, long long n, float* slab, void* stream)
 int g4r_grad_clip_coef(const float* slabs, long long n_slabs, float pre_scale, float max_norm, float* out2,
                        void* stream);
 
+/* ---- fp16 twins of the inference entry points ---------------------------------------------
+ * The demo serves the model in fp16 (gpt4roi/app.py:74-98,271: `model.half()`, `images.half()`, `bboxes.half()`).
+ * Every entry point below has the signature, argument meaning and error behaviour of its `_bf16` namesake above,
+ * with "bf16" read as "fp16" for every 16-bit tensor (activations, weights, norm / bias vectors, RoPE tables, KV
+ * cache); fp32 arguments (statistics, scale / shift, split-K slabs, fp32 residual streams) are unchanged, and the
+ * arithmetic is the same (fp32 accumulation, the same rounding points, tcgen05 kind::f16 with the F16 operand
+ * format).  Built from the same sources with -DG4R_ACT_HALF (gpt4roi_b200/csrc/act_type.cuh).  RoIAlign and the
+ * splice take a dtype argument / are 2-byte copies and need no twin; the training step is bf16 only
+ * (train_stage*.sh --bf16 True). */
+int g4r_gemm_f16(const void* A, long long lda, const void* B, long long ldb,
+                  void* D, long long ldd, int M, int N, int K,
+                  const void* bias, int bias_f32,
+                  const void* residual, long long ldr,
+                  int act, int out_f32, int k_splits, void* stream);
+int g4r_gemm_f16_ex(const void* A, long long lda, const void* B, long long ldb,
+                     void* D, long long ldd, int M, int N, int K,
+                     const void* bias, int bias_f32,
+                     const void* residual, long long ldr, int residual_f32, int bias_round_bf16,
+                     int act, int out_f32, int k_splits, void* stream);
+int g4r_gemm_qkv_rope_f16(const void* A, long long lda, const void* B, long long ldb,
+                           void* D, long long ldd, int M, int N, int K,
+                           const void* rope_cos, const void* rope_sin, int rope_cols, int L, int pos0,
+                           const int* pos0_dev /* device int32 overriding pos0 (CUDA-graph decode) or NULL */,
+                           void* stream);
+int g4r_conv_nhwc_f16(const void* X, const void* Wt, void* Y,
+                       int n_img, int H, int W, int Cin, int Cout, int ksize, int levels,
+                       const void* bias, int bias_f32, int act,
+                       float* gn_stats, int gn_groups, void* stream);
+int g4r_attention_tc_f16(const void* q, const void* k, const void* v, void* out,
+                          long long ld, long long bs, long long ldo, long long bso,
+                          int B, int H, int L, int head_dim, int causal, float scale,
+                          const int* seqlens, void* stream);
+int g4r_attention_f16(const void* q, const void* k, const void* v, void* out,
+                       long long ld, long long bs, long long ldo, long long bso,
+                       int B, int H, int L, int head_dim, int causal, float scale,
+                       const int* seqlens /* device int32 [B] or NULL: keys >= seqlens[b] are masked */,
+                       void* stream);
+int g4r_layernorm_f16(const void* x, long long ldx, const void* w, const void* b,
+                       void* out, long long ldo, int M, int D, float eps, void* stream);
+int g4r_rmsnorm_f16(const void* x, long long ldx, const void* w,
+                     void* out, long long ldo, int M, int D, float eps, void* stream);
+int g4r_rope_inplace_f16(void* qkv, long long ld, const void* cos_t, const void* sin_t,
+                          int rows, int L, int n_heads_qk, int head_dim, void* stream);
+int g4r_patchify_f16(const void* img, void* out, int B, int S, int ps, int Kpad, void* stream);
+int g4r_vit_embed_f16(const void* patch, const void* cls, const void* pos, void* out,
+                       int B, int P, int D, void* stream);
+int g4r_upsample_tokens_coords_f16(const void* tok, long long ldt, long long bst, void* out,
+                                    int B, int G, int Ho, int C, int Cpad, void* stream);
+int g4r_upsample_tokens_coords_f32_f16(const void* tok, long long ldt, long long bst, void* out,
+                                   int B, int G, int Ho, int C, int Cpad, void* stream);
+int g4r_layernorm_ex_f16(const void* x, long long ldx, int x_f32, const void* w, const void* b,
+                     void* out, long long ldo, int out_f32, int M, int D, float eps, void* stream);
+int g4r_rmsnorm_ex_f16(const void* x, long long ldx, int x_f32, const void* w, void* out, long long ldo, int M, int D,
+                   float eps, void* stream);
+int g4r_cast_f32_f16(const void* x, long long ld, long long bst, void* out,
+                      int B, int rows_per_batch, int D, void* stream);
+int g4r_fuse_gather_f16(const void* own, const float* own_sc, const float* own_sh, int H,
+                         const void* top, const float* top_sc, const float* top_sh, int Ht,
+                         const void* down, const float* down_sc, const float* down_sh, int Hd,
+                         void* out, int B, int C, void* stream);
+int g4r_gn_finalize_f16(const float* stats, const void* gamma, const void* beta,
+                    float* scale, float* shift, int B, int C, int groups, int slots,
+                    float count, float eps, void* stream);
+int g4r_pos_embed_mlp_f16(const float* boxes, const void* w0, const void* b0, const void* g2,
+                      const void* be2, const void* w3, const void* b3, const void* g5,
+                      const void* be5, float* out, int K, float eps, void* stream);
+int g4r_affine_relu_nhwc_f16(const void* z, const float* scale, const float* shift, void* out, int B,
+                              long long pix_per_img, int C, void* stream);
+int g4r_add_bias_pos_cast_f16(const float* acc, int splits, const void* bias, const float* pos, void* out,
+                          int K, int D, void* stream);
+int g4r_decode_gemm_f16(const void* x, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M,
+                         int N, int K, const void* norm_w, float norm_eps, int act, const void* residual, long long ldr,
+                         const void* rope_cos, const void* rope_sin, int rope_cols, int pos0, const int* pos_dev,
+                         void* kcache, void* vcache, int cache_lmax, int cache_hd, void* stream);
+int g4r_kv_append_f16(const void* qkv, long long ld, void* kcache, void* vcache,
+                       int B, int Ln, int pos0, const int* pos_dev /* overrides pos0 when non-NULL */,
+                       int Lmax, int HD, void* stream);
+int g4r_decode_attention_f16(const void* q, long long ldq, const void* kcache, const void* vcache,
+                              void* out, long long ldo, int B, int H, int head_dim, int kv_len,
+                              const int* pos_dev /* kv_len = *pos_dev + 1 when non-NULL; kv_len then sizes smem */,
+                              int Lmax, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
