@@ -96,7 +96,7 @@ def synthetic_inputs(cfg, B, k_per_img, T, seed=0):
         bx = torch.cat([p[:, 0, :], p[:, 1, :]], 1)
         bx[:, 2:] = torch.maximum(bx[:, 2:], bx[:, :2] + 2.0 / cfg.image_size).clamp(max=1.0)
         boxes.append(bx)
-    images = torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=g).to(torch.bfloat16)
+    images = torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=g).to(getattr(cfg, 'torch_dtype', torch.bfloat16))
     return ids, images, boxes
 
 
@@ -500,7 +500,7 @@ def run_ours(args):
     dist_utils.init('nccl', dev)   # NCCL only for the barrier + max-over-ranks time (no data-path collective in the prefill)
     pk, how = peaks()
 
-    cfg = EngineConfig(image_size=WORKLOAD['image_size'], n_layers=args.layers, vit_layers=24)
+    cfg = EngineConfig(image_size=WORKLOAD['image_size'], n_layers=args.layers, vit_layers=24, dtype=args.dtype)
     B, K, T = WORKLOAD['batch_per_gpu'], WORKLOAD['rois_per_image'], WORKLOAD['text_tokens']
     sd, vit_sd = random_state_dicts(cfg, dev, seed=0)
     eng = PrefillEngine(cfg, sd, vit_sd, dev)
@@ -557,8 +557,8 @@ def run_ours(args):
     #      timed region ends when the last copy has landed. ---
     copy_stream = torch.cuda.Stream(device=dev)
     V = cfg.vocab
-    h_out = [torch.empty((B, L, V), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
-    d_snap = [torch.empty((B, L, V), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    h_out = [torch.empty((B, L, V), dtype=cfg.torch_dtype).pin_memory() for _ in range(2)]
+    d_snap = [torch.empty((B, L, V), dtype=cfg.torch_dtype, device=dev) for _ in range(2)]
     ev_copied = [torch.cuda.Event() for _ in range(2)]
 
     def e2e_step(i):
@@ -662,7 +662,7 @@ def run_ours(args):
     cpu = cpu_reference_sample() if (world == 1 and not args.no_cpu_baseline) else None
     line = dict(metric=METRIC, value=value, unit='samples/s',
                 n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic',
                 config=dict(workload='configs[1]: batch %d/GPU, 336px, %d RoIs/img, %d-tok prompt (L=%d), '
                                      'CLIP-ViT-L/14 + SPI + LLaMA-7B (%d layers) + lm_head, full logits' %
                                      (B, K, T, L, cfg.n_layers),
@@ -689,6 +689,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--layers', type=int, default=32, help=argparse.SUPPRESS)  # debugging only; 32 = LLaMA-7B
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp16'],
+                    help="16-bit storage type of the prefill / decode kernels (fp16 = the demo's mode; training extras stay bf16)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roialign', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='headline only (no config2 / decode / train_step extras)')

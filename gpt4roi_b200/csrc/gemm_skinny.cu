@@ -90,7 +90,9 @@ __device__ __forceinline__ uint4 norm8(const uint4& x, const uint4& w, float rst
   return o;
 }
 
-template <int MT, int MB, int WARPS, bool ROPE, bool NORM = false>
+// DEPTH: k-blocks each warp keeps in flight (register double buffering): with DEPTH = 2 a warp that owns two k-blocks
+// (o_proj: K = 4096 over 16 warps) requests its whole share before the first MMA -- one HBM latency instead of two.
+template <int MT, int MB, int WARPS, bool ROPE, bool NORM = false, int DEPTH = 1>
 __global__ void __launch_bounds__(WARPS * 32)
 gemm_skinny_bf16(const SkinnyParams p) {
   constexpr int KB = 128;        // k per warp iteration: 4 sub-blocks of 32 (one 16-byte load per row each)
@@ -137,8 +139,8 @@ gemm_skinny_bf16(const SkinnyParams p) {
   // predecessor (programmatic dependent launch, common.cuh) -- its tail and this kernel's ramp-up overlap.
   const int kstep = KS * WARPS * KB;
   int k0 = (rank * WARPS + warp) * KB;
-  uint4 a[4][MT][2];
-  auto load_w = [&](int kb) {
+  uint4 a[DEPTH][4][MT][2];
+  auto load_w = [&](uint4 (&aw)[4][MT][2], int kb) {
 #pragma unroll
     for (int s = 0; s < 4; s++) {
       // K % 32 == 0: a sub-block is whole or absent.  Loads are unconditional (absent blocks / rows re-read element 0
@@ -150,11 +152,13 @@ gemm_skinny_bf16(const SkinnyParams p) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const uint4 v = ldg_stream16(wrow[j][h] + kk);
-          a[s][j][h] = kok ? v : make_uint4(0, 0, 0, 0);
+          aw[s][j][h] = kok ? v : make_uint4(0, 0, 0, 0);
         }
     }
   };
-  if (k0 < p.K) load_w(k0);
+#pragma unroll
+  for (int d = 0; d < DEPTH; d++)
+    if (k0 + d * kstep < p.K) load_w(a[d], k0 + d * kstep);
   pdl_sync(p.pdl);
 
   if constexpr (NORM) {
@@ -180,10 +184,10 @@ gemm_skinny_bf16(const SkinnyParams p) {
 #pragma unroll
   for (int i = 0; i < MB; i++) rstd[i] = NORM ? s_rstd[i * 8 + g] : 1.f;
 
-  // activation fragments of a k-block; like the weights they are fetched one block ahead, so that all loads of a block
-  // are issued back to back (left inside the loop body, ptxas strings them out between the dependent HMMAs)
-  uint4 b[4][MB];
-  auto load_x = [&](int kb) {
+  // activation fragments of a k-block; like the weights they are fetched DEPTH blocks ahead, so that all loads of a
+  // block are issued back to back (left inside the loop body, ptxas strings them out between the dependent HMMAs)
+  uint4 b[DEPTH][4][MB];
+  auto load_x = [&](uint4 (&bx)[4][MB], int kb) {
 #pragma unroll
     for (int s = 0; s < 4; s++) {
       const bool kok = kb + 32 * s < p.K;
@@ -191,30 +195,37 @@ gemm_skinny_bf16(const SkinnyParams p) {
 #pragma unroll
       for (int i = 0; i < MB; i++) {
         const uint4 v = ldg_act16(xrow[i] + kk);   // rows >= M alias row 0; their outputs are never stored
-        b[s][i] = kok ? v : make_uint4(0, 0, 0, 0);
+        bx[s][i] = kok ? v : make_uint4(0, 0, 0, 0);
       }
       if constexpr (NORM) {
         const uint4 w8 = __ldg(reinterpret_cast<const uint4*>(p.norm_w + kk + 8 * t));
 #pragma unroll
-        for (int i = 0; i < MB; i++) b[s][i] = norm8(b[s][i], w8, rstd[i]);
+        for (int i = 0; i < MB; i++) bx[s][i] = norm8(bx[s][i], w8, rstd[i]);
       }
     }
   };
-  if (k0 < p.K) load_x(k0);
+#pragma unroll
+  for (int d = 0; d < DEPTH; d++)
+    if (k0 + d * kstep < p.K) load_x(b[d], k0 + d * kstep);
 #pragma unroll 1
-  for (; k0 < p.K; k0 += kstep) {
+  for (; k0 < p.K; k0 += DEPTH * kstep) {
 #pragma unroll
-    for (int s = 0; s < 4; s++)
+    for (int d = 0; d < DEPTH; d++) {
+      const int kd = k0 + d * kstep;
+      if (kd >= p.K) break;       // warp-uniform
 #pragma unroll
-      for (int j = 0; j < MT; j++)
+      for (int s = 0; s < 4; s++)
 #pragma unroll
-        for (int i = 0; i < MB; i++) {
-          mma_16816(acc[j][i], a[s][j][0].x, a[s][j][1].x, a[s][j][0].y, a[s][j][1].y, b[s][i].x, b[s][i].y);
-          mma_16816(acc[j][i], a[s][j][0].z, a[s][j][1].z, a[s][j][0].w, a[s][j][1].w, b[s][i].z, b[s][i].w);
-        }
-    if (k0 + kstep < p.K) {   // next block: in flight across the loop edge
-      load_w(k0 + kstep);
-      load_x(k0 + kstep);
+        for (int j = 0; j < MT; j++)
+#pragma unroll
+          for (int i = 0; i < MB; i++) {
+            mma_16816(acc[j][i], a[d][s][j][0].x, a[d][s][j][1].x, a[d][s][j][0].y, a[d][s][j][1].y, b[d][s][i].x, b[d][s][i].y);
+            mma_16816(acc[j][i], a[d][s][j][0].z, a[d][s][j][1].z, a[d][s][j][0].w, a[d][s][j][1].w, b[d][s][i].z, b[d][s][i].w);
+          }
+      if (kd + DEPTH * kstep < p.K) {   // refill this slot: in flight across the loop edge
+        load_w(a[d], kd + DEPTH * kstep);
+        load_x(b[d], kd + DEPTH * kstep);
+      }
     }
   }
 
@@ -320,16 +331,26 @@ static int skinny_target_ctas() {
   return v;
 }
 
-template <int MT, int MB, int WARPS, bool ROPE, bool NORM = false>
+template <int MT, int MB, int WARPS, bool ROPE, bool NORM = false, int DEPTH = 1>
 static int launch_skinny(const SkinnyParams& p, unsigned tiles, cudaStream_t st) {
   // cluster split-K factor: enough CTAs for several waves, every warp keeps >= 1 k-block of 128
   int ks = 1;
   while (ks < 8 && (int)tiles * ks < skinny_target_ctas() && p.K >= 2 * ks * WARPS * 128) ks *= 2;
   SkinnyParams q = p;
   q.pdl = pdl_mode();
-  G4R_CUDA(launch_pdl(gemm_skinny_bf16<MT, MB, WARPS, ROPE, NORM>, dim3(tiles, ks, 1), dim3(WARPS * 32), 0, st,
+  G4R_CUDA(launch_pdl(gemm_skinny_bf16<MT, MB, WARPS, ROPE, NORM, DEPTH>, dim3(tiles, ks, 1), dim3(WARPS * 32), 0, st,
                       dim3(1, ks, 1), q));
   return G4R_OK;
+}
+
+// 32-row tiles, M <= 8: 4 warps (4 CTAs per SM) or 8 warps (2 CTAs per SM, twice the bytes in flight per CTA).  What
+// separates them is the partially filled last wave: pick the CTA size whose wave count rounds up the least
+// (gate/up, 688 tiles: 1.16 waves of 592 slots vs 2.32 of 296 -> 8 warps, 38.0 -> 35.4 us; lm_head, 1001 tiles:
+// 1.69 vs 3.38 -> 4 warps, 45.4 vs 48.4 us).
+static bool wide_prefers_8_warps(int tiles) {
+  const double w4 = (double)tiles / (4.0 * num_sms()), w8 = (double)tiles / (2.0 * num_sms());
+  auto waste = [](double w) { const double c = (double)(long long)(w + 0.999999); return c / w; };
+  return waste(w8) < 0.95 * waste(w4);
 }
 
 // Called by gemm_impl (gemm_tcgen05.cu) when the shape qualifies; returns -1 when it does not.
@@ -355,11 +376,14 @@ int gemm_skinny_dispatch(const void* A, long long lda, const void* B, long long 
   const bool wide = (N + 31) / 32 >= 2 * num_sms();
   if (wide) {
     const unsigned grid = (unsigned)((N + 31) / 32);
-    return M <= 8 ? launch_skinny<2, 1, 4, false>(p, grid, st) : launch_skinny<2, 2, 4, false>(p, grid, st);
+    if (M > 8) return launch_skinny<2, 2, 4, false>(p, grid, st);
+    return wide_prefers_8_warps((int)grid) ? launch_skinny<2, 1, 8, false>(p, grid, st) : launch_skinny<2, 1, 4, false>(p, grid, st);
   }
   const unsigned grid = (unsigned)((N + 15) / 16);
-  // 16-row tiles give few CTAs (N/16): 16 warps each keep >= 100 KB of weight loads in flight per SM
-  return M <= 8 ? launch_skinny<1, 1, 16, false>(p, grid, st) : launch_skinny<1, 2, 16, false>(p, grid, st);
+  // 16-row tiles give few CTAs (N/16 = 256 for the 4096-row projections).  M <= 8: 8 warps with two k-blocks in flight
+  // each (128 registers -> 2 CTAs per SM, so all 256 CTAs are resident at once and request half the matrix up front):
+  // o_proj 11.4 -> 8.4 us, down_proj 21.5 -> 17.8 us (B200, profiles/r2_decode_pdl_depth.md).  M <= 16: 16 warps.
+  return M <= 8 ? launch_skinny<1, 1, 8, false, false, 2>(p, grid, st) : launch_skinny<1, 2, 16, false>(p, grid, st);
 }
 
 // Decode-step fused entry (M <= 16): [RMSNorm ->] GEMM [-> RoPE + KV-cache write | SwiGLU | residual].
@@ -380,11 +404,12 @@ int gemm_skinny_fused(const SkinnyParams& p0, cudaStream_t st) {
   if (wide) {
     const unsigned grid = (unsigned)((p.N + 31) / 32);
     if (norm) return p.M <= 8 ? launch_skinny<2, 1, 4, false, true>(p, grid, st) : launch_skinny<2, 2, 4, false, true>(p, grid, st);
-    return p.M <= 8 ? launch_skinny<2, 1, 4, false>(p, grid, st) : launch_skinny<2, 2, 4, false>(p, grid, st);
+    if (p.M > 8) return launch_skinny<2, 2, 4, false>(p, grid, st);
+    return wide_prefers_8_warps((int)grid) ? launch_skinny<2, 1, 8, false>(p, grid, st) : launch_skinny<2, 1, 4, false>(p, grid, st);
   }
   const unsigned grid = (unsigned)((p.N + 15) / 16);
   if (norm) return p.M <= 8 ? launch_skinny<1, 1, 16, false, true>(p, grid, st) : launch_skinny<1, 2, 16, false, true>(p, grid, st);
-  return p.M <= 8 ? launch_skinny<1, 1, 16, false>(p, grid, st) : launch_skinny<1, 2, 16, false>(p, grid, st);
+  return p.M <= 8 ? launch_skinny<1, 1, 8, false, false, 2>(p, grid, st) : launch_skinny<1, 2, 16, false>(p, grid, st);
 }
 
 }  // namespace g4r

@@ -21,6 +21,8 @@ reference's own bf16 mode misses by 36x at this depth: 3.6e-2):
   * bf16 stream: every stage within 1.25x the reference-under-autocast's own error, logits within 4e-2 / 5e-2 (measured 3.05e-2 / 3.36e-2);
   * engine vs the bf16-autocast reference (same dtype, two independent sets of bf16 roundings) within 1.6x the
     larger of the two anchor errors;
+  * fp16 engine (EngineConfig(dtype='fp16'), the demo's mode): three more mantissa bits -- logits within 8e-3 rel-L2 /
+    1.2e-2 max-rel of the fp32 anchor at 32 layers, every stage closer to the anchor than the bf16-autocast reference;
   * greedy next-token agreement with the fp32 anchor no worse than the bf16-autocast reference's own agreement minus
     one point (the disagreements are near-ties of random-init logits).
 Weights: seeded random init of the real architecture with the reference's init scales (no checkpoints offline)."""
@@ -91,6 +93,13 @@ def test_full_7b_forward_through_the_seam_vs_fp32_and_bf16_oracles():
     got16 = run(eng16)
     del eng16
     torch.cuda.empty_cache()
+    # fp16 mode (the demo's dtype, gpt4roi/app.py:74-98): the same weights (bf16 values are fp16-representable down to
+    # 6e-5; below that the absolute error is < 6e-8) through the `_f16` kernels
+    eng_h = PrefillEngine(EngineConfig(image_size=336, vit_layers=24, n_layers=32, dtype='fp16'), sd, vit_sd, DEV)
+    assert eng_h.dt == torch.float16
+    got_h = run(eng_h)
+    del eng_h
+    torch.cuda.empty_cache()
 
     # ---- oracles ------------------------------------------------------------------------------------------
     def collect(ref_logits, inter):
@@ -107,7 +116,8 @@ def test_full_7b_forward_through_the_seam_vs_fp32_and_bf16_oracles():
                                         return_intermediates=True, hidden_layers=depth))
     order = ['vit%d' % l for l in cfg.level_layers] + ['region', 'embeds'] + ['h%d' % n for n in depth] + ['logits']
     agree16 = (r16['logits'].argmax(-1) == r32['logits'].argmax(-1)).float().mean().item()
-    for name, g, slack, lim in (('bf16 stream (default)', got, 1.25, (4e-2, 5e-2)), ('fp32 stream', got16, 1.0, (3e-2, 4e-2))):
+    for name, g, slack, lim in (('bf16 stream (default)', got, 1.25, (4e-2, 5e-2)), ('fp32 stream', got16, 1.0, (3e-2, 4e-2)),
+                                ('fp16 engine (demo dtype)', got_h, 1.0, (8e-3, 1.2e-2))):
         print('\n[%s]\nstage      | engine vs fp32      | bf16-ref vs fp32    | engine vs bf16-ref   (rel-L2 / max-rel)' % name)
         rows = {}
         for k in order:

@@ -39,6 +39,9 @@ def timed_graph(fn, n_iter=5):
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    if os.environ.get('G4R_BENCH_PDL'):     # launch the chain the way the decode step does (programmatic dependent launch)
+        from gpt4roi_b200 import lib
+        lib.set_pdl(True)
     hid, ffn, H, D, V = 4096, 11008, 32, 128, 32006
     R = 8   # weight copies (>= 33 MB each -> well past the 126 MB L2 in rotation)
     torch.manual_seed(0)
