@@ -85,6 +85,36 @@ def test_mmcv_ext_dropin_module():
         m.nms()
 
 
+def test_reference_wrapper_runs_over_the_dropin_and_never_falls_back():
+    """The reference's UNMODIFIED `mmcv.ops.roi_align` / `RoIAlign` (mmcv-1.4.7/mmcv/ops/roi_align.py) imported with
+    `gpt4roi_b200.mmcv_ext.install()` in place of `mmcv._ext`: `import mmcv.ops` succeeds (ext_loader only asserts
+    hasattr), the wrapper's forward lands in OUR entry point, and on a box without a GPU that entry raises instead of
+    computing on the CPU.  Needs the reference tree (build container); the same call pattern runs on the GPU in
+    tests/test_roi_align_gpu.py::test_mmcv_ext_module_as_the_reference_wrapper_calls_it."""
+    import subprocess
+    import sys
+    if not os.path.isdir('/root/reference/mmcv'):
+        pytest.skip('reference tree not present')
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from tests.golden import ref_shims; ref_shims.install(use_b200=True)\n"
+        "import torch, mmcv.ops\n"
+        "R = sys.modules['mmcv.ops.roi_align']\n"
+        "import importlib; ours = importlib.import_module('gpt4roi_b200.roi_align')\n"
+        "assert R.__file__.startswith('/root/reference/'), R.__file__\n"
+        "assert R.ext_module.roi_align_forward is ours.roi_align_forward\n"
+        "layer = R.RoIAlign((7, 7), 0.5, 2)\n"
+        "try:\n"
+        "    layer(torch.zeros(1, 4, 8, 8), torch.tensor([[0., 0., 0., 4., 4.]]))\n"
+        "except RuntimeError as e:\n"
+        "    assert 'CUDA' in str(e) or 'cuda' in str(e), e\n"
+        "    print('LOUD')\n"
+        "else:\n"
+        "    raise SystemExit('the drop-in computed on the CPU')\n") % (ROOT, os.path.join(ROOT, 'tests', 'golden'))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'LOUD' in r.stdout, r.stderr[-2000:] + r.stdout[-500:]
+
+
 def test_product_never_imports_oracle():
     bad = []
     for dp, _, fns in os.walk(os.path.join(ROOT, 'gpt4roi_b200')):
