@@ -65,23 +65,23 @@ def test_mmcv_ext_module_as_the_reference_wrapper_calls_it():
         out_h, out_w = kat['pool_h'], kat['pool_w']
         output = x.new_zeros((rois.size(0), x.size(1), out_h, out_w))
         argmax_y, argmax_x = x.new_zeros(0), x.new_zeros(0)                      # pool_mode 'avg': roi_align.py:88-90
-        ext.roi_align_forward(x, rois, output, argmax_y, argmax_x, pooled_height=out_h, pooled_width=out_w,
+        ext.roi_align_forward(x, rois, output, argmax_y, argmax_x, aligned_height=out_h, aligned_width=out_w,
                               spatial_scale=kat['spatial_scale'], sampling_ratio=kat['sampling_ratio'], pool_mode=1,
                               aligned=True)
         assert np.array_equal(output.cpu().numpy(), np.array(case['output'], dtype=np.float32))
         grad_output = torch.ones_like(output)
         grad_input = grad_output.new_zeros(x.shape)
-        ext.roi_align_backward(grad_output, rois, argmax_y, argmax_x, grad_input, pooled_height=out_h,
-                               pooled_width=out_w, spatial_scale=kat['spatial_scale'],
+        ext.roi_align_backward(grad_output, rois, argmax_y, argmax_x, grad_input, aligned_height=out_h,
+                               aligned_width=out_w, spatial_scale=kat['spatial_scale'],
                                sampling_ratio=kat['sampling_ratio'], pool_mode=1, aligned=True)
         assert np.allclose(grad_input.cpu().numpy(), np.array(case['grad_input']), atol=1e-3)
     rng = np.random.default_rng(5)
     xin = rng.standard_normal((2, 64, 48, 48)).astype(np.float32)
-    rois_np = make_rois(rng, 12, 2, 336.0)
+    rois_np = make_rois(rng, 2, 6, 336.0)                                    # 2 images x 6 boxes
     want, _, _ = O.roi_align_forward(xin, rois_np, 14, SCALES[2], 2, 'avg', True)
     x, rois = _t(xin), _t(rois_np)
     output = x.new_zeros((12, 64, 14, 14))
-    ext.roi_align_forward(x, rois, output, x.new_zeros(0), x.new_zeros(0), pooled_height=14, pooled_width=14,
+    ext.roi_align_forward(x, rois, output, x.new_zeros(0), x.new_zeros(0), aligned_height=14, aligned_width=14,
                           spatial_scale=SCALES[2], sampling_ratio=2, pool_mode=1, aligned=True)
     assert np.array_equal(output.cpu().numpy(), want)
     with pytest.raises(NotImplementedError):
