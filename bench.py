@@ -404,7 +404,11 @@ def decode_extra(eng, cfg, dev, pk, n_new=48):
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / (n_new - 4)
-        out['batch%d' % B] = dict(ms_per_token=ms, tokens_per_s=B * 1e3 / ms, frac_of_weight_stream_floor=floor_ms / ms)
+        # bytes one step must stream: every decoder / lm_head weight once + the K and V rows of all cached positions
+        kv_bytes = 2 * B * (ids.shape[1] + 4 + (n_new - 4) / 2) * cfg.hidden * 2 * cfg.n_layers
+        floor_kv_ms = (wbytes + kv_bytes) / (pk['hbm_gbs'] * 1e9) * 1e3
+        out['batch%d' % B] = dict(ms_per_token=ms, tokens_per_s=B * 1e3 / ms, frac_of_weight_stream_floor=floor_ms / ms,
+                                  weight_plus_kv_floor_ms=floor_kv_ms, frac_of_weight_plus_kv_floor=floor_kv_ms / ms)
         del stepper, cache
     out['weight_stream_floor_ms'] = floor_ms
     out['note'] = ('floor = bf16 decoder + lm_head weight bytes / measured HBM bandwidth; greedy sampling (arg-max on the host '
